@@ -1,0 +1,387 @@
+// capi.cu — the C ABI of include/sgufp_b200.h: handle, HBM layout, launches, result conversion.
+//
+// Host-side mirror of GuroSolver (/root/reference/grb.h:17-104).  There is no CPU fallback:
+// every compute entry point needs a CUDA device and fails with SGUFP_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <climits>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sgufp_b200.h"
+#include "k1_cut.cuh"
+#include "model.hpp"
+
+using namespace sgufp;
+
+namespace {
+thread_local std::string g_create_error;
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+}  // namespace
+
+struct sgufp_ctx {
+    Model M;
+    int S = 0, m_pad = 0, device = 0, sm_count = 0;
+    long long scen_off = 0, S_total = 0;
+    double *d_u = nullptr, *d_l = nullptr;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DevBuf<int32_t> d_plans, d_plan_off, d_ray_i32;
+    DevBuf<unsigned long long> d_sums;
+    DevBuf<long long> d_finf, d_ray_scratch;
+    DevBuf<double> d_obj;
+    DevBuf<uint8_t> d_status;
+    std::string err;
+    int last_launches = 0;
+    float last_ms = 0.f;
+    int W() const { return 1 + M.L + M.m; }
+};
+
+#define CU(ctx, call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                      \
+            return SGUFP_ERR_CUDA;                                                                 \
+        }                                                                                          \
+    } while (0)
+
+static int fail(sgufp_ctx *c, int code, const std::string &msg) { c->err = msg; return code; }
+
+// ---- helpers shared by the one-GPU and the sharded entry points --------------------------------
+struct Batch {
+    std::vector<Plan> plans;
+    std::vector<int32_t> words, off;
+    int max_nch = 0, max_nopen = 0;
+};
+
+static int make_batch(sgufp_ctx *c, const int16_t *paths, int K, int L, Batch &B) {
+    if (!paths || K < 1 || L < 0 || L > c->M.L) return fail(c, SGUFP_ERR_ARG, "paths: need K >= 1 and 0 <= L <= totalLayers");
+    B.plans.resize(K); B.off.resize(K);
+    for (int k = 0; k < K; k++) {
+        std::string e;
+        if (int rc = build_plan(c->M, paths + (size_t)k * L, L, B.plans[k], e)) return fail(c, rc, "path " + std::to_string(k) + ": " + e);
+        B.off[k] = (int32_t)B.words.size();
+        B.words.insert(B.words.end(), B.plans[k].words.begin(), B.plans[k].words.end());
+        B.max_nch = std::max(B.max_nch, B.plans[k].nch);
+        B.max_nopen = std::max(B.max_nopen, B.plans[k].nopen);
+    }
+    return 0;
+}
+
+static int launch_batch(sgufp_ctx *c, const Batch &B, int K, unsigned long long *d_sums, long long *d_finf, double *d_obj,
+                        uint8_t *d_status, cudaStream_t st) {
+    CU(c, c->d_plans.reserve(B.words.size()));
+    CU(c, c->d_plan_off.reserve(K));
+    CU(c, cudaMemcpyAsync(c->d_plans.p, B.words.data(), B.words.size() * 4, cudaMemcpyHostToDevice, st));
+    CU(c, cudaMemcpyAsync(c->d_plan_off.p, B.off.data(), (size_t)K * 4, cudaMemcpyHostToDevice, st));
+    CU(c, cudaMemsetAsync(d_sums, 0, (size_t)K * c->W() * 8, st));
+    std::vector<long long> inf(K, LLONG_MAX);
+    CU(c, cudaMemcpyAsync(d_finf, inf.data(), (size_t)K * 8, cudaMemcpyHostToDevice, st));
+    CU(c, cudaStreamSynchronize(st));  // `inf`, B.words are host temporaries
+    K1Launch p{};
+    p.cap_u = c->d_u; p.cap_l = c->d_l; p.S = c->S; p.m = c->M.m; p.m_pad = c->m_pad; p.scen_offset = c->scen_off;
+    p.plans = c->d_plans.p; p.plan_off = c->d_plan_off.p; p.K = K; p.W = c->W(); p.L = c->M.L;
+    p.sums = d_sums; p.first_inf = d_finf; p.obj = d_obj; p.status = d_status;
+    p.max_nch = B.max_nch; p.max_nopen = B.max_nopen; p.nc = c->M.nc; p.nav = c->M.nav;
+    if (c->S > 0) CU(c, k1_launch(p, st, c->sm_count, &c->last_launches));
+    return 0;
+}
+
+// kinds used by the ray: a dangling end arc books into its FREE multiplier, everything else by endpoints
+static void ray_arrays(const sgufp_ctx *c, const Plan &P, std::vector<int32_t> &ts, std::vector<int32_t> &hs, std::vector<int32_t> &info,
+                       std::vector<int32_t> &pair_layer, std::vector<int32_t> &next, std::vector<int32_t> &aq, std::vector<int32_t> &first_wire, int &nn) {
+    const Model &M = c->M;
+    const int m = M.m;
+    std::vector<int32_t> wire(m, -1);
+    nn = M.nc;
+    for (int a = 0; a < m; a++) if (P.match_out[a] >= 0) wire[a] = nn++;
+    ts.assign(m, 0); hs.assign(m, 0); info.assign(m, 0); pair_layer.assign(m, -1); next.assign(m, -1); aq.assign(m, 0);
+    first_wire.assign(std::max(1, M.nav), -1);
+    for (int a = 0; a < m; a++) {
+        const int t = M.tail[a], h = M.head[a];
+        ts[a] = M.active[t] ? (P.match_in[a] >= 0 ? wire[P.match_in[a]] : -1) : M.cn[t];
+        hs[a] = M.active[h] ? (P.match_out[a] >= 0 ? wire[a] : -1) : M.cn[h];
+        int kind;
+        if (hs[a] < 0) kind = KIND_SIGMA; else if (ts[a] < 0) kind = KIND_PHI;
+        else kind = M.active[h] ? KIND_SIGMA : (M.active[t] ? KIND_PHI : KIND_GAMMA);
+        info[a] = kind | ((M.arc_layer[a] + 1) << 2);
+        if (P.match_out[a] >= 0) { pair_layer[a] = M.arc_layer[a]; next[a] = P.match_out[a]; }
+        aq[a] = (M.av_index[t] + 1) | ((M.av_index[h] + 1) << 16);
+    }
+    for (int i = 0; i < M.nav; i++) {
+        const int q = M.av_node[i];
+        for (int e = M.in_ptr[q]; e < M.in_ptr[q + 1]; e++)
+            if (P.match_out[M.in_arc[e]] >= 0) { first_wire[i] = wire[M.in_arc[e]]; break; }
+    }
+}
+
+static int run_ray(sgufp_ctx *c, const Plan &P, long long global_s, unsigned long long *d_sums, cudaStream_t st) {
+    const long long sl = global_s - c->scen_off;
+    if (sl < 0 || sl >= c->S) return fail(c, SGUFP_ERR_ARG, "ray: scenario is not in this rank's block");
+    std::vector<int32_t> ts, hs, info, pl, nx, aq, fw;
+    int nn = 0;
+    ray_arrays(c, P, ts, hs, info, pl, nx, aq, fw, nn);
+    const int m = c->M.m, nav = std::max(1, c->M.nav);
+    std::vector<int32_t> pack;
+    pack.reserve((size_t)6 * m + nav);
+    for (auto *v : {&ts, &hs, &info, &pl, &nx, &aq}) pack.insert(pack.end(), v->begin(), v->end());
+    pack.insert(pack.end(), fw.begin(), fw.end());
+    CU(c, c->d_ray_i32.reserve(pack.size()));
+    CU(c, c->d_ray_scratch.reserve((size_t)2 * nn + (size_t)(2 * m + 4 * nn) / 2 + 8));
+    CU(c, cudaMemcpyAsync(c->d_ray_i32.p, pack.data(), pack.size() * 4, cudaMemcpyHostToDevice, st));
+    CU(c, cudaMemsetAsync(d_sums, 0, (size_t)c->W() * 8, st));
+    CU(c, cudaStreamSynchronize(st));
+    RayLaunch r{};
+    r.cap_u = c->d_u; r.cap_l = c->d_l; r.s_local = (int)sl; r.m = m; r.m_pad = c->m_pad; r.nn = nn;
+    const int32_t *b = c->d_ray_i32.p;
+    r.arc_ts = b; r.arc_hs = b + m; r.arc_info = b + 2 * m; r.arc_pair_layer = b + 3 * m; r.arc_next = b + 4 * m; r.arc_q = b + 5 * m;
+    r.av_first_wire = b + 6 * m; r.nav = c->M.nav; r.L = c->M.L;
+    r.scratch = reinterpret_cast<int32_t *>(c->d_ray_scratch.p);
+    r.sums = d_sums;
+    CU(c, ray_launch(r, st, &c->last_launches));
+    return 0;
+}
+
+// exact integer sums -> Inavap::Cut (cutToCut, Cut.h:406-421)
+static void finalize_one(const sgufp_ctx *c, const Plan &P, const long long *sums, bool feas, int *cut_type, double *rhs,
+                         uint64_t *keys, double *vals, int *nnz, double *coef_dense) {
+    const Model &M = c->M;
+    const int L = M.L, T = M.T;
+    const double div = feas ? 1.0 : (double)c->S_total;   // `double scenarios` (grb.cpp:169); no 1/S on a ray (grb.cpp:301-347)
+    const PlanHeader *H = reinterpret_cast<const PlanHeader *>(P.words.data());
+    const int32_t *plan_info = P.words.data() + H->o_arc_info;
+    auto kind = [&](int a) -> int {
+        if (!feas) return plan_info[a] & 3;
+        const int t = M.tail[a], h = M.head[a];
+        if (M.active[h] && P.match_out[a] < 0) return KIND_SIGMA;
+        if (M.active[t] && P.match_in[a] < 0) return KIND_PHI;
+        return M.active[h] ? KIND_SIGMA : (M.active[t] ? KIND_PHI : KIND_GAMMA);
+    };
+    if (cut_type) *cut_type = feas ? SGUFP_CUT_FEASIBILITY : SGUFP_CUT_OPTIMALITY;
+    if (rhs) *rhs = (double)sums[0] / div;
+    std::vector<double> coef(T);
+    for (int ell = 0; ell < L; ell++) {
+        const int a = M.layer_arc[ell];
+        const long long sig = kind(a) == KIND_SIGMA ? sums[1 + L + a] : 0;
+        for (int s = M.slot_base[ell]; s < M.slot_base[ell + 1]; s++) {
+            const int b = M.slot_out[s];
+            long long v = sig;
+            if (P.match_out[a] == b) v -= sums[1 + ell];
+            if (kind(b) == KIND_PHI) v += sums[1 + L + b];
+            coef[s] = (double)v / div;
+        }
+    }
+    if (coef_dense) std::memcpy(coef_dense, coef.data(), T * sizeof(double));
+    int k = 0;
+    for (int r = 0; r < T; r++) {
+        const int s = M.slot_sorted[r];
+        if (coef[s] == 0) continue;   // `if (v == 0) continue;` (Cut.h:412)
+        if (keys && vals) {
+            const uint64_t i = (uint64_t)M.tail[M.slot_in[s]], q = (uint64_t)M.head[M.slot_in[s]], j = (uint64_t)M.head[M.slot_out[s]];
+            keys[k] = q | (i << 16) | (j << 32);   // getKey (Cut.h:342-344)
+            vals[k] = coef[s];
+        }
+        k++;
+    }
+    if (nnz) *nnz = k;
+}
+
+extern "C" {
+
+const char *sgufp_last_error(const sgufp_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int sgufp_create(sgufp_ctx **out, int n, int m, int S, const int32_t *tail, const int32_t *head, const int32_t *upper,
+                 const int32_t *lower, const int32_t *reward0, const int32_t *vbar, int nvbar, int device,
+                 int64_t scenario_offset, int64_t S_total) {
+    if (!out) { g_create_error = "out is null"; return SGUFP_ERR_ARG; }
+    *out = nullptr;
+    if (S < 0 || S_total < 1 || scenario_offset < 0 || scenario_offset + S > S_total || (S > 0 && (!upper || !lower))) {
+        g_create_error = "scenario block must lie inside [0, S_total)"; return SGUFP_ERR_ARG;
+    }
+    sgufp_ctx *c = new sgufp_ctx();
+    auto bail = [&](int code, const std::string &msg) { g_create_error = msg; sgufp_destroy(c); return code; };
+    std::string e;
+    if (int rc = c->M.build(n, m, tail, head, reward0, vbar, nvbar, e)) return bail(rc, e);
+    for (size_t i = 0; i < (size_t)m * S; i++)
+        if (upper[i] < 0 || lower[i] < 0 || upper[i] >= (1 << 20) || lower[i] >= (1 << 20))
+            return bail(SGUFP_ERR_LIMITS, "capacities must lie in [0, 2^20) (DESIGN.md §5)");
+    c->S = S; c->scen_off = scenario_offset; c->S_total = S_total; c->device = device;
+    c->m_pad = (m + 1) & ~1;   // rows 16-byte aligned for 128-bit loads
+#define CUC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return bail(SGUFP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } while (0)
+    CUC(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUC(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return bail(SGUFP_ERR_CUDA, std::string("device ") + prop.name + " is not sm_100-class; the kernels are built for sm_100a only");
+    c->sm_count = prop.multiProcessorCount;
+    CUC(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    CUC(cudaEventCreate(&c->ev0));
+    CUC(cudaEventCreate(&c->ev1));
+    if (S > 0) {
+        const size_t cells = (size_t)S * c->m_pad;
+        CUC(cudaMalloc(&c->d_u, cells * sizeof(double)));
+        CUC(cudaMalloc(&c->d_l, cells * sizeof(double)));
+        int32_t *tmp = nullptr;
+        CUC(cudaMalloc(&tmp, (size_t)m * S * 4));
+        int launches = 0;
+        cudaError_t e1 = cudaMemcpyAsync(tmp, upper, (size_t)m * S * 4, cudaMemcpyHostToDevice, c->st);
+        if (e1 == cudaSuccess) e1 = relayout_launch(tmp, c->d_u, m, S, c->m_pad, c->st, &launches);
+        if (e1 == cudaSuccess) e1 = cudaMemcpyAsync(tmp, lower, (size_t)m * S * 4, cudaMemcpyHostToDevice, c->st);
+        if (e1 == cudaSuccess) e1 = relayout_launch(tmp, c->d_l, m, S, c->m_pad, c->st, &launches);
+        if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(c->st);
+        cudaFree(tmp);
+        CUC(e1);
+    }
+#undef CUC
+    *out = c;
+    return SGUFP_OK;
+}
+
+void sgufp_destroy(sgufp_ctx *c) {
+    if (!c) return;
+    if (c->d_u) cudaFree(c->d_u);
+    if (c->d_l) cudaFree(c->d_l);
+    c->d_plans.release(); c->d_plan_off.release(); c->d_ray_i32.release(); c->d_sums.release(); c->d_finf.release();
+    c->d_ray_scratch.release(); c->d_obj.release(); c->d_status.release();
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->st) cudaStreamDestroy(c->st);
+    delete c;
+}
+
+int sgufp_dims(const sgufp_ctx *c, int *L, int *T, int *nvbar) {
+    if (!c) return SGUFP_ERR_ARG;
+    if (L) *L = c->M.L;
+    if (T) *T = c->M.T;
+    if (nvbar) *nvbar = (int)c->M.vbar.size();
+    return 0;
+}
+int sgufp_vbar_order(const sgufp_ctx *c, int32_t *vbar) {
+    if (!c || !vbar) return SGUFP_ERR_ARG;
+    std::memcpy(vbar, c->M.vbar.data(), c->M.vbar.size() * 4);
+    return 0;
+}
+int sgufp_processing_order(const sgufp_ctx *c, int32_t *layer_arc) {
+    if (!c || !layer_arc) return SGUFP_ERR_ARG;
+    std::memcpy(layer_arc, c->M.layer_arc.data(), (size_t)c->M.L * 4);
+    return 0;
+}
+int sgufp_slots(const sgufp_ctx *c, int32_t *si, int32_t *sq, int32_t *sj, int32_t *lex_rank) {
+    if (!c) return SGUFP_ERR_ARG;
+    for (int s = 0; s < c->M.T; s++) {
+        if (si) si[s] = c->M.tail[c->M.slot_in[s]];
+        if (sq) sq[s] = c->M.head[c->M.slot_in[s]];
+        if (sj) sj[s] = c->M.head[c->M.slot_out[s]];
+        if (lex_rank) lex_rank[s] = c->M.slot_lex_rank[s];
+    }
+    return 0;
+}
+int sgufp_partial_width(const sgufp_ctx *c) { return c ? c->W() : SGUFP_ERR_ARG; }
+
+int sgufp_paths_partial(sgufp_ctx *c, const int16_t *paths, int K, int L, int64_t *sums_device, int64_t *first_inf_device,
+                        double *obj_device, uint8_t *status_device, void *cuda_stream) {
+    if (!c || !sums_device || !first_inf_device) return SGUFP_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    c->last_launches = 0;
+    Batch B;
+    if (int rc = make_batch(c, paths, K, L, B)) return rc;
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->st;
+    return launch_batch(c, B, K, reinterpret_cast<unsigned long long *>(sums_device), reinterpret_cast<long long *>(first_inf_device),
+                        obj_device, status_device, st);
+}
+
+int sgufp_ray_partial(sgufp_ctx *c, const int16_t *path, int L, int64_t global_scenario, int64_t *sums_device, void *cuda_stream) {
+    if (!c || !sums_device) return SGUFP_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    Batch B;
+    if (int rc = make_batch(c, path, 1, L, B)) return rc;
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->st;
+    return run_ray(c, B.plans[0], global_scenario, reinterpret_cast<unsigned long long *>(sums_device), st);
+}
+
+int sgufp_finalize_paths(sgufp_ctx *c, const int16_t *paths, int K, int L, const int64_t *sums_host, const int64_t *first_inf_host,
+                         int *cut_type, double *rhs, uint64_t *keys, double *vals, int *nnz, double *coef_dense) {
+    if (!c || !sums_host || !first_inf_host) return SGUFP_ERR_ARG;
+    Batch B;
+    if (int rc = make_batch(c, paths, K, L, B)) return rc;
+    const int T = c->M.T, W = c->W();
+    for (int k = 0; k < K; k++)
+        finalize_one(c, B.plans[k], reinterpret_cast<const long long *>(sums_host) + (size_t)k * W, first_inf_host[k] != LLONG_MAX,
+                     cut_type ? cut_type + k : nullptr, rhs ? rhs + k : nullptr, keys ? keys + (size_t)k * T : nullptr,
+                     vals ? vals + (size_t)k * T : nullptr, nnz ? nnz + k : nullptr, coef_dense ? coef_dense + (size_t)k * T : nullptr);
+    return 0;
+}
+
+int sgufp_solve_paths(sgufp_ctx *c, const int16_t *paths, int K, int L, int *cut_type, double *rhs, uint64_t *keys, double *vals,
+                      int *nnz, double *coef_dense, double *obj, uint8_t *status, int64_t *first_infeasible) {
+    if (!c) return SGUFP_ERR_ARG;
+    if (c->scen_off != 0 || c->S != c->S_total)
+        return fail(c, SGUFP_ERR_ARG, "handle holds a scenario shard: use sgufp_paths_partial + all-reduce + sgufp_finalize_paths");
+    CU(c, cudaSetDevice(c->device));
+    c->last_launches = 0;
+    Batch B;
+    if (int rc = make_batch(c, paths, K, L, B)) return rc;
+    const int W = c->W(), T = c->M.T;
+    const size_t KS = (size_t)K * c->S;
+    CU(c, c->d_sums.reserve((size_t)K * W));
+    CU(c, c->d_finf.reserve(K));
+    if (obj) CU(c, c->d_obj.reserve(KS));
+    if (status) CU(c, c->d_status.reserve(KS));
+    CU(c, cudaEventRecord(c->ev0, c->st));
+    if (int rc = launch_batch(c, B, K, c->d_sums.p, c->d_finf.p, obj ? c->d_obj.p : nullptr, status ? c->d_status.p : nullptr, c->st)) return rc;
+    std::vector<long long> sums((size_t)K * W), finf(K);
+    CU(c, cudaMemcpyAsync(sums.data(), c->d_sums.p, sums.size() * 8, cudaMemcpyDeviceToHost, c->st));
+    CU(c, cudaMemcpyAsync(finf.data(), c->d_finf.p, (size_t)K * 8, cudaMemcpyDeviceToHost, c->st));
+    if (obj) CU(c, cudaMemcpyAsync(obj, c->d_obj.p, KS * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    if (status) CU(c, cudaMemcpyAsync(status, c->d_status.p, KS, cudaMemcpyDeviceToHost, c->st));
+    CU(c, cudaStreamSynchronize(c->st));
+    for (int k = 0; k < K; k++) {
+        if (finf[k] == LLONG_MAX) continue;
+        // the lowest-index infeasible scenario alone defines the cut (grb.cpp:284-351)
+        if (int rc = run_ray(c, B.plans[k], finf[k], c->d_sums.p + (size_t)k * W, c->st)) return rc;
+        CU(c, cudaMemcpyAsync(sums.data() + (size_t)k * W, c->d_sums.p + (size_t)k * W, (size_t)W * 8, cudaMemcpyDeviceToHost, c->st));
+        CU(c, cudaStreamSynchronize(c->st));
+    }
+    CU(c, cudaEventRecord(c->ev1, c->st));
+    CU(c, cudaEventSynchronize(c->ev1));
+    CU(c, cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+    for (int k = 0; k < K; k++) {
+        const bool feas = finf[k] != LLONG_MAX;
+        finalize_one(c, B.plans[k], sums.data() + (size_t)k * W, feas, cut_type ? cut_type + k : nullptr, rhs ? rhs + k : nullptr,
+                     keys ? keys + (size_t)k * T : nullptr, vals ? vals + (size_t)k * T : nullptr, nnz ? nnz + k : nullptr,
+                     coef_dense ? coef_dense + (size_t)k * T : nullptr);
+        if (first_infeasible) first_infeasible[k] = feas ? finf[k] : -1;
+    }
+    return SGUFP_OK;
+}
+
+int sgufp_solve_path(sgufp_ctx *c, const int16_t *path, int L, int *cut_type, double *rhs, uint64_t *keys, double *vals, int *nnz,
+                     double *coef_dense, double *obj, uint8_t *status, int64_t *first_infeasible) {
+    return sgufp_solve_paths(c, path, 1, L, cut_type, rhs, keys, vals, nnz, coef_dense, obj, status, first_infeasible);
+}
+
+uint64_t sgufp_cut_hash(const uint64_t *keys, const double *vals, int nnz) { return cut_hash(keys, vals, nnz); }
+
+int sgufp_last_stats(const sgufp_ctx *c, int *kernel_launches, float *device_ms) {
+    if (!c) return SGUFP_ERR_ARG;
+    if (kernel_launches) *kernel_launches = c->last_launches;
+    if (device_ms) *device_ms = c->last_ms;
+    return 0;
+}
+
+}  // extern "C"

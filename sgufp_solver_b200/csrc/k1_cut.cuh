@@ -1,0 +1,44 @@
+// k1_cut.cuh — launch interface of the scenario-cut kernels (implementation in k1_cut.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace sgufp {
+
+struct K1Launch {
+    const double *cap_u, *cap_l;  // [S][m_pad] scenario-major fp64 in HBM
+    int S, m, m_pad;
+    long long scen_offset;        // global index of local scenario 0
+    const int32_t *plans;         // device pool of K plans
+    const int32_t *plan_off;      // [K] word offset of each plan
+    int K, W, L;
+    unsigned long long *sums;     // [K][W] exact integer accumulators (two's complement)
+    long long *first_inf;         // [K] lowest infeasible global scenario (init LLONG_MAX)
+    double *obj;                  // [K][S] or nullptr
+    uint8_t *status;              // [K][S] or nullptr
+    int max_nch, max_nopen, nc, nav;
+};
+
+// Returns cudaSuccess or the launch error.  *launches is incremented by the kernels launched.
+cudaError_t k1_launch(const K1Launch &p, cudaStream_t st, int sm_count, int *launches);
+
+struct RayLaunch {
+    const double *cap_u, *cap_l;
+    int s_local, m, m_pad, nn;    // nn = split-graph nodes
+    const int32_t *arc_ts, *arc_hs;   // [m] split-graph endpoints, -1 = dangling end
+    const int32_t *arc_info;          // [m] kind | (layer+1)<<2 with RAY kinds
+    const int32_t *arc_pair_layer;    // [m] for a matched in-arc: its layer, else -1
+    const int32_t *arc_next;          // [m] matched out-arc of a matched in-arc, else -1
+    const int32_t *arc_q;             // [m] (tail_av+1) | (head_av+1)<<16
+    const int32_t *av_first_wire;     // [nav] split node of the first matched pair, -1 if none
+    int nav, L;
+    int32_t *scratch;                 // device scratch, >= 8*(nn+m)+64 words
+    unsigned long long *sums;         // [W]
+};
+cudaError_t ray_launch(const RayLaunch &p, cudaStream_t st, int *launches);
+
+// scenario-major fp64 re-layout of the reference's arc-major int32 capacity arrays
+cudaError_t relayout_launch(const int32_t *src /*[m][S] device*/, double *dst /*[S][m_pad]*/, int m, int S, int m_pad,
+                            cudaStream_t st, int *launches);
+
+}  // namespace sgufp

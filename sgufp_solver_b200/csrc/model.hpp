@@ -1,0 +1,74 @@
+// model.hpp — host-side instance model and per-candidate evaluation plan.
+//
+// Mirrors what the reference derives once per instance:
+//   Network::Network / shuffleVBarNodes / processingOrder   /root/reference/Network.cpp:10-186
+//   the (i,q,j) coefficient keys GuroSolver pre-seeds       /root/reference/grb.h:60-68
+// and what it derives once per candidate:
+//   path -> y-bar                                            /root/reference/grb.cpp:141-150
+// The plan is the scenario-invariant part of the subproblem: with y-bar fixed the
+// second stage is a max-reward flow on a CONTRACTED graph whose arcs are chains of network arcs
+// glued through matched V-bar pairs.  Only capacities differ between scenarios.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace sgufp {
+
+enum ArcKind : int8_t { KIND_GAMMA = 0, KIND_SIGMA = 1, KIND_PHI = 2 };
+
+struct Model {
+    int n = 0, m = 0;
+    std::vector<int32_t> tail, head, rew;
+    std::vector<int32_t> in_ptr, in_arc, out_ptr, out_arc, out_index;
+    std::vector<int32_t> vbar;               // after the shuffle
+    std::vector<uint8_t> is_vbar, active, is_root;
+    int L = 0, T = 0;
+    std::vector<int32_t> layer_arc, arc_layer, slot_base, slot_in, slot_out, slot_lex_rank, slot_sorted;
+    int nc = 1;                              // contracted nodes, 0 = root
+    std::vector<int32_t> cn;                 // node -> contracted id (0 root, -1 active V-bar)
+    int nav = 0;                             // active V-bar nodes
+    std::vector<int32_t> av_index;           // node -> compact active-V-bar index or -1
+    std::vector<int32_t> av_node;
+
+    // returns 0 or a negative SGUFP_ERR_* code, `err` explains
+    int build(int n, int m, const int32_t *tail, const int32_t *head, const int32_t *rew0, const int32_t *vbar,
+              int nvbar, std::string &err);
+    int indeg(int v) const { return in_ptr[v + 1] - in_ptr[v]; }
+    int outdeg(int v) const { return out_ptr[v + 1] - out_ptr[v]; }
+};
+
+// Flat, device-uploadable description of one candidate.  All arrays are int32 and live in one
+// pool so that a batch of K plans is a single host->device copy.
+struct PlanHeader {
+    int32_t nch, nopen, nc, nav, m, L;
+    // offsets (in int32 units, relative to the plan's base) of the arrays below
+    int32_t o_arc_cp;      // [m]      (chain << 10) | position-in-chain
+    int32_t o_arc_info;    // [m]      kind | (layer+1) << 2     (layer of the arc as a V-bar in-arc, -1 if none)
+    int32_t o_arc_pre;     // [m]      prefix reward of the chain up to and including the arc
+    int32_t o_ch_ends;     // [nch]    (sv+1) | (ev+1) << 16     (contracted ids, 0 = dangling)
+    int32_t o_ch_r;        // [nch]    chain reward
+    int32_t o_ch_ptr;      // [nch+1]
+    int32_t o_ch_arcs;     // [m]      arcs in chain order
+    int32_t o_ch_q;        // [nch]    (qs_av+1) | (qe_av+1) << 16  compact V-bar index of a dangling end, 0 = none
+    int32_t o_av_ptr;      // [nav+1]  matched in-arcs of each active V-bar node, in incomingArcs order
+    int32_t o_av_arcs;     // [#matched]
+    int32_t o_fb_ptr;      // [nav+1]  fallback chains (end-anchored chains starting at the node) for nodes without a matched pair
+    int32_t o_fb_ch;       // [#fallback]
+    int32_t total;         // int32 words used by this plan, header included
+    int32_t pad;
+};
+
+struct Plan {
+    std::vector<int32_t> words;   // PlanHeader followed by the arrays
+    std::vector<int32_t> match_out, match_in;
+    int nch = 0, nopen = 0;
+};
+
+// returns 0 / SGUFP_ERR_ARG / SGUFP_ERR_MATCHING / SGUFP_ERR_CYCLIC
+int build_plan(const Model &M, const int16_t *path, int plen, Plan &P, std::string &err);
+
+// Inavap::Cut hash (Cut.h:243-251)
+uint64_t cut_hash(const uint64_t *keys, const double *vals, int nnz);
+
+}  // namespace sgufp
