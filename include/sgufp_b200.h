@@ -27,6 +27,9 @@ extern "C" {
 #define SGUFP_ERR_LIMITS (-5)   /* exceeds a packing limit of the kernels         */
 #define SGUFP_ERR_CUDA (-6)     /* CUDA runtime error / no device                                    */
 
+#define SGUFP_DEVICE_NONE (-1)  /* sgufp_create: build the host-side model only (dims, orders, slots,
+                                   sgufp_finalize_paths); every compute entry point then fails */
+
 #define SGUFP_CUT_OPTIMALITY 0 /* CutType, /root/reference/Cut.h:22-25 */
 #define SGUFP_CUT_FEASIBILITY 1
 
@@ -103,6 +106,9 @@ uint64_t sgufp_cut_hash(const uint64_t *keys, const double *vals, int nnz);
 /* Counters of the last compute call on this handle: kernels launched, device milliseconds
  * (CUDA events on the handle's stream). */
 int sgufp_last_stats(const sgufp_ctx *ctx, int *kernel_launches, float *device_ms);
+/* Device time of the last K1 launch alone (CUDA events recorded on the launching stream right
+ * around the kernel); blocks until that launch has finished. */
+int sgufp_last_kernel_ms(sgufp_ctx *ctx, float *kernel_ms);
 
 #ifdef __cplusplus
 }

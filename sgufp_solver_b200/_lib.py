@@ -31,6 +31,7 @@ SIGNATURES = {
     "sgufp_finalize_paths": (C.c_int, [vp, i16p, C.c_int, C.c_int, i64p, i64p, cip, dp, u64p, dp, cip, dp]),
     "sgufp_cut_hash": (C.c_uint64, [u64p, dp, C.c_int]),
     "sgufp_last_stats": (C.c_int, [vp, cip, C.POINTER(C.c_float)]),
+    "sgufp_last_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
 }
 
 

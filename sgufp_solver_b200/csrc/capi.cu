@@ -40,7 +40,7 @@ struct sgufp_ctx {
     long long scen_off = 0, S_total = 0;
     double *d_u = nullptr, *d_l = nullptr;
     cudaStream_t st = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
     DevBuf<int32_t> d_plans, d_plan_off, d_ray_i32;
     DevBuf<unsigned long long> d_sums;
     DevBuf<long long> d_finf, d_ray_scratch;
@@ -49,6 +49,7 @@ struct sgufp_ctx {
     std::string err;
     int last_launches = 0;
     float last_ms = 0.f;
+    bool kernel_timed = false;
     int W() const { return 1 + M.L + M.m; }
 };
 
@@ -99,7 +100,13 @@ static int launch_batch(sgufp_ctx *c, const Batch &B, int K, unsigned long long 
     p.plans = c->d_plans.p; p.plan_off = c->d_plan_off.p; p.K = K; p.W = c->W(); p.L = c->M.L;
     p.sums = d_sums; p.first_inf = d_finf; p.obj = d_obj; p.status = d_status;
     p.max_nch = B.max_nch; p.max_nopen = B.max_nopen; p.nc = c->M.nc; p.nav = c->M.nav;
-    if (c->S > 0) CU(c, k1_launch(p, st, c->sm_count, &c->last_launches));
+    c->kernel_timed = false;
+    if (c->S > 0) {
+        CU(c, cudaEventRecord(c->evk0, st));
+        CU(c, k1_launch(p, st, c->sm_count, &c->last_launches));
+        CU(c, cudaEventRecord(c->evk1, st));
+        c->kernel_timed = true;
+    }
     return 0;
 }
 
@@ -211,19 +218,20 @@ int sgufp_create(sgufp_ctx **out, int n, int m, int S, const int32_t *tail, cons
                  int64_t scenario_offset, int64_t S_total) {
     if (!out) { g_create_error = "out is null"; return SGUFP_ERR_ARG; }
     *out = nullptr;
-    if (S < 0 || S_total < 1 || scenario_offset < 0 || scenario_offset + S > S_total || (S > 0 && (!upper || !lower))) {
+    if (S < 0 || S_total < 1 || scenario_offset < 0 || scenario_offset + S > S_total || (S > 0 && device != SGUFP_DEVICE_NONE && (!upper || !lower))) {
         g_create_error = "scenario block must lie inside [0, S_total)"; return SGUFP_ERR_ARG;
     }
     sgufp_ctx *c = new sgufp_ctx();
     auto bail = [&](int code, const std::string &msg) { g_create_error = msg; sgufp_destroy(c); return code; };
     std::string e;
     if (int rc = c->M.build(n, m, tail, head, reward0, vbar, nvbar, e)) return bail(rc, e);
-    for (size_t i = 0; i < (size_t)m * S; i++)
+    for (size_t i = 0; upper && lower && i < (size_t)m * S; i++)
         if (upper[i] < 0 || lower[i] < 0 || upper[i] >= (1 << 20) || lower[i] >= (1 << 20))
             return bail(SGUFP_ERR_LIMITS, "capacities must lie in [0, 2^20) (DESIGN.md §5)");
     c->S = S; c->scen_off = scenario_offset; c->S_total = S_total; c->device = device;
     c->m_pad = (m + 1) & ~1;   // rows 16-byte aligned for 128-bit loads
 #define CUC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return bail(SGUFP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } while (0)
+    if (device == SGUFP_DEVICE_NONE) { *out = c; return SGUFP_OK; }   // model only: no compute entry point will run
     CUC(cudaSetDevice(device));
     cudaDeviceProp prop;
     CUC(cudaGetDeviceProperties(&prop, device));
@@ -232,6 +240,8 @@ int sgufp_create(sgufp_ctx **out, int n, int m, int S, const int32_t *tail, cons
     CUC(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     CUC(cudaEventCreate(&c->ev0));
     CUC(cudaEventCreate(&c->ev1));
+    CUC(cudaEventCreate(&c->evk0));
+    CUC(cudaEventCreate(&c->evk1));
     if (S > 0) {
         const size_t cells = (size_t)S * c->m_pad;
         CUC(cudaMalloc(&c->d_u, cells * sizeof(double)));
@@ -260,6 +270,8 @@ void sgufp_destroy(sgufp_ctx *c) {
     c->d_ray_scratch.release(); c->d_obj.release(); c->d_status.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->evk0) cudaEventDestroy(c->evk0);
+    if (c->evk1) cudaEventDestroy(c->evk1);
     if (c->st) cudaStreamDestroy(c->st);
     delete c;
 }
@@ -296,6 +308,7 @@ int sgufp_partial_width(const sgufp_ctx *c) { return c ? c->W() : SGUFP_ERR_ARG;
 int sgufp_paths_partial(sgufp_ctx *c, const int16_t *paths, int K, int L, int64_t *sums_device, int64_t *first_inf_device,
                         double *obj_device, uint8_t *status_device, void *cuda_stream) {
     if (!c || !sums_device || !first_inf_device) return SGUFP_ERR_ARG;
+    if (c->device == SGUFP_DEVICE_NONE) return fail(c, SGUFP_ERR_CUDA, "handle was created with SGUFP_DEVICE_NONE: it holds the model only, there is no CPU compute path");
     CU(c, cudaSetDevice(c->device));
     c->last_launches = 0;
     Batch B;
@@ -307,6 +320,7 @@ int sgufp_paths_partial(sgufp_ctx *c, const int16_t *paths, int K, int L, int64_
 
 int sgufp_ray_partial(sgufp_ctx *c, const int16_t *path, int L, int64_t global_scenario, int64_t *sums_device, void *cuda_stream) {
     if (!c || !sums_device) return SGUFP_ERR_ARG;
+    if (c->device == SGUFP_DEVICE_NONE) return fail(c, SGUFP_ERR_CUDA, "handle was created with SGUFP_DEVICE_NONE: it holds the model only, there is no CPU compute path");
     CU(c, cudaSetDevice(c->device));
     Batch B;
     if (int rc = make_batch(c, path, 1, L, B)) return rc;
@@ -332,6 +346,7 @@ int sgufp_solve_paths(sgufp_ctx *c, const int16_t *paths, int K, int L, int *cut
     if (!c) return SGUFP_ERR_ARG;
     if (c->scen_off != 0 || c->S != c->S_total)
         return fail(c, SGUFP_ERR_ARG, "handle holds a scenario shard: use sgufp_paths_partial + all-reduce + sgufp_finalize_paths");
+    if (c->device == SGUFP_DEVICE_NONE) return fail(c, SGUFP_ERR_CUDA, "handle was created with SGUFP_DEVICE_NONE: it holds the model only, there is no CPU compute path");
     CU(c, cudaSetDevice(c->device));
     c->last_launches = 0;
     Batch B;
@@ -381,6 +396,14 @@ int sgufp_last_stats(const sgufp_ctx *c, int *kernel_launches, float *device_ms)
     if (!c) return SGUFP_ERR_ARG;
     if (kernel_launches) *kernel_launches = c->last_launches;
     if (device_ms) *device_ms = c->last_ms;
+    return 0;
+}
+
+int sgufp_last_kernel_ms(sgufp_ctx *c, float *kernel_ms) {
+    if (!c || !kernel_ms) return SGUFP_ERR_ARG;
+    if (!c->kernel_timed) return fail(c, SGUFP_ERR_ARG, "no K1 launch has been recorded on this handle");
+    CU(c, cudaEventSynchronize(c->evk1));
+    CU(c, cudaEventElapsedTime(kernel_ms, c->evk0, c->evk1));
     return 0;
 }
 

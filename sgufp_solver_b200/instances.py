@@ -83,12 +83,14 @@ def make_layered(
     lower_prob: float = 0.0,
     name: str = "synthetic",
     vbar_nodes: Optional[Sequence[int]] = None,
+    cap_stream: int = 0,
 ) -> Instance:
     """Layered DAG per SURVEY.md §8d.  `layer_sizes` are the interior layers (the last one is the
     demand layer); a source and a sink are added.  `lower_prob` is the per-(source arc, scenario)
     probability of a positive lower bound (exercises feasibility cuts); 0 gives the pure
     throughput variant."""
-    rng = np.random.default_rng(seed)
+    rng = np.random.default_rng([seed, 0])      # topology, rewards, V-bar: independent of S
+    rng_cap = np.random.default_rng([seed, 1, cap_stream])  # per-scenario capacities (one stream per scenario block)
     layers: List[List[int]] = []
     nid = 1
     for sz in layer_sizes:
@@ -121,13 +123,13 @@ def make_layered(
     head = np.array([b for _, b in arcs], dtype=np.int32)
 
     base_u = rng.integers(5, 21, size=m_real)
-    noise = rng.uniform(0.5, 1.5, size=(m_real, S))
+    noise = rng_cap.uniform(0.5, 1.5, size=(S, m_real)).T   # scenario-major draw: scenario s is the same for every S
     upper = np.maximum(1, np.rint(base_u[:, None] * noise)).astype(np.int32)
     lower = np.zeros((m_real, S), dtype=np.int32)
     if lower_prob > 0:
         src = np.nonzero(tail == 0)[0]
-        mask = rng.random((len(src), S)) < lower_prob
-        vals = rng.integers(1, 4, size=(len(src), S))
+        mask = rng_cap.random((S, len(src))).T < lower_prob
+        vals = rng_cap.integers(1, 4, size=(S, len(src))).T
         lower[src] = np.where(mask, vals, 0).astype(np.int32)
         lower = np.minimum(lower, upper)  # l <= u on every single arc; chains may still be infeasible
     r0 = np.where(head == sink, rng.integers(10, 31, size=m_real), rng.integers(-5, 1, size=m_real))
@@ -150,31 +152,32 @@ def config1(S: int = 50, lower_prob: float = 0.0) -> Instance:
     """C1: the Appendix-A topology (n=10, m=17, V-bar={4,5}) with S scenarios."""
     arcs = [(0, 1), (0, 2), (0, 3), (1, 4), (2, 4), (3, 4), (1, 5), (2, 5), (3, 5),
             (4, 6), (4, 7), (4, 8), (5, 7), (5, 8), (6, 9), (7, 9), (8, 9)]
-    rng = np.random.default_rng(SEED0 + 1)
+    rng = np.random.default_rng([SEED0 + 1, 0])
+    rng_cap = np.random.default_rng([SEED0 + 1, 1])
     m = len(arcs)
     tail = np.array([a for a, _ in arcs], dtype=np.int32)
     head = np.array([b for _, b in arcs], dtype=np.int32)
     base_u = rng.integers(5, 21, size=m)
-    upper = np.maximum(1, np.rint(base_u[:, None] * rng.uniform(0.5, 1.5, size=(m, S)))).astype(np.int32)
+    upper = np.maximum(1, np.rint(base_u[:, None] * rng_cap.uniform(0.5, 1.5, size=(S, m)).T)).astype(np.int32)
     lower = np.zeros((m, S), dtype=np.int32)
     if lower_prob > 0:
         src = np.nonzero(tail == 0)[0]
-        mask = rng.random((len(src), S)) < lower_prob
-        lower[src] = np.where(mask, rng.integers(1, 4, size=(len(src), S)), 0)
+        mask = rng_cap.random((S, len(src))).T < lower_prob
+        lower[src] = np.where(mask, rng_cap.integers(1, 4, size=(S, len(src))).T, 0)
         lower = np.minimum(lower, upper)
     r0 = np.where(head == 9, rng.integers(10, 31, size=m), rng.integers(-5, 1, size=m))
     reward = np.repeat(r0[:, None], S, axis=1).astype(np.int32)
     return Instance(10, m, S, tail, head, lower, upper, reward, np.array([4, 5], dtype=np.int32), "C1")
 
 
-def config2(S: int = 1000, lower_prob: float = 0.0) -> Instance:
+def config2(S: int = 1000, lower_prob: float = 0.0, cap_stream: int = 0) -> Instance:
     """C2: n=50 (1+8+4x8+8+1), m=200, S=1000."""
-    return make_layered([8, 8, 8, 8, 8, 8], 200, S, SEED0 + 2, 0.6, lower_prob, "C2")
+    return make_layered([8, 8, 8, 8, 8, 8], 200, S, SEED0 + 2, 0.6, lower_prob, "C2", cap_stream=cap_stream)
 
 
-def config4(S: int = 10000, lower_prob: float = 0.0) -> Instance:
+def config4(S: int = 10000, lower_prob: float = 0.0, cap_stream: int = 0) -> Instance:
     """C4/C5 network: n=200 (1+6x33+1), m=1000."""
-    return make_layered([33, 33, 33, 33, 33, 33], 1000, S, SEED0 + 4, 0.75, lower_prob, "C4")
+    return make_layered([33, 33, 33, 33, 33, 33], 1000, S, SEED0 + 4, 0.75, lower_prob, "C4", cap_stream=cap_stream)
 
 
 def random_paths(net, K: int, seed: int, unmatched_prob: float = 0.1) -> np.ndarray:

@@ -152,3 +152,9 @@ class GuroSolver:
         a, b = C.c_int(), C.c_float()
         _lib.lib().sgufp_last_stats(self.h, C.byref(a), C.byref(b))
         return a.value, b.value
+
+    def last_kernel_ms(self) -> float:
+        """Device time of the last K1 launch (CUDA events on the launching stream)."""
+        t = C.c_float()
+        self._check(_lib.lib().sgufp_last_kernel_ms(self.h, C.byref(t)))
+        return t.value

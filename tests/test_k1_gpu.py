@@ -1,0 +1,177 @@
+"""K1 parity on a real B200, through the C ABI (sgufp_solve_paths / sgufp_paths_partial).
+
+Bar (BASELINE.json north_star): subproblem feasibility status exactly; objectives, cut
+coefficients and constants within 1e-9 relative.  The kernels accumulate exact integers, so the
+integer sums are compared BIT-EXACTLY with Oracle B's and only the final fp64 fold carries the
+1e-9 tolerance (the reference folds `(cap / S) * dual` scenario by scenario, grb.cpp:241-278)."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+import sgufp_solver_b200 as sg
+from oracle.oracle import OracleNet
+from sgufp_solver_b200 import instances as I
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+def _compare(inst, gs, net, paths, res):
+    for k in range(len(paths)):
+        oc = net.solve_path(paths[k])
+        assert oc.cut_type == res.cut_type[k]
+        assert oc.first_infeasible == res.first_infeasible[k]
+        div = 1.0 if oc.cut_type else float(inst.S)
+        assert res.rhs[k] == oc.isum[0] / div                                   # exact integers, one division
+        assert (res.coef_dense[k, :gs.T] == oc.isum[1:] / div).all()
+        scale = max(1.0, np.abs(oc.coef_dense).max())
+        assert abs(res.rhs[k] - oc.rhs) <= RTOL * max(1.0, abs(oc.rhs))         # vs the reference-order fp64 fold
+        assert np.abs(res.coef_dense[k, :gs.T] - oc.coef_dense).max() <= RTOL * scale
+        if oc.cut_type == 0:
+            assert (res.status[k] == oc.status).all()
+            assert (res.obj[k] == oc.obj).all()
+        else:
+            s = oc.first_infeasible                                              # scenarios before the first infeasible one agree
+            assert (res.status[k, :s] == 0).all() and res.status[k, s] == 1
+            assert (res.obj[k, :s] == oc.obj[:s]).all()
+        cut = res.cut(k)
+        nz = [(int(kk), v) for kk, v in zip(oc.keys, oc.vals) if abs(v) > 1e-12 * scale]
+        assert [int(x) for x in cut.keys] == [a for a, _ in nz]                  # same keys, same (i,q,j) order
+        assert np.allclose(cut.vals, [b for _, b in nz], rtol=RTOL, atol=RTOL * scale)
+
+
+CASES = [
+    ("c1", lambda: I.config1(S=50), 8, 1, 0.15),
+    ("c1_lb", lambda: I.config1(S=50, lower_prob=0.3), 8, 2, 0.3),
+    ("c1_all_unmatched", lambda: I.config1(S=8), 2, 3, 1.0),
+    ("c2", lambda: I.config2(S=200), 6, 3, 0.1),
+    ("c2_lb", lambda: I.config2(S=200, lower_prob=0.05), 6, 4, 0.3),
+    ("c4", lambda: I.config4(S=64), 3, 5, 0.1),
+    ("c4_lb", lambda: I.config4(S=64, lower_prob=0.02), 3, 6, 0.3),
+    ("odd_m_single_scenario", lambda: I.make_layered([3, 4, 3], 21, 1, 77, 0.8, 0.0, "odd"), 4, 7, 0.2),
+]
+
+
+@pytest.mark.parametrize("name,make,K,seed,unm", CASES, ids=[c[0] for c in CASES])
+def test_parity_with_oracle(name, make, K, seed, unm):
+    inst = make()
+    net = OracleNet(inst)
+    gs = sg.GuroSolver(inst)
+    assert gs.layer_arc.tolist() == net.layer_arc.tolist() and gs.T == net.T
+    paths = I.random_paths(net, K, seed, unm)
+    res = gs.solve_paths(paths)
+    launches, ms = gs.last_stats()
+    assert launches >= 1 and ms > 0                                               # the CUDA path ran
+    _compare(inst, gs, net, paths, res)
+
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "k1_*.json")))
+MAKERS = {"k1_c1": lambda: I.config1(S=50), "k1_c1_lb": lambda: I.config1(S=50, lower_prob=0.1),
+          "k1_c2_small": lambda: I.config2(S=40), "k1_c2_small_lb": lambda: I.config2(S=40, lower_prob=0.08)}
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-5] for p in GOLD])
+def test_golden_vectors(path):
+    g = json.load(open(path))
+    inst = MAKERS[g["instance"]]()
+    gs = sg.GuroSolver(inst)
+    paths = np.array([c["path"] for c in g["cuts"]], np.int16)
+    res = gs.solve_paths(paths)
+    for k, c in enumerate(g["cuts"]):
+        div = 1.0 if c["cut_type"] else float(inst.S)
+        assert res.cut_type[k] == c["cut_type"] and res.first_infeasible[k] == c["first_infeasible"]
+        assert res.rhs[k] == c["isum"][0] / div
+        assert (res.coef_dense[k, :gs.T] == np.array(c["isum"][1:]) / div).all()
+        if c["obj"] is not None:
+            assert res.obj[k].tolist() == c["obj"] and res.status[k].tolist() == c["status"]
+
+
+def test_reference_interface_single_path():
+    """solveSubProblem(path) -> (CutType, Inavap::Cut): same answer as the batched call; hash as Cut.h:243-251."""
+    from oracle import ref_dd
+    inst = I.config1(S=50)
+    gs = sg.GuroSolver(inst)
+    net = OracleNet(inst)
+    paths = I.random_paths(net, 3, 21, 0.2)
+    batch = gs.solve_paths(paths)
+    for k in range(3):
+        ctype, cut = gs.solveSubProblem(paths[k])
+        assert ctype == batch.cut_type[k] and cut == batch.cut(k)
+        assert cut.keys.tolist() == batch.cut(k).keys.tolist() and cut.vals.tolist() == batch.cut(k).vals.tolist()
+        if ref_dd.available():
+            assert cut.hash_val == ref_dd.cut_hash(cut.RHS, cut.keys, cut.vals)
+
+
+def test_full_size_c2_properties():
+    """configs[1] at full size (S=1000, K=64): size-independent properties."""
+    inst = I.config2(S=1000)
+    gs = sg.GuroSolver(inst)
+    net = OracleNet(inst)
+    paths = I.random_paths(net, 64, 31, 0.1)
+    a = gs.solve_paths(paths)
+    b = gs.solve_paths(paths)
+    assert (a.rhs == b.rhs).all() and (a.coef_dense == b.coef_dense).all() and (a.obj == b.obj).all()      # run-to-run bit-identical
+    assert (a.cut_type == 0).all() and (a.status == 0).all()
+    # y-bar in slot order
+    slot = {}
+    t = 0
+    for l, arc in enumerate(gs.layer_arc):
+        for bo in gs.out_arcs(inst.head[arc]):
+            slot[(l, bo)] = t; t += 1
+    for k in range(64):
+        y = np.zeros(gs.T)
+        for l, bo in enumerate(paths[k]):
+            if bo >= 0:
+                y[slot[(l, int(bo))]] = 1
+        val = a.rhs[k] + a.coef_dense[k, :gs.T] @ y
+        assert abs(val - a.obj[k].mean()) <= RTOL * max(1.0, abs(val))            # RHS + coef.y == mean objective
+    # every cut is valid at every other candidate (weak duality)
+    truth = a.obj.mean(axis=1)
+    ys = np.zeros((64, gs.T))
+    for k in range(64):
+        for l, bo in enumerate(paths[k]):
+            if bo >= 0:
+                ys[k, slot[(l, int(bo))]] = 1
+    vals = a.rhs[:, None] + a.coef_dense[:, :gs.T] @ ys.T                         # [cut, point]
+    assert (vals >= truth[None, :] - 1e-6).all()
+    # sampled scenarios against the oracle
+    for k in (0, 17, 63):
+        oc = net.solve_path(paths[k])
+        assert (a.obj[k] == oc.obj).all() and a.rhs[k] == oc.isum[0] / inst.S
+
+
+def test_sharded_partials_add_up():
+    """Linearity: partial sums of two scenario blocks (sgufp_paths_partial) == the one-block sums."""
+    import ctypes as C
+    import torch
+    from sgufp_solver_b200 import _lib
+    from sgufp_solver_b200.distributed import I64_MAX, finalize
+    inst = I.config2(S=300, lower_prob=0.0)
+    net = OracleNet(inst)
+    paths = I.random_paths(net, 5, 41, 0.2)
+    full = sg.GuroSolver(inst).solve_paths(paths)
+    tot = None
+    for lo, hi in ((0, 130), (130, 300)):
+        part = sg.GuroSolver(inst.scenario_slice(lo, hi), scenario_offset=lo, S_total=inst.S)
+        sums = torch.zeros((5, part.W), dtype=torch.int64, device="cuda")
+        finf = torch.zeros((5,), dtype=torch.int64, device="cuda")
+        rc = _lib.lib().sgufp_paths_partial(part.h, paths.ctypes.data_as(_lib.i16p), 5, paths.shape[1], C.c_void_p(sums.data_ptr()),
+                                            C.c_void_p(finf.data_ptr()), None, None, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0
+        torch.cuda.synchronize()
+        assert (finf.cpu().numpy() == I64_MAX).all()
+        tot = sums.cpu().numpy() if tot is None else tot + sums.cpu().numpy()
+        last = part
+    res = finalize(last, paths, tot, np.full(5, I64_MAX, np.int64))
+    assert (res.rhs == full.rhs).all() and (res.coef_dense == full.coef_dense).all()
+
+
+def test_bad_path_is_rejected():
+    inst = I.config1(S=4)
+    gs = sg.GuroSolver(inst)
+    with pytest.raises(sg.solver.SgufpError) as e:
+        gs.solveSubProblem(np.array([9, 9, -1, -1, -1, -1], np.int16))
+    assert e.value.code == -2
