@@ -200,7 +200,8 @@ def main():
     sums = torch.empty((K, W), dtype=torch.int64, device=dev)
     finf = torch.empty((K,), dtype=torch.int64, device=dev)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev)   # a real stream: the C ABI treats NULL as 'the handle's own stream'
+    torch.cuda.set_stream(stream)
 
     def device_step():
         rc = lib.sgufp_paths_partial(solver.h, paths.ctypes.data_as(_lib.i16p), K, paths.shape[1], C.c_void_p(sums.data_ptr()),

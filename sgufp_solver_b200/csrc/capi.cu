@@ -94,7 +94,7 @@ static int launch_batch(sgufp_ctx *c, const Batch &B, int K, unsigned long long 
     CU(c, cudaMemsetAsync(d_sums, 0, (size_t)K * c->W() * 8, st));
     std::vector<long long> inf(K, LLONG_MAX);
     CU(c, cudaMemcpyAsync(d_finf, inf.data(), (size_t)K * 8, cudaMemcpyHostToDevice, st));
-    CU(c, cudaStreamSynchronize(st));  // `inf`, B.words are host temporaries
+    // B.words and `inf` are pageable host temporaries: cudaMemcpyAsync has staged them before it returns
     K1Launch p{};
     p.cap_u = c->d_u; p.cap_l = c->d_l; p.S = c->S; p.m = c->M.m; p.m_pad = c->m_pad; p.scen_offset = c->scen_off;
     p.plans = c->d_plans.p; p.plan_off = c->d_plan_off.p; p.K = K; p.W = c->W(); p.L = c->M.L;

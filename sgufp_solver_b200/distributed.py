@@ -59,6 +59,8 @@ class ShardedGuroSolver:
         self.device = torch.device("cuda", device)
         self.solver = GuroSolver(inst, device=device, scenario_offset=lo, S_total=self.S_total)
         self.W, self.T, self.L = self.solver.W, self.solver.T, self.solver.L
+        # a real (non-default) stream: kernel, all-reduce and read-back are ordered on it
+        self.stream = torch.cuda.Stream(self.device)
         self._sums = None
         self._finf = None
 
@@ -70,9 +72,8 @@ class ShardedGuroSolver:
         if self._sums is None or self._sums.shape[0] != K:
             self._sums = torch.empty((K, self.W), dtype=torch.int64, device=self.device)
             self._finf = torch.empty((K,), dtype=torch.int64, device=self.device)
-        stream = torch.cuda.current_stream(self.device)
         rc = _lib.lib().sgufp_paths_partial(self.solver.h, p.ctypes.data_as(i16p), K, plen, C.c_void_p(self._sums.data_ptr()),
-                                            C.c_void_p(self._finf.data_ptr()), None, None, C.c_void_p(stream.cuda_stream))
+                                            C.c_void_p(self._finf.data_ptr()), None, None, C.c_void_p(self.stream.cuda_stream))
         self.solver._check(rc)
         return self._sums, self._finf
 
@@ -81,20 +82,21 @@ class ShardedGuroSolver:
         import torch.distributed as dist
         p = np.ascontiguousarray(paths, dtype=np.int16)
         K, plen = p.shape
-        sums, finf = self.partial(p)
-        reduce_partials(sums, finf, self.group)
-        finf_h = finf.cpu().numpy()
-        # feasibility: the rank owning the lowest infeasible scenario builds the ray, everyone gets it
-        for k in np.nonzero(finf_h != I64_MAX)[0]:
-            own = owner_of(int(finf_h[k]), self.S_total, self.world)
-            if own == self.rank:
-                stream = torch.cuda.current_stream(self.device)
-                rc = _lib.lib().sgufp_ray_partial(self.solver.h, p[k].ctypes.data_as(i16p), plen, int(finf_h[k]),
-                                                  C.c_void_p(sums[k].data_ptr()), C.c_void_p(stream.cuda_stream))
-                self.solver._check(rc)
-            if self.world > 1:
-                dist.broadcast(sums[k], src=own, group=self.group)
-        return finalize(self.solver, p, sums.cpu().numpy(), finf_h)
+        with torch.cuda.stream(self.stream):
+            sums, finf = self.partial(p)
+            reduce_partials(sums, finf, self.group)
+            finf_h = finf.cpu().numpy()
+            # feasibility: the rank owning the lowest infeasible scenario builds the ray, everyone gets it
+            for k in np.nonzero(finf_h != I64_MAX)[0]:
+                own = owner_of(int(finf_h[k]), self.S_total, self.world)
+                if own == self.rank:
+                    rc = _lib.lib().sgufp_ray_partial(self.solver.h, p[k].ctypes.data_as(i16p), plen, int(finf_h[k]),
+                                                      C.c_void_p(sums[k].data_ptr()), C.c_void_p(self.stream.cuda_stream))
+                    self.solver._check(rc)
+                if self.world > 1:
+                    dist.broadcast(sums[k], src=own, group=self.group)
+            sums_h = sums.cpu().numpy()
+        return finalize(self.solver, p, sums_h, finf_h)
 
     def solveSubProblem(self, path):
         res = self.solve_paths(np.asarray(path, dtype=np.int16)[None, :])

@@ -158,8 +158,9 @@ def test_sharded_partials_add_up():
         part = sg.GuroSolver(inst.scenario_slice(lo, hi), scenario_offset=lo, S_total=inst.S)
         sums = torch.zeros((5, part.W), dtype=torch.int64, device="cuda")
         finf = torch.zeros((5,), dtype=torch.int64, device="cuda")
+        st = torch.cuda.Stream()
         rc = _lib.lib().sgufp_paths_partial(part.h, paths.ctypes.data_as(_lib.i16p), 5, paths.shape[1], C.c_void_p(sums.data_ptr()),
-                                            C.c_void_p(finf.data_ptr()), None, None, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                                            C.c_void_p(finf.data_ptr()), None, None, C.c_void_p(st.cuda_stream))
         assert rc == 0
         torch.cuda.synchronize()
         assert (finf.cpu().numpy() == I64_MAX).all()
