@@ -1,0 +1,74 @@
+/*
+ * sgufp_b200_dd.h — C ABI of the decision-diagram half of the hot path (K2).
+ *
+ * Replaces the members of `Inavap::RelaxedDDNew` (/root/reference/DD.h:797-808, DD.cpp:3528-4229)
+ * and `Inavap::RestrictedDDNew` (/root/reference/DD.h:713-728, DD.cpp:3090-3505) that
+ * NodeExplorer::process calls (/root/reference/NodeExplorer.cpp:922-981).  The diagram is built on
+ * the host exactly as the reference builds it; the layer-wise longest path with cut-adjusted arc
+ * weights runs on the GPU.  Same conventions as sgufp_b200.h: host pointers, 0 / negative codes.
+ * A diagram belongs to the sgufp_ctx it was created from (network model, device, stream) and, like
+ * the reference's, to one host thread.
+ */
+#ifndef SGUFP_B200_DD_H
+#define SGUFP_B200_DD_H
+#include "sgufp_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGUFP_DD_RELAXED 0    /* RelaxedDDNew: collapse threshold RELAXED_MAX_WIDTH = 120 (DD.h:732) */
+#define SGUFP_DD_RESTRICTED 1 /* RestrictedDDNew(max_width) (DD.h:710) */
+
+typedef struct sgufp_dd sgufp_dd;
+
+int sgufp_dd_create(sgufp_ctx *ctx, int kind, int max_width, sgufp_dd **out);
+void sgufp_dd_destroy(sgufp_dd *dd);
+
+/* buildTree(Node) (DD.cpp:3528) / compile(Node) (DD.cpp:3090).  The node is (states, solutionVector,
+ * globalLayer) of `Inavap::Node` (DD.h:456-479); an empty node with globalLayer 0 is the root.
+ * cutset_nodes (may be NULL): restricted DD only, the size of the exact cut-set, or -1 if the tree
+ * is exact (DD.cpp:3157-3158); fetch it with sgufp_dd_cutset. */
+int sgufp_dd_build(sgufp_dd *dd, const int16_t *states, int nstates, const int16_t *solution, int nsolution,
+                   int global_layer, int *cutset_nodes);
+int sgufp_dd_is_exact(const sgufp_dd *dd); /* isTreeExact(): 1 / 0 */
+
+/* Structure, for inspection and parity tests.  Layers exclude the terminal node; arcs include the
+ * terminal arcs.  dump: nodes in tree order; per in-arc the POSITION of its tail in the previous
+ * layer and its decision, in stored in-arc order (node_inptr has nodes+1 entries). */
+int sgufp_dd_num_layers(const sgufp_dd *dd);
+int sgufp_dd_layer_sizes(const sgufp_dd *dd, int32_t *sizes /*[num_layers]*/);
+int sgufp_dd_counts(const sgufp_dd *dd, int64_t *nodes, int64_t *arcs);
+int sgufp_dd_dump(sgufp_dd *dd, int32_t *node_layer, double *node_state, int64_t *node_inptr, int32_t *arc_tailpos,
+                  int32_t *arc_decision, double *terminal_weight /*[last layer]*/);
+
+/* applyOptimalityCut(cut, optimal, upperbound) -> bound (DD.cpp:3932-4023, 3425-3505) and
+ * applyFeasibilityCut(cut) -> feasible (DD.cpp:3842-3930, 3340-3423).  The cut is an Inavap::Cut:
+ * RHS + nnz (key,value) pairs.  `optimal`/`upperbound` are ignored by the restricted DD, whose
+ * reference signature has none. */
+int sgufp_dd_apply_optimality(sgufp_dd *dd, double rhs, const uint64_t *keys, const double *vals, int nnz,
+                              double optimal, double upperbound, double *bound);
+int sgufp_dd_apply_feasibility(sgufp_dd *dd, double rhs, const uint64_t *keys, const double *vals, int nnz,
+                               int *feasible);
+
+/* getSolution() / getMaxPath() (DD.cpp:3825-3840, 3290-3305): returns the path length. */
+int sgufp_dd_solution(const sgufp_dd *dd, int16_t *path, int capacity);
+/* getCutset(ub) (DD.cpp:4179-4218) for the relaxed DD; the cut-set of the last compile for the
+ * restricted DD.  Nodes are flattened as (globalLayer, #states, states..., #solution, solution...);
+ * returns the number of int32 words written or SGUFP_ERR_ARG if `capacity` is too small. */
+int sgufp_dd_cutset(const sgufp_dd *dd, double ub, int32_t *words, int capacity);
+
+/* Batched K2: apply the same C optimality cuts to B diagrams in ONE launch pair.
+ * cut c is rhs[c] + (keys,vals)[cut_ptr[c] .. cut_ptr[c+1]).  For every diagram the terminal arc
+ * weights become min(previous, min over the C cuts) and bound[b] = max over terminal arcs — what C
+ * sequential applyOptimalityCut calls leave behind on an exact diagram.  Bound-based arc pruning of
+ * non-exact diagrams (DD.cpp:3987-4021) is NOT performed here; node states are those of cut C-1. */
+int sgufp_dd_apply_optimality_batch(sgufp_dd **dds, int B, const double *rhs, const uint64_t *keys, const double *vals,
+                                    const int32_t *cut_ptr, int C, double *bound /*[B]*/);
+/* Device time of the last K2 launch pair on the diagram's context, and arcs touched by it
+ * (sum over diagrams and cuts of in-arcs + terminal arcs). */
+int sgufp_dd_last_stats(const sgufp_dd *dd, float *kernel_ms, int64_t *arcs_touched, int *kernel_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGUFP_B200_DD_H */

@@ -7,7 +7,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsgufp_b200.so")
-SOURCES = ["capi.cu", "k1_cut.cu", "k2_dd.cu", "dd_host.cpp", "model.cpp"]
+SOURCES = ["capi.cu", "capi_dd.cu", "k1_cut.cu", "k2_dd.cu", "dd_host.cpp", "model.cpp"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-shared"]
 
@@ -20,7 +20,7 @@ def stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "sgufp_b200.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", h) for h in ("sgufp_b200.h", "sgufp_b200_dd.h")]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 

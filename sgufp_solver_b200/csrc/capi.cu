@@ -9,60 +9,14 @@
 #include <string>
 #include <vector>
 
-#include "../../include/sgufp_b200.h"
+#include "ctx.hpp"
 #include "k1_cut.cuh"
-#include "model.hpp"
 
 using namespace sgufp;
 
 namespace {
 thread_local std::string g_create_error;
-
-template <typename T>
-struct DevBuf {
-    T *p = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t n) {
-        if (n <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
-        if (e == cudaSuccess) cap = n;
-        return e;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
 }  // namespace
-
-struct sgufp_ctx {
-    Model M;
-    int S = 0, m_pad = 0, device = 0, sm_count = 0;
-    long long scen_off = 0, S_total = 0;
-    double *d_u = nullptr, *d_l = nullptr;
-    cudaStream_t st = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
-    DevBuf<int32_t> d_plans, d_plan_off, d_ray_i32;
-    DevBuf<unsigned long long> d_sums;
-    DevBuf<long long> d_finf, d_ray_scratch;
-    DevBuf<double> d_obj;
-    DevBuf<uint8_t> d_status;
-    std::string err;
-    int last_launches = 0;
-    float last_ms = 0.f;
-    bool kernel_timed = false;
-    int W() const { return 1 + M.L + M.m; }
-};
-
-#define CU(ctx, call)                                                                              \
-    do {                                                                                           \
-        cudaError_t e__ = (call);                                                                  \
-        if (e__ != cudaSuccess) {                                                                  \
-            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                      \
-            return SGUFP_ERR_CUDA;                                                                 \
-        }                                                                                          \
-    } while (0)
-
-static int fail(sgufp_ctx *c, int code, const std::string &msg) { c->err = msg; return code; }
 
 // ---- helpers shared by the one-GPU and the sharded entry points --------------------------------
 struct Batch {

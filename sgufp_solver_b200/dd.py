@@ -1,0 +1,290 @@
+"""Host-side mirror of the reference's decision-diagram interface (K2 behind the C ABI).
+
+`RelaxedDDNew` / `RestrictedDDNew` keep the member names, argument meaning and results of
+`/root/reference/DD.h:797-808` and `DD.h:713-728`.  The diagram structure is built on the host
+exactly as the reference builds it; every `apply*Cut` runs the layer-wise longest path on the GPU.
+`apply_optimality_batch` is the batched form: B diagrams x C cuts in one launch pair.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import cip, dp, i16p, i64p, ip, u64p, vp
+
+DD_SIGNATURES = {
+    "sgufp_dd_create": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp)]),
+    "sgufp_dd_destroy": (None, [vp]),
+    "sgufp_dd_build": (C.c_int, [vp, i16p, C.c_int, i16p, C.c_int, C.c_int, cip]),
+    "sgufp_dd_is_exact": (C.c_int, [vp]),
+    "sgufp_dd_num_layers": (C.c_int, [vp]),
+    "sgufp_dd_layer_sizes": (C.c_int, [vp, ip]),
+    "sgufp_dd_counts": (C.c_int, [vp, i64p, i64p]),
+    "sgufp_dd_dump": (C.c_int, [vp, ip, dp, i64p, ip, ip, dp]),
+    "sgufp_dd_apply_optimality": (C.c_int, [vp, C.c_double, u64p, dp, C.c_int, C.c_double, C.c_double, dp]),
+    "sgufp_dd_apply_feasibility": (C.c_int, [vp, C.c_double, u64p, dp, C.c_int, cip]),
+    "sgufp_dd_solution": (C.c_int, [vp, i16p, C.c_int]),
+    "sgufp_dd_cutset": (C.c_int, [vp, C.c_double, ip, C.c_int]),
+    "sgufp_dd_apply_optimality_batch": (C.c_int, [C.POINTER(vp), C.c_int, dp, u64p, dp, ip, C.c_int, dp]),
+    "sgufp_dd_last_stats": (C.c_int, [vp, C.POINTER(C.c_float), i64p, cip]),
+}
+_bound = False
+
+
+def _lib_dd():
+    global _bound
+    L = _lib.lib()
+    if not _bound:
+        for name, (res, args) in DD_SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _bound = True
+    return L
+
+
+_lib.DD_SIGNATURES = DD_SIGNATURES
+
+DOUBLE_MIN = -np.finfo(np.float64).max   # Inavap::DOUBLE_MIN (DD.h:453)
+DOUBLE_MAX = np.finfo(np.float64).max
+
+
+class Node:
+    """`Inavap::Node` (DD.h:456-479)."""
+
+    def __init__(self, states=(), solutionVector=(), lb=DOUBLE_MIN, ub=DOUBLE_MIN, globalLayer=0):
+        self.states = list(states)
+        self.solutionVector = list(solutionVector)
+        self.lb, self.ub, self.globalLayer = lb, ub, int(globalLayer)
+
+    def __repr__(self):
+        return f"Node(gl={self.globalLayer}, states={self.states}, sol={self.solutionVector})"
+
+
+def _cut_arrays(cut):
+    keys = np.ascontiguousarray(cut.keys, dtype=np.uint64)
+    vals = np.ascontiguousarray(cut.vals, dtype=np.float64)
+    return keys, vals
+
+
+def _unpack_nodes(buf, k, ub=DOUBLE_MIN) -> List[Node]:
+    out, i = [], 0
+    while i < k:
+        gl = int(buf[i]); ns = int(buf[i + 1]); st = buf[i + 2:i + 2 + ns].tolist(); i += 2 + ns
+        nl = int(buf[i]); sol = buf[i + 1:i + 1 + nl].tolist(); i += 1 + nl
+        out.append(Node(st, sol, DOUBLE_MIN, ub, gl))
+    return out
+
+
+class _DDBase:
+    KIND = 0
+
+    def __init__(self, solver, width: int = 0):
+        """`solver` is the `GuroSolver` handle that owns the network model (Network.h:69-117)."""
+        L = _lib_dd()
+        self.solver = solver
+        h = vp()
+        solver._check(L.sgufp_dd_create(solver.h, self.KIND, int(width), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            _lib_dd().sgufp_dd_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _build(self, node: Node) -> int:
+        st = np.ascontiguousarray(node.states, dtype=np.int16)
+        so = np.ascontiguousarray(node.solutionVector, dtype=np.int16)
+        n = C.c_int(0)
+        self.solver._check(_lib_dd().sgufp_dd_build(self.h, st.ctypes.data_as(i16p), len(st), so.ctypes.data_as(i16p), len(so),
+                                                   int(node.globalLayer), C.byref(n)))
+        return n.value
+
+    def isTreeExact(self) -> bool:
+        return bool(_lib_dd().sgufp_dd_is_exact(self.h))
+
+    def layer_sizes(self) -> np.ndarray:
+        """Sizes of tree[0..], terminal layer included (always 1) to match the reference's `tree`."""
+        n = _lib_dd().sgufp_dd_num_layers(self.h)
+        out = np.zeros(n, np.int32)
+        _lib_dd().sgufp_dd_layer_sizes(self.h, out.ctypes.data_as(ip))
+        return np.append(out, 1).astype(np.int32)
+
+    def counts(self) -> Tuple[int, int]:
+        a, b = C.c_int64(), C.c_int64()
+        _lib_dd().sgufp_dd_counts(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def dump(self):
+        nn, na = self.counts()
+        sizes = self.layer_sizes()
+        nlast = int(sizes[-2])
+        na_in = na - nlast
+        node_layer = np.zeros(nn, np.int32); node_state = np.zeros(nn); inptr = np.zeros(nn + 1, np.int64)
+        tailpos = np.zeros(max(1, na_in), np.int32); dec = np.zeros(max(1, na_in), np.int32); term = np.zeros(max(1, nlast))
+        self.solver._check(_lib_dd().sgufp_dd_dump(self.h, node_layer.ctypes.data_as(ip), node_state.ctypes.data_as(dp), inptr.ctypes.data_as(i64p),
+                                                  tailpos.ctypes.data_as(ip), dec.ctypes.data_as(ip), term.ctypes.data_as(dp)))
+        return dict(node_layer=node_layer, node_state=node_state, in_ptr=inptr, arc_tailpos=tailpos[:na_in], arc_decision=dec[:na_in],
+                    terminal_weight=term[:nlast])
+
+    def getSolution(self) -> np.ndarray:
+        buf = np.zeros(self.solver.L + 8, np.int16)
+        k = _lib_dd().sgufp_dd_solution(self.h, buf.ctypes.data_as(i16p), len(buf))
+        if k < 0:
+            self.solver._check(k)
+        return buf[:k].copy()
+
+    def last_stats(self):
+        ms, arcs, n = C.c_float(), C.c_int64(), C.c_int()
+        _lib_dd().sgufp_dd_last_stats(self.h, C.byref(ms), C.byref(arcs), C.byref(n))
+        return ms.value, arcs.value, n.value
+
+    def _cutset(self, ub) -> List[Node]:
+        buf = np.zeros(1 << 22, np.int32)
+        k = _lib_dd().sgufp_dd_cutset(self.h, float(ub), buf.ctypes.data_as(ip), len(buf))
+        if k < 0:
+            self.solver._check(k)
+        return _unpack_nodes(buf, k, ub)
+
+
+class RelaxedDDNew(_DDBase):
+    """`Inavap::RelaxedDDNew` (DD.h:734-810)."""
+    KIND = 0
+
+    def buildTree(self, node: Node = None) -> None:
+        self._build(node or Node())
+
+    def applyOptimalityCut(self, cut, optimal: float, upperbound: float) -> float:
+        keys, vals = _cut_arrays(cut)
+        b = C.c_double()
+        self.solver._check(_lib_dd().sgufp_dd_apply_optimality(self.h, float(cut.RHS), keys.ctypes.data_as(u64p), vals.ctypes.data_as(dp), len(keys),
+                                                              float(optimal), float(upperbound), C.byref(b)))
+        return b.value
+
+    def applyFeasibilityCut(self, cut) -> int:
+        keys, vals = _cut_arrays(cut)
+        f = C.c_int()
+        self.solver._check(_lib_dd().sgufp_dd_apply_feasibility(self.h, float(cut.RHS), keys.ctypes.data_as(u64p), vals.ctypes.data_as(dp), len(keys), C.byref(f)))
+        return f.value
+
+    def getCutset(self, ub: float) -> List[Node]:
+        return self._cutset(ub)
+
+
+class RestrictedDDNew(_DDBase):
+    """`Inavap::RestrictedDDNew` (DD.h:653-730); `width` is the runtime max_width (DD.h:710)."""
+    KIND = 1
+
+    def __init__(self, solver, width: int):
+        super().__init__(solver, width)
+        self._cs = None
+
+    def compile(self, node: Node = None):
+        """Returns the exact cut-set (list of Node) or None when the tree is exact (`nullopt`)."""
+        n = self._build(node or Node())
+        return None if n < 0 else self._cutset(DOUBLE_MIN)
+
+    buildTree = compile
+
+    def applyOptimalityCut(self, cut) -> float:
+        keys, vals = _cut_arrays(cut)
+        b = C.c_double()
+        self.solver._check(_lib_dd().sgufp_dd_apply_optimality(self.h, float(cut.RHS), keys.ctypes.data_as(u64p), vals.ctypes.data_as(dp), len(keys),
+                                                              0.0, 0.0, C.byref(b)))
+        return b.value
+
+    def applyFeasibilityCut(self, cut) -> int:
+        keys, vals = _cut_arrays(cut)
+        f = C.c_int()
+        self.solver._check(_lib_dd().sgufp_dd_apply_feasibility(self.h, float(cut.RHS), keys.ctypes.data_as(u64p), vals.ctypes.data_as(dp), len(keys), C.byref(f)))
+        return f.value
+
+    def getMaxPath(self) -> np.ndarray:
+        return self.getSolution()
+
+
+def apply_optimality_batch(dds: Sequence[_DDBase], cuts) -> np.ndarray:
+    """B diagrams x C optimality cuts in one launch pair; returns bound[B] (DD.cpp:3975-3984)."""
+    L = _lib_dd()
+    B, Cn = len(dds), len(cuts)
+    hs = (vp * B)(*[d.h for d in dds])
+    rhs = np.array([c.RHS for c in cuts], np.float64)
+    ptr = np.zeros(Cn + 1, np.int32)
+    for i, c in enumerate(cuts):
+        ptr[i + 1] = ptr[i] + len(c.keys)
+    keys = np.concatenate([np.asarray(c.keys, np.uint64) for c in cuts]) if ptr[-1] else np.zeros(1, np.uint64)
+    vals = np.concatenate([np.asarray(c.vals, np.float64) for c in cuts]) if ptr[-1] else np.zeros(1, np.float64)
+    keys = np.ascontiguousarray(keys); vals = np.ascontiguousarray(vals)
+    bound = np.zeros(B)
+    dds[0].solver._check(L.sgufp_dd_apply_optimality_batch(hs, B, rhs.ctypes.data_as(dp), keys.ctypes.data_as(u64p), vals.ctypes.data_as(dp),
+                                                           ptr.ctypes.data_as(ip), Cn, bound.ctypes.data_as(dp)))
+    return bound
+
+
+def random_cut(solver, rng, cut_type=0):
+    """A pseudo-cut over the network's own keys, as tests2.cpp:262-291 (getActualCut) builds them."""
+    from .solver import Cut, getKey
+    keys, vals = [], []
+    order = np.lexsort((solver.slot_j[:solver.T], solver.slot_q[:solver.T], solver.slot_i[:solver.T]))
+    for s in order:
+        if rng.integers(0, 11) % 2 == 0:
+            keys.append(getKey(solver.slot_q[s], solver.slot_i[s], solver.slot_j[s]))
+            vals.append(float(rng.uniform(-100, 100)))
+    rhs = float(rng.uniform(-100, 100))
+    rhs = rhs * 10 if cut_type == 0 else abs(rhs) * 7
+    return Cut(rhs, keys, vals)
+
+
+def bench_longest_path(device: int = 0, B: int = 64, Cn: int = 64, width: int = 1024, reps: int = 5):
+    """DD arcs/s of K2 on config C3: C2 network, restricted width `width`, B diagrams x C cuts."""
+    from . import instances as I
+    from .solver import GuroSolver
+    inst = I.config2(S=1)
+    solver = GuroSolver(inst, device=device)
+    rng = np.random.default_rng(5)
+    dds = []
+    for _ in range(B):
+        d = RestrictedDDNew(solver, width)
+        d.compile()
+        dds.append(d)
+    cuts = [random_cut(solver, rng) for _ in range(Cn)]
+    apply_optimality_batch(dds, cuts)
+    times = []
+    for _ in range(reps):
+        apply_optimality_batch(dds, cuts)
+        ms, arcs, launches = dds[0].last_stats()
+        times.append(ms)
+    ms = float(np.median(times))
+    nodes, arcs1 = dds[0].counts()
+    bytes_alg = B * Cn * (arcs1 * 16 + nodes * 8) + Cn * solver.T * 8
+    return {"metric": "dd_arcs_per_sec", "value": arcs / (ms / 1e3), "unit": "arcs/s", "kernel_ms": ms, "arcs_per_launch": int(arcs),
+            "config": f"C3: C2 network, RestrictedDDNew width {width}, {B} diagrams x {Cn} cuts per launch",
+            "achieved_GBps": bytes_alg / (ms / 1e3) / 1e9, "gpu_launches": launches}
+
+
+def smoke():
+    from . import instances as I
+    from .solver import GuroSolver
+    inst = I.config1(S=2)
+    solver = GuroSolver(inst, device=0)
+    dd = RelaxedDDNew(solver)
+    dd.buildTree()
+    from .solver import Cut, getKey
+    keys, vals, v = [], [], 1.5
+    for a in solver.layer_arc:
+        i, q = int(inst.tail[a]), int(inst.head[a])
+        for b in solver.out_arcs(q):
+            keys.append(getKey(q, i, int(inst.head[b]))); vals.append(v); v += 0.75
+    bound = dd.applyOptimalityCut(Cut(-3.25, keys, vals), -1e300, 1e300)
+    sol = dd.getSolution().tolist()
+    assert bound == 32.0 and sol == [9, 10, 11, -1, 12, 13], (bound, sol)   # SURVEY.md Appendix A.3 (reference output)
+    print(f"dd smoke ok: bound={bound} solution={sol}")
