@@ -22,6 +22,7 @@ struct sgufp_dd {
     DevBuf<double> d_term;
     K2DD dev{};
     bool uploaded = false, term_dirty = true;
+    unsigned long uploaded_version = 0;
 };
 
 namespace {
@@ -30,7 +31,7 @@ int upload(sgufp_dd *d) {
     sgufp_ctx *c = d->ctx;
     if (c->device == SGUFP_DEVICE_NONE) return fail(c, SGUFP_ERR_CUDA, "handle was created with SGUFP_DEVICE_NONE: there is no CPU compute path for K2");
     CU(c, cudaSetDevice(c->device));
-    const bool was_dirty = d->dd->dirty() || !d->uploaded;
+    const bool was_dirty = !d->uploaded || d->uploaded_version != d->dd->version();
     const DDCsr &C = d->dd->flatten();
     if (was_dirty) {
         std::vector<int32_t> pack;
@@ -47,6 +48,7 @@ int upload(sgufp_dd *d) {
         d->dev.nlayers = C.nlayers; d->dev.nroot = (int)C.root_slot.size(); d->dev.nnodes = C.nnodes; d->dev.nlast = C.nlast;
         d->dev.max_width = C.max_width;
         d->uploaded = true;
+        d->uploaded_version = d->dd->version();
         d->term_dirty = true;
     }
     if (d->term_dirty) {

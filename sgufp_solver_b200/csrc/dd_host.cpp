@@ -35,7 +35,7 @@ int HostDD::slot_of(int g, int decision) const {
 void HostDD::build(const NodeSpec &root, std::vector<NodeSpec> *cutset) {
     const Model &M = *M_;
     nodes_.clear(); arcs_.clear(); tree_.clear(); term_.clear(); last_coef_.clear();
-    exact_ = true; dirty_ = true;
+    exact_ = true; dirty_ = true; version_++;
     start_ = root.global_layer;
     root_solution_ = root.solution;
     const int r = new_node();
@@ -256,7 +256,7 @@ double HostDD::finish_optimality(const std::vector<double> &coef, const std::vec
                 auto &hin = nodes_[arcs_[a].head].in; hin.erase(std::remove(hin.begin(), hin.end(), a), hin.end());
                 auto &tout = nodes_[arcs_[a].tail].out; tout.erase(std::remove(tout.begin(), tout.end(), a), tout.end());
             }
-            dirty_ = true;
+            dirty_ = true; version_++;
         }
     }
     return terminal;
@@ -296,7 +296,7 @@ void HostDD::remove_last_layer_nodes(const std::vector<int32_t> &ids) {
         tree_[l].swap(keep);
         if (is_last) term_.swap(keep_term);
     }
-    dirty_ = true;
+    dirty_ = true; version_++;
 }
 
 int HostDD::finish_feasibility(const std::vector<double> &coef, const std::vector<double> &states) {
@@ -321,7 +321,7 @@ int HostDD::finish_feasibility(const std::vector<double> &coef, const std::vecto
                 if (!d.count(tree_[llayer][i])) { keep.push_back(tree_[llayer][i]); keep_term.push_back(term_[i]); }
                 else nodes_[tree_[llayer][i]].out.clear();
             tree_[llayer].swap(keep); term_.swap(keep_term);
-            dirty_ = true;
+            dirty_ = true; version_++;
         }
         return term_.empty() ? 0 : 1;
     }
@@ -349,7 +349,7 @@ int HostDD::finish_feasibility(const std::vector<double> &coef, const std::vecto
                 auto &hin = nodes_[arcs_[a].head].in; hin.erase(std::remove(hin.begin(), hin.end(), a), hin.end());
                 auto &tout = nodes_[arcs_[a].tail].out; tout.erase(std::remove(tout.begin(), tout.end(), a), tout.end());
             }
-            dirty_ = true;
+            dirty_ = true; version_++;
         }
     }
     return 1;

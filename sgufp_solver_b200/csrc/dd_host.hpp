@@ -67,6 +67,7 @@ public:
     // 2. the host finishes with exactly the reference's sequential semantics
     const DDCsr &flatten();
     bool dirty() const { return dirty_; }
+    unsigned long version() const { return version_; }   // bumped by every structural change
     // dense coefficient vector of a sparse Inavap::Cut: first matching key wins (Cut.h:275-282)
     void densify(const uint64_t *keys, const double *vals, int nnz, std::vector<double> &coef) const;
     // `states` in CSR node order, `term` = terminal arc weights after min with the last-layer states
@@ -96,6 +97,7 @@ private:
     std::vector<int16_t> root_solution_;
     int start_ = 0;
     bool exact_ = true, dirty_ = true;
+    unsigned long version_ = 0;
     DDCsr csr_;
     std::vector<double> last_coef_;
 
