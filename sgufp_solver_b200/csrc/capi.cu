@@ -64,40 +64,12 @@ static int launch_batch(sgufp_ctx *c, const Batch &B, int K, unsigned long long 
     return 0;
 }
 
-// kinds used by the ray: a dangling end arc books into its FREE multiplier, everything else by endpoints
-static void ray_arrays(const sgufp_ctx *c, const Plan &P, std::vector<int32_t> &ts, std::vector<int32_t> &hs, std::vector<int32_t> &info,
-                       std::vector<int32_t> &pair_layer, std::vector<int32_t> &next, std::vector<int32_t> &aq, std::vector<int32_t> &first_wire, int &nn) {
-    const Model &M = c->M;
-    const int m = M.m;
-    std::vector<int32_t> wire(m, -1);
-    nn = M.nc;
-    for (int a = 0; a < m; a++) if (P.match_out[a] >= 0) wire[a] = nn++;
-    ts.assign(m, 0); hs.assign(m, 0); info.assign(m, 0); pair_layer.assign(m, -1); next.assign(m, -1); aq.assign(m, 0);
-    first_wire.assign(std::max(1, M.nav), -1);
-    for (int a = 0; a < m; a++) {
-        const int t = M.tail[a], h = M.head[a];
-        ts[a] = M.active[t] ? (P.match_in[a] >= 0 ? wire[P.match_in[a]] : -1) : M.cn[t];
-        hs[a] = M.active[h] ? (P.match_out[a] >= 0 ? wire[a] : -1) : M.cn[h];
-        int kind;
-        if (hs[a] < 0) kind = KIND_SIGMA; else if (ts[a] < 0) kind = KIND_PHI;
-        else kind = M.active[h] ? KIND_SIGMA : (M.active[t] ? KIND_PHI : KIND_GAMMA);
-        info[a] = kind | ((M.arc_layer[a] + 1) << 2);
-        if (P.match_out[a] >= 0) { pair_layer[a] = M.arc_layer[a]; next[a] = P.match_out[a]; }
-        aq[a] = (M.av_index[t] + 1) | ((M.av_index[h] + 1) << 16);
-    }
-    for (int i = 0; i < M.nav; i++) {
-        const int q = M.av_node[i];
-        for (int e = M.in_ptr[q]; e < M.in_ptr[q + 1]; e++)
-            if (P.match_out[M.in_arc[e]] >= 0) { first_wire[i] = wire[M.in_arc[e]]; break; }
-    }
-}
-
 static int run_ray(sgufp_ctx *c, const Plan &P, long long global_s, unsigned long long *d_sums, cudaStream_t st) {
     const long long sl = global_s - c->scen_off;
     if (sl < 0 || sl >= c->S) return fail(c, SGUFP_ERR_ARG, "ray: scenario is not in this rank's block");
     std::vector<int32_t> ts, hs, info, pl, nx, aq, fw;
     int nn = 0;
-    ray_arrays(c, P, ts, hs, info, pl, nx, aq, fw, nn);
+    ray_arrays(c->M, P, ts, hs, info, pl, nx, aq, fw, nn);
     const int m = c->M.m, nav = std::max(1, c->M.nav);
     std::vector<int32_t> pack;
     pack.reserve((size_t)6 * m + nav);

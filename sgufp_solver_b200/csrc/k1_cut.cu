@@ -4,24 +4,29 @@
 // for every (candidate k, scenario s) it solves the second-stage LP exactly and adds the
 // scenario's dual contribution cap x dual (grb.cpp:238-281) into exact integer accumulators.
 //
-// Mapping: one warp per (candidate, scenario); a persistent grid of
-// sm_count x CTAS_PER_SM CTAs strides over the K*S work items scenario-minor, so neighbouring
-// warps stream neighbouring rows of the scenario-major fp64 capacity arrays with coalesced
-// 128-bit loads.  The candidate's contracted graph (chains) is read-only and
-// stays in L1; all per-scenario state (chain capacities, flows, labels, potentials) lives in the
-// warp's slice of shared memory.  No tensor cores: this is integer graph work.
+// Mapping: one TILE of 8, 16 or 32 lanes per (candidate, scenario) — small
+// contracted graphs put several scenarios in one warp; a persistent grid of
+// sm_count x resident-CTAs strides over the K*S work items scenario-minor, so neighbouring tiles
+// stream neighbouring rows of the scenario-major fp64 capacity arrays with coalesced 128-bit
+// loads.  The candidate's contracted graph (chains + head-sorted residual slots) is
+// read-only and stays in L1; all per-scenario state lives in the tile's slice of shared memory.
+// No tensor cores: this is integer graph work.
 //
 // Per work item:
 //   1. stream u_s, l_s; segmented min/max into chain capacities (shared-memory atomics, packed
 //      with the position of the FIRST least-capacity / LAST greatest-lower-bound arc)
-//   2. optimal flow by successive shortest paths; labels are (distance, hops) packed in one
-//      int so that a warp-wide atomicMin relaxation yields an acyclic predecessor structure
+//   2. optimal flow, one shortest-path LEVEL at a time: a pull-style label correction over the
+//      head-sorted slots (each lane reduces a contiguous slot range in registers and issues one
+//      atomicMin per head it touches; labels are (distance, hops) in one int), then a blocking
+//      flow on the tight sub-graph by a backward depth-first search with current-arc pointers
+//      (every tight slot is scanned once per level, every path found is pushed immediately)
 //   3. SPEC-LP potentials (algorithm-independent) by label correction from the root
 //   4. lift to (gamma, beta, sigma, phi, lambda, mu), multiply by the capacities and add to the
 //      candidate's accumulators; write objective + status
 #include "k1_cut.cuh"
 
 #include <climits>
+#include <cstdlib>
 
 #include "model.hpp"
 
@@ -30,41 +35,66 @@ namespace sgufp {
 namespace {
 
 constexpr int HB = 10;                 // hop bits of a label
-constexpr int LAB_BIAS = 1 << 20;      // distance bias so that labels are positive ints
-constexpr int LAB_INF = 0x7fffffff;
+constexpr int LAB_BIAS = 1 << 19;      // |distance| < 2^18 (checked at create) => 0 < distance + bias < 2^20
+constexpr int LAB_INF = 0x3fffffff;    // every real label is < 2^30; label + increment never overflows an int
 constexpr int NEG_INF = INT_MIN / 4;
 constexpr int WARPS = 8;               // warps per CTA
-constexpr unsigned FULL = 0xffffffffu;
 
 struct PlanView {
     const PlanHeader *h;
     const int32_t *arc_cp, *arc_info, *arc_pre, *ch_ends, *ch_r, *ch_ptr, *ch_arcs, *ch_q, *av_ptr, *av_arcs, *fb_ptr, *fb_ch;
+    const int32_t *slot_th, *slot_cs, *slot_ch, *ch_slots, *node_in;
     __device__ explicit PlanView(const int32_t *base) {
         h = reinterpret_cast<const PlanHeader *>(base);
         arc_cp = base + h->o_arc_cp; arc_info = base + h->o_arc_info; arc_pre = base + h->o_arc_pre;
         ch_ends = base + h->o_ch_ends; ch_r = base + h->o_ch_r; ch_ptr = base + h->o_ch_ptr; ch_arcs = base + h->o_ch_arcs;
         ch_q = base + h->o_ch_q; av_ptr = base + h->o_av_ptr; av_arcs = base + h->o_av_arcs; fb_ptr = base + h->o_fb_ptr; fb_ch = base + h->o_fb_ch;
+        slot_th = base + h->o_slot_th; slot_cs = base + h->o_slot_cs; slot_ch = base + h->o_slot_ch; ch_slots = base + h->o_ch_slots;
+        node_in = base + h->o_node_in;
     }
 };
 
-struct WarpMem {  // this warp's slice of shared memory
-    int *up, *lo, *x, *lab, *pred, *pot, *aq, *exc;
+struct TileMem {  // this tile's slice of shared memory
+    int *up, *lo, *x, *lab, *pred, *pot, *exc, *aq;
+};
+
+template <int TILE>
+struct Lanes {    // the TILE lanes that work on one scenario
+    unsigned mask;
+    int tl;
+    __device__ Lanes() {
+        const int lane = threadIdx.x & 31;
+        tl = lane & (TILE - 1);
+        mask = TILE == 32 ? 0xffffffffu : (((1u << TILE) - 1u) << (lane & ~(TILE - 1)));
+    }
+    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+    __device__ __forceinline__ bool any(bool p) const { return __any_sync(mask, p) != 0; }
+    __device__ __forceinline__ long long sum(long long v) const {
+        for (int o = TILE / 2; o; o >>= 1) v += __shfl_xor_sync(mask, v, o, TILE);
+        return v;
+    }
+    __device__ __forceinline__ unsigned long long min_u64(unsigned long long v) const {
+        for (int o = TILE / 2; o; o >>= 1) { const unsigned long long t = __shfl_xor_sync(mask, v, o, TILE); v = t < v ? t : v; }
+        return v;
+    }
 };
 
 __device__ __forceinline__ int lab_dist(int lab) { return (lab >> HB) - LAB_BIAS; }
 
-// Label-correcting shortest paths from `src` over residual arcs.  MERGED: the root is one node
-// (index 0) that is never relabelled; otherwise arcs entering the root end at index nc.
-template <bool MERGED>
-__device__ void shortest_paths(int src, const PlanView &P, int nopen, int nc, int lane, WarpMem &w) {
-    for (int v = lane; v <= nc; v += 32) w.lab[v] = LAB_INF;
-    __syncwarp();
-    if (lane == 0) w.lab[src] = LAB_BIAS << HB;
-    __syncwarp();
+// Label-correcting shortest paths from `src` over the residual arcs of the contracted graph
+// (push style: every lane relaxes its chains, shared-memory atomicMin on the packed label).
+// MERGED: the root is one node (index 0) that is never relabelled; otherwise arcs entering the
+// root end at index nc.
+template <int TILE, bool MERGED>
+__device__ void shortest_paths(int src, const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TileMem &w, int &fuel) {
+    for (int v = T.tl; v <= nc; v += TILE) w.lab[v] = LAB_INF;
+    T.sync();
+    if (T.tl == 0) w.lab[src] = LAB_BIAS << HB;
+    T.sync();
     bool changed;
     do {
         changed = false;
-        for (int c = lane; c < nopen; c += 32) {
+        for (int c = T.tl; c < nopen; c += TILE) {
             const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1, r = P.ch_r[c];
             const int xc = w.x[c], up = w.up[c] >> HB, lo = w.lo[c] >> HB;
             if (xc < up && !(MERGED && ev == 0)) {
@@ -84,15 +114,20 @@ __device__ void shortest_paths(int src, const PlanView &P, int nopen, int nc, in
                 }
             }
         }
-        __syncwarp();
-        changed = __any_sync(FULL, changed);
+        T.sync();
+        changed = T.any(changed) && --fuel > 0;
     } while (changed);
 }
 
-// One tight residual arc per labelled node; hops strictly decrease along it, so following
-// predecessors always reaches the source.
-__device__ void mark_predecessors(const PlanView &P, int nopen, int nc, int lane, WarpMem &w) {
-    for (int c = lane; c < nopen; c += 32) {
+// One tight residual arc per labelled node (pred = 2*chain + direction, -1 = none).  The hop count
+// strictly decreases along a tight arc, so following predecessors can only end at the source.
+template <int TILE, bool CLEAR>
+__device__ void mark_predecessors(const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TileMem &w) {
+    if (CLEAR) {   // only a re-walk under labels older than the flow can meet a node without a tight in-arc
+        for (int v = T.tl; v <= nc; v += TILE) w.pred[v] = -1;
+        T.sync();
+    }
+    for (int c = T.tl; c < nopen; c += TILE) {
         const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1, r = P.ch_r[c];
         const int xc = w.x[c], up = w.up[c] >> HB, lo = w.lo[c] >> HB;
         if (xc < up) {
@@ -104,14 +139,18 @@ __device__ void mark_predecessors(const PlanView &P, int nopen, int nc, int lane
             if (lu != LAB_INF && lu + r * (1 << HB) + 1 == w.lab[t]) w.pred[t] = 2 * c + 1;
         }
     }
-    __syncwarp();
+    T.sync();
 }
 
-// lane 0 only: bottleneck of the predecessor path src -> dst, then push it
-__device__ int augment(int src, int dst, int limit, const PlanView &P, WarpMem &w) {
+// Lane 0 of the tile: follow the predecessors dst -> src, then push the bottleneck.  Returns the
+// amount pushed, 0 if the walk meets a node without a tight residual in-arc (only possible when the
+// labels are older than the flow, i.e. on a re-walk after an augmentation).
+__device__ int augment(int src, int dst, int limit, const PlanView &P, TileMem &w) {
     int v = dst, d = limit;
     while (v != src) {
-        const int p = w.pred[v], c = p >> 1, e = P.ch_ends[c];
+        const int p = w.pred[v];
+        if (p < 0) return 0;
+        const int c = p >> 1, e = P.ch_ends[c];
         int res;
         if (p & 1) { res = w.x[c] - (w.lo[c] >> HB); v = (e >> 16) - 1; } else { res = (w.up[c] >> HB) - w.x[c]; v = (e & 0xffff) - 1; }
         d = min(d, res);
@@ -124,21 +163,13 @@ __device__ int augment(int src, int dst, int limit, const PlanView &P, WarpMem &
     return d;
 }
 
-__device__ __forceinline__ long long warp_sum(long long v) {
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    return v;
-}
-__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
-    for (int o = 16; o; o >>= 1) { unsigned long long t = __shfl_xor_sync(FULL, v, o); v = t < v ? t : v; }
-    return v;
-}
-
 // Forced flow from lower bounds (rare): route every excess / deficit along shortest residual
 // paths.  Returns false if some forced flow cannot be routed (scenario infeasible).
-__device__ bool route_lower_bounds(const PlanView &P, int nopen, int nc, int lane, WarpMem &w) {
-    for (int v = lane; v <= nc; v += 32) w.exc[v] = 0;
-    __syncwarp();
-    for (int c = lane; c < nopen; c += 32) {
+template <int TILE>
+__device__ bool route_lower_bounds(const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TileMem &w, int &fuel) {
+    for (int v = T.tl; v <= nc; v += TILE) w.exc[v] = 0;
+    T.sync();
+    for (int c = T.tl; c < nopen; c += TILE) {
         const int lo = w.lo[c] >> HB;
         if (lo > 0) {
             const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1;
@@ -146,37 +177,37 @@ __device__ bool route_lower_bounds(const PlanView &P, int nopen, int nc, int lan
             if (sv > 0) atomicSub(&w.exc[sv], lo);
         }
     }
-    __syncwarp();
+    T.sync();
     for (int v = 1; v < nc; v++) {
-        while (w.exc[v] > 0) {
-            shortest_paths<false>(v, P, nopen, nc, lane, w);
+        while (w.exc[v] > 0 && --fuel > 0) {
+            shortest_paths<TILE, false>(v, P, nopen, nc, T, w, fuel);
             unsigned long long best = ~0ull;
-            for (int t = lane; t <= nc; t += 32)
+            for (int t = T.tl; t <= nc; t += TILE)
                 if ((t == nc || (t > 0 && w.exc[t] < 0)) && w.lab[t] != LAB_INF) {
-                    unsigned long long key = ((unsigned long long)(unsigned)w.lab[t] << 32) | (unsigned)t;
+                    const unsigned long long key = ((unsigned long long)(unsigned)w.lab[t] << 32) | (unsigned)t;
                     best = key < best ? key : best;
                 }
-            best = warp_min_u64(best);
+            best = T.min_u64(best);
             if (best == ~0ull) return false;
             const int t = (int)(best & 0xffffffffu);
-            mark_predecessors(P, nopen, nc, lane, w);
-            if (lane == 0) {
+            mark_predecessors<TILE, false>(P, nopen, nc, T, w);
+            if (T.tl == 0) {
                 int lim = w.exc[v];
                 if (t != nc) lim = min(lim, -w.exc[t]);
                 const int d = augment(v, t, lim, P, w);
                 w.exc[v] -= d;
                 if (t != nc) w.exc[t] += d;
             }
-            __syncwarp();
+            T.sync();
         }
     }
     for (int v = 1; v < nc; v++) {
-        while (w.exc[v] < 0) {
-            shortest_paths<false>(0, P, nopen, nc, lane, w);
+        while (w.exc[v] < 0 && --fuel > 0) {
+            shortest_paths<TILE, false>(0, P, nopen, nc, T, w, fuel);
             if (w.lab[v] == LAB_INF) return false;
-            mark_predecessors(P, nopen, nc, lane, w);
-            if (lane == 0) w.exc[v] += augment(0, v, -w.exc[v], P, w);
-            __syncwarp();
+            mark_predecessors<TILE, false>(P, nopen, nc, T, w);
+            if (T.tl == 0) w.exc[v] += augment(0, v, -w.exc[v], P, w);
+            T.sync();
         }
     }
     return true;
@@ -185,52 +216,53 @@ __device__ bool route_lower_bounds(const PlanView &P, int nopen, int nc, int lan
 // SPEC-LP potentials: pot[v] = -(shortest residual distance from the root);
 // nodes the root cannot reach get the least labels consistent with the labelled ones; nodes cut
 // off both ways get a zero-rooted completion.
-__device__ void canonical_potentials(const PlanView &P, int nopen, int nc, int lane, WarpMem &w) {
-    shortest_paths<true>(0, P, nopen, nc, lane, w);
+template <int TILE>
+__device__ void canonical_potentials(const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TileMem &w, int &fuel) {
+    shortest_paths<TILE, true>(0, P, nopen, nc, T, w, fuel);
     bool missing = false;
-    for (int v = lane; v < nc; v += 32) {
+    for (int v = T.tl; v < nc; v += TILE) {
         const int l = w.lab[v];
         if (l == LAB_INF) { missing = true; w.pot[v] = NEG_INF; w.pred[v] = 0; } else { w.pot[v] = lab_dist(l); w.pred[v] = 1; }
     }
-    __syncwarp();
-    if (__any_sync(FULL, missing)) {
-        // pot[] holds d here; pred[] is the state: 1 labelled by phase 1, 0 not yet, 2 isolated
+    T.sync();
+    if (T.any(missing)) {
+        // pot[] holds d here; cur[] is the state: 1 labelled by phase 1, 0 not yet, 2 isolated
         bool changed;
         do {
             changed = false;
-            for (int c = lane; c < nopen; c += 32) {
+            for (int c = T.tl; c < nopen; c += TILE) {
                 const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1, r = P.ch_r[c];
                 const int xc = w.x[c], up = w.up[c] >> HB, lo = w.lo[c] >> HB;
                 if (xc < up && w.pred[sv] == 0) { const int db = w.pot[ev]; if (db > NEG_INF && db + r > atomicMax(&w.pot[sv], db + r)) changed = true; }
                 if (xc > lo && w.pred[ev] == 0) { const int da = w.pot[sv]; if (da > NEG_INF && da - r > atomicMax(&w.pot[ev], da - r)) changed = true; }
             }
-            __syncwarp();
-            changed = __any_sync(FULL, changed);
+            T.sync();
+            changed = T.any(changed) && --fuel > 0;
         } while (changed);
         bool iso = false;
-        for (int v = lane; v < nc; v += 32)
+        for (int v = T.tl; v < nc; v += TILE)
             if (w.pot[v] == NEG_INF) { w.pot[v] = 0; w.pred[v] = 2; iso = true; }
-        __syncwarp();
-        if (__any_sync(FULL, iso)) {
+        T.sync();
+        if (T.any(iso)) {
             do {
                 changed = false;
-                for (int c = lane; c < nopen; c += 32) {
+                for (int c = T.tl; c < nopen; c += TILE) {
                     const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1, r = P.ch_r[c];
                     const int xc = w.x[c], up = w.up[c] >> HB, lo = w.lo[c] >> HB;
                     if (xc < up && w.pred[ev] == 2) { const int cand = w.pot[sv] - r; if (cand < atomicMin(&w.pot[ev], cand)) changed = true; }
                     if (xc > lo && w.pred[sv] == 2) { const int cand = w.pot[ev] + r; if (cand < atomicMin(&w.pot[sv], cand)) changed = true; }
                 }
-                __syncwarp();
-                changed = __any_sync(FULL, changed);
+                T.sync();
+                changed = T.any(changed) && --fuel > 0;
             } while (changed);
         }
     }
-    for (int v = lane; v < nc; v += 32) w.pot[v] = -w.pot[v];
-    __syncwarp();
+    for (int v = T.tl; v < nc; v += TILE) w.pot[v] = -w.pot[v];
+    T.sync();
 }
 
 // wire potential at the HEAD of arc a (a matched in-arc, or any arc of a chain)
-__device__ __forceinline__ int head_potential(int a, const PlanView &P, int nopen, const WarpMem &w) {
+__device__ __forceinline__ int head_potential(int a, const PlanView &P, int nopen, const TileMem &w) {
     const int cp = P.arc_cp[a], c = cp >> 10, pos = cp & 1023, pre = P.arc_pre[a];
     const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1;
     if (c < nopen) {
@@ -243,36 +275,45 @@ __device__ __forceinline__ int head_potential(int a, const PlanView &P, int nope
     return pre;
 }
 
-__global__ void __launch_bounds__(WARPS * 32) k1_cut_eval(K1Launch p, int words_per_warp) {
+template <int TILE, bool REWALK>
+__global__ void __launch_bounds__(WARPS * 32, 4) k1_cut_eval(K1Launch p, int words_per_tile) {
+#ifdef SGUFP_K1_EMULATE
+    int *smem = sgufp_emul_smem;   // tests/cpp/k1_emul.cpp: the kernel body compiled for the host, TILE = 1
+#else
     extern __shared__ int smem[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    WarpMem w;
+#endif
+    const Lanes<TILE> T;
+    constexpr int TILES_PER_CTA = WARPS * 32 / TILE;
+    const int tile_in_cta = threadIdx.x / TILE;
+    TileMem w;
     {
-        int *base = smem + (size_t)wid * words_per_warp;
+        int *base = smem + (size_t)tile_in_cta * words_per_tile;
         w.up = base; base += p.max_nch;
         w.lo = base; base += p.max_nch;
         w.x = base; base += p.max_nopen;
-        w.lab = base; base += p.nc + 1;
-        w.pred = base; base += p.nc + 1;
-        w.pot = base; base += p.nc + 1;
-        w.exc = base; base += p.nc + 1;
+        w.lab = base; base += p.nc + 2;
+        w.pred = base; base += p.nc + 2;
+        w.pot = base; base += p.nc + 2;
+        w.exc = base; base += p.nc + 2;
         w.aq = base;
     }
     const long long items = (long long)p.K * p.S;
-    const long long stride = (long long)gridDim.x * WARPS;
-    for (long long item = (long long)blockIdx.x * WARPS + wid; item < items; item += stride) {
+    const long long stride = (long long)gridDim.x * TILES_PER_CTA;
+    for (long long item = (long long)blockIdx.x * TILES_PER_CTA + tile_in_cta; item < items; item += stride) {
         const int k = (int)(item / p.S), s = (int)(item - (long long)k * p.S);
+        if (*reinterpret_cast<volatile long long *>(p.first_inf + k) < 0) continue;   // this candidate was aborted: drain
+        int fuel = 1 << 20;   // passes + levels a work item may spend (tile-uniform)
         const PlanView P(p.plans + p.plan_off[k]);
         const int nch = P.h->nch, nopen = P.h->nopen, nc = P.h->nc, nav = P.h->nav, m = p.m;
         unsigned long long *sums = p.sums + (size_t)k * p.W;
         const double *row_u = p.cap_u + (size_t)s * p.m_pad, *row_l = p.cap_l + (size_t)s * p.m_pad;
 
         // 1. chain capacities
-        for (int c = lane; c < nch; c += 32) { w.up[c] = LAB_INF; w.lo[c] = 0; }
-        __syncwarp();
+        for (int c = T.tl; c < nch; c += TILE) { w.up[c] = INT_MAX; w.lo[c] = 0; }
+        T.sync();
         {
             const double2 *ru = reinterpret_cast<const double2 *>(row_u), *rl = reinterpret_cast<const double2 *>(row_l);
-            for (int a2 = lane; a2 < p.m_pad / 2; a2 += 32) {
+            for (int a2 = T.tl; a2 < p.m_pad / 2; a2 += TILE) {
                 const double2 u2 = __ldg(ru + a2), l2 = __ldg(rl + a2);
                 const int a = 2 * a2;
                 {
@@ -287,38 +328,54 @@ __global__ void __launch_bounds__(WARPS * 32) k1_cut_eval(K1Launch p, int words_
                 }
             }
         }
-        __syncwarp();
+        T.sync();
         bool bad = false, forced = false;
-        for (int c = lane; c < nch; c += 32) {
+        for (int c = T.tl; c < nch; c += TILE) {
             const int lo = w.lo[c] >> HB;
-            if (c < nopen) { w.x[c] = lo; bad |= lo > (w.up[c] >> HB); forced |= lo > 0; } else bad |= lo > 0;
+            if (c < nopen) {
+                const int up = w.up[c] >> HB;
+                w.x[c] = lo; bad |= lo > up; forced |= lo > 0;
+            } else bad |= lo > 0;
         }
-        __syncwarp();
-        bad = __any_sync(FULL, bad);
-        forced = __any_sync(FULL, forced);
+        T.sync();
+        bad = T.any(bad);
+        forced = T.any(forced);
         // 2. optimal flow
-        if (!bad && forced) bad = !route_lower_bounds(P, nopen, nc, lane, w);
+        if (!bad && forced) bad = !route_lower_bounds<TILE>(P, nopen, nc, T, w, fuel);
         if (bad) {
-            if (lane == 0) {
+            if (T.tl == 0) {
                 atomicMin(p.first_inf + k, p.scen_offset + s);
                 if (p.status) p.status[(size_t)k * p.S + s] = 1;
                 if (p.obj) p.obj[(size_t)k * p.S + s] = 0.0;
             }
+            T.sync();
             continue;
         }
-        for (;;) {
-            shortest_paths<false>(0, P, nopen, nc, lane, w);
+        while (fuel > 0) {   // one label computation per iteration, then as many pushes as its tight arcs allow
+            shortest_paths<TILE, false>(0, P, nopen, nc, T, w, fuel);
             const int lt = w.lab[nc];
             if (lt == LAB_INF || lab_dist(lt) >= 0) break;
-            mark_predecessors(P, nopen, nc, lane, w);
-            if (lane == 0) augment(0, nc, INT_MAX, P, w);
-            __syncwarp();
+            // A path of arcs that are tight under these labels stays a shortest path after other
+            // pushes (distances only grow), so keep re-marking and walking until a walk dead-ends.
+            int pushed;
+            do {
+                mark_predecessors<TILE, REWALK>(P, nopen, nc, T, w);
+                pushed = 0;
+                if (T.tl == 0) pushed = augment(0, nc, INT_MAX, P, w);
+                T.sync();
+                pushed = __shfl_sync(T.mask, pushed, 0, TILE);
+            } while (REWALK && pushed > 0 && --fuel > 0);
         }
         // 3. potentials
-        canonical_potentials(P, nopen, nc, lane, w);
+        canonical_potentials<TILE>(P, nopen, nc, T, w, fuel);
+        if (fuel <= 0) {   // a bound that no valid instance reaches: refuse to answer rather than spin
+            if (T.tl == 0) atomicMin(p.first_inf + k, -1LL);
+            T.sync();
+            continue;
+        }
         // 4. lifting + folding
         long long rhs = 0, objv = 0;
-        for (int c = lane; c < nopen; c += 32) {
+        for (int c = T.tl; c < nopen; c += TILE) {
             const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1, r = P.ch_r[c];
             const int dp = w.pot[ev] - w.pot[sv];
             const int g = r - dp, up = w.up[c] >> HB, lo = w.lo[c] >> HB;
@@ -330,7 +387,7 @@ __global__ void __launch_bounds__(WARPS * 32) k1_cut_eval(K1Launch p, int words_
                 if ((info & 3) == KIND_GAMMA) rhs += v; else atomicAdd(sums + 1 + p.L + a, (unsigned long long)v);
             } else if (g < 0) rhs -= (long long)lo * (-g);
         }
-        for (int i = lane; i < nav; i += 32) {
+        for (int i = T.tl; i < nav; i += TILE) {
             const int b0 = P.av_ptr[i], b1 = P.av_ptr[i + 1];
             int alpha = 0;
             if (b1 > b0) {
@@ -360,8 +417,8 @@ __global__ void __launch_bounds__(WARPS * 32) k1_cut_eval(K1Launch p, int words_
             }
             w.aq[i] = alpha;
         }
-        __syncwarp();
-        for (int c = nopen + lane; c < nch; c += 32) {
+        T.sync();
+        for (int c = nopen + T.tl; c < nch; c += TILE) {
             const int b0 = P.ch_ptr[c], b1 = P.ch_ptr[c + 1], first = P.ch_arcs[b0], last = P.ch_arcs[b1 - 1];
             const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1;
             const int q = P.ch_q[c], qs = (q & 0xffff) - 1, qe = (q >> 16) - 1;
@@ -387,14 +444,14 @@ __global__ void __launch_bounds__(WARPS * 32) k1_cut_eval(K1Launch p, int words_
                 if (v > 0) atomicAdd(sums + 1 + p.L + last, (unsigned long long)((long long)(int)row_u[last] * v));
             }
         }
-        rhs = warp_sum(rhs);
-        objv = warp_sum(objv);
-        if (lane == 0) {
+        rhs = T.sum(rhs);
+        objv = T.sum(objv);
+        if (T.tl == 0) {
             if (rhs) atomicAdd(sums, (unsigned long long)rhs);
             if (p.status) p.status[(size_t)k * p.S + s] = 0;
             if (p.obj) p.obj[(size_t)k * p.S + s] = (double)objv;
         }
-        __syncwarp();
+        T.sync();
     }
 }
 
@@ -478,6 +535,7 @@ __global__ void k1_ray(RayLaunch p) {
     }
 }
 
+#ifndef SGUFP_K1_EMULATE
 // [m][S] int32 (the reference's per-arc vectors) -> [S][m_pad] fp64, 32x32 tiles through shared memory
 __global__ void relayout_caps(const int32_t *__restrict__ src, double *__restrict__ dst, int m, int S, int m_pad) {
     __shared__ int tile[32][33];
@@ -493,27 +551,52 @@ __global__ void relayout_caps(const int32_t *__restrict__ src, double *__restric
     }
 }
 
+#endif  // SGUFP_K1_EMULATE
+
 }  // namespace
 
-cudaError_t k1_launch(const K1Launch &p, cudaStream_t st, int sm_count, int *launches) {
-    const int words = 2 * p.max_nch + p.max_nopen + 4 * (p.nc + 1) + p.nav + 2;
-    const size_t smem = (size_t)WARPS * words * sizeof(int);
+#ifndef SGUFP_K1_EMULATE
+template <int TILE, bool REWALK>
+static cudaError_t launch_tile(const K1Launch &p, cudaStream_t st, int sm_count) {
+    const int words = 2 * p.max_nch + p.max_nopen + 4 * (p.nc + 2) + p.nav + 2;
+    constexpr int tiles = WARPS * 32 / TILE;
+    const size_t smem = (size_t)tiles * words * sizeof(int);
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-    cudaError_t e = cudaFuncSetAttribute(k1_cut_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k1_cut_eval<TILE, REWALK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_cut_eval, WARPS * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_cut_eval<TILE, REWALK>, WARPS * 32, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     const long long items = (long long)p.K * p.S;
-    long long want = (items + WARPS - 1) / WARPS;
+    long long want = (items + tiles - 1) / tiles;
     long long grid = (long long)sm_count * per_sm;   // persistent: a whole number of CTAs per SM
     if (want < grid) grid = want;
     if (grid < 1) grid = 1;
-    k1_cut_eval<<<(unsigned)grid, WARPS * 32, smem, st>>>(p, words);
-    if (launches) (*launches)++;
+    k1_cut_eval<TILE, REWALK><<<(unsigned)grid, WARPS * 32, smem, st>>>(p, words);
     return cudaGetLastError();
 }
+
+int k1_tile_for(int max_nopen) {
+    if (const char *e = getenv("SGUFP_K1_TILE")) { const int t = atoi(e); if (t == 8 || t == 16 || t == 32) return t; }
+    (void)max_nopen;                                  // measured (profiles/): sub-warp tiles lose to divergence between tiles
+    return 32;
+}
+
+cudaError_t k1_launch(const K1Launch &p, cudaStream_t st, int sm_count, int *launches) {
+    if (launches) (*launches)++;
+    int tile = k1_tile_for(p.max_nopen);
+    // fall back to a wider tile (fewer tiles per CTA) if the per-CTA shared memory does not fit
+    for (;;) {
+        const char *rw = getenv("SGUFP_K1_REWALK");
+        const bool rewalk = rw && rw[0] == '1';   // measured slower on C2 and C4 (profiles/r01_k1_variants.md): off by default
+        cudaError_t e = tile == 8 ? launch_tile<8, true>(p, st, sm_count) : tile == 16 ? launch_tile<16, true>(p, st, sm_count)
+                        : rewalk ? launch_tile<32, true>(p, st, sm_count) : launch_tile<32, false>(p, st, sm_count);
+        if (e == cudaErrorInvalidConfiguration && tile < 32) { tile *= 2; cudaGetLastError(); continue; }
+        return e;
+    }
+}
+
 
 cudaError_t ray_launch(const RayLaunch &p, cudaStream_t st, int *launches) {
     k1_ray<<<1, 32, 0, st>>>(p);
@@ -527,5 +610,7 @@ cudaError_t relayout_launch(const int32_t *src, double *dst, int m, int S, int m
     if (launches) (*launches)++;
     return cudaGetLastError();
 }
+
+#endif  // SGUFP_K1_EMULATE
 
 }  // namespace sgufp

@@ -140,8 +140,8 @@ int Model::build(int n_, int m_, const int32_t *tail_, const int32_t *head_, con
     }
     long long sum_abs = 0;
     for (int a = 0; a < m; a++) sum_abs += std::abs((long long)rew[a]);
-    if (nc > 1000 || sum_abs >= (1 << 19) || nav > 32000) {
-        err = "packing limit: contracted nodes <= 1000, sum |reward| < 2^19 (DESIGN.md §5)";
+    if (nc > 1000 || sum_abs >= (1 << 18) || nav > 32000) {
+        err = "packing limit: contracted nodes <= 1000, sum |reward| < 2^18 (DESIGN.md §5)";
         return SGUFP_ERR_LIMITS;
     }
     return 0;
@@ -234,6 +234,30 @@ int build_plan(const Model &M, const int16_t *path, int plen, Plan &P, std::stri
     }
     av_ptr[M.nav] = (int)av_arcs.size(); fb_ptr[M.nav] = (int)fb_ch.size();
 
+    // residual slots of the contracted graph, sorted by head node
+    struct Slot { int tail, head, cs, ch; };
+    std::vector<Slot> slots;
+    slots.reserve(2 * nopen);
+    for (int c = 0; c < nopen; c++) {
+        const Ch &ch = chains[c];
+        slots.push_back({ch.sv, ch.ev == 0 ? M.nc : ch.ev, -ch.r * 1024 + 1, 2 * c});
+        slots.push_back({ch.ev, ch.sv == 0 ? M.nc : ch.sv, ch.r * 1024 + 1, 2 * c + 1});
+    }
+    std::sort(slots.begin(), slots.end(), [](const Slot &a, const Slot &b) {
+        if (a.head != b.head) return a.head < b.head;
+        if (a.tail != b.tail) return a.tail < b.tail;
+        return a.ch < b.ch;
+    });
+    std::vector<int32_t> slot_th(slots.size()), slot_cs(slots.size()), slot_ch(slots.size()), ch_slots(nopen, 0), node_in(M.nc + 2, 0);
+    for (size_t s = 0; s < slots.size(); s++) {
+        slot_th[s] = slots[s].tail | (slots[s].head << 16);
+        slot_cs[s] = slots[s].cs;
+        slot_ch[s] = slots[s].ch;
+        if (slots[s].ch & 1) ch_slots[slots[s].ch >> 1] |= (int32_t)s << 16; else ch_slots[slots[s].ch >> 1] |= (int32_t)s;
+        node_in[slots[s].head + 1]++;
+    }
+    for (int v = 0; v <= M.nc; v++) node_in[v + 1] += node_in[v];
+
     PlanHeader H{};
     H.nch = nch; H.nopen = nopen; H.nc = M.nc; H.nav = M.nav; H.m = m; H.L = M.L;
     std::vector<int32_t> &W = P.words;
@@ -242,10 +266,39 @@ int build_plan(const Model &M, const int16_t *path, int plen, Plan &P, std::stri
     H.o_arc_cp = put(arc_cp); H.o_arc_info = put(arc_info); H.o_arc_pre = put(arc_pre);
     H.o_ch_ends = put(ch_ends); H.o_ch_r = put(ch_r); H.o_ch_ptr = put(ch_ptr); H.o_ch_arcs = put(ch_arcs); H.o_ch_q = put(ch_q);
     H.o_av_ptr = put(av_ptr); H.o_av_arcs = put(av_arcs); H.o_fb_ptr = put(fb_ptr); H.o_fb_ch = put(fb_ch);
+    H.o_slot_th = put(slot_th); H.o_slot_cs = put(slot_cs); H.o_slot_ch = put(slot_ch); H.o_ch_slots = put(ch_slots); H.o_node_in = put(node_in);
     while (W.size() & 3) W.push_back(0);  // keep every plan 16-byte aligned inside a batch
     H.total = (int32_t)W.size();
     std::memcpy(W.data(), &H, sizeof(H));
     return 0;
+}
+
+// Split-graph arrays of the feasibility-ray kernel (k1_ray).  A dangling end arc books into its
+// FREE multiplier, every other arc by its endpoints (rule 6).
+void ray_arrays(const Model &M, const Plan &P, std::vector<int32_t> &ts, std::vector<int32_t> &hs, std::vector<int32_t> &info,
+                std::vector<int32_t> &pair_layer, std::vector<int32_t> &next, std::vector<int32_t> &aq, std::vector<int32_t> &first_wire, int &nn) {
+    const int m = M.m;
+    std::vector<int32_t> wire(m, -1);
+    nn = M.nc;
+    for (int a = 0; a < m; a++) if (P.match_out[a] >= 0) wire[a] = nn++;
+    ts.assign(m, 0); hs.assign(m, 0); info.assign(m, 0); pair_layer.assign(m, -1); next.assign(m, -1); aq.assign(m, 0);
+    first_wire.assign(std::max(1, M.nav), -1);
+    for (int a = 0; a < m; a++) {
+        const int t = M.tail[a], h = M.head[a];
+        ts[a] = M.active[t] ? (P.match_in[a] >= 0 ? wire[P.match_in[a]] : -1) : M.cn[t];
+        hs[a] = M.active[h] ? (P.match_out[a] >= 0 ? wire[a] : -1) : M.cn[h];
+        int kind;
+        if (hs[a] < 0) kind = KIND_SIGMA; else if (ts[a] < 0) kind = KIND_PHI;
+        else kind = M.active[h] ? KIND_SIGMA : (M.active[t] ? KIND_PHI : KIND_GAMMA);
+        info[a] = kind | ((M.arc_layer[a] + 1) << 2);
+        if (P.match_out[a] >= 0) { pair_layer[a] = M.arc_layer[a]; next[a] = P.match_out[a]; }
+        aq[a] = (M.av_index[t] + 1) | ((M.av_index[h] + 1) << 16);
+    }
+    for (int i = 0; i < M.nav; i++) {
+        const int q = M.av_node[i];
+        for (int e = M.in_ptr[q]; e < M.in_ptr[q + 1]; e++)
+            if (P.match_out[M.in_arc[e]] >= 0) { first_wire[i] = wire[M.in_arc[e]]; break; }
+    }
 }
 
 uint64_t cut_hash(const uint64_t *keys, const double *vals, int nnz) {

@@ -55,6 +55,13 @@ struct PlanHeader {
     int32_t o_av_arcs;     // [#matched]
     int32_t o_fb_ptr;      // [nav+1]  fallback chains (end-anchored chains starting at the node) for nodes without a matched pair
     int32_t o_fb_ch;       // [#fallback]
+    // residual "slots": two per open chain (forward sv->ev cost -r, backward ev->sv cost +r),
+    // sorted by head node; an arc entering the root has head index nc (the root seen as a path END)
+    int32_t o_slot_th;     // [2*nopen]  tail | head << 16
+    int32_t o_slot_cs;     // [2*nopen]  (cost << 10) + 1   (label increment: distance in the high bits, one hop)
+    int32_t o_slot_ch;     // [2*nopen]  chain << 1 | (1 if backward)
+    int32_t o_ch_slots;    // [nopen]    position of the forward slot | position of the backward slot << 16
+    int32_t o_node_in;     // [nc+2]     slot range of each head node (index nc = root-in)
     int32_t total;         // int32 words used by this plan, header included
     int32_t pad;
 };
@@ -67,6 +74,9 @@ struct Plan {
 
 // returns 0 / SGUFP_ERR_ARG / SGUFP_ERR_MATCHING / SGUFP_ERR_CYCLIC
 int build_plan(const Model &M, const int16_t *path, int plen, Plan &P, std::string &err);
+
+void ray_arrays(const Model &M, const Plan &P, std::vector<int32_t> &ts, std::vector<int32_t> &hs, std::vector<int32_t> &info,
+                std::vector<int32_t> &pair_layer, std::vector<int32_t> &next, std::vector<int32_t> &aq, std::vector<int32_t> &first_wire, int &nn);
 
 // Inavap::Cut hash (Cut.h:243-251)
 uint64_t cut_hash(const uint64_t *keys, const double *vals, int nnz);

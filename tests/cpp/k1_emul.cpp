@@ -1,0 +1,96 @@
+// k1_emul.cpp — TEST INFRASTRUCTURE.  The body of the K1 kernels (sgufp_solver_b200/csrc/k1_cut.cu)
+// compiled for the HOST with one lane per scenario (TILE = 1) so that the kernel's algorithm —
+// plan decoding, level-wise shortest paths, blocking flow, SPEC-LP potentials, lifting — can be
+// checked against Oracle B in the CPU test suite, where there is no GPU.  The warp-level parallel
+// execution itself is only exercised by the `-m gpu` tests.  Never part of the product.
+#define SGUFP_K1_EMULATE
+#define __CUDA_RUNTIME_H__          // skip <cuda_runtime.h>
+#include <algorithm>
+#include <climits>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+typedef int cudaError_t;
+typedef void *cudaStream_t;
+struct double2 { double x, y; };
+struct EmulIdx { int x = 0, y = 0; };
+static EmulIdx threadIdx, blockIdx;
+static struct { int x = 1, y = 1; } gridDim, blockDim;
+static int *sgufp_emul_smem = nullptr;
+#define __device__
+#define __global__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __restrict__
+using std::max;
+using std::min;
+static inline int atomicMin(int *p, int v) { int o = *p; if (v < o) *p = v; return o; }
+static inline int atomicMax(int *p, int v) { int o = *p; if (v > o) *p = v; return o; }
+static inline int atomicAdd(int *p, int v) { int o = *p; *p += v; return o; }
+static inline int atomicSub(int *p, int v) { int o = *p; *p -= v; return o; }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
+static inline long long atomicMin(long long *p, long long v) { long long o = *p; if (v < o) *p = v; return o; }
+static inline void __syncwarp(unsigned = 0xffffffffu) {}
+static inline int __any_sync(unsigned, int p) { return p; }
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int, int = 32) { return v; }
+template <class T> static inline T __shfl_sync(unsigned, T v, int, int = 32) { return v; }
+static inline double2 __ldg(const double2 *p) { return *p; }
+
+#include "../../sgufp_solver_b200/csrc/k1_cut.cu"
+#include "../../sgufp_solver_b200/csrc/model.cpp"
+
+using namespace sgufp;
+
+// Same contract as sgufp_paths_partial + sgufp_ray_partial, on the host.  sums: [K][W] (W = 1+L+m),
+// first_inf: [K], obj/status: [K][S].  ray_sums[K][W]: filled for candidates with an infeasible scenario.
+extern "C" int emul_paths(int n, int m, int S, const int32_t *tail, const int32_t *head, const int32_t *upper, const int32_t *lower,
+                          const int32_t *rew0, const int32_t *vbar, int nvbar, const int16_t *paths, int K, int L,
+                          long long *sums, long long *first_inf, double *obj, uint8_t *status, long long *ray_sums) {
+    Model M;
+    std::string err;
+    if (int rc = M.build(n, m, tail, head, rew0, vbar, nvbar, err)) return rc;
+    const int m_pad = (m + 1) & ~1, W = 1 + M.L + m;
+    std::vector<double> cu((size_t)S * m_pad, 0.0), cl((size_t)S * m_pad, 0.0);
+    for (int a = 0; a < m; a++)
+        for (int s = 0; s < S; s++) { cu[(size_t)s * m_pad + a] = upper[(size_t)a * S + s]; cl[(size_t)s * m_pad + a] = lower[(size_t)a * S + s]; }
+    std::vector<Plan> plans(K);
+    std::vector<int32_t> words, off(K);
+    int max_nch = 0, max_nopen = 0;
+    for (int k = 0; k < K; k++) {
+        if (int rc = build_plan(M, paths + (size_t)k * L, L, plans[k], err)) return rc;
+        off[k] = (int32_t)words.size();
+        words.insert(words.end(), plans[k].words.begin(), plans[k].words.end());
+        max_nch = std::max(max_nch, plans[k].nch); max_nopen = std::max(max_nopen, plans[k].nopen);
+    }
+    std::memset(sums, 0, (size_t)K * W * 8);
+    for (int k = 0; k < K; k++) first_inf[k] = LLONG_MAX;
+    K1Launch p{};
+    p.cap_u = cu.data(); p.cap_l = cl.data(); p.S = S; p.m = m; p.m_pad = m_pad; p.scen_offset = 0;
+    p.plans = words.data(); p.plan_off = off.data(); p.K = K; p.W = W; p.L = M.L;
+    p.sums = reinterpret_cast<unsigned long long *>(sums); p.first_inf = first_inf; p.obj = obj; p.status = status;
+    p.max_nch = max_nch; p.max_nopen = max_nopen; p.nc = M.nc; p.nav = M.nav;
+    const int wpt = 2 * max_nch + max_nopen + 4 * (M.nc + 2) + M.nav + 2;
+    std::vector<int> smem((size_t)WARPS * 32 * wpt, 0);
+    sgufp_emul_smem = smem.data();
+    threadIdx.x = 0; blockIdx.x = 0; gridDim.x = 1;
+    // one "thread" walks all items: with TILE = 1 the tile stride is WARPS*32, so visit every tile slot of the CTA
+    for (int t = 0; t < WARPS * 32; t++) { threadIdx.x = t; k1_cut_eval<1, false>(p, wpt); }
+    for (int k = 0; k < K; k++) {
+        if (first_inf[k] == LLONG_MAX || first_inf[k] < 0) continue;
+        std::vector<int32_t> ts, hs, info, pl, nx, aq, fw;
+        int nn = 0;
+        ray_arrays(M, plans[k], ts, hs, info, pl, nx, aq, fw, nn);
+        std::vector<long long> scratch((size_t)2 * nn + (size_t)(2 * m + 4 * nn) / 2 + 8);
+        std::memset(ray_sums + (size_t)k * W, 0, (size_t)W * 8);
+        RayLaunch r{};
+        r.cap_u = cu.data(); r.cap_l = cl.data(); r.s_local = (int)first_inf[k]; r.m = m; r.m_pad = m_pad; r.nn = nn;
+        r.arc_ts = ts.data(); r.arc_hs = hs.data(); r.arc_info = info.data(); r.arc_pair_layer = pl.data(); r.arc_next = nx.data(); r.arc_q = aq.data();
+        r.av_first_wire = fw.data(); r.nav = M.nav; r.L = M.L; r.scratch = reinterpret_cast<int32_t *>(scratch.data());
+        r.sums = reinterpret_cast<unsigned long long *>(ray_sums + (size_t)k * W);
+        threadIdx.x = 0; blockIdx.x = 0;
+        k1_ray(r);
+    }
+    return 0;
+}

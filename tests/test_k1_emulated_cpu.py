@@ -1,0 +1,95 @@
+"""The K1 kernel BODY on the CPU (tests/cpp/k1_emul.cpp compiles sgufp_solver_b200/csrc/k1_cut.cu for
+the host with one lane per scenario) against Oracle B: statuses, objectives and the exact integer
+partial sums of every accumulator must be identical.  This checks the kernel's algorithm (plan
+decoding, level-wise shortest paths, blocking flow, SPEC-LP potentials, lifting, the feasibility
+ray) where there is no GPU; the warp-parallel execution is covered by the `-m gpu` tests.
+Test infrastructure only — the product never runs this build."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import wlayout_partial
+from oracle.oracle import OracleNet
+from sgufp_solver_b200 import instances as I
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+I64_MAX = np.iinfo(np.int64).max
+
+
+@pytest.fixture(scope="module")
+def emul(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("emul") / "libk1_emul.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-w", "-fPIC", "-shared", f"-I{ROOT}/tests/cpp/emul_stub", f"-I{ROOT}/include",
+                           f"{ROOT}/tests/cpp/k1_emul.cpp", "-o", so])
+    L = C.CDLL(so)
+    ip, i16p = C.POINTER(C.c_int32), C.POINTER(C.c_int16)
+    L.emul_paths.restype = C.c_int
+    L.emul_paths.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip, ip, ip, ip, ip, C.c_int, i16p, C.c_int, C.c_int,
+                             C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_double), C.POINTER(C.c_uint8), C.POINTER(C.c_longlong)]
+    return L
+
+
+def run_emul(L, inst, net, paths):
+    ip, i16p = C.POINTER(C.c_int32), C.POINTER(C.c_int16)
+    K, plen = paths.shape
+    W = 1 + net.L + inst.m
+    arr = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    t, h, u, lo, r0, vb = arr(inst.tail), arr(inst.head), arr(inst.upper), arr(inst.lower), arr(inst.reward[:, 0]), arr(inst.vbar)
+    p = np.ascontiguousarray(paths, dtype=np.int16)
+    sums = np.zeros((K, W), np.int64); finf = np.zeros(K, np.int64); obj = np.zeros((K, inst.S)); st = np.zeros((K, inst.S), np.uint8)
+    ray = np.zeros((K, W), np.int64)
+    rc = L.emul_paths(inst.n, inst.m, inst.S, t.ctypes.data_as(ip), h.ctypes.data_as(ip), u.ctypes.data_as(ip), lo.ctypes.data_as(ip),
+                      r0.ctypes.data_as(ip), vb.ctypes.data_as(ip), len(vb), p.ctypes.data_as(i16p), K, plen,
+                      sums.ctypes.data_as(C.POINTER(C.c_longlong)), finf.ctypes.data_as(C.POINTER(C.c_longlong)),
+                      obj.ctypes.data_as(C.POINTER(C.c_double)), st.ctypes.data_as(C.POINTER(C.c_uint8)), ray.ctypes.data_as(C.POINTER(C.c_longlong)))
+    assert rc == 0
+    return sums, finf, obj, st, ray
+
+
+def ray_wlayout(net, inst, path, s):
+    d = net.scenario_ray(path, s)
+    L, m = net.L, net.m
+    out = np.zeros(1 + L + m, np.int64)
+    u = inst.upper[:, s].astype(np.int64); lo = inst.lower[:, s].astype(np.int64)
+    out[0] = int((u * d["gamma"]).sum() - (lo * d["beta"]).sum())
+    t = 0
+    for l, a in enumerate(net.layer_arc):
+        for b in net.out_arcs(inst.head[a]):
+            v = int(u[a] * d["lambda"][t] + u[b] * d["mu"][t]); t += 1
+            out[0] += v; out[1 + l] += v
+    out[1 + L:] = u * d["sigma"] + u * d["phi"]
+    return out
+
+
+CASES = [
+    ("c1", lambda: I.config1(S=30), 6, 1, 0.15),
+    ("c1_lb", lambda: I.config1(S=30, lower_prob=0.3), 8, 2, 0.3),
+    ("c1_all_unmatched", lambda: I.config1(S=5), 2, 3, 1.0),
+    ("c2", lambda: I.config2(S=12), 4, 3, 0.1),
+    ("c2_lb", lambda: I.config2(S=12, lower_prob=0.1), 4, 4, 0.3),
+    ("c4_lb", lambda: I.config4(S=3, lower_prob=0.05), 2, 6, 0.3),
+    ("odd_m", lambda: I.make_layered([3, 4, 3], 21, 4, 77, 0.8, 0.1, "odd"), 4, 7, 0.2),
+]
+
+
+@pytest.mark.parametrize("name,make,K,seed,unm", CASES, ids=[c[0] for c in CASES])
+def test_kernel_body_matches_oracle(emul, name, make, K, seed, unm):
+    inst = make()
+    net = OracleNet(inst)
+    paths = I.random_paths(net, K, seed, unm)
+    sums, finf, obj, st, ray = run_emul(emul, inst, net, paths)
+    for k in range(K):
+        want, first_bad = wlayout_partial(net, inst, paths[k], 0, inst.S)
+        oc = net.solve_path(paths[k])
+        assert (finf[k] if finf[k] != I64_MAX else -1) == oc.first_infeasible == (-1 if first_bad is None else first_bad)
+        for s in range(inst.S):
+            d = net.scenario_duals(paths[k], s)
+            assert st[k, s] == d["status"]
+            if d["status"] == 0:
+                assert obj[k, s] == d["obj"]
+        assert (sums[k] == want).all(), np.nonzero(sums[k] != want)
+        if first_bad is not None:
+            assert (ray[k] == ray_wlayout(net, inst, paths[k], first_bad)).all()
