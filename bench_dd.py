@@ -1,0 +1,89 @@
+#!/usr/bin/env python
+"""bench_dd.py — DD arcs/s of K2 (the second half of BASELINE.json's metric) on one B200.
+
+Config C3 (BASELINE.json configs[2]): C2 network, RestrictedDDNew width sweep 64..4096 and the
+RelaxedDDNew, B diagrams x C cuts per launch pair.  Prints one JSON line per point.
+  value      arcs touched per second = B*C*(in-arcs + terminal arcs) / CUDA-event time of
+             k2_longest_path + k2_terminal (events on the launching stream)
+  roofline   algorithmic bytes 16 B/arc + 8 B/node per (diagram, cut) + 8*T B per cut
+             over the same time, against MEASURED_PEAKS.json's HBM copy bandwidth
+  cpu        Oracle A (the unmodified reference class compiled in oracle/_ref) applying the same
+             cuts to one diagram on one host core, if the library is present
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--widths", default="64,128,256,512,1024,2048,4096")
+    ap.add_argument("--B", type=int, default=64)
+    ap.add_argument("--C", type=int, default=64)
+    ap.add_argument("--reps", type=int, default=7)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    import torch
+    from sgufp_solver_b200 import instances as I
+    from sgufp_solver_b200.dd import RelaxedDDNew, RestrictedDDNew, apply_optimality_batch, random_cut
+    from sgufp_solver_b200.solver import GuroSolver
+    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    inst = I.config2(S=1)
+    solver = GuroSolver(inst, device=0)
+    rng = np.random.default_rng(5)
+    cuts = [random_cut(solver, rng) for _ in range(args.C)]
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    ref_net = None
+    if not args.no_cpu:
+        try:
+            from oracle import ref_dd
+            if ref_dd.available():
+                ref_net = ref_dd.RefNetwork(inst)
+        except Exception:
+            ref_net = None
+    points = [("restricted", int(w)) for w in args.widths.split(",")] + [("relaxed", 120)]
+    for kind, w in points:
+        dds = []
+        for _ in range(args.B):
+            d = RestrictedDDNew(solver, w) if kind == "restricted" else RelaxedDDNew(solver)
+            d.compile() if kind == "restricted" else d.buildTree()
+            dds.append(d)
+        for _ in range(3):
+            apply_optimality_batch(dds, cuts)
+        times = []
+        for _ in range(args.reps):
+            flush.zero_(); torch.cuda.synchronize()
+            apply_optimality_batch(dds, cuts)
+            ms, arcs, launches = dds[0].last_stats()
+            times.append(ms)
+        ms = float(np.median(times))
+        nodes1, arcs1 = dds[0].counts()
+        bytes_alg = args.B * args.C * (arcs1 * 16 + nodes1 * 8) + args.C * solver.T * 8
+        line = {"metric": "dd_arcs_per_sec", "value": arcs / (ms / 1e3), "unit": "arcs/s", "kind": kind, "width": w, "kernel_ms": ms,
+                "diagrams": args.B, "cuts": args.C, "arcs_per_diagram": arcs1, "nodes_per_diagram": nodes1, "gpu_launches": launches,
+                "roofline": {"bound": "hbm", "achieved": bytes_alg / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": bytes_alg / (ms / 1e3) / 1e9 / peak, "bytes_per_launch": bytes_alg},
+                "l2": "flushed (512 MiB write) before every timed launch"}
+        if ref_net is not None:
+            r = ref_dd.RefRestrictedDD(ref_net, w) if kind == "restricted" else ref_dd.RefRelaxedDD(ref_net)
+            r.compile() if kind == "restricted" else r.build()
+            t0 = time.perf_counter()
+            for c in cuts:
+                r.apply_opt(c.RHS, c.keys, c.vals) if kind == "restricted" else r.apply_opt(c.RHS, c.keys, c.vals, -1e300, 1e300)
+            dt = time.perf_counter() - t0
+            line["cpu_reference"] = {"value": arcs1 * args.C / dt, "unit": "arcs/s", "cores": 1, "kind": "reference",
+                                     "sample": f"1 diagram x {args.C} cuts, unmodified reference class (oracle/_ref)"}
+        print(json.dumps(line), flush=True)
+        for d in dds:
+            d.close()
+
+
+if __name__ == "__main__":
+    main()

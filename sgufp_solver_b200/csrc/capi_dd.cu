@@ -34,17 +34,28 @@ int upload(sgufp_dd *d) {
     const bool was_dirty = !d->uploaded || d->uploaded_version != d->dd->version();
     const DDCsr &C = d->dd->flatten();
     if (was_dirty) {
-        std::vector<int32_t> pack;
-        pack.reserve(C.layer_ptr.size() + C.in_ptr.size() + 2 * C.arc_tail.size() + C.root_slot.size());
-        const size_t o_lp = 0; pack.insert(pack.end(), C.layer_ptr.begin(), C.layer_ptr.end());
-        const size_t o_ip = pack.size(); pack.insert(pack.end(), C.in_ptr.begin(), C.in_ptr.end());
-        const size_t o_at = pack.size(); pack.insert(pack.end(), C.arc_tail.begin(), C.arc_tail.end());
-        const size_t o_as = pack.size(); pack.insert(pack.end(), C.arc_slot.begin(), C.arc_slot.end());
-        const size_t o_rs = pack.size(); pack.insert(pack.end(), C.root_slot.begin(), C.root_slot.end());
-        CU(c, d->d_i32.reserve(pack.size()));
+        // layer_info (int4) | arc_ts (int2) | in_ptr | root_slot, one upload
+        std::vector<int32_t> pack((size_t)4 * C.nlayers + (size_t)2 * C.narcs, 0);
+        for (int l = 0; l < C.nlayers; l++) {
+            const int v0 = C.layer_ptr[l], v1 = C.layer_ptr[l + 1];
+            bool uniform = l > 0;
+            for (int v = v0; v < v1 && uniform; v++) uniform = C.in_ptr[v + 1] - C.in_ptr[v] == 1;
+            pack[4 * l] = v0; pack[4 * l + 1] = C.in_ptr[v0]; pack[4 * l + 2] = v1 - v0; pack[4 * l + 3] = uniform ? 1 : 0;
+            if (l > 0)
+                for (int e = C.in_ptr[v0]; e < C.in_ptr[v1]; e++) {
+                    pack[(size_t)4 * C.nlayers + 2 * e] = C.arc_tail[e] - C.layer_ptr[l - 1];
+                    pack[(size_t)4 * C.nlayers + 2 * e + 1] = C.arc_slot[e];
+                }
+        }
+        const size_t o_ts = (size_t)4 * C.nlayers, o_ip = pack.size();
+        pack.insert(pack.end(), C.in_ptr.begin(), C.in_ptr.end());
+        const size_t o_rs = pack.size();
+        pack.insert(pack.end(), C.root_slot.begin(), C.root_slot.end());
+        CU(c, d->d_i32.reserve(pack.size() + 4));
         CU(c, cudaMemcpyAsync(d->d_i32.p, pack.data(), pack.size() * 4, cudaMemcpyHostToDevice, c->st));
-        d->dev.layer_ptr = d->d_i32.p + o_lp; d->dev.in_ptr = d->d_i32.p + o_ip; d->dev.arc_tail = d->d_i32.p + o_at;
-        d->dev.arc_slot = d->d_i32.p + o_as; d->dev.root_slot = d->d_i32.p + o_rs;
+        d->dev.layer_info = reinterpret_cast<const int4 *>(d->d_i32.p);
+        d->dev.arc_ts = reinterpret_cast<const int2 *>(d->d_i32.p + o_ts);
+        d->dev.in_ptr = d->d_i32.p + o_ip; d->dev.root_slot = d->d_i32.p + o_rs;
         d->dev.nlayers = C.nlayers; d->dev.nroot = (int)C.root_slot.size(); d->dev.nnodes = C.nnodes; d->dev.nlast = C.nlast;
         d->dev.max_width = C.max_width;
         d->uploaded = true;
@@ -62,7 +73,7 @@ int upload(sgufp_dd *d) {
 }
 
 struct Scratch {   // per-context scratch for the batch call
-    DevBuf<double> coef, rhs, states, bound;
+    DevBuf<double> coef, rhs, states, last, bound;
     DevBuf<K2DD> dds;
 };
 Scratch &scratch_of(sgufp_ctx *c) {
@@ -79,33 +90,37 @@ int run_k2(sgufp_ctx *c, sgufp_dd **dds, int B, const std::vector<std::vector<do
     const int T = std::max(1, c->M.T), Tpad = (T + 1) & ~1;
     Scratch &S = scratch_of(c);
     std::vector<K2DD> hd(B);
-    long long off = 0, arcs = 0;
-    int maxw = 0;
+    long long off = 0, loff = 0, arcs = 0;
+    int maxw = 1;
     for (int b = 0; b < B; b++) {
         if (dds[b]->ctx != c) return fail(c, SGUFP_ERR_ARG, "all diagrams of a batch must belong to one context");
         if (int rc = upload(dds[b])) return rc;
+        maxw = std::max(maxw, dds[b]->dev.max_width);
+    }
+    const bool in_smem = k2_states_in_smem(Tpad, maxw);   // else: one global state block per (diagram, cut)
+    for (int b = 0; b < B; b++) {
         hd[b] = dds[b]->dev;
-        hd[b].state_off = off;
-        off += (long long)hd[b].nnodes * C;
+        hd[b].state_off = off; hd[b].last_off = loff;
+        off += (long long)hd[b].nnodes * (in_smem ? 1 : C);
+        loff += (long long)hd[b].nlast * C;
         arcs += (long long)dds[b]->dd->count_arcs() * C;
-        maxw = std::max(maxw, hd[b].max_width);
     }
     std::vector<double> cf((size_t)C * Tpad, 0.0);
     for (int k = 0; k < C; k++) std::copy(coefs[k].begin(), coefs[k].begin() + T, cf.begin() + (size_t)k * Tpad);
-    CU(c, S.coef.reserve(cf.size())); CU(c, S.rhs.reserve(C)); CU(c, S.states.reserve((size_t)off)); CU(c, S.bound.reserve(B)); CU(c, S.dds.reserve(B));
+    CU(c, S.coef.reserve(cf.size())); CU(c, S.rhs.reserve(C)); CU(c, S.states.reserve((size_t)off)); CU(c, S.last.reserve((size_t)loff)); CU(c, S.bound.reserve(B)); CU(c, S.dds.reserve(B));
     CU(c, cudaMemcpyAsync(S.coef.p, cf.data(), cf.size() * 8, cudaMemcpyHostToDevice, c->st));
     CU(c, cudaMemcpyAsync(S.rhs.p, rhs, (size_t)C * 8, cudaMemcpyHostToDevice, c->st));
     CU(c, cudaMemcpyAsync(S.dds.p, hd.data(), (size_t)B * sizeof(K2DD), cudaMemcpyHostToDevice, c->st));
     c->dd_launches = 0;
     CU(c, cudaEventRecord(c->evk0, c->st));
-    CU(c, k2_launch(S.dds.p, B, S.coef.p, S.rhs.p, C, Tpad, S.states.p, maxw, c->st, &c->dd_launches));
-    if (update_terminal) CU(c, k2_terminal_launch(S.dds.p, B, C, S.states.p, S.bound.p, c->st, &c->dd_launches));
+    CU(c, k2_launch(S.dds.p, B, S.coef.p, S.rhs.p, C, Tpad, S.states.p, S.last.p, maxw, c->st, &c->dd_launches));
+    if (update_terminal) CU(c, k2_terminal_launch(S.dds.p, B, C, S.last.p, S.bound.p, c->st, &c->dd_launches));
     CU(c, cudaEventRecord(c->evk1, c->st));
     if (states_last_cut) {
         states_last_cut->resize(B);
         for (int b = 0; b < B; b++) {
             (*states_last_cut)[b].resize(hd[b].nnodes);
-            CU(c, cudaMemcpyAsync((*states_last_cut)[b].data(), S.states.p + hd[b].state_off + (size_t)(C - 1) * hd[b].nnodes,
+            CU(c, cudaMemcpyAsync((*states_last_cut)[b].data(), S.states.p + hd[b].state_off + (in_smem ? 0 : (size_t)(C - 1) * hd[b].nnodes),
                                   (size_t)hd[b].nnodes * 8, cudaMemcpyDeviceToHost, c->st));
         }
     }
