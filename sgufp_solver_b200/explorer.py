@@ -1,0 +1,114 @@
+"""The caller of the hot path: the Benders loop on one branch-and-bound node.
+
+`NodeExplorer.process` mirrors `Inavap::NodeExplorer::process`
+(`/root/reference/NodeExplorer.cpp:915-986`) line for line on top of the
+B200-backed `GuroSolver` (K1) and `RelaxedDDNew` (K2): build the relaxed diagram of the node, apply
+the global cuts, then — on an exact diagram — alternate argmax path -> scenario cuts -> cut
+application until a path repeats.  `Container` mirrors the reference's cut list (`Cut.h:448-485`,
+new cuts are pushed to the FRONT).  `solve` is a minimal sequential driver over the cut-set nodes:
+the reference's parallel `DDSolver` (queues, threads) is out of scope.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+from .dd import DOUBLE_MAX, DOUBLE_MIN, Node, RelaxedDDNew
+from .solver import FEASIBILITY, GuroSolver
+
+SUCCESS, PRUNED_BY_FEASIBILITY_CUT, PRUNED_BY_OPTIMALITY_CUT = 0, 1, 2   # OutObj::STATUS_OP
+
+
+class Container:
+    """`Inavap::Container` (Cut.h:448-485): singly linked, push-front; iteration starts at the newest cut."""
+
+    def __init__(self):
+        self._cuts: List = []
+
+    def add(self, cut) -> None:
+        self._cuts.insert(0, cut)
+
+    def __iter__(self):
+        return iter(list(self._cuts))
+
+    def __len__(self):
+        return len(self._cuts)
+
+
+class OutObject:
+    """`Inavap::OutObject` (NodeExplorer.h:86-103)."""
+
+    def __init__(self, lb, ub, nodes, status):
+        self.lb, self.ub, self.nodes, self.status = lb, ub, nodes, status
+
+
+class NodeExplorer:
+    def __init__(self, solver: GuroSolver):
+        self.solver = solver                      # NodeExplorer.h:115
+        self.relaxedDD = RelaxedDDNew(solver)     # NodeExplorer.h:116 (one diagram, rebuilt per node)
+        self.cuts_generated = 0
+
+    def process(self, node: Node, optimalLB: float, globalFeasCuts: Container, globalOptCuts: Container) -> OutObject:
+        upperBound = node.ub
+        dd = self.relaxedDD
+        dd.buildTree(node)                                                          # :922
+        feas = list(globalFeasCuts)
+        opt = list(globalOptCuts)
+        if dd.isTreeExact():                                                        # :931
+            for cut in feas:                                                        # :935-938
+                if not dd.applyFeasibilityCut(cut):
+                    return OutObject(DOUBLE_MIN, DOUBLE_MIN, [], PRUNED_BY_FEASIBILITY_CUT)
+            for cut in opt:                                                         # :940-944
+                upperBound = dd.applyOptimalityCut(cut, optimalLB, upperBound)
+                if upperBound <= optimalLB:
+                    return OutObject(DOUBLE_MIN, DOUBLE_MIN, [], PRUNED_BY_OPTIMALITY_CUT)
+            allSolutions = []
+            while True:                                                             # :949-971
+                path = dd.getSolution().tolist()
+                if path in allSolutions:
+                    return OutObject(upperBound, upperBound, [], SUCCESS)           # :951-953
+                allSolutions.append(path)
+                cutType, cut = self.solver.solveSubProblem(path)                    # :957  (K1)
+                self.cuts_generated += 1
+                if cutType == FEASIBILITY:
+                    globalFeasCuts.add(cut)
+                    if not dd.applyFeasibilityCut(cut):                             # (K2)
+                        return OutObject(DOUBLE_MIN, DOUBLE_MIN, [], PRUNED_BY_FEASIBILITY_CUT)
+                else:
+                    globalOptCuts.add(cut)
+                    upperBound = dd.applyOptimalityCut(cut, optimalLB, upperBound)  # (K2)
+                    if upperBound <= optimalLB:
+                        return OutObject(DOUBLE_MIN, DOUBLE_MIN, [], PRUNED_BY_OPTIMALITY_CUT)
+        for cut in feas:                                                            # :975-978
+            if not dd.applyFeasibilityCut(cut):
+                return OutObject(DOUBLE_MIN, DOUBLE_MIN, [], PRUNED_BY_FEASIBILITY_CUT)
+        for cut in opt:                                                             # :980-983
+            upperBound = min(dd.applyOptimalityCut(cut, optimalLB, upperBound), upperBound)
+            if upperBound <= optimalLB:
+                return OutObject(DOUBLE_MIN, DOUBLE_MIN, [], PRUNED_BY_OPTIMALITY_CUT)
+        return OutObject(DOUBLE_MIN, upperBound, dd.getCutset(upperBound), SUCCESS)  # :985
+
+
+def solve(solver: GuroSolver, known_lb: float = DOUBLE_MIN, max_nodes: int = 100000):
+    """Sequential depth-first branch and bound over cut-set nodes (stand-in for DDSolver.cpp:658-776:
+    pop a node, prune on ub <= incumbent, process, raise the incumbent, push the children).
+    Returns (optimum, nodes processed, cuts generated)."""
+    explorer = NodeExplorer(solver)
+    feas, opt = Container(), Container()
+    best = known_lb
+    root = Node(ub=DOUBLE_MAX)
+    stack = [root]
+    processed = 0
+    while stack and processed < max_nodes:
+        node = stack.pop()
+        if node.ub <= best:                                   # DDSolver.cpp:707-711
+            continue
+        out = explorer.process(node, best, feas, opt)          # DDSolver.cpp:712
+        processed += 1
+        if out.status != SUCCESS:
+            continue
+        if out.lb > best:                                      # DDSolver.cpp:723-731
+            best = out.lb
+        for child in out.nodes:                                # DDSolver.cpp:744-748
+            if child.ub > best:
+                stack.append(child)
+    return best, processed, explorer.cuts_generated

@@ -1,0 +1,39 @@
+"""BASELINE.json configs[0]: a small SGUFP instance solved end to end by the Benders loop of
+NodeExplorer::process (NodeExplorer.cpp:915-986) running on K1 + K2, checked the way the
+reference checks itself (main.cpp:26,43,76): |optimum - extensive-form MIP optimum| <= 1e-5."""
+import numpy as np
+import pytest
+
+import sgufp_solver_b200 as sg
+from ref_mip import solve_extensive_form
+from sgufp_solver_b200 import instances as I
+from sgufp_solver_b200.explorer import solve
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("S,lower_prob", [(50, 0.0), (20, 0.15)])
+def test_c1_end_to_end(S, lower_prob):
+    inst = I.config1(S=S, lower_prob=lower_prob)
+    mip = solve_extensive_form(inst)
+    solver = sg.GuroSolver(inst)
+    if mip is None:                                        # lower bounds can make every first-stage choice infeasible
+        best, nodes, cuts = solve(solver)
+        assert best < -1e300
+        return
+    best, nodes, cuts = solve(solver)
+    assert abs(best - mip) <= 1e-5, (best, mip, nodes, cuts)
+    assert cuts >= 2
+
+
+def test_mid_instance_with_branching():
+    """A diagram that is NOT exact at the root (NodeExplorer.cpp:973-985): cut-set nodes are explored one
+    by one by the minimal sequential driver.  The reference's parallel DDSolver is out of scope, so
+    this only checks what must hold for ANY number of processed nodes: every incumbent is the value
+    of a real first-stage solution, hence <= the MIP optimum, and it improves on the trivial bound."""
+    inst = I.make_layered([4, 5, 5, 4], 48, 12, 123, 0.7, 0.0, "mid")
+    mip = solve_extensive_form(inst)
+    solver = sg.GuroSolver(inst)
+    best, nodes, cuts = solve(solver, max_nodes=150)
+    assert mip is not None and best <= mip + 1e-6, (best, mip)
+    assert best > 0 and cuts >= 10 and nodes == 150
