@@ -42,7 +42,11 @@ class OutObject:
 
 
 class NodeExplorer:
-    def __init__(self, solver: GuroSolver):
+    def __init__(self, solver: GuroSolver, batch_global_cuts: bool = False):
+        # batch_global_cuts: on an EXACT diagram the loop over the global optimality
+        # cuts (NodeExplorer.cpp:940-944) has no side effect but the terminal minima, so all of them are
+        # applied in ONE K2 launch pair; the bound and the prune decision are the sequential ones.
+        self.batch_global_cuts = batch_global_cuts
         self.solver = solver                      # NodeExplorer.h:115
         self.relaxedDD = RelaxedDDNew(solver)     # NodeExplorer.h:116 (one diagram, rebuilt per node)
         self.cuts_generated = 0
@@ -57,6 +61,12 @@ class NodeExplorer:
             for cut in feas:                                                        # :935-938
                 if not dd.applyFeasibilityCut(cut):
                     return OutObject(DOUBLE_MIN, DOUBLE_MIN, [], PRUNED_BY_FEASIBILITY_CUT)
+            if self.batch_global_cuts and len(opt) > 1:
+                from .dd import apply_optimality_batch
+                upperBound = float(apply_optimality_batch([dd], opt)[0])
+                if upperBound <= optimalLB:
+                    return OutObject(DOUBLE_MIN, DOUBLE_MIN, [], PRUNED_BY_OPTIMALITY_CUT)
+                opt = []
             for cut in opt:                                                         # :940-944
                 upperBound = dd.applyOptimalityCut(cut, optimalLB, upperBound)
                 if upperBound <= optimalLB:
@@ -88,11 +98,11 @@ class NodeExplorer:
         return OutObject(DOUBLE_MIN, upperBound, dd.getCutset(upperBound), SUCCESS)  # :985
 
 
-def solve(solver: GuroSolver, known_lb: float = DOUBLE_MIN, max_nodes: int = 100000):
+def solve(solver: GuroSolver, known_lb: float = DOUBLE_MIN, max_nodes: int = 100000, batch_global_cuts: bool = False):
     """Sequential depth-first branch and bound over cut-set nodes (stand-in for DDSolver.cpp:658-776:
     pop a node, prune on ub <= incumbent, process, raise the incumbent, push the children).
     Returns (optimum, nodes processed, cuts generated)."""
-    explorer = NodeExplorer(solver)
+    explorer = NodeExplorer(solver, batch_global_cuts)
     feas, opt = Container(), Container()
     best = known_lb
     root = Node(ub=DOUBLE_MAX)

@@ -197,3 +197,35 @@ def random_paths(net, K: int, seed: int, unmatched_prob: float = 0.1) -> np.ndar
                 used.add(b)
                 out[k, ell] = b
     return out
+
+
+# ---- on-disk formats either side of the path -----------------------------------
+def read_text(path: str, name: str = "file") -> Instance:
+    """Parser of the reference's instance format (`Network::Network`, Network.cpp:18-63):
+    `n m S`, then per arc `tail head (lb ub reward) x S`, one separator token, then V-bar ids."""
+    with open(path) as f:
+        tok = f.read().split()
+    n, m, S = int(tok[0]), int(tok[1]), int(tok[2])
+    body = np.array(tok[3:3 + m * (2 + 3 * S)], dtype=np.int64).reshape(m, 2 + 3 * S)
+    tail, head = body[:, 0].astype(np.int32), body[:, 1].astype(np.int32)
+    trip = body[:, 2:].reshape(m, S, 3)
+    rest = tok[3 + m * (2 + 3 * S) + 1:]           # one token is skipped (`file >> temp`, Network.cpp:53)
+    vbar = np.array([int(x) for x in rest], dtype=np.int32)
+    return Instance(n, m, S, tail, head, np.ascontiguousarray(trip[:, :, 0], dtype=np.int32),
+                    np.ascontiguousarray(trip[:, :, 1], dtype=np.int32), np.ascontiguousarray(trip[:, :, 2], dtype=np.int32), vbar, name)
+
+
+def save_binary(inst: Instance, path: str) -> None:
+    """Scenario-count-proof cache: the text format is O(m*S) tokens (C5: 3e8 integers); this is one
+    compressed .npz with the arrays exactly as `NetworkArc` holds them."""
+    np.savez_compressed(path, n=inst.n, m=inst.m, S=inst.S, tail=inst.tail, head=inst.head, lower=inst.lower, upper=inst.upper,
+                        reward0=inst.reward[:, 0], reward_varies=bool((inst.reward != inst.reward[:, :1]).any()),
+                        reward=inst.reward if (inst.reward != inst.reward[:, :1]).any() else np.zeros((0, 0), np.int32),
+                        vbar=inst.vbar, name=inst.name)
+
+
+def load_binary(path: str) -> Instance:
+    z = np.load(path if path.endswith(".npz") else path + ".npz", allow_pickle=False)
+    S = int(z["S"])
+    reward = z["reward"] if bool(z["reward_varies"]) else np.repeat(z["reward0"][:, None], S, axis=1).astype(np.int32)
+    return Instance(int(z["n"]), int(z["m"]), S, z["tail"], z["head"], z["lower"], z["upper"], reward, z["vbar"], str(z["name"]))

@@ -37,3 +37,27 @@ def test_mid_instance_with_branching():
     best, nodes, cuts = solve(solver, max_nodes=150)
     assert mip is not None and best <= mip + 1e-6, (best, mip)
     assert best > 0 and cuts >= 10 and nodes == 150
+
+
+def test_batched_global_cuts_give_the_same_node_result():
+    """NodeExplorer with the global optimality cuts applied in one K2 launch pair
+    returns exactly what the sequential loop returns on an exact diagram."""
+    from sgufp_solver_b200.dd import Node
+    from sgufp_solver_b200.explorer import Container, NodeExplorer
+    inst = I.config1(S=30)
+    solver = sg.GuroSolver(inst)
+    warm = NodeExplorer(solver)
+    feas, opt = Container(), Container()
+    first = warm.process(Node(ub=1e300), -1e300, feas, opt)           # fills the global cut lists
+    assert len(opt) >= 2
+    a = NodeExplorer(solver, batch_global_cuts=False).process(Node(ub=1e300), -1e300, Container(), _copy(opt))
+    b = NodeExplorer(solver, batch_global_cuts=True).process(Node(ub=1e300), -1e300, Container(), _copy(opt))
+    assert (a.lb, a.ub, a.status) == (b.lb, b.ub, b.status) == (first.lb, first.ub, first.status)
+
+
+def _copy(container):
+    from sgufp_solver_b200.explorer import Container
+    c = Container()
+    for cut in reversed(list(container)):
+        c.add(cut)
+    return c
