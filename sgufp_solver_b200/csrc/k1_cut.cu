@@ -32,6 +32,10 @@
 
 namespace sgufp {
 
+#ifdef SGUFP_K1_STATS
+__device__ unsigned long long g_k1_stats[4];   // passes, label computations
+#endif
+
 namespace {
 
 constexpr int HB = 10;                 // hop bits of a label
@@ -44,6 +48,7 @@ struct PlanView {
     const PlanHeader *h;
     const int32_t *arc_cp, *arc_info, *arc_pre, *ch_ends, *ch_r, *ch_ptr, *ch_arcs, *ch_q, *av_ptr, *av_arcs, *fb_ptr, *fb_ch;
     const int32_t *slot_th, *slot_cs, *slot_ch, *ch_slots, *node_in;
+    const int2 *ch_sr;
     __device__ explicit PlanView(const int32_t *base) {
         h = reinterpret_cast<const PlanHeader *>(base);
         arc_cp = base + h->o_arc_cp; arc_info = base + h->o_arc_info; arc_pre = base + h->o_arc_pre;
@@ -51,11 +56,12 @@ struct PlanView {
         ch_q = base + h->o_ch_q; av_ptr = base + h->o_av_ptr; av_arcs = base + h->o_av_arcs; fb_ptr = base + h->o_fb_ptr; fb_ch = base + h->o_fb_ch;
         slot_th = base + h->o_slot_th; slot_cs = base + h->o_slot_cs; slot_ch = base + h->o_slot_ch; ch_slots = base + h->o_ch_slots;
         node_in = base + h->o_node_in;
+        ch_sr = reinterpret_cast<const int2 *>(base + h->o_ch_sr);
     }
 };
 
 struct TileMem {  // this tile's slice of shared memory
-    int *up, *lo, *x, *lab, *pred, *pot, *exc, *aq;
+    int *up, *lo, *x, *res, *lab, *pred, *pot, *exc, *aq;
 };
 
 template <int TILE>
@@ -95,72 +101,101 @@ __device__ void shortest_paths(int src, const PlanView &P, int nopen, int nc, co
     do {
         changed = false;
         for (int c = T.tl; c < nopen; c += TILE) {
-            const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1, r = P.ch_r[c];
-            const int xc = w.x[c], up = w.up[c] >> HB, lo = w.lo[c] >> HB;
-            if (xc < up && !(MERGED && ev == 0)) {
+            const int2 sr = P.ch_sr[c];            // static: ends | reward, one 64-bit load
+            const int f = w.res[c];                // dynamic: bit 0 forward residual, bit 1 backward residual
+            const int sv = (sr.x & 0xffff) - 1, ev = (sr.x >> 16) - 1;
+            if ((f & 1) && !(MERGED && ev == 0)) {
                 const int lu = w.lab[sv];
                 if (lu != LAB_INF) {
-                    const int cand = lu - r * (1 << HB) + 1;
+                    const int cand = lu - sr.y * (1 << HB) + 1;
                     const int t = (!MERGED && ev == 0) ? nc : ev;
-                    if (cand < atomicMin(&w.lab[t], cand)) changed = true;
+                    if (cand < atomicMin(&w.lab[t], cand)) { changed = true; w.pred[t] = 2 * c; }
                 }
             }
-            if (xc > lo && !(MERGED && sv == 0)) {
+            if ((f & 2) && !(MERGED && sv == 0)) {
                 const int lu = w.lab[ev];
                 if (lu != LAB_INF) {
-                    const int cand = lu + r * (1 << HB) + 1;
+                    const int cand = lu + sr.y * (1 << HB) + 1;
                     const int t = (!MERGED && sv == 0) ? nc : sv;
-                    if (cand < atomicMin(&w.lab[t], cand)) changed = true;
+                    if (cand < atomicMin(&w.lab[t], cand)) { changed = true; w.pred[t] = 2 * c + 1; }
                 }
             }
         }
         T.sync();
         changed = T.any(changed) && --fuel > 0;
+#ifdef SGUFP_K1_STATS
+        if (T.tl == 0) atomicAdd(&g_k1_stats[0], 1ull);
+#endif
     } while (changed);
+#ifdef SGUFP_K1_STATS
+    if (T.tl == 0) atomicAdd(&g_k1_stats[1], 1ull);
+#endif
 }
 
-// One tight residual arc per labelled node (pred = 2*chain + direction, -1 = none).  The hop count
-// strictly decreases along a tight arc, so following predecessors can only end at the source.
-template <int TILE, bool CLEAR>
+// One tight residual arc per labelled node (pred = 2*chain + direction).  Only needed when the
+// predecessor written next to a label update lost a race with a better update of the same pass.
+template <int TILE>
 __device__ void mark_predecessors(const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TileMem &w) {
-    if (CLEAR) {   // only a re-walk under labels older than the flow can meet a node without a tight in-arc
-        for (int v = T.tl; v <= nc; v += TILE) w.pred[v] = -1;
-        T.sync();
-    }
     for (int c = T.tl; c < nopen; c += TILE) {
-        const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1, r = P.ch_r[c];
-        const int xc = w.x[c], up = w.up[c] >> HB, lo = w.lo[c] >> HB;
-        if (xc < up) {
+        const int2 sr = P.ch_sr[c];
+        const int f = w.res[c];
+        const int sv = (sr.x & 0xffff) - 1, ev = (sr.x >> 16) - 1;
+        if (f & 1) {
             const int lu = w.lab[sv], t = ev == 0 ? nc : ev;
-            if (lu != LAB_INF && lu - r * (1 << HB) + 1 == w.lab[t]) w.pred[t] = 2 * c;
+            if (lu != LAB_INF && lu - sr.y * (1 << HB) + 1 == w.lab[t]) w.pred[t] = 2 * c;
         }
-        if (xc > lo) {
+        if (f & 2) {
             const int lu = w.lab[ev], t = sv == 0 ? nc : sv;
-            if (lu != LAB_INF && lu + r * (1 << HB) + 1 == w.lab[t]) w.pred[t] = 2 * c + 1;
+            if (lu != LAB_INF && lu + sr.y * (1 << HB) + 1 == w.lab[t]) w.pred[t] = 2 * c + 1;
         }
     }
     T.sync();
 }
 
-// Lane 0 of the tile: follow the predecessors dst -> src, then push the bottleneck.  Returns the
-// amount pushed, 0 if the walk meets a node without a tight residual in-arc (only possible when the
-// labels are older than the flow, i.e. on a re-walk after an augmentation).
-__device__ int augment(int src, int dst, int limit, const PlanView &P, TileMem &w) {
+// Lane 0 of the tile: follow the predecessors dst -> src, then push the bottleneck.  A label is
+// (distance, hops), so a predecessor is usable iff its arc still has residual capacity and is
+// TIGHT (label(tail) + increment == label(head)); the hop count then drops by one per step and the
+// walk can only end at src.  Returns the amount pushed, or -1 if some predecessor is not tight
+// (stale, or overwritten by a racing lane): the caller re-marks and walks again.
+__device__ int augment(int src, int dst, int limit, const PlanView &P, int nc, TileMem &w) {
     int v = dst, d = limit;
     while (v != src) {
-        const int p = w.pred[v];
-        if (p < 0) return 0;
-        const int c = p >> 1, e = P.ch_ends[c];
-        int res;
-        if (p & 1) { res = w.x[c] - (w.lo[c] >> HB); v = (e >> 16) - 1; } else { res = (w.up[c] >> HB) - w.x[c]; v = (e & 0xffff) - 1; }
+        const int p = w.pred[v], c = p >> 1;
+        if ((unsigned)c >= (unsigned)P.h->nopen) return -1;
+        const int2 sr = P.ch_sr[c];
+        const int sv = (sr.x & 0xffff) - 1, ev = (sr.x >> 16) - 1;
+        int u, res, inc;
+        int head;   // pred[v] may be a leftover of another candidate's plan: the arc must really end at v
+        if (p & 1) { u = ev; head = sv == 0 ? nc : sv; res = w.x[c] - (w.lo[c] >> HB); inc = sr.y * (1 << HB) + 1; }
+        else { u = sv; head = ev == 0 ? nc : ev; res = (w.up[c] >> HB) - w.x[c]; inc = -sr.y * (1 << HB) + 1; }
+        if (head != v || res <= 0 || w.lab[u] == LAB_INF || w.lab[u] + inc != w.lab[v]) return -1;
         d = min(d, res);
+        v = u;
     }
     v = dst;
     while (v != src) {
-        const int p = w.pred[v], c = p >> 1, e = P.ch_ends[c];
-        if (p & 1) { w.x[c] -= d; v = (e >> 16) - 1; } else { w.x[c] += d; v = (e & 0xffff) - 1; }
+        const int p = w.pred[v], c = p >> 1;
+        const int2 sr = P.ch_sr[c];
+        int xc;
+        if (p & 1) { xc = (w.x[c] -= d); v = (sr.x >> 16) - 1; } else { xc = (w.x[c] += d); v = (sr.x & 0xffff) - 1; }
+        w.res[c] = (xc < (w.up[c] >> HB) ? 1 : 0) | (xc > (w.lo[c] >> HB) ? 2 : 0);
     }
     return d;
+}
+
+// augment, falling back to one marking pass when a captured predecessor is not usable
+template <int TILE>
+__device__ void push_path(int src, int dst, int limit, const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TileMem &w, int *pushed) {
+    int d = 0;
+    if (T.tl == 0) d = augment(src, dst, limit, P, nc, w);
+    d = __shfl_sync(T.mask, d, 0, TILE);
+    if (d < 0) {
+        mark_predecessors<TILE>(P, nopen, nc, T, w);
+        if (T.tl == 0) d = augment(src, dst, limit, P, nc, w);
+        d = __shfl_sync(T.mask, d, 0, TILE);
+    }
+    T.sync();
+    if (pushed) *pushed = d;
 }
 
 // Forced flow from lower bounds (rare): route every excess / deficit along shortest residual
@@ -190,24 +225,23 @@ __device__ bool route_lower_bounds(const PlanView &P, int nopen, int nc, const L
             best = T.min_u64(best);
             if (best == ~0ull) return false;
             const int t = (int)(best & 0xffffffffu);
-            mark_predecessors<TILE, false>(P, nopen, nc, T, w);
-            if (T.tl == 0) {
-                int lim = w.exc[v];
-                if (t != nc) lim = min(lim, -w.exc[t]);
-                const int d = augment(v, t, lim, P, w);
-                w.exc[v] -= d;
-                if (t != nc) w.exc[t] += d;
-            }
+            int lim = w.exc[v], d = 0;
+            if (t != nc) lim = min(lim, -w.exc[t]);
+            push_path<TILE>(v, t, lim, P, nopen, nc, T, w, &d);
+            if (T.tl == 0 && d > 0) { w.exc[v] -= d; if (t != nc) w.exc[t] += d; }
             T.sync();
+            if (d <= 0) return false;
         }
     }
     for (int v = 1; v < nc; v++) {
         while (w.exc[v] < 0 && --fuel > 0) {
             shortest_paths<TILE, false>(0, P, nopen, nc, T, w, fuel);
             if (w.lab[v] == LAB_INF) return false;
-            mark_predecessors<TILE, false>(P, nopen, nc, T, w);
-            if (T.tl == 0) w.exc[v] += augment(0, v, -w.exc[v], P, w);
+            int d = 0;
+            push_path<TILE>(0, v, -w.exc[v], P, nopen, nc, T, w, &d);
+            if (T.tl == 0 && d > 0) w.exc[v] += d;
             T.sync();
+            if (d <= 0) return false;
         }
     }
     return true;
@@ -275,7 +309,7 @@ __device__ __forceinline__ int head_potential(int a, const PlanView &P, int nope
     return pre;
 }
 
-template <int TILE, bool REWALK>
+template <int TILE>
 __global__ void __launch_bounds__(WARPS * 32, 4) k1_cut_eval(K1Launch p, int words_per_tile) {
 #ifdef SGUFP_K1_EMULATE
     int *smem = sgufp_emul_smem;   // tests/cpp/k1_emul.cpp: the kernel body compiled for the host, TILE = 1
@@ -291,6 +325,7 @@ __global__ void __launch_bounds__(WARPS * 32, 4) k1_cut_eval(K1Launch p, int wor
         w.up = base; base += p.max_nch;
         w.lo = base; base += p.max_nch;
         w.x = base; base += p.max_nopen;
+        w.res = base; base += p.max_nopen;
         w.lab = base; base += p.nc + 2;
         w.pred = base; base += p.nc + 2;
         w.pot = base; base += p.nc + 2;
@@ -335,6 +370,7 @@ __global__ void __launch_bounds__(WARPS * 32, 4) k1_cut_eval(K1Launch p, int wor
             if (c < nopen) {
                 const int up = w.up[c] >> HB;
                 w.x[c] = lo; bad |= lo > up; forced |= lo > 0;
+                w.res[c] = lo < up ? 1 : 0;          // x == lo: forward residual only
             } else bad |= lo > 0;
         }
         T.sync();
@@ -355,16 +391,9 @@ __global__ void __launch_bounds__(WARPS * 32, 4) k1_cut_eval(K1Launch p, int wor
             shortest_paths<TILE, false>(0, P, nopen, nc, T, w, fuel);
             const int lt = w.lab[nc];
             if (lt == LAB_INF || lab_dist(lt) >= 0) break;
-            // A path of arcs that are tight under these labels stays a shortest path after other
-            // pushes (distances only grow), so keep re-marking and walking until a walk dead-ends.
-            int pushed;
-            do {
-                mark_predecessors<TILE, REWALK>(P, nopen, nc, T, w);
-                pushed = 0;
-                if (T.tl == 0) pushed = augment(0, nc, INT_MAX, P, w);
-                T.sync();
-                pushed = __shfl_sync(T.mask, pushed, 0, TILE);
-            } while (REWALK && pushed > 0 && --fuel > 0);
+            int d = 0;
+            push_path<TILE>(0, nc, INT_MAX, P, nopen, nc, T, w, &d);
+            if (d <= 0) fuel = 0;   // cannot happen: the labels were just computed
         }
         // 3. potentials
         canonical_potentials<TILE>(P, nopen, nc, T, w, fuel);
@@ -556,16 +585,16 @@ __global__ void relayout_caps(const int32_t *__restrict__ src, double *__restric
 }  // namespace
 
 #ifndef SGUFP_K1_EMULATE
-template <int TILE, bool REWALK>
+template <int TILE>
 static cudaError_t launch_tile(const K1Launch &p, cudaStream_t st, int sm_count) {
-    const int words = 2 * p.max_nch + p.max_nopen + 4 * (p.nc + 2) + p.nav + 2;
+    const int words = 2 * p.max_nch + 2 * p.max_nopen + 4 * (p.nc + 2) + p.nav + 2;
     constexpr int tiles = WARPS * 32 / TILE;
     const size_t smem = (size_t)tiles * words * sizeof(int);
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-    cudaError_t e = cudaFuncSetAttribute(k1_cut_eval<TILE, REWALK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k1_cut_eval<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_cut_eval<TILE, REWALK>, WARPS * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_cut_eval<TILE>, WARPS * 32, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     const long long items = (long long)p.K * p.S;
@@ -573,7 +602,7 @@ static cudaError_t launch_tile(const K1Launch &p, cudaStream_t st, int sm_count)
     long long grid = (long long)sm_count * per_sm;   // persistent: a whole number of CTAs per SM
     if (want < grid) grid = want;
     if (grid < 1) grid = 1;
-    k1_cut_eval<TILE, REWALK><<<(unsigned)grid, WARPS * 32, smem, st>>>(p, words);
+    k1_cut_eval<TILE><<<(unsigned)grid, WARPS * 32, smem, st>>>(p, words);
     return cudaGetLastError();
 }
 
@@ -588,10 +617,7 @@ cudaError_t k1_launch(const K1Launch &p, cudaStream_t st, int sm_count, int *lau
     int tile = k1_tile_for(p.max_nopen);
     // fall back to a wider tile (fewer tiles per CTA) if the per-CTA shared memory does not fit
     for (;;) {
-        const char *rw = getenv("SGUFP_K1_REWALK");
-        const bool rewalk = rw && rw[0] == '1';   // measured slower on C2 and C4 (profiles/r01_k1_variants.md): off by default
-        cudaError_t e = tile == 8 ? launch_tile<8, true>(p, st, sm_count) : tile == 16 ? launch_tile<16, true>(p, st, sm_count)
-                        : rewalk ? launch_tile<32, true>(p, st, sm_count) : launch_tile<32, false>(p, st, sm_count);
+        cudaError_t e = tile == 8 ? launch_tile<8>(p, st, sm_count) : tile == 16 ? launch_tile<16>(p, st, sm_count) : launch_tile<32>(p, st, sm_count);
         if (e == cudaErrorInvalidConfiguration && tile < 32) { tile *= 2; cudaGetLastError(); continue; }
         return e;
     }
@@ -614,3 +640,14 @@ cudaError_t relayout_launch(const int32_t *src, double *dst, int m, int S, int m
 #endif  // SGUFP_K1_EMULATE
 
 }  // namespace sgufp
+
+#if defined(SGUFP_K1_STATS) && !defined(SGUFP_K1_EMULATE)
+// debug build only (-DSGUFP_K1_STATS): relaxation passes / label computations since the last call
+extern "C" int sgufp_debug_k1_stats(unsigned long long *out4) {
+    unsigned long long z[4] = {0, 0, 0, 0};
+    cudaError_t e = cudaMemcpyFromSymbol(out4, sgufp::g_k1_stats, sizeof(z));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(sgufp::g_k1_stats, z, sizeof(z));
+    return e == cudaSuccess ? 0 : -6;
+}
+#endif
+

@@ -267,6 +267,11 @@ int build_plan(const Model &M, const int16_t *path, int plen, Plan &P, std::stri
     H.o_ch_ends = put(ch_ends); H.o_ch_r = put(ch_r); H.o_ch_ptr = put(ch_ptr); H.o_ch_arcs = put(ch_arcs); H.o_ch_q = put(ch_q);
     H.o_av_ptr = put(av_ptr); H.o_av_arcs = put(av_arcs); H.o_fb_ptr = put(fb_ptr); H.o_fb_ch = put(fb_ch);
     H.o_slot_th = put(slot_th); H.o_slot_cs = put(slot_cs); H.o_slot_ch = put(slot_ch); H.o_ch_slots = put(ch_slots); H.o_node_in = put(node_in);
+    {
+        std::vector<int32_t> sr(2 * nopen);
+        for (int c = 0; c < nopen; c++) { sr[2 * c] = ch_ends[c]; sr[2 * c + 1] = ch_r[c]; }
+        H.o_ch_sr = put(sr);   // W.size() is even here (header even, every array padded to even)
+    }
     while (W.size() & 3) W.push_back(0);  // keep every plan 16-byte aligned inside a batch
     H.total = (int32_t)W.size();
     std::memcpy(W.data(), &H, sizeof(H));

@@ -15,6 +15,7 @@
 typedef int cudaError_t;
 typedef void *cudaStream_t;
 struct double2 { double x, y; };
+struct int2 { int x, y; };
 struct EmulIdx { int x = 0, y = 0; };
 static EmulIdx threadIdx, blockIdx;
 static struct { int x = 1, y = 1; } gridDim, blockDim;
@@ -71,12 +72,12 @@ extern "C" int emul_paths(int n, int m, int S, const int32_t *tail, const int32_
     p.plans = words.data(); p.plan_off = off.data(); p.K = K; p.W = W; p.L = M.L;
     p.sums = reinterpret_cast<unsigned long long *>(sums); p.first_inf = first_inf; p.obj = obj; p.status = status;
     p.max_nch = max_nch; p.max_nopen = max_nopen; p.nc = M.nc; p.nav = M.nav;
-    const int wpt = 2 * max_nch + max_nopen + 4 * (M.nc + 2) + M.nav + 2;
+    const int wpt = 2 * max_nch + 2 * max_nopen + 4 * (M.nc + 2) + M.nav + 2;
     std::vector<int> smem((size_t)WARPS * 32 * wpt, 0);
     sgufp_emul_smem = smem.data();
     threadIdx.x = 0; blockIdx.x = 0; gridDim.x = 1;
     // one "thread" walks all items: with TILE = 1 the tile stride is WARPS*32, so visit every tile slot of the CTA
-    for (int t = 0; t < WARPS * 32; t++) { threadIdx.x = t; k1_cut_eval<1, false>(p, wpt); }
+    for (int t = 0; t < WARPS * 32; t++) { threadIdx.x = t; k1_cut_eval<1>(p, wpt); }
     for (int k = 0; k < K; k++) {
         if (first_inf[k] == LLONG_MAX || first_inf[k] < 0) continue;
         std::vector<int32_t> ts, hs, info, pl, nx, aq, fw;
