@@ -190,6 +190,7 @@ int sgufp_create(sgufp_ctx **out, int n, int m, int S, const int32_t *tail, cons
 
 void sgufp_destroy(sgufp_ctx *c) {
     if (!c) return;
+    if (c->dd_scratch && c->dd_scratch_free) c->dd_scratch_free(c->dd_scratch);
     if (c->d_u) cudaFree(c->d_u);
     if (c->d_l) cudaFree(c->d_l);
     c->d_plans.release(); c->d_plan_off.release(); c->d_ray_i32.release(); c->d_sums.release(); c->d_finf.release();

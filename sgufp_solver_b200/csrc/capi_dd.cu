@@ -77,10 +77,15 @@ struct Scratch {   // per-context scratch for the batch call
     DevBuf<K2DD> dds;
 };
 Scratch &scratch_of(sgufp_ctx *c) {
-    static thread_local std::vector<std::pair<sgufp_ctx *, Scratch *>> tab;
-    for (auto &p : tab) if (p.first == c) return *p.second;
-    tab.emplace_back(c, new Scratch());
-    return *tab.back().second;
+    if (!c->dd_scratch) {
+        c->dd_scratch = new Scratch();
+        c->dd_scratch_free = [](void *p) {
+            Scratch *s = static_cast<Scratch *>(p);
+            s->coef.release(); s->rhs.release(); s->states.release(); s->last.release(); s->bound.release(); s->dds.release();
+            delete s;
+        };
+    }
+    return *static_cast<Scratch *>(c->dd_scratch);
 }
 
 // densify C cuts, run K2 over B diagrams, read back what the host semantics need

@@ -42,6 +42,8 @@ struct sgufp_ctx {
     float dd_kernel_ms = 0.f;
     long long dd_arcs = 0;
     int dd_launches = 0;
+    void *dd_scratch = nullptr;                 // K2 batch scratch (capi_dd.cu), freed through dd_scratch_free
+    void (*dd_scratch_free)(void *) = nullptr;
     int W() const { return 1 + M.L + M.m; }
 };
 
