@@ -4,6 +4,7 @@
 // every compute entry point needs a CUDA device and fails with SGUFP_ERR_CUDA otherwise.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <climits>
 #include <cstring>
 #include <string>
@@ -53,7 +54,7 @@ static int launch_batch(sgufp_ctx *c, const Batch &B, int K, unsigned long long 
     p.cap_u = c->d_u; p.cap_l = c->d_l; p.S = c->S; p.m = c->M.m; p.m_pad = c->m_pad; p.scen_offset = c->scen_off;
     p.plans = c->d_plans.p; p.plan_off = c->d_plan_off.p; p.K = K; p.W = c->W(); p.L = c->M.L;
     p.sums = d_sums; p.first_inf = d_finf; p.obj = d_obj; p.status = d_status;
-    p.max_nch = B.max_nch; p.max_nopen = B.max_nopen; p.nc = c->M.nc; p.nav = c->M.nav;
+    p.max_nch = B.max_nch; p.max_nopen = B.max_nopen; p.nc = c->M.nc; p.nav = c->M.nav; p.max_cap = c->max_cap;
     c->kernel_timed = false;
     if (c->S > 0) {
         CU(c, cudaEventRecord(c->evk0, st));
@@ -151,9 +152,11 @@ int sgufp_create(sgufp_ctx **out, int n, int m, int S, const int32_t *tail, cons
     auto bail = [&](int code, const std::string &msg) { g_create_error = msg; sgufp_destroy(c); return code; };
     std::string e;
     if (int rc = c->M.build(n, m, tail, head, reward0, vbar, nvbar, e)) return bail(rc, e);
-    for (size_t i = 0; upper && lower && i < (size_t)m * S; i++)
+    for (size_t i = 0; upper && lower && i < (size_t)m * S; i++) {
+        c->max_cap = std::max(c->max_cap, std::max(upper[i], lower[i]));
         if (upper[i] < 0 || lower[i] < 0 || upper[i] >= (1 << 20) || lower[i] >= (1 << 20))
             return bail(SGUFP_ERR_LIMITS, "capacities must lie in [0, 2^20) (DESIGN.md §5)");
+    }
     c->S = S; c->scen_off = scenario_offset; c->S_total = S_total; c->device = device;
     c->m_pad = (m + 1) & ~1;   // rows 16-byte aligned for 128-bit loads
 #define CUC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return bail(SGUFP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } while (0)

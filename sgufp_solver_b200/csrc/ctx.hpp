@@ -24,7 +24,7 @@ struct DevBuf {
 
 struct sgufp_ctx {
     sgufp::Model M;
-    int S = 0, m_pad = 0, device = 0, sm_count = 0;
+    int S = 0, m_pad = 0, device = 0, sm_count = 0, max_cap = 0;
     long long scen_off = 0, S_total = 0;
     double *d_u = nullptr, *d_l = nullptr;
     cudaStream_t st = nullptr;

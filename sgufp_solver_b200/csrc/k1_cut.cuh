@@ -17,6 +17,7 @@ struct K1Launch {
     double *obj;                  // [K][S] or nullptr
     uint8_t *status;              // [K][S] or nullptr
     int max_nch, max_nopen, nc, nav;
+    int max_cap;                  // largest capacity of the instance (the lane variant keeps 16-bit state)
 };
 
 // Returns cudaSuccess or the launch error.  *launches is incremented by the kernels launched.

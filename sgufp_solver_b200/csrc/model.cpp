@@ -186,6 +186,15 @@ int build_plan(const Model &M, const int16_t *path, int plen, Plan &P, std::stri
         (c.sv >= 0 && c.ev >= 0 ? open_ch : closed_ch).push_back(c);
     }
     if (covered != m) { err = "matched pairs form a cycle"; return SGUFP_ERR_CYCLIC; }
+    {   // open chains in topological order of their tail (Gauss-Seidel label correction converges in few passes)
+        std::vector<int32_t> depth(M.nc, 0);
+        for (int it = 0, changed = 1; changed && it <= M.nc; it++) {
+            changed = 0;
+            for (const Ch &c : open_ch)
+                if (c.ev != 0 && depth[c.ev] < depth[c.sv] + 1) { depth[c.ev] = depth[c.sv] + 1; changed = 1; }
+        }
+        std::stable_sort(open_ch.begin(), open_ch.end(), [&](const Ch &a, const Ch &b) { return depth[a.sv] < depth[b.sv]; });
+    }
     const int nopen = (int)open_ch.size(), nch = nopen + (int)closed_ch.size();
     P.nch = nch; P.nopen = nopen;
     std::vector<Ch> chains(open_ch);
@@ -271,6 +280,17 @@ int build_plan(const Model &M, const int16_t *path, int plen, Plan &P, std::stri
         std::vector<int32_t> sr(2 * nopen);
         for (int c = 0; c < nopen; c++) { sr[2 * c] = ch_ends[c]; sr[2 * c + 1] = ch_r[c]; }
         H.o_ch_sr = put(sr);   // W.size() is even here (header even, every array padded to even)
+        std::vector<int32_t> pk, in4(M.nc + 2, 0);
+        size_t s = 0;
+        for (int v = 0; v <= M.nc; v++) {
+            in4[v] = (int32_t)(pk.size() / 2);
+            for (; s < slots.size() && slots[s].head == v; s++) { pk.push_back(slots[s].tail | (slots[s].ch << 16)); pk.push_back(slots[s].cs); }
+            while ((pk.size() / 2) & 3) { pk.push_back(M.nc + 1); pk.push_back(0); }   // padding slot: tail nc+1 is never labelled
+        }
+        in4[M.nc + 1] = (int32_t)(pk.size() / 2);
+        while (W.size() & 3) W.push_back(0);   // int4 loads: 16-byte aligned (plans start on 16-byte boundaries)
+        H.o_slot_pk = put(pk);
+        H.o_node_in4 = put(in4);
     }
     while (W.size() & 3) W.push_back(0);  // keep every plan 16-byte aligned inside a batch
     H.total = (int32_t)W.size();

@@ -63,8 +63,11 @@ struct PlanHeader {
     int32_t o_ch_slots;    // [nopen]    position of the forward slot | position of the backward slot << 16
     int32_t o_node_in;     // [nc+2]     slot range of each head node (index nc = root-in)
     int32_t o_ch_sr;       // [nopen]    int2 {ends, reward}: the static half of a chain in one 64-bit load (8-byte aligned)
-    int32_t total;         // int32 words used by this plan, header included
-    int32_t pad[1];        // keeps the header an even number of words so that o_ch_sr can be 8-byte aligned
+    int32_t o_slot_pk;     // int2 {tail | (2*chain+dir) << 16, label increment} per slot, every node's list padded to a multiple of 4
+                           // with slots whose tail is the never-labelled node nc+1; 16-byte aligned
+    int32_t o_node_in4;    // [nc+2]     ranges of the padded lists
+    int32_t pad2;          // keeps the header an even number of words
+    int32_t total;         // int32 words used by this plan, header included        // keeps the header an even number of words so that o_ch_sr can be 8-byte aligned
 };
 
 struct Plan {

@@ -16,6 +16,7 @@ typedef int cudaError_t;
 typedef void *cudaStream_t;
 struct double2 { double x, y; };
 struct int2 { int x, y; };
+struct int4 { int x, y, z, w; };
 struct EmulIdx { int x = 0, y = 0; };
 static EmulIdx threadIdx, blockIdx;
 static struct { int x = 1, y = 1; } gridDim, blockDim;
@@ -48,7 +49,7 @@ using namespace sgufp;
 // first_inf: [K], obj/status: [K][S].  ray_sums[K][W]: filled for candidates with an infeasible scenario.
 extern "C" int emul_paths(int n, int m, int S, const int32_t *tail, const int32_t *head, const int32_t *upper, const int32_t *lower,
                           const int32_t *rew0, const int32_t *vbar, int nvbar, const int16_t *paths, int K, int L,
-                          long long *sums, long long *first_inf, double *obj, uint8_t *status, long long *ray_sums) {
+                          long long *sums, long long *first_inf, double *obj, uint8_t *status, long long *ray_sums, int lane_variant) {
     Model M;
     std::string err;
     if (int rc = M.build(n, m, tail, head, rew0, vbar, nvbar, err)) return rc;
@@ -71,12 +72,18 @@ extern "C" int emul_paths(int n, int m, int S, const int32_t *tail, const int32_
     p.cap_u = cu.data(); p.cap_l = cl.data(); p.S = S; p.m = m; p.m_pad = m_pad; p.scen_offset = 0;
     p.plans = words.data(); p.plan_off = off.data(); p.K = K; p.W = W; p.L = M.L;
     p.sums = reinterpret_cast<unsigned long long *>(sums); p.first_inf = first_inf; p.obj = obj; p.status = status;
-    p.max_nch = max_nch; p.max_nopen = max_nopen; p.nc = M.nc; p.nav = M.nav;
+    p.max_nch = max_nch; p.max_nopen = max_nopen; p.nc = M.nc; p.nav = M.nav; p.max_cap = 65535;
     const int wpt = 2 * max_nch + 2 * max_nopen + 4 * (M.nc + 2) + M.nav + 2;
     std::vector<int> smem((size_t)WARPS * 32 * wpt, 0);
     sgufp_emul_smem = smem.data();
     threadIdx.x = 0; blockIdx.x = 0; gridDim.x = 1;
     // one "thread" walks all items: with TILE = 1 the tile stride is WARPS*32, so visit every tile slot of the CTA
+    if (lane_variant) {   // the lane-per-scenario kernel with one lane
+        std::vector<int> lsm(((size_t)2 * (M.nc + 2) * 4 + (size_t)(M.nav + 1) * 4 + (size_t)3 * max_nopen * 2 + (size_t)(M.nc + 2) * 2 + max_nopen) / 4 + 16, 0);
+        sgufp_emul_smem = lsm.data();
+        threadIdx.x = 0; blockIdx.x = 0; gridDim.x = 1;
+        k1_lane_eval<1>(p, 0);
+    } else
     for (int t = 0; t < WARPS * 32; t++) { threadIdx.x = t; k1_cut_eval<1>(p, wpt); }
     for (int k = 0; k < K; k++) {
         if (first_inf[k] == LLONG_MAX || first_inf[k] < 0) continue;

@@ -28,11 +28,11 @@ def emul(tmp_path_factory):
     ip, i16p = C.POINTER(C.c_int32), C.POINTER(C.c_int16)
     L.emul_paths.restype = C.c_int
     L.emul_paths.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip, ip, ip, ip, ip, C.c_int, i16p, C.c_int, C.c_int,
-                             C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_double), C.POINTER(C.c_uint8), C.POINTER(C.c_longlong)]
+                             C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_double), C.POINTER(C.c_uint8), C.POINTER(C.c_longlong), C.c_int]
     return L
 
 
-def run_emul(L, inst, net, paths):
+def run_emul(L, inst, net, paths, lane_variant=0):
     ip, i16p = C.POINTER(C.c_int32), C.POINTER(C.c_int16)
     K, plen = paths.shape
     W = 1 + net.L + inst.m
@@ -44,7 +44,7 @@ def run_emul(L, inst, net, paths):
     rc = L.emul_paths(inst.n, inst.m, inst.S, t.ctypes.data_as(ip), h.ctypes.data_as(ip), u.ctypes.data_as(ip), lo.ctypes.data_as(ip),
                       r0.ctypes.data_as(ip), vb.ctypes.data_as(ip), len(vb), p.ctypes.data_as(i16p), K, plen,
                       sums.ctypes.data_as(C.POINTER(C.c_longlong)), finf.ctypes.data_as(C.POINTER(C.c_longlong)),
-                      obj.ctypes.data_as(C.POINTER(C.c_double)), st.ctypes.data_as(C.POINTER(C.c_uint8)), ray.ctypes.data_as(C.POINTER(C.c_longlong)))
+                      obj.ctypes.data_as(C.POINTER(C.c_double)), st.ctypes.data_as(C.POINTER(C.c_uint8)), ray.ctypes.data_as(C.POINTER(C.c_longlong)), int(lane_variant))
     assert rc == 0
     return sums, finf, obj, st, ray
 
@@ -75,12 +75,13 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("variant", ["warp", "lane"])
 @pytest.mark.parametrize("name,make,K,seed,unm", CASES, ids=[c[0] for c in CASES])
-def test_kernel_body_matches_oracle(emul, name, make, K, seed, unm):
+def test_kernel_body_matches_oracle(emul, name, make, K, seed, unm, variant):
     inst = make()
     net = OracleNet(inst)
     paths = I.random_paths(net, K, seed, unm)
-    sums, finf, obj, st, ray = run_emul(emul, inst, net, paths)
+    sums, finf, obj, st, ray = run_emul(emul, inst, net, paths, lane_variant=(variant == "lane"))
     for k in range(K):
         want, first_bad = wlayout_partial(net, inst, paths[k], 0, inst.S)
         oc = net.solve_path(paths[k])
