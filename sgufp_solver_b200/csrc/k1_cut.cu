@@ -313,15 +313,15 @@ __device__ __forceinline__ int head_potential(int a, const PlanView &P, int nope
     return pre;
 }
 
-template <int TILE>
-__global__ void __launch_bounds__(WARPS * 32, 4) k1_cut_eval(K1Launch p, int words_per_tile) {
+template <int TILE, int NW>
+__global__ void __launch_bounds__(NW * 32, NW == 8 ? 4 : 1) k1_cut_eval(K1Launch p, int words_per_tile) {
 #ifdef SGUFP_K1_EMULATE
     int *smem = sgufp_emul_smem;   // tests/cpp/k1_emul.cpp: the kernel body compiled for the host, TILE = 1
 #else
     extern __shared__ int smem[];
 #endif
     const Lanes<TILE> T;
-    constexpr int TILES_PER_CTA = WARPS * 32 / TILE;
+    constexpr int TILES_PER_CTA = NW * 32 / TILE;
     const int tile_in_cta = threadIdx.x / TILE;
     TileMem w;
     {
@@ -943,16 +943,16 @@ __global__ void relayout_caps(const int32_t *__restrict__ src, double *__restric
 }  // namespace
 
 #ifndef SGUFP_K1_EMULATE
-template <int TILE>
-static cudaError_t launch_tile(const K1Launch &p, cudaStream_t st, int sm_count) {
+template <int TILE, int NW>
+static cudaError_t launch_tile_nw(const K1Launch &p, cudaStream_t st, int sm_count) {
     const int words = 2 * p.max_nch + 2 * p.max_nopen + 4 * (p.nc + 2) + p.nav + 2;
-    constexpr int tiles = WARPS * 32 / TILE;
+    constexpr int tiles = NW * 32 / TILE;
     const size_t smem = (size_t)tiles * words * sizeof(int);
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-    cudaError_t e = cudaFuncSetAttribute(k1_cut_eval<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k1_cut_eval<TILE, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_cut_eval<TILE>, WARPS * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_cut_eval<TILE, NW>, NW * 32, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     const long long items = (long long)p.K * p.S;
@@ -960,8 +960,17 @@ static cudaError_t launch_tile(const K1Launch &p, cudaStream_t st, int sm_count)
     long long grid = (long long)sm_count * per_sm;   // persistent: a whole number of CTAs per SM
     if (want < grid) grid = want;
     if (grid < 1) grid = 1;
-    k1_cut_eval<TILE><<<(unsigned)grid, WARPS * 32, smem, st>>>(p, words);
+    k1_cut_eval<TILE, NW><<<(unsigned)grid, NW * 32, smem, st>>>(p, words);
     return cudaGetLastError();
+}
+
+// 8 warps per CTA; large networks (state of one scenario in the tens of KB) fall back to 2 or 1
+template <int TILE>
+static cudaError_t launch_tile(const K1Launch &p, cudaStream_t st, int sm_count) {
+    cudaError_t e = launch_tile_nw<TILE, WARPS>(p, st, sm_count);
+    if (e == cudaErrorInvalidConfiguration) { cudaGetLastError(); e = launch_tile_nw<TILE, 2>(p, st, sm_count); }
+    if (e == cudaErrorInvalidConfiguration) { cudaGetLastError(); e = launch_tile_nw<TILE, 1>(p, st, sm_count); }
+    return e;
 }
 
 int k1_tile_for(int max_nopen) {

@@ -52,6 +52,8 @@ CASES = [
     ("c4", lambda: I.config4(S=64), 3, 5, 0.1),
     ("c4_lb", lambda: I.config4(S=64, lower_prob=0.02), 3, 6, 0.3),
     ("odd_m_single_scenario", lambda: I.make_layered([3, 4, 3], 21, 1, 77, 0.8, 0.0, "odd"), 4, 7, 0.2),
+    # a network whose per-scenario state (~60 KB) no longer fits 8 warps per CTA: the 2-warp launch
+    ("large_m6000", lambda: I.make_layered([100, 100, 100, 100, 100, 90], 6000, 3, 99, 0.7, 0.01, "large"), 2, 8, 0.2),
 ]
 
 
@@ -176,3 +178,22 @@ def test_bad_path_is_rejected():
     with pytest.raises(sg.solver.SgufpError) as e:
         gs.solveSubProblem(np.array([9, 9, -1, -1, -1, -1], np.int16))
     assert e.value.code == -2
+
+
+@pytest.mark.parametrize("name,make,K,seed,unm", [c for c in CASES if c[0] in ("c1_lb", "c2", "c2_lb", "odd_m_single_scenario")],
+                         ids=["c1_lb", "c2", "c2_lb", "odd_m_single_scenario"])
+def test_lane_variant_gives_the_same_cuts(name, make, K, seed, unm, monkeypatch):
+    """The lane-per-scenario kernel (SGUFP_K1_MODE=lane) is a second, independently written K1: same
+    statuses, objectives and bit-identical cuts as the default warp-per-scenario kernel and as Oracle B."""
+    inst = make()
+    net = OracleNet(inst)
+    gs = sg.GuroSolver(inst)
+    paths = I.random_paths(net, K, seed, unm)
+    monkeypatch.setenv("SGUFP_K1_MODE", "warp")
+    a = gs.solve_paths(paths)
+    monkeypatch.setenv("SGUFP_K1_MODE", "lane")
+    b = gs.solve_paths(paths)
+    assert (a.cut_type == b.cut_type).all() and (a.first_infeasible == b.first_infeasible).all()
+    assert (a.rhs == b.rhs).all() and (a.coef_dense == b.coef_dense).all()
+    assert (a.status == b.status).all() and (a.obj == b.obj).all()
+    _compare(inst, gs, net, paths, b)
