@@ -4,22 +4,21 @@
 // for every (candidate k, scenario s) it solves the second-stage LP exactly and adds the
 // scenario's dual contribution cap x dual (grb.cpp:238-281) into exact integer accumulators.
 //
-// Mapping: one TILE of 8, 16 or 32 lanes per (candidate, scenario) — small
-// contracted graphs put several scenarios in one warp; a persistent grid of
-// sm_count x resident-CTAs strides over the K*S work items scenario-minor, so neighbouring tiles
+// Mapping: one warp per (candidate, scenario); a persistent grid of
+// sm_count x resident-CTAs strides over the K*S work items scenario-minor, so neighbouring warps
 // stream neighbouring rows of the scenario-major fp64 capacity arrays with coalesced 128-bit
-// loads.  The candidate's contracted graph (chains + head-sorted residual slots) is
-// read-only and stays in L1; all per-scenario state lives in the tile's slice of shared memory.
+// loads.  The candidate's contracted graph (chains) is read-only and stays in L1;
+// all per-scenario state lives in the warp's slice of shared memory.
 // No tensor cores: this is integer graph work.
 //
 // Per work item:
 //   1. stream u_s, l_s; segmented min/max into chain capacities (shared-memory atomics, packed
 //      with the position of the FIRST least-capacity / LAST greatest-lower-bound arc)
-//   2. optimal flow, one shortest-path LEVEL at a time: a pull-style label correction over the
-//      head-sorted slots (each lane reduces a contiguous slot range in registers and issues one
-//      atomicMin per head it touches; labels are (distance, hops) in one int), then a blocking
-//      flow on the tight sub-graph by a backward depth-first search with current-arc pointers
-//      (every tight slot is scanned once per level, every path found is pushed immediately)
+//   2. optimal flow, primal-dual: a push-style label correction gives the shortest residual
+//      distances (one per DISTINCT path length); the chains that are tight under those labels are
+//      compacted once, and breadth-first searches over that short list (the reached set is one
+//      register, one warp reduction per level) find and saturate every shortest path of that
+//      length before the labels are computed again
 //   3. SPEC-LP potentials (algorithm-independent) by label correction from the root
 //   4. lift to (gamma, beta, sigma, phi, lambda, mu), multiply by the capacities and add to the
 //      candidate's accumulators; write objective + status
@@ -33,52 +32,80 @@
 namespace sgufp {
 
 #ifdef SGUFP_K1_STATS
-__device__ unsigned long long g_k1_stats[4];   // passes, label computations
+__device__ unsigned long long g_k1_stats[4];   // relaxation passes, label computations, breadth-first searches, work items
 #endif
 
 namespace {
 
-constexpr int HB = 10;                 // hop bits of a label
-constexpr int LAB_BIAS = 1 << 19;      // |distance| < 2^18 (checked at create) => 0 < distance + bias < 2^20
-constexpr int LAB_INF = 0x3fffffff;    // every real label is < 2^30; label + increment never overflows an int
+constexpr int HB = 10;                 // position bits packed under a chain capacity; hop bits of a lane-variant label
+constexpr int LAB_BIAS = 1 << 19;      // lane variant: |distance| < 2^18 (checked at create) => 0 < distance + bias < 2^20
+constexpr int LAB_INF = 0x3fffffff;    // "unreached"; label + increment never overflows an int
 constexpr int NEG_INF = INT_MIN / 4;
 constexpr int WARPS = 8;               // warps per CTA
 
 struct PlanView {
     const PlanHeader *h;
     const int32_t *arc_cp, *arc_info, *arc_pre, *ch_ends, *ch_r, *ch_ptr, *ch_arcs, *ch_q, *av_ptr, *av_arcs, *fb_ptr, *fb_ch;
-    const int32_t *slot_th, *slot_cs, *slot_ch, *ch_slots, *node_in;
-    const int2 *ch_sr;
-    const int4 *slot_pk4;          // padded residual slots, two per int4
+    const int2 *ch_st;             // static half of an open chain (model.hpp)
+    const int4 *slot_pk4;          // lane variant: padded residual slots, two per int4
     const int32_t *node_in4;
     __device__ explicit PlanView(const int32_t *base) {
         h = reinterpret_cast<const PlanHeader *>(base);
         arc_cp = base + h->o_arc_cp; arc_info = base + h->o_arc_info; arc_pre = base + h->o_arc_pre;
         ch_ends = base + h->o_ch_ends; ch_r = base + h->o_ch_r; ch_ptr = base + h->o_ch_ptr; ch_arcs = base + h->o_ch_arcs;
         ch_q = base + h->o_ch_q; av_ptr = base + h->o_av_ptr; av_arcs = base + h->o_av_arcs; fb_ptr = base + h->o_fb_ptr; fb_ch = base + h->o_fb_ch;
-        slot_th = base + h->o_slot_th; slot_cs = base + h->o_slot_cs; slot_ch = base + h->o_slot_ch; ch_slots = base + h->o_ch_slots;
-        node_in = base + h->o_node_in;
-        ch_sr = reinterpret_cast<const int2 *>(base + h->o_ch_sr);
+        ch_st = reinterpret_cast<const int2 *>(base + h->o_ch_st);
         slot_pk4 = reinterpret_cast<const int4 *>(base + h->o_slot_pk);
         node_in4 = base + h->o_node_in4;
     }
 };
 
-struct TileMem {  // this tile's slice of shared memory
-    int *up, *lo, *x, *res, *lab, *pred, *pot, *exc, *aq;
+// the static half of an open chain, unpacked
+struct ChainEnds {
+    int sv, ev, hf, hb, r;
+    __device__ __forceinline__ explicit ChainEnds(const int2 st) {
+        sv = st.x & 1023; ev = (st.x >> 10) & 1023; hf = (st.x >> 20) & 1023; hb = st.y & 1023; r = st.y >> 10;
+    }
 };
 
+struct TileMem {  // this tile's slice of shared memory
+    int *up, *lo, *x, *res, *lab, *pred, *pot, *exc, *aq;
+    unsigned *rw;                         // reached set (+ a scratch row for the list search)
+    int *tc;                              // larger graphs: the tight-chain list
+    unsigned *tin, *tout, *hist;          // small graphs: bit sets of the tight residual graph, search levels
+    int *path;
+    unsigned short *tab;
+};
+
+__host__ __device__ inline int reach_words(int nc) { return (nc + 1 + 31) >> 5; }   // bit sets over the label indices 0..nc
+
+// int32 words of shared memory per tile (the launcher and the host emulation size the buffer with it)
+constexpr int SMALL_NC = 31;              // label indices 0..nc fit one 32-bit set
+__host__ __device__ inline int k1_search_words(int nc, int max_nopen) {   // bit sets + levels + path + pair table, or the tight-chain list
+    return nc <= SMALL_NC ? 32 + 32 + 34 + 34 + 32 * 32 / 2 : max_nopen;
+}
+__host__ __device__ inline int k1_words_per_tile(const K1Launch &p) {
+    return 2 * p.max_nch + 2 * p.max_nopen + 4 * (p.nc + 2) + p.nav + 2 + 2 * reach_words(p.nc) + k1_search_words(p.nc, p.max_nopen);
+}
+
 template <int TILE>
-struct Lanes {    // the TILE lanes that work on one scenario
-    unsigned mask;
-    int tl;
+struct Lanes {    // the TILE lanes that work on one scenario (32 on the GPU; 1 in the host emulation)
+    unsigned mask, lt;
+    int tl, base;
     __device__ Lanes() {
-        const int lane = threadIdx.x & 31;
+        const int lane = TILE == 1 ? 0 : (int)(threadIdx.x & 31);
         tl = lane & (TILE - 1);
-        mask = TILE == 32 ? 0xffffffffu : (((1u << TILE) - 1u) << (lane & ~(TILE - 1)));
+        base = lane & ~(TILE - 1);
+        mask = TILE == 32 ? 0xffffffffu : (((1u << TILE) - 1u) << base);
+        lt = (1u << tl) - 1u;
     }
     __device__ __forceinline__ void sync() const { __syncwarp(mask); }
     __device__ __forceinline__ bool any(bool p) const { return __any_sync(mask, p) != 0; }
+    __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(mask, p) & mask) >> base; }
+    __device__ __forceinline__ unsigned reduce_or(unsigned v) const {
+        if constexpr (TILE == 32) return __reduce_or_sync(mask, v);
+        else { for (int o = TILE / 2; o; o >>= 1) v |= __shfl_xor_sync(mask, v, o, TILE); return v; }
+    }
     __device__ __forceinline__ long long sum(long long v) const {
         for (int o = TILE / 2; o; o >>= 1) v += __shfl_xor_sync(mask, v, o, TILE);
         return v;
@@ -89,40 +116,36 @@ struct Lanes {    // the TILE lanes that work on one scenario
     }
 };
 
-__device__ __forceinline__ int lab_dist(int lab) { return (lab >> HB) - LAB_BIAS; }
+__device__ __forceinline__ int lab_dist(int lab) { return (lab >> HB) - LAB_BIAS; }   // lane variant
 
-// Label-correcting shortest paths from `src` over the residual arcs of the contracted graph
-// (push style: every lane relaxes its chains, shared-memory atomicMin on the packed label).
+// Label-correcting shortest distances from `src` over the residual arcs of the contracted graph
+// (push style: every lane relaxes its chains, shared-memory atomicMin on the label).  One 64-bit
+// load brings the static half of a chain, one word of flags its residual state.
 // MERGED: the root is one node (index 0) that is never relabelled; otherwise arcs entering the
 // root end at index nc.
-template <int TILE, bool MERGED>
+// WARM: the nodes of the set w.rw (those a failed search could still reach over tight residual
+// arcs) keep their labels — they are still exact, see reach_* — and only the others start over.
+template <int TILE, bool MERGED, bool WARM>
 __device__ void shortest_paths(int src, const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TileMem &w, int &fuel) {
-    for (int v = T.tl; v <= nc; v += TILE) w.lab[v] = LAB_INF;
+    for (int v = T.tl; v <= nc; v += TILE)
+        if (!WARM || !((w.rw[v >> 5] >> (v & 31)) & 1)) w.lab[v] = LAB_INF;
     T.sync();
-    if (T.tl == 0) w.lab[src] = LAB_BIAS << HB;
+    if (!WARM && T.tl == 0) w.lab[src] = 0;
     T.sync();
     bool changed;
     do {
         changed = false;
         for (int c = T.tl; c < nopen; c += TILE) {
-            const int2 sr = P.ch_sr[c];            // static: ends | reward, one 64-bit load
-            const int f = w.res[c];                // dynamic: bit 0 forward residual, bit 1 backward residual
-            const int sv = (sr.x & 0xffff) - 1, ev = (sr.x >> 16) - 1;
-            if ((f & 1) && !(MERGED && ev == 0)) {
-                const int lu = w.lab[sv];
-                if (lu != LAB_INF) {
-                    const int cand = lu - sr.y * (1 << HB) + 1;
-                    const int t = (!MERGED && ev == 0) ? nc : ev;
-                    if (cand < atomicMin(&w.lab[t], cand)) { changed = true; w.pred[t] = 2 * c; }
-                }
+            const int f = w.res[c];                // bit 0 forward residual, bit 1 backward residual
+            const ChainEnds e(P.ch_st[c]);
+            const int ls = w.lab[e.sv], le = w.lab[e.ev];
+            if ((f & 1) && ls != LAB_INF && !(MERGED && e.hf == nc)) {
+                const int cand = ls - e.r;
+                if (cand < w.lab[e.hf]) { atomicMin(&w.lab[e.hf], cand); changed = true; }
             }
-            if ((f & 2) && !(MERGED && sv == 0)) {
-                const int lu = w.lab[ev];
-                if (lu != LAB_INF) {
-                    const int cand = lu + sr.y * (1 << HB) + 1;
-                    const int t = (!MERGED && sv == 0) ? nc : sv;
-                    if (cand < atomicMin(&w.lab[t], cand)) { changed = true; w.pred[t] = 2 * c + 1; }
-                }
+            if ((f & 2) && le != LAB_INF && !(MERGED && e.hb == nc)) {
+                const int cand = le + e.r;
+                if (cand < w.lab[e.hb]) { atomicMin(&w.lab[e.hb], cand); changed = true; }
             }
         }
         T.sync();
@@ -136,76 +159,192 @@ __device__ void shortest_paths(int src, const PlanView &P, int nopen, int nc, co
 #endif
 }
 
-// One tight residual arc per labelled node (pred = 2*chain + direction).  Only needed when the
-// predecessor written next to a label update lost a race with a better update of the same pass.
+// ---- shortest paths of one length: searches over the TIGHT residual arcs ------------------------
+// An arc is tight when label(tail) + cost == label(head).  Tightness depends on the labels only, so
+// it is computed once per label computation (bits 2 and 3 of a chain's flag word) and stays valid
+// while flow is pushed along tight arcs: the labels remain feasible potentials, every tight
+// residual path is a shortest path, and a node that a complete search still reaches keeps its
+// exact label (its tight path is a shortest path; no path can be shorter than the potential).
+//
+// Contracted graphs of up to 31 nodes (SMALL, config C2): the tight residual graph is two rows of
+// bit sets per node (tout[u] = heads, tin[v] = tails) plus a table tab[v][u] with one usable arc per
+// pair, all kept up to date under pushes.  A breadth-first level is then one OR-reduction over the
+// warp, the path is read back one level per hop, and the hops are updated in parallel.
+// Larger graphs: a compacted list of the tight chains, scanned once per level.
+
 template <int TILE>
-__device__ void mark_predecessors(const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TileMem &w) {
+__device__ void tight_small(const PlanView &P, int nopen, const Lanes<TILE> &T, TileMem &w) {
+    for (int i = T.tl; i < 64; i += TILE) w.tin[i] = 0u;    // tin[32] and tout[32] are adjacent
+    T.sync();
     for (int c = T.tl; c < nopen; c += TILE) {
-        const int2 sr = P.ch_sr[c];
-        const int f = w.res[c];
-        const int sv = (sr.x & 0xffff) - 1, ev = (sr.x >> 16) - 1;
-        if (f & 1) {
-            const int lu = w.lab[sv], t = ev == 0 ? nc : ev;
-            if (lu != LAB_INF && lu - sr.y * (1 << HB) + 1 == w.lab[t]) w.pred[t] = 2 * c;
-        }
-        if (f & 2) {
-            const int lu = w.lab[ev], t = sv == 0 ? nc : sv;
-            if (lu != LAB_INF && lu + sr.y * (1 << HB) + 1 == w.lab[t]) w.pred[t] = 2 * c + 1;
-        }
+        const ChainEnds e(P.ch_st[c]);
+        const int ls = w.lab[e.sv], le = w.lab[e.ev], f = w.res[c] & 3;
+        int tf = 0;
+        if (ls != LAB_INF && ls - e.r == w.lab[e.hf]) tf |= 1;
+        if (le != LAB_INF && le + e.r == w.lab[e.hb]) tf |= 2;
+        w.res[c] = f | (tf << 2);
+        if (f & tf & 1) { atomicOr(&w.tin[e.hf], 1u << e.sv); atomicOr(&w.tout[e.sv], 1u << e.hf); w.tab[e.hf * 32 + e.sv] = (unsigned short)(2 * c); }
+        if (f & tf & 2) { atomicOr(&w.tin[e.hb], 1u << e.ev); atomicOr(&w.tout[e.ev], 1u << e.hb); w.tab[e.hb * 32 + e.ev] = (unsigned short)(2 * c + 1); }
     }
     T.sync();
 }
 
-// Lane 0 of the tile: follow the predecessors dst -> src, then push the bottleneck.  A label is
-// (distance, hops), so a predecessor is usable iff its arc still has residual capacity and is
-// TIGHT (label(tail) + increment == label(head)); the hop count then drops by one per step and the
-// walk can only end at src.  Returns the amount pushed, or -1 if some predecessor is not tight
-// (stale, or overwritten by a racing lane): the caller re-marks and walks again.
-__device__ int augment(int src, int dst, int limit, const PlanView &P, int nc, TileMem &w) {
-    int v = dst, d = limit;
-    while (v != src) {
-        const int p = w.pred[v], c = p >> 1;
-        if ((unsigned)c >= (unsigned)P.h->nopen) return -1;
-        const int2 sr = P.ch_sr[c];
-        const int sv = (sr.x & 0xffff) - 1, ev = (sr.x >> 16) - 1;
-        int u, res, inc;
-        int head;   // pred[v] may be a leftover of another candidate's plan: the arc must really end at v
-        if (p & 1) { u = ev; head = sv == 0 ? nc : sv; res = w.x[c] - (w.lo[c] >> HB); inc = sr.y * (1 << HB) + 1; }
-        else { u = sv; head = ev == 0 ? nc : ev; res = (w.up[c] >> HB) - w.x[c]; inc = -sr.y * (1 << HB) + 1; }
-        if (head != v || res <= 0 || w.lab[u] == LAB_INF || w.lab[u] + inc != w.lab[v]) return -1;
-        d = min(d, res);
+// Breadth-first search src -> dst; hist[l] = the nodes first reached at level l.  Returns the level
+// of dst, or 0 if it cannot be reached — then w.rw[0] holds the complete reached set.
+template <int TILE>
+__device__ int reach_small(int src, int dst, int nc, const Lanes<TILE> &T, TileMem &w) {
+    unsigned R = 1u << src, F = R;
+    int lev = 0;
+    if (T.tl == 0) w.hist[0] = F;
+    for (;;) {
+        unsigned nb = 0;
+        for (int u = T.tl; u <= nc; u += TILE)
+            if ((F >> u) & 1) nb |= w.tout[u];
+        nb = T.reduce_or(nb) & ~R;
+        if (!nb) { if (T.tl == 0) w.rw[0] = R; T.sync(); return 0; }
+        R |= nb; F = nb; lev++;
+        if (T.tl == 0) w.hist[lev] = F;
+        if ((R >> dst) & 1) { T.sync(); return lev; }
+    }
+}
+
+// Push along a path dst -> src that drops one level per hop.  Every lane walks it (broadcast
+// loads) for the bottleneck; then one lane per hop moves the flow and updates the bit sets.
+template <int TILE>
+__device__ int push_small(int dst, int limit, int lev, int nc, const Lanes<TILE> &T, TileMem &w) {
+    int v = dst, d = limit, h = 0;
+    for (int l = lev; l > 0; l--, h++) {
+        const unsigned m = w.tin[v] & w.hist[l - 1];
+        if (!m) { d = 0; break; }              // cannot happen: v was reached from level l-1
+        const int u = __ffs(m) - 1, s = w.tab[v * 32 + u], c = s >> 1, xc = w.x[c];
+        d = min(d, (s & 1) ? xc - (w.lo[c] >> HB) : (w.up[c] >> HB) - xc);
+        if (T.tl == 0) w.path[h] = s | (u << 16) | (v << 21);
         v = u;
     }
-    v = dst;
-    while (v != src) {
-        const int p = w.pred[v], c = p >> 1;
-        const int2 sr = P.ch_sr[c];
-        int xc;
-        if (p & 1) { xc = (w.x[c] -= d); v = (sr.x >> 16) - 1; } else { xc = (w.x[c] += d); v = (sr.x & 0xffff) - 1; }
-        w.res[c] = (xc < (w.up[c] >> HB) ? 1 : 0) | (xc > (w.lo[c] >> HB) ? 2 : 0);
+    T.sync();
+    if (d <= 0) return 0;
+    for (int i = T.tl; i < h; i += TILE) {
+        const int rec = w.path[i], s = rec & 0xffff, u = (rec >> 16) & 31, vv = (rec >> 21) & 31, c = s >> 1, dir = s & 1;
+        const int xc = w.x[c] + (dir ? -d : d);
+        w.x[c] = xc;
+        const int nf = (xc < (w.up[c] >> HB) ? 1 : 0) | (xc > (w.lo[c] >> HB) ? 2 : 0) | (w.res[c] & 12);
+        w.res[c] = nf;
+        if (!((nf >> dir) & 1)) { atomicAnd(&w.tin[vv], ~(1u << u)); atomicAnd(&w.tout[u], ~(1u << vv)); }   // saturated
+        if ((nf >> (2 + (dir ^ 1))) & 1) {     // the reverse arc has residual capacity now and is tight
+            const int rt = vv == nc ? 0 : vv, rh = u == 0 ? nc : u;
+            atomicOr(&w.tin[rh], 1u << rt); atomicOr(&w.tout[rt], 1u << rh);
+            w.tab[rh * 32 + rt] = (unsigned short)(s ^ 1);
+        }
     }
+    T.sync();
     return d;
 }
 
-// augment, falling back to one marking pass when a captured predecessor is not usable
+// list variant: the tight chains compacted into w.tc as chain | flags << 16
 template <int TILE>
-__device__ void push_path(int src, int dst, int limit, const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TileMem &w, int *pushed) {
-    int d = 0;
-    if (T.tl == 0) d = augment(src, dst, limit, P, nc, w);
-    d = __shfl_sync(T.mask, d, 0, TILE);
-    if (d < 0) {
-        mark_predecessors<TILE>(P, nopen, nc, T, w);
-        if (T.tl == 0) d = augment(src, dst, limit, P, nc, w);
-        d = __shfl_sync(T.mask, d, 0, TILE);
+__device__ int tight_list(const PlanView &P, int nopen, const Lanes<TILE> &T, TileMem &w) {
+    int n = 0;
+    for (int c0 = 0; c0 < nopen; c0 += TILE) {     // tile-uniform trip count
+        const int c = c0 + T.tl;
+        int tf = 0;
+        if (c < nopen) {
+            const ChainEnds e(P.ch_st[c]);
+            const int ls = w.lab[e.sv], le = w.lab[e.ev];
+            if (ls != LAB_INF && ls - e.r == w.lab[e.hf]) tf |= 1;
+            if (le != LAB_INF && le + e.r == w.lab[e.hb]) tf |= 2;
+        }
+        const unsigned b = T.ballot(tf != 0);
+        if (tf) w.tc[n + __popc(b & T.lt)] = c | (tf << 16);
+        n += __popc(b);
     }
     T.sync();
-    if (pushed) *pushed = d;
+    return n;
 }
+
+// list variant of the search, level synchronous: a node joins with a predecessor
+// (tail | (2*chain+dir) << 10) from an EARLIER level, so the predecessors form a tree rooted at src.
+// If dst is not reached, w.rw holds the complete reached set.
+template <int TILE>
+__device__ bool reach_list(int src, int dst, const PlanView &P, int ntc, int nword, const Lanes<TILE> &T, TileMem &w) {
+    unsigned *R = w.rw, *N = w.rw + nword;
+    for (int i = T.tl; i < nword; i += TILE) { R[i] = i == (src >> 5) ? 1u << (src & 31) : 0u; N[i] = 0u; }
+    T.sync();
+    for (;;) {
+        for (int i = T.tl; i < ntc; i += TILE) {
+            const int en = w.tc[i], c = en & 0xffff, f = w.res[c] & (en >> 16);
+            if (f) {
+                const ChainEnds e(P.ch_st[c]);
+                if ((f & 1) && ((R[e.sv >> 5] >> (e.sv & 31)) & 1) && !((R[e.hf >> 5] >> (e.hf & 31)) & 1)) {
+                    atomicOr(&N[e.hf >> 5], 1u << (e.hf & 31)); w.pred[e.hf] = e.sv | ((2 * c) << 10);
+                }
+                if ((f & 2) && ((R[e.ev >> 5] >> (e.ev & 31)) & 1) && !((R[e.hb >> 5] >> (e.hb & 31)) & 1)) {
+                    atomicOr(&N[e.hb >> 5], 1u << (e.hb & 31)); w.pred[e.hb] = e.ev | ((2 * c + 1) << 10);
+                }
+            }
+        }
+        T.sync();
+        bool grew = false;
+        for (int i = T.tl; i < nword; i += TILE) { const unsigned nb = N[i]; if (nb) { R[i] |= nb; N[i] = 0u; grew = true; } }
+        T.sync();
+        if ((R[dst >> 5] >> (dst & 31)) & 1) return true;
+        if (!T.any(grew)) return false;
+    }
+}
+
+// list variant of the push: every lane walks the predecessor tree dst -> src, lane 0 writes
+template <int TILE>
+__device__ int push_list(int src, int dst, int limit, int nc, const Lanes<TILE> &T, TileMem &w) {
+    int v = dst, d = limit, hops = 0;
+    while (v != src) {
+        const int p = w.pred[v], s = p >> 10, c = s >> 1, xc = w.x[c];
+        d = min(d, (s & 1) ? xc - (w.lo[c] >> HB) : (w.up[c] >> HB) - xc);
+        v = p & 1023;
+        if (++hops > nc + 1) { d = 0; break; }
+    }
+    T.sync();                              // every lane has its bottleneck before lane 0 moves the flow
+    if (d <= 0) return 0;
+    v = dst;
+    while (v != src) {
+        const int p = w.pred[v], s = p >> 10, c = s >> 1;
+        if (T.tl == 0) {
+            const int xc = w.x[c] + ((s & 1) ? -d : d);
+            w.x[c] = xc;
+            w.res[c] = (xc < (w.up[c] >> HB) ? 1 : 0) | (xc > (w.lo[c] >> HB) ? 2 : 0);
+        }
+        v = p & 1023;
+    }
+    T.sync();
+    return d;
+}
+
+// What one label computation allows: search + push over its tight arcs, until none is left.
+template <int TILE>
+struct TightPaths {
+    const PlanView &P;
+    const Lanes<TILE> &T;
+    TileMem &w;
+    int nopen, nc, nword, ntc;
+    bool small;
+    __device__ TightPaths(const PlanView &P_, const Lanes<TILE> &T_, TileMem &w_, int nopen_, int nc_)
+        : P(P_), T(T_), w(w_), nopen(nopen_), nc(nc_), nword(reach_words(nc_)), ntc(0), small(nc_ <= SMALL_NC) {}
+    __device__ void prepare() { if (small) tight_small<TILE>(P, nopen, T, w); else ntc = tight_list<TILE>(P, nopen, T, w); }
+    // one search and, if dst is reachable, one push of at most `limit`; returns the amount pushed (0: not reachable)
+    __device__ int augment(int src, int dst, int limit) {
+#ifdef SGUFP_K1_STATS
+        if (T.tl == 0) atomicAdd(&g_k1_stats[2], 1ull);
+#endif
+        if (small) {
+            const int lev = reach_small<TILE>(src, dst, nc, T, w);
+            return lev ? push_small<TILE>(dst, limit, lev, nc, T, w) : 0;
+        }
+        return reach_list<TILE>(src, dst, P, ntc, nword, T, w) ? push_list<TILE>(src, dst, limit, nc, T, w) : 0;
+    }
+};
 
 // Forced flow from lower bounds (rare): route every excess / deficit along shortest residual
 // paths.  Returns false if some forced flow cannot be routed (scenario infeasible).
 template <int TILE>
-__device__ bool route_lower_bounds(const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TileMem &w, int &fuel) {
+__device__ bool route_lower_bounds(const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TileMem &w, TightPaths<TILE> &TP, int &fuel) {
     for (int v = T.tl; v <= nc; v += TILE) w.exc[v] = 0;
     T.sync();
     for (int c = T.tl; c < nopen; c += TILE) {
@@ -219,33 +358,34 @@ __device__ bool route_lower_bounds(const PlanView &P, int nopen, int nc, const L
     T.sync();
     for (int v = 1; v < nc; v++) {
         while (w.exc[v] > 0 && --fuel > 0) {
-            shortest_paths<TILE, false>(v, P, nopen, nc, T, w, fuel);
-            unsigned long long best = ~0ull;
+            shortest_paths<TILE, false, false>(v, P, nopen, nc, T, w, fuel);
+            unsigned long long best = ~0ull;   // nearest of: the root, a node with a deficit
             for (int t = T.tl; t <= nc; t += TILE)
                 if ((t == nc || (t > 0 && w.exc[t] < 0)) && w.lab[t] != LAB_INF) {
-                    const unsigned long long key = ((unsigned long long)(unsigned)w.lab[t] << 32) | (unsigned)t;
+                    const unsigned long long key = ((unsigned long long)(unsigned)(w.lab[t] - NEG_INF) << 32) | (unsigned)t;
                     best = key < best ? key : best;
                 }
             best = T.min_u64(best);
             if (best == ~0ull) return false;
             const int t = (int)(best & 0xffffffffu);
-            int lim = w.exc[v], d = 0;
+            int lim = w.exc[v];
             if (t != nc) lim = min(lim, -w.exc[t]);
-            push_path<TILE>(v, t, lim, P, nopen, nc, T, w, &d);
-            if (T.tl == 0 && d > 0) { w.exc[v] -= d; if (t != nc) w.exc[t] += d; }
-            T.sync();
+            TP.prepare();
+            const int d = TP.augment(v, t, lim);
             if (d <= 0) return false;
+            if (T.tl == 0) { w.exc[v] -= d; if (t != nc) w.exc[t] += d; }
+            T.sync();
         }
     }
     for (int v = 1; v < nc; v++) {
         while (w.exc[v] < 0 && --fuel > 0) {
-            shortest_paths<TILE, false>(0, P, nopen, nc, T, w, fuel);
+            shortest_paths<TILE, false, false>(0, P, nopen, nc, T, w, fuel);
             if (w.lab[v] == LAB_INF) return false;
-            int d = 0;
-            push_path<TILE>(0, v, -w.exc[v], P, nopen, nc, T, w, &d);
-            if (T.tl == 0 && d > 0) w.exc[v] += d;
-            T.sync();
+            TP.prepare();
+            const int d = TP.augment(0, v, -w.exc[v]);
             if (d <= 0) return false;
+            if (T.tl == 0) w.exc[v] += d;
+            T.sync();
         }
     }
     return true;
@@ -256,11 +396,11 @@ __device__ bool route_lower_bounds(const PlanView &P, int nopen, int nc, const L
 // off both ways get a zero-rooted completion.
 template <int TILE>
 __device__ void canonical_potentials(const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TileMem &w, int &fuel) {
-    shortest_paths<TILE, true>(0, P, nopen, nc, T, w, fuel);
+    shortest_paths<TILE, true, false>(0, P, nopen, nc, T, w, fuel);
     bool missing = false;
     for (int v = T.tl; v < nc; v += TILE) {
         const int l = w.lab[v];
-        if (l == LAB_INF) { missing = true; w.pot[v] = NEG_INF; w.pred[v] = 0; } else { w.pot[v] = lab_dist(l); w.pred[v] = 1; }
+        if (l == LAB_INF) { missing = true; w.pot[v] = NEG_INF; w.pred[v] = 0; } else { w.pot[v] = l; w.pred[v] = 1; }
     }
     T.sync();
     if (T.any(missing)) {
@@ -314,7 +454,7 @@ __device__ __forceinline__ int head_potential(int a, const PlanView &P, int nope
 }
 
 template <int TILE, int NW>
-__global__ void __launch_bounds__(NW * 32, NW == 8 ? 4 : 1) k1_cut_eval(K1Launch p, int words_per_tile) {
+__global__ void __launch_bounds__(NW * 32, NW == 8 ? 4 : NW == 4 ? 8 : 1) k1_cut_eval(K1Launch p, int words_per_tile) {
 #ifdef SGUFP_K1_EMULATE
     int *smem = sgufp_emul_smem;   // tests/cpp/k1_emul.cpp: the kernel body compiled for the host, TILE = 1
 #else
@@ -334,7 +474,11 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 4 : 1) k1_cut_eval(K1Launch
         w.pred = base; base += p.nc + 2;
         w.pot = base; base += p.nc + 2;
         w.exc = base; base += p.nc + 2;
-        w.aq = base;
+        w.aq = base; base += p.nav + 2;
+        w.rw = reinterpret_cast<unsigned *>(base); base += 2 * reach_words(p.nc);
+        w.tc = base;                               // one of the two layouts, by the size of the contracted graph
+        w.tin = reinterpret_cast<unsigned *>(base); w.tout = w.tin + 32; w.hist = w.tout + 32;
+        w.path = base + 98; w.tab = reinterpret_cast<unsigned short *>(base + 132);
     }
     const long long items = (long long)p.K * p.S;
     const long long stride = (long long)gridDim.x * TILES_PER_CTA;
@@ -381,7 +525,8 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 4 : 1) k1_cut_eval(K1Launch
         bad = T.any(bad);
         forced = T.any(forced);
         // 2. optimal flow
-        if (!bad && forced) bad = !route_lower_bounds<TILE>(P, nopen, nc, T, w, fuel);
+        TightPaths<TILE> TP(P, T, w, nopen, nc);
+        if (!bad && forced) bad = !route_lower_bounds<TILE>(P, nopen, nc, T, w, TP, fuel);
         if (bad) {
             if (T.tl == 0) {
                 atomicMin(p.first_inf + k, p.scen_offset + s);
@@ -391,13 +536,18 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 4 : 1) k1_cut_eval(K1Launch
             T.sync();
             continue;
         }
-        while (fuel > 0) {   // one label computation per iteration, then as many pushes as its tight arcs allow
-            shortest_paths<TILE, false>(0, P, nopen, nc, T, w, fuel);
+#ifdef SGUFP_K1_STATS
+        if (T.tl == 0) atomicAdd(&g_k1_stats[3], 1ull);
+#endif
+        // one label computation per distinct path length; in between, breadth-first searches over the
+        // tight chains find the other shortest paths of that length (labels stay feasible potentials)
+        for (bool warm = false; fuel > 0; warm = true) {
+            if (warm) shortest_paths<TILE, false, true>(0, P, nopen, nc, T, w, fuel);
+            else shortest_paths<TILE, false, false>(0, P, nopen, nc, T, w, fuel);
             const int lt = w.lab[nc];
-            if (lt == LAB_INF || lab_dist(lt) >= 0) break;
-            int d = 0;
-            push_path<TILE>(0, nc, INT_MAX, P, nopen, nc, T, w, &d);
-            if (d <= 0) fuel = 0;   // cannot happen: the labels were just computed
+            if (lt == LAB_INF || lt >= 0) break;
+            TP.prepare();
+            while (--fuel > 0 && TP.augment(0, nc, INT_MAX) > 0) {}   // until the search fails: it leaves the reached set for the warm start
         }
         // 3. potentials
         canonical_potentials<TILE>(P, nopen, nc, T, w, fuel);
@@ -943,40 +1093,51 @@ __global__ void relayout_caps(const int32_t *__restrict__ src, double *__restric
 }  // namespace
 
 #ifndef SGUFP_K1_EMULATE
-template <int TILE, int NW>
-static cudaError_t launch_tile_nw(const K1Launch &p, cudaStream_t st, int sm_count) {
-    const int words = 2 * p.max_nch + 2 * p.max_nopen + 4 * (p.nc + 2) + p.nav + 2;
-    constexpr int tiles = NW * 32 / TILE;
-    const size_t smem = (size_t)tiles * words * sizeof(int);
+template <int NW>
+static cudaError_t launch_warp_nw(const K1Launch &p, cudaStream_t st, int sm_count, int *resident_warps, bool dry) {
+    const int words = k1_words_per_tile(p);
+    const size_t smem = (size_t)NW * words * sizeof(int);
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-    cudaError_t e = cudaFuncSetAttribute(k1_cut_eval<TILE, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k1_cut_eval<32, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_cut_eval<TILE, NW>, NW * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_cut_eval<32, NW>, NW * 32, smem);
     if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
+    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    *resident_warps = per_sm * NW;
+    if (dry) return cudaSuccess;
     const long long items = (long long)p.K * p.S;
-    long long want = (items + tiles - 1) / tiles;
+    long long want = (items + NW - 1) / NW;
     long long grid = (long long)sm_count * per_sm;   // persistent: a whole number of CTAs per SM
     if (want < grid) grid = want;
     if (grid < 1) grid = 1;
-    k1_cut_eval<TILE, NW><<<(unsigned)grid, NW * 32, smem, st>>>(p, words);
+    k1_cut_eval<32, NW><<<(unsigned)grid, NW * 32, smem, st>>>(p, words);
     return cudaGetLastError();
 }
 
-// 8 warps per CTA; large networks (state of one scenario in the tens of KB) fall back to 2 or 1
-template <int TILE>
-static cudaError_t launch_tile(const K1Launch &p, cudaStream_t st, int sm_count) {
-    cudaError_t e = launch_tile_nw<TILE, WARPS>(p, st, sm_count);
-    if (e == cudaErrorInvalidConfiguration) { cudaGetLastError(); e = launch_tile_nw<TILE, 2>(p, st, sm_count); }
-    if (e == cudaErrorInvalidConfiguration) { cudaGetLastError(); e = launch_tile_nw<TILE, 1>(p, st, sm_count); }
-    return e;
+static cudaError_t launch_warp_dispatch(int nw, const K1Launch &p, cudaStream_t st, int sm_count, int *rw, bool dry) {
+    switch (nw) {
+        case 8: return launch_warp_nw<8>(p, st, sm_count, rw, dry);
+        case 4: return launch_warp_nw<4>(p, st, sm_count, rw, dry);
+        case 2: return launch_warp_nw<2>(p, st, sm_count, rw, dry);
+        default: return launch_warp_nw<1>(p, st, sm_count, rw, dry);
+    }
 }
 
-int k1_tile_for(int max_nopen) {
-    if (const char *e = getenv("SGUFP_K1_TILE")) { const int t = atoi(e); if (t == 8 || t == 16 || t == 32) return t; }
-    (void)max_nopen;                                  // measured (profiles/): sub-warp tiles lose to divergence between tiles
-    return 32;
+// Warps per CTA: the count that keeps most warps resident per SM (shared memory per warp grows with
+// the network: 2.5 KB at C2, 12 KB at C4, tens of KB beyond); ties go to the larger CTA.
+static cudaError_t launch_warp(const K1Launch &p, cudaStream_t st, int sm_count) {
+    int best_nw = 0, best = 0;
+    for (int nw = WARPS; nw >= 1; nw >>= 1) {
+        int rw = 0;
+        const cudaError_t e = launch_warp_dispatch(nw, p, st, sm_count, &rw, true);
+        if (e == cudaErrorInvalidConfiguration) { cudaGetLastError(); continue; }
+        if (e != cudaSuccess) return e;
+        if (rw > best) { best = rw; best_nw = nw; }
+    }
+    if (!best_nw) return cudaErrorInvalidConfiguration;
+    int rw = 0;
+    return launch_warp_dispatch(best_nw, p, st, sm_count, &rw, false);
 }
 
 static size_t lane_bytes_per_warp(const K1Launch &p) {
@@ -1015,13 +1176,7 @@ bool k1_use_lane_variant(const K1Launch &p) {
 cudaError_t k1_launch(const K1Launch &p, cudaStream_t st, int sm_count, int *launches) {
     if (launches) (*launches)++;
     if (k1_use_lane_variant(p)) return launch_lane(p, st, sm_count);
-    int tile = k1_tile_for(p.max_nopen);
-    // fall back to a wider tile (fewer tiles per CTA) if the per-CTA shared memory does not fit
-    for (;;) {
-        cudaError_t e = tile == 8 ? launch_tile<8>(p, st, sm_count) : tile == 16 ? launch_tile<16>(p, st, sm_count) : launch_tile<32>(p, st, sm_count);
-        if (e == cudaErrorInvalidConfiguration && tile < 32) { tile *= 2; cudaGetLastError(); continue; }
-        return e;
-    }
+    return launch_warp(p, st, sm_count);
 }
 
 cudaError_t ray_launch(const RayLaunch &p, cudaStream_t st, int *launches) {

@@ -257,16 +257,6 @@ int build_plan(const Model &M, const int16_t *path, int plen, Plan &P, std::stri
         if (a.tail != b.tail) return a.tail < b.tail;
         return a.ch < b.ch;
     });
-    std::vector<int32_t> slot_th(slots.size()), slot_cs(slots.size()), slot_ch(slots.size()), ch_slots(nopen, 0), node_in(M.nc + 2, 0);
-    for (size_t s = 0; s < slots.size(); s++) {
-        slot_th[s] = slots[s].tail | (slots[s].head << 16);
-        slot_cs[s] = slots[s].cs;
-        slot_ch[s] = slots[s].ch;
-        if (slots[s].ch & 1) ch_slots[slots[s].ch >> 1] |= (int32_t)s << 16; else ch_slots[slots[s].ch >> 1] |= (int32_t)s;
-        node_in[slots[s].head + 1]++;
-    }
-    for (int v = 0; v <= M.nc; v++) node_in[v + 1] += node_in[v];
-
     PlanHeader H{};
     H.nch = nch; H.nopen = nopen; H.nc = M.nc; H.nav = M.nav; H.m = m; H.L = M.L;
     std::vector<int32_t> &W = P.words;
@@ -275,11 +265,15 @@ int build_plan(const Model &M, const int16_t *path, int plen, Plan &P, std::stri
     H.o_arc_cp = put(arc_cp); H.o_arc_info = put(arc_info); H.o_arc_pre = put(arc_pre);
     H.o_ch_ends = put(ch_ends); H.o_ch_r = put(ch_r); H.o_ch_ptr = put(ch_ptr); H.o_ch_arcs = put(ch_arcs); H.o_ch_q = put(ch_q);
     H.o_av_ptr = put(av_ptr); H.o_av_arcs = put(av_arcs); H.o_fb_ptr = put(fb_ptr); H.o_fb_ch = put(fb_ch);
-    H.o_slot_th = put(slot_th); H.o_slot_cs = put(slot_cs); H.o_slot_ch = put(slot_ch); H.o_ch_slots = put(ch_slots); H.o_node_in = put(node_in);
     {
-        std::vector<int32_t> sr(2 * nopen);
-        for (int c = 0; c < nopen; c++) { sr[2 * c] = ch_ends[c]; sr[2 * c + 1] = ch_r[c]; }
-        H.o_ch_sr = put(sr);   // W.size() is even here (header even, every array padded to even)
+        std::vector<int32_t> st(2 * nopen);
+        for (int c = 0; c < nopen; c++) {
+            const Ch &ch = chains[c];
+            const int hf = ch.ev == 0 ? M.nc : ch.ev, hb = ch.sv == 0 ? M.nc : ch.sv;
+            st[2 * c] = ch.sv | (ch.ev << 10) | (hf << 20);
+            st[2 * c + 1] = hb | (int32_t)((uint32_t)ch.r << 10);
+        }
+        H.o_ch_st = put(st);   // W.size() is even here (header even, every array padded to even)
         std::vector<int32_t> pk, in4(M.nc + 2, 0);
         size_t s = 0;
         for (int v = 0; v <= M.nc; v++) {

@@ -55,20 +55,18 @@ struct PlanHeader {
     int32_t o_av_arcs;     // [#matched]
     int32_t o_fb_ptr;      // [nav+1]  fallback chains (end-anchored chains starting at the node) for nodes without a matched pair
     int32_t o_fb_ch;       // [#fallback]
-    // residual "slots": two per open chain (forward sv->ev cost -r, backward ev->sv cost +r),
-    // sorted by head node; an arc entering the root has head index nc (the root seen as a path END)
-    int32_t o_slot_th;     // [2*nopen]  tail | head << 16
-    int32_t o_slot_cs;     // [2*nopen]  (cost << 10) + 1   (label increment: distance in the high bits, one hop)
-    int32_t o_slot_ch;     // [2*nopen]  chain << 1 | (1 if backward)
-    int32_t o_ch_slots;    // [nopen]    position of the forward slot | position of the backward slot << 16
-    int32_t o_node_in;     // [nc+2]     slot range of each head node (index nc = root-in)
-    int32_t o_ch_sr;       // [nopen]    int2 {ends, reward}: the static half of a chain in one 64-bit load (8-byte aligned)
+    int32_t o_ch_st;       // [nopen]    int2, the static half of an open chain in one 64-bit load (8-byte aligned):
+                           //            x = sv | ev << 10 | hf << 20,  y = hb | reward << 10, where hf / hb are the label
+                           //            indices of the heads of the forward (sv->ev, cost -r) and backward (ev->sv, cost +r)
+                           //            residual arcs: an arc entering the root ends at index nc (the root seen as a path END)
+    // residual slots of the lane-per-scenario variant: sorted by head node
     int32_t o_slot_pk;     // int2 {tail | (2*chain+dir) << 16, label increment} per slot, every node's list padded to a multiple of 4
                            // with slots whose tail is the never-labelled node nc+1; 16-byte aligned
     int32_t o_node_in4;    // [nc+2]     ranges of the padded lists
-    int32_t pad2;          // keeps the header an even number of words
-    int32_t total;         // int32 words used by this plan, header included        // keeps the header an even number of words so that o_ch_sr can be 8-byte aligned
+    int32_t total;         // int32 words used by this plan, header included (the header is an even number of words)
 };
+
+static_assert(sizeof(PlanHeader) % 8 == 0, "64-bit records follow the header");
 
 struct Plan {
     std::vector<int32_t> words;   // PlanHeader followed by the arrays

@@ -22,6 +22,7 @@ static EmulIdx threadIdx, blockIdx;
 static struct { int x = 1, y = 1; } gridDim, blockDim;
 static int *sgufp_emul_smem = nullptr;
 #define __device__
+#define __host__
 #define __global__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
@@ -34,6 +35,12 @@ static inline int atomicAdd(int *p, int v) { int o = *p; *p += v; return o; }
 static inline int atomicSub(int *p, int v) { int o = *p; *p -= v; return o; }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
 static inline long long atomicMin(long long *p, long long v) { long long o = *p; if (v < o) *p = v; return o; }
+static inline unsigned atomicOr(unsigned *p, unsigned v) { unsigned o = *p; *p |= v; return o; }
+static inline unsigned atomicAnd(unsigned *p, unsigned v) { unsigned o = *p; *p &= v; return o; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
+static inline unsigned __reduce_or_sync(unsigned, unsigned v) { return v; }
 static inline void __syncwarp(unsigned = 0xffffffffu) {}
 static inline int __any_sync(unsigned, int p) { return p; }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int, int = 32) { return v; }
@@ -73,7 +80,7 @@ extern "C" int emul_paths(int n, int m, int S, const int32_t *tail, const int32_
     p.plans = words.data(); p.plan_off = off.data(); p.K = K; p.W = W; p.L = M.L;
     p.sums = reinterpret_cast<unsigned long long *>(sums); p.first_inf = first_inf; p.obj = obj; p.status = status;
     p.max_nch = max_nch; p.max_nopen = max_nopen; p.nc = M.nc; p.nav = M.nav; p.max_cap = 65535;
-    const int wpt = 2 * max_nch + 2 * max_nopen + 4 * (M.nc + 2) + M.nav + 2;
+    const int wpt = k1_words_per_tile(p);
     std::vector<int> smem((size_t)WARPS * 32 * wpt, 0);
     sgufp_emul_smem = smem.data();
     threadIdx.x = 0; blockIdx.x = 0; gridDim.x = 1;

@@ -72,6 +72,8 @@ CASES = [
     ("c2_lb", lambda: I.config2(S=12, lower_prob=0.1), 4, 4, 0.3),
     ("c4_lb", lambda: I.config4(S=3, lower_prob=0.05), 2, 6, 0.3),
     ("odd_m", lambda: I.make_layered([3, 4, 3], 21, 4, 77, 0.8, 0.1, "odd"), 4, 7, 0.2),
+    # > 255 contracted nodes: the searches run over the tight-chain list instead of per-node bit sets
+    ("wide_lb", lambda: I.make_layered([70, 70, 70, 70, 60], 1500, 2, 98, 0.3, 0.02, "wide"), 2, 9, 0.2),
 ]
 
 

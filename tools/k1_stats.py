@@ -1,0 +1,49 @@
+"""Developer tool: per-evaluation work counters of K1 (relaxation passes, label computations,
+breadth-first searches) from a -DSGUFP_K1_STATS build of the library.
+
+    python tools/k1_stats.py --build          # here (nvcc, no GPU): builds sgufp_solver_b200/libsgufp_b200_stats.so
+    python tools/k1_stats.py c2 c4            # on a GPU box: runs the bench workloads once and prints the counters
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from sgufp_solver_b200 import build as B  # noqa: E402
+
+STATS_LIB = os.path.join(B.HERE, "libsgufp_b200_stats.so")
+
+
+def build():
+    cmd = ["/usr/local/cuda/bin/nvcc"] + B.NVCC_FLAGS + ["-DSGUFP_K1_STATS", "-o", STATS_LIB] + B.sources()
+    subprocess.check_call(cmd)
+
+
+def main():
+    if "--build" in sys.argv:
+        build()
+        return
+    from sgufp_solver_b200 import _lib
+    _lib.LIB_PATH = STATS_LIB
+    import numpy as np
+    from sgufp_solver_b200 import instances as I
+    from sgufp_solver_b200.solver import GuroSolver
+    L = _lib.lib()
+    L.sgufp_debug_k1_stats.restype = C.c_int
+    L.sgufp_debug_k1_stats.argtypes = [C.POINTER(C.c_ulonglong)]
+    out = (C.c_ulonglong * 4)()
+    for name in [a for a in sys.argv[1:] if not a.startswith("-")]:
+        inst, K = {"c2": (lambda: (I.config2(S=1000), 64)), "c4": (lambda: (I.config4(S=2000), 8))}[name]()
+        solver = GuroSolver(inst)
+        paths = I.random_paths(solver, K, 31, 0.1)
+        L.sgufp_debug_k1_stats(out)
+        solver.solve_paths(np.asarray(paths, dtype=np.int16))
+        L.sgufp_debug_k1_stats(out)
+        ev = max(1, out[3])
+        print(f"{name}: evals {out[3]}  passes/eval {out[0] / ev:.1f}  label computations/eval {out[1] / ev:.1f}  searches/eval {out[2] / ev:.1f}  ms {solver.last_kernel_ms():.3f}")
+
+
+if __name__ == "__main__":
+    main()
