@@ -42,6 +42,9 @@ constexpr int LAB_BIAS = 1 << 19;      // lane variant: |distance| < 2^18 (check
 constexpr int LAB_INF = 0x3fffffff;    // "unreached"; label + increment never overflows an int
 constexpr int NEG_INF = INT_MIN / 4;
 constexpr int WARPS = 8;               // warps per CTA
+#ifndef SGUFP_K1_MINBLOCKS
+#define SGUFP_K1_MINBLOCKS 4            // resident CTAs per SM the register allocation aims at (64 registers per thread)
+#endif
 
 struct PlanView {
     const PlanHeader *h;
@@ -60,7 +63,7 @@ struct PlanView {
     }
 };
 
-// the static half of an open chain, unpacked
+// the static half of an open chain, unpacked (model.hpp)
 struct ChainEnds {
     int sv, ev, hf, hb, r;
     __device__ __forceinline__ explicit ChainEnds(const int2 st) {
@@ -68,14 +71,23 @@ struct ChainEnds {
     }
 };
 
-struct TileMem {  // this tile's slice of shared memory
-    int *up, *lo, *x, *res, *lab, *pred, *pot, *exc, *aq;
-    unsigned *rw;                         // reached set (+ a scratch row for the list search)
-    int *tc;                              // larger graphs: the tight-chain list
-    unsigned *tin, *tout, *hist;          // small graphs: bit sets of the tight residual graph, search levels
-    int *path;
-    unsigned short *tab;
+// This tile's slice of shared memory, as word OFFSETS into the CTA's buffer: indexing the
+// __shared__ symbol directly keeps every access a plain LDS/STS/ATOMS with a register + immediate
+// address (pointers kept in a struct are generic and cost an address computation per use).
+struct TileMem {
+    int tin, tout, hist, path, tab;       // small graphs: bit sets of the tight residual graph, search levels, path, pair table
+    int tc;                               // larger graphs: the tight-chain list (same place)
+    int rw;                               // reached set (+ a scratch row for the list search)
+    int up, lo, x, res, lab, pred, pot, exc, aq;
 };
+#ifdef SGUFP_K1_EMULATE
+#define k1_smem sgufp_emul_smem           // tests/cpp/k1_emul.cpp: the kernel body compiled for the host
+#else
+extern __shared__ int k1_smem[];
+#endif
+#define SI(off) (k1_smem[off])
+#define SU(off) (reinterpret_cast<unsigned *>(k1_smem)[off])
+#define SH(off) (reinterpret_cast<unsigned short *>(k1_smem)[off])
 
 __host__ __device__ inline int reach_words(int nc) { return (nc + 1 + 31) >> 5; }   // bit sets over the label indices 0..nc
 
@@ -128,24 +140,24 @@ __device__ __forceinline__ int lab_dist(int lab) { return (lab >> HB) - LAB_BIAS
 template <int TILE, bool MERGED, bool WARM>
 __device__ void shortest_paths(int src, const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TileMem &w, int &fuel) {
     for (int v = T.tl; v <= nc; v += TILE)
-        if (!WARM || !((w.rw[v >> 5] >> (v & 31)) & 1)) w.lab[v] = LAB_INF;
+        if (!WARM || !((SU(w.rw + (v >> 5)) >> (v & 31)) & 1)) SI(w.lab + v) = LAB_INF;
     T.sync();
-    if (!WARM && T.tl == 0) w.lab[src] = 0;
+    if (!WARM && T.tl == 0) SI(w.lab + src) = 0;
     T.sync();
     bool changed;
     do {
         changed = false;
         for (int c = T.tl; c < nopen; c += TILE) {
-            const int f = w.res[c];                // bit 0 forward residual, bit 1 backward residual
+            const int f = SI(w.res + c);                // bit 0 forward residual, bit 1 backward residual
             const ChainEnds e(P.ch_st[c]);
-            const int ls = w.lab[e.sv], le = w.lab[e.ev];
+            const int ls = SI(w.lab + e.sv), le = SI(w.lab + e.ev);
             if ((f & 1) && ls != LAB_INF && !(MERGED && e.hf == nc)) {
                 const int cand = ls - e.r;
-                if (cand < w.lab[e.hf]) { atomicMin(&w.lab[e.hf], cand); changed = true; }
+                if (cand < SI(w.lab + e.hf)) { atomicMin(&SI(w.lab + e.hf), cand); changed = true; }
             }
             if ((f & 2) && le != LAB_INF && !(MERGED && e.hb == nc)) {
                 const int cand = le + e.r;
-                if (cand < w.lab[e.hb]) { atomicMin(&w.lab[e.hb], cand); changed = true; }
+                if (cand < SI(w.lab + e.hb)) { atomicMin(&SI(w.lab + e.hb), cand); changed = true; }
             }
         }
         T.sync();
@@ -174,36 +186,36 @@ __device__ void shortest_paths(int src, const PlanView &P, int nopen, int nc, co
 
 template <int TILE>
 __device__ void tight_small(const PlanView &P, int nopen, const Lanes<TILE> &T, TileMem &w) {
-    for (int i = T.tl; i < 64; i += TILE) w.tin[i] = 0u;    // tin[32] and tout[32] are adjacent
+    for (int i = T.tl; i < 64; i += TILE) SU(w.tin + i) = 0u;    // tin[32] and tout[32] are adjacent
     T.sync();
     for (int c = T.tl; c < nopen; c += TILE) {
         const ChainEnds e(P.ch_st[c]);
-        const int ls = w.lab[e.sv], le = w.lab[e.ev], f = w.res[c] & 3;
+        const int ls = SI(w.lab + e.sv), le = SI(w.lab + e.ev), f = SI(w.res + c) & 3;
         int tf = 0;
-        if (ls != LAB_INF && ls - e.r == w.lab[e.hf]) tf |= 1;
-        if (le != LAB_INF && le + e.r == w.lab[e.hb]) tf |= 2;
-        w.res[c] = f | (tf << 2);
-        if (f & tf & 1) { atomicOr(&w.tin[e.hf], 1u << e.sv); atomicOr(&w.tout[e.sv], 1u << e.hf); w.tab[e.hf * 32 + e.sv] = (unsigned short)(2 * c); }
-        if (f & tf & 2) { atomicOr(&w.tin[e.hb], 1u << e.ev); atomicOr(&w.tout[e.ev], 1u << e.hb); w.tab[e.hb * 32 + e.ev] = (unsigned short)(2 * c + 1); }
+        if (ls != LAB_INF && ls - e.r == SI(w.lab + e.hf)) tf |= 1;
+        if (le != LAB_INF && le + e.r == SI(w.lab + e.hb)) tf |= 2;
+        SI(w.res + c) = f | (tf << 2);
+        if (f & tf & 1) { atomicOr(&SU(w.tin + e.hf), 1u << e.sv); atomicOr(&SU(w.tout + e.sv), 1u << e.hf); SH(2 * w.tab + e.hf * 32 + e.sv) = (unsigned short)(2 * c); }
+        if (f & tf & 2) { atomicOr(&SU(w.tin + e.hb), 1u << e.ev); atomicOr(&SU(w.tout + e.ev), 1u << e.hb); SH(2 * w.tab + e.hb * 32 + e.ev) = (unsigned short)(2 * c + 1); }
     }
     T.sync();
 }
 
 // Breadth-first search src -> dst; hist[l] = the nodes first reached at level l.  Returns the level
-// of dst, or 0 if it cannot be reached — then w.rw[0] holds the complete reached set.
+// of dst, or 0 if it cannot be reached — then SU(w.rw + 0) holds the complete reached set.
 template <int TILE>
 __device__ int reach_small(int src, int dst, int nc, const Lanes<TILE> &T, TileMem &w) {
     unsigned R = 1u << src, F = R;
     int lev = 0;
-    if (T.tl == 0) w.hist[0] = F;
+    if (T.tl == 0) SU(w.hist + 0) = F;
     for (;;) {
         unsigned nb = 0;
         for (int u = T.tl; u <= nc; u += TILE)
-            if ((F >> u) & 1) nb |= w.tout[u];
+            if ((F >> u) & 1) nb |= SU(w.tout + u);
         nb = T.reduce_or(nb) & ~R;
-        if (!nb) { if (T.tl == 0) w.rw[0] = R; T.sync(); return 0; }
+        if (!nb) { if (T.tl == 0) SU(w.rw + 0) = R; T.sync(); return 0; }
         R |= nb; F = nb; lev++;
-        if (T.tl == 0) w.hist[lev] = F;
+        if (T.tl == 0) SU(w.hist + lev) = F;
         if ((R >> dst) & 1) { T.sync(); return lev; }
     }
 }
@@ -214,26 +226,26 @@ template <int TILE>
 __device__ int push_small(int dst, int limit, int lev, int nc, const Lanes<TILE> &T, TileMem &w) {
     int v = dst, d = limit, h = 0;
     for (int l = lev; l > 0; l--, h++) {
-        const unsigned m = w.tin[v] & w.hist[l - 1];
+        const unsigned m = SU(w.tin + v) & SU(w.hist + l - 1);
         if (!m) { d = 0; break; }              // cannot happen: v was reached from level l-1
-        const int u = __ffs(m) - 1, s = w.tab[v * 32 + u], c = s >> 1, xc = w.x[c];
-        d = min(d, (s & 1) ? xc - (w.lo[c] >> HB) : (w.up[c] >> HB) - xc);
-        if (T.tl == 0) w.path[h] = s | (u << 16) | (v << 21);
+        const int u = __ffs(m) - 1, s = SH(2 * w.tab + v * 32 + u), c = s >> 1, xc = SI(w.x + c);
+        d = min(d, (s & 1) ? xc - (SI(w.lo + c) >> HB) : (SI(w.up + c) >> HB) - xc);
+        if (T.tl == 0) SI(w.path + h) = s | (u << 16) | (v << 21);
         v = u;
     }
     T.sync();
     if (d <= 0) return 0;
     for (int i = T.tl; i < h; i += TILE) {
-        const int rec = w.path[i], s = rec & 0xffff, u = (rec >> 16) & 31, vv = (rec >> 21) & 31, c = s >> 1, dir = s & 1;
-        const int xc = w.x[c] + (dir ? -d : d);
-        w.x[c] = xc;
-        const int nf = (xc < (w.up[c] >> HB) ? 1 : 0) | (xc > (w.lo[c] >> HB) ? 2 : 0) | (w.res[c] & 12);
-        w.res[c] = nf;
-        if (!((nf >> dir) & 1)) { atomicAnd(&w.tin[vv], ~(1u << u)); atomicAnd(&w.tout[u], ~(1u << vv)); }   // saturated
+        const int rec = SI(w.path + i), s = rec & 0xffff, u = (rec >> 16) & 31, vv = (rec >> 21) & 31, c = s >> 1, dir = s & 1;
+        const int xc = SI(w.x + c) + (dir ? -d : d);
+        SI(w.x + c) = xc;
+        const int nf = (xc < (SI(w.up + c) >> HB) ? 1 : 0) | (xc > (SI(w.lo + c) >> HB) ? 2 : 0) | (SI(w.res + c) & 12);
+        SI(w.res + c) = nf;
+        if (!((nf >> dir) & 1)) { atomicAnd(&SU(w.tin + vv), ~(1u << u)); atomicAnd(&SU(w.tout + u), ~(1u << vv)); }   // saturated
         if ((nf >> (2 + (dir ^ 1))) & 1) {     // the reverse arc has residual capacity now and is tight
             const int rt = vv == nc ? 0 : vv, rh = u == 0 ? nc : u;
-            atomicOr(&w.tin[rh], 1u << rt); atomicOr(&w.tout[rt], 1u << rh);
-            w.tab[rh * 32 + rt] = (unsigned short)(s ^ 1);
+            atomicOr(&SU(w.tin + rh), 1u << rt); atomicOr(&SU(w.tout + rt), 1u << rh);
+            SH(2 * w.tab + rh * 32 + rt) = (unsigned short)(s ^ 1);
         }
     }
     T.sync();
@@ -249,12 +261,12 @@ __device__ int tight_list(const PlanView &P, int nopen, const Lanes<TILE> &T, Ti
         int tf = 0;
         if (c < nopen) {
             const ChainEnds e(P.ch_st[c]);
-            const int ls = w.lab[e.sv], le = w.lab[e.ev];
-            if (ls != LAB_INF && ls - e.r == w.lab[e.hf]) tf |= 1;
-            if (le != LAB_INF && le + e.r == w.lab[e.hb]) tf |= 2;
+            const int ls = SI(w.lab + e.sv), le = SI(w.lab + e.ev);
+            if (ls != LAB_INF && ls - e.r == SI(w.lab + e.hf)) tf |= 1;
+            if (le != LAB_INF && le + e.r == SI(w.lab + e.hb)) tf |= 2;
         }
         const unsigned b = T.ballot(tf != 0);
-        if (tf) w.tc[n + __popc(b & T.lt)] = c | (tf << 16);
+        if (tf) SI(w.tc + n + __popc(b & T.lt)) = c | (tf << 16);
         n += __popc(b);
     }
     T.sync();
@@ -266,27 +278,27 @@ __device__ int tight_list(const PlanView &P, int nopen, const Lanes<TILE> &T, Ti
 // If dst is not reached, w.rw holds the complete reached set.
 template <int TILE>
 __device__ bool reach_list(int src, int dst, const PlanView &P, int ntc, int nword, const Lanes<TILE> &T, TileMem &w) {
-    unsigned *R = w.rw, *N = w.rw + nword;
-    for (int i = T.tl; i < nword; i += TILE) { R[i] = i == (src >> 5) ? 1u << (src & 31) : 0u; N[i] = 0u; }
+    const int R = w.rw, N = w.rw + nword;   // offsets of the reached set and of this level's joiners
+    for (int i = T.tl; i < nword; i += TILE) { SU(R + (i)) = i == (src >> 5) ? 1u << (src & 31) : 0u; SU(N + (i)) = 0u; }
     T.sync();
     for (;;) {
         for (int i = T.tl; i < ntc; i += TILE) {
-            const int en = w.tc[i], c = en & 0xffff, f = w.res[c] & (en >> 16);
+            const int en = SI(w.tc + i), c = en & 0xffff, f = SI(w.res + c) & (en >> 16);
             if (f) {
                 const ChainEnds e(P.ch_st[c]);
-                if ((f & 1) && ((R[e.sv >> 5] >> (e.sv & 31)) & 1) && !((R[e.hf >> 5] >> (e.hf & 31)) & 1)) {
-                    atomicOr(&N[e.hf >> 5], 1u << (e.hf & 31)); w.pred[e.hf] = e.sv | ((2 * c) << 10);
+                if ((f & 1) && ((SU(R + (e.sv >> 5)) >> (e.sv & 31)) & 1) && !((SU(R + (e.hf >> 5)) >> (e.hf & 31)) & 1)) {
+                    atomicOr(&SU(N + (e.hf >> 5)), 1u << (e.hf & 31)); SI(w.pred + e.hf) = e.sv | ((2 * c) << 10);
                 }
-                if ((f & 2) && ((R[e.ev >> 5] >> (e.ev & 31)) & 1) && !((R[e.hb >> 5] >> (e.hb & 31)) & 1)) {
-                    atomicOr(&N[e.hb >> 5], 1u << (e.hb & 31)); w.pred[e.hb] = e.ev | ((2 * c + 1) << 10);
+                if ((f & 2) && ((SU(R + (e.ev >> 5)) >> (e.ev & 31)) & 1) && !((SU(R + (e.hb >> 5)) >> (e.hb & 31)) & 1)) {
+                    atomicOr(&SU(N + (e.hb >> 5)), 1u << (e.hb & 31)); SI(w.pred + e.hb) = e.ev | ((2 * c + 1) << 10);
                 }
             }
         }
         T.sync();
         bool grew = false;
-        for (int i = T.tl; i < nword; i += TILE) { const unsigned nb = N[i]; if (nb) { R[i] |= nb; N[i] = 0u; grew = true; } }
+        for (int i = T.tl; i < nword; i += TILE) { const unsigned nb = SU(N + (i)); if (nb) { SU(R + (i)) |= nb; SU(N + (i)) = 0u; grew = true; } }
         T.sync();
-        if ((R[dst >> 5] >> (dst & 31)) & 1) return true;
+        if ((SU(R + (dst >> 5)) >> (dst & 31)) & 1) return true;
         if (!T.any(grew)) return false;
     }
 }
@@ -296,8 +308,8 @@ template <int TILE>
 __device__ int push_list(int src, int dst, int limit, int nc, const Lanes<TILE> &T, TileMem &w) {
     int v = dst, d = limit, hops = 0;
     while (v != src) {
-        const int p = w.pred[v], s = p >> 10, c = s >> 1, xc = w.x[c];
-        d = min(d, (s & 1) ? xc - (w.lo[c] >> HB) : (w.up[c] >> HB) - xc);
+        const int p = SI(w.pred + v), s = p >> 10, c = s >> 1, xc = SI(w.x + c);
+        d = min(d, (s & 1) ? xc - (SI(w.lo + c) >> HB) : (SI(w.up + c) >> HB) - xc);
         v = p & 1023;
         if (++hops > nc + 1) { d = 0; break; }
     }
@@ -305,11 +317,11 @@ __device__ int push_list(int src, int dst, int limit, int nc, const Lanes<TILE> 
     if (d <= 0) return 0;
     v = dst;
     while (v != src) {
-        const int p = w.pred[v], s = p >> 10, c = s >> 1;
+        const int p = SI(w.pred + v), s = p >> 10, c = s >> 1;
         if (T.tl == 0) {
-            const int xc = w.x[c] + ((s & 1) ? -d : d);
-            w.x[c] = xc;
-            w.res[c] = (xc < (w.up[c] >> HB) ? 1 : 0) | (xc > (w.lo[c] >> HB) ? 2 : 0);
+            const int xc = SI(w.x + c) + ((s & 1) ? -d : d);
+            SI(w.x + c) = xc;
+            SI(w.res + c) = (xc < (SI(w.up + c) >> HB) ? 1 : 0) | (xc > (SI(w.lo + c) >> HB) ? 2 : 0);
         }
         v = p & 1023;
     }
@@ -345,46 +357,46 @@ struct TightPaths {
 // paths.  Returns false if some forced flow cannot be routed (scenario infeasible).
 template <int TILE>
 __device__ bool route_lower_bounds(const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TileMem &w, TightPaths<TILE> &TP, int &fuel) {
-    for (int v = T.tl; v <= nc; v += TILE) w.exc[v] = 0;
+    for (int v = T.tl; v <= nc; v += TILE) SI(w.exc + v) = 0;
     T.sync();
     for (int c = T.tl; c < nopen; c += TILE) {
-        const int lo = w.lo[c] >> HB;
+        const int lo = SI(w.lo + c) >> HB;
         if (lo > 0) {
             const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1;
-            if (ev > 0) atomicAdd(&w.exc[ev], lo);
-            if (sv > 0) atomicSub(&w.exc[sv], lo);
+            if (ev > 0) atomicAdd(&SI(w.exc + ev), lo);
+            if (sv > 0) atomicSub(&SI(w.exc + sv), lo);
         }
     }
     T.sync();
     for (int v = 1; v < nc; v++) {
-        while (w.exc[v] > 0 && --fuel > 0) {
+        while (SI(w.exc + v) > 0 && --fuel > 0) {
             shortest_paths<TILE, false, false>(v, P, nopen, nc, T, w, fuel);
             unsigned long long best = ~0ull;   // nearest of: the root, a node with a deficit
             for (int t = T.tl; t <= nc; t += TILE)
-                if ((t == nc || (t > 0 && w.exc[t] < 0)) && w.lab[t] != LAB_INF) {
-                    const unsigned long long key = ((unsigned long long)(unsigned)(w.lab[t] - NEG_INF) << 32) | (unsigned)t;
+                if ((t == nc || (t > 0 && SI(w.exc + t) < 0)) && SI(w.lab + t) != LAB_INF) {
+                    const unsigned long long key = ((unsigned long long)(unsigned)(SI(w.lab + t) - NEG_INF) << 32) | (unsigned)t;
                     best = key < best ? key : best;
                 }
             best = T.min_u64(best);
             if (best == ~0ull) return false;
             const int t = (int)(best & 0xffffffffu);
-            int lim = w.exc[v];
-            if (t != nc) lim = min(lim, -w.exc[t]);
+            int lim = SI(w.exc + v);
+            if (t != nc) lim = min(lim, -SI(w.exc + t));
             TP.prepare();
             const int d = TP.augment(v, t, lim);
             if (d <= 0) return false;
-            if (T.tl == 0) { w.exc[v] -= d; if (t != nc) w.exc[t] += d; }
+            if (T.tl == 0) { SI(w.exc + v) -= d; if (t != nc) SI(w.exc + t) += d; }
             T.sync();
         }
     }
     for (int v = 1; v < nc; v++) {
-        while (w.exc[v] < 0 && --fuel > 0) {
+        while (SI(w.exc + v) < 0 && --fuel > 0) {
             shortest_paths<TILE, false, false>(0, P, nopen, nc, T, w, fuel);
-            if (w.lab[v] == LAB_INF) return false;
+            if (SI(w.lab + v) == LAB_INF) return false;
             TP.prepare();
-            const int d = TP.augment(0, v, -w.exc[v]);
+            const int d = TP.augment(0, v, -SI(w.exc + v));
             if (d <= 0) return false;
-            if (T.tl == 0) w.exc[v] += d;
+            if (T.tl == 0) SI(w.exc + v) += d;
             T.sync();
         }
     }
@@ -399,8 +411,8 @@ __device__ void canonical_potentials(const PlanView &P, int nopen, int nc, const
     shortest_paths<TILE, true, false>(0, P, nopen, nc, T, w, fuel);
     bool missing = false;
     for (int v = T.tl; v < nc; v += TILE) {
-        const int l = w.lab[v];
-        if (l == LAB_INF) { missing = true; w.pot[v] = NEG_INF; w.pred[v] = 0; } else { w.pot[v] = l; w.pred[v] = 1; }
+        const int l = SI(w.lab + v);
+        if (l == LAB_INF) { missing = true; SI(w.pot + v) = NEG_INF; SI(w.pred + v) = 0; } else { SI(w.pot + v) = l; SI(w.pred + v) = 1; }
     }
     T.sync();
     if (T.any(missing)) {
@@ -410,32 +422,32 @@ __device__ void canonical_potentials(const PlanView &P, int nopen, int nc, const
             changed = false;
             for (int c = T.tl; c < nopen; c += TILE) {
                 const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1, r = P.ch_r[c];
-                const int xc = w.x[c], up = w.up[c] >> HB, lo = w.lo[c] >> HB;
-                if (xc < up && w.pred[sv] == 0) { const int db = w.pot[ev]; if (db > NEG_INF && db + r > atomicMax(&w.pot[sv], db + r)) changed = true; }
-                if (xc > lo && w.pred[ev] == 0) { const int da = w.pot[sv]; if (da > NEG_INF && da - r > atomicMax(&w.pot[ev], da - r)) changed = true; }
+                const int xc = SI(w.x + c), up = SI(w.up + c) >> HB, lo = SI(w.lo + c) >> HB;
+                if (xc < up && SI(w.pred + sv) == 0) { const int db = SI(w.pot + ev); if (db > NEG_INF && db + r > atomicMax(&SI(w.pot + sv), db + r)) changed = true; }
+                if (xc > lo && SI(w.pred + ev) == 0) { const int da = SI(w.pot + sv); if (da > NEG_INF && da - r > atomicMax(&SI(w.pot + ev), da - r)) changed = true; }
             }
             T.sync();
             changed = T.any(changed) && --fuel > 0;
         } while (changed);
         bool iso = false;
         for (int v = T.tl; v < nc; v += TILE)
-            if (w.pot[v] == NEG_INF) { w.pot[v] = 0; w.pred[v] = 2; iso = true; }
+            if (SI(w.pot + v) == NEG_INF) { SI(w.pot + v) = 0; SI(w.pred + v) = 2; iso = true; }
         T.sync();
         if (T.any(iso)) {
             do {
                 changed = false;
                 for (int c = T.tl; c < nopen; c += TILE) {
                     const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1, r = P.ch_r[c];
-                    const int xc = w.x[c], up = w.up[c] >> HB, lo = w.lo[c] >> HB;
-                    if (xc < up && w.pred[ev] == 2) { const int cand = w.pot[sv] - r; if (cand < atomicMin(&w.pot[ev], cand)) changed = true; }
-                    if (xc > lo && w.pred[sv] == 2) { const int cand = w.pot[ev] + r; if (cand < atomicMin(&w.pot[sv], cand)) changed = true; }
+                    const int xc = SI(w.x + c), up = SI(w.up + c) >> HB, lo = SI(w.lo + c) >> HB;
+                    if (xc < up && SI(w.pred + ev) == 2) { const int cand = SI(w.pot + sv) - r; if (cand < atomicMin(&SI(w.pot + ev), cand)) changed = true; }
+                    if (xc > lo && SI(w.pred + sv) == 2) { const int cand = SI(w.pot + ev) + r; if (cand < atomicMin(&SI(w.pot + sv), cand)) changed = true; }
                 }
                 T.sync();
                 changed = T.any(changed) && --fuel > 0;
             } while (changed);
         }
     }
-    for (int v = T.tl; v < nc; v += TILE) w.pot[v] = -w.pot[v];
+    for (int v = T.tl; v < nc; v += TILE) SI(w.pot + v) = -SI(w.pot + v);
     T.sync();
 }
 
@@ -444,28 +456,26 @@ __device__ __forceinline__ int head_potential(int a, const PlanView &P, int nope
     const int cp = P.arc_cp[a], c = cp >> 10, pos = cp & 1023, pre = P.arc_pre[a];
     const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1;
     if (c < nopen) {
-        const int r = P.ch_r[c], dp = w.pot[ev] - w.pot[sv];
+        const int r = P.ch_r[c], dp = SI(w.pot + ev) - SI(w.pot + sv);
         const int g = max(0, r - dp), b = max(0, dp - r);
-        return w.pot[sv] + pre - (pos >= (w.up[c] & 1023) ? g : 0) + (pos >= (w.lo[c] & 1023) ? b : 0);
+        return SI(w.pot + sv) + pre - (pos >= (SI(w.up + c) & 1023) ? g : 0) + (pos >= (SI(w.lo + c) & 1023) ? b : 0);
     }
-    if (sv >= 0) return w.pot[sv] + pre;
-    if (ev >= 0) return w.pot[ev] - (P.ch_r[c] - pre);
+    if (sv >= 0) return SI(w.pot + sv) + pre;
+    if (ev >= 0) return SI(w.pot + ev) - (P.ch_r[c] - pre);
     return pre;
 }
 
 template <int TILE, int NW>
-__global__ void __launch_bounds__(NW * 32, NW == 8 ? 4 : NW == 4 ? 8 : 1) k1_cut_eval(K1Launch p, int words_per_tile) {
-#ifdef SGUFP_K1_EMULATE
-    int *smem = sgufp_emul_smem;   // tests/cpp/k1_emul.cpp: the kernel body compiled for the host, TILE = 1
-#else
-    extern __shared__ int smem[];
-#endif
+__global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 4 ? 2 * SGUFP_K1_MINBLOCKS : 1) k1_cut_eval(K1Launch p, int words_per_tile) {
     const Lanes<TILE> T;
     constexpr int TILES_PER_CTA = NW * 32 / TILE;
     const int tile_in_cta = threadIdx.x / TILE;
     TileMem w;
     {
-        int *base = smem + (size_t)tile_in_cta * words_per_tile;
+        int base = tile_in_cta * words_per_tile;   // the fixed-size arrays first: constant offsets from the tile base
+        w.tin = base; w.tout = base + 32; w.hist = base + 64; w.path = base + 98; w.tab = base + 132;
+        w.tc = base; base += k1_search_words(p.nc, p.max_nopen);
+        w.rw = base; base += 2 * reach_words(p.nc);
         w.up = base; base += p.max_nch;
         w.lo = base; base += p.max_nch;
         w.x = base; base += p.max_nopen;
@@ -474,11 +484,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 4 : NW == 4 ? 8 : 1) k1_cut
         w.pred = base; base += p.nc + 2;
         w.pot = base; base += p.nc + 2;
         w.exc = base; base += p.nc + 2;
-        w.aq = base; base += p.nav + 2;
-        w.rw = reinterpret_cast<unsigned *>(base); base += 2 * reach_words(p.nc);
-        w.tc = base;                               // one of the two layouts, by the size of the contracted graph
-        w.tin = reinterpret_cast<unsigned *>(base); w.tout = w.tin + 32; w.hist = w.tout + 32;
-        w.path = base + 98; w.tab = reinterpret_cast<unsigned short *>(base + 132);
+        w.aq = base;
     }
     const long long items = (long long)p.K * p.S;
     const long long stride = (long long)gridDim.x * TILES_PER_CTA;
@@ -492,7 +498,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 4 : NW == 4 ? 8 : 1) k1_cut
         const double *row_u = p.cap_u + (size_t)s * p.m_pad, *row_l = p.cap_l + (size_t)s * p.m_pad;
 
         // 1. chain capacities
-        for (int c = T.tl; c < nch; c += TILE) { w.up[c] = INT_MAX; w.lo[c] = 0; }
+        for (int c = T.tl; c < nch; c += TILE) { SI(w.up + c) = INT_MAX; SI(w.lo + c) = 0; }
         T.sync();
         {
             const double2 *ru = reinterpret_cast<const double2 *>(row_u), *rl = reinterpret_cast<const double2 *>(row_l);
@@ -501,24 +507,24 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 4 : NW == 4 ? 8 : 1) k1_cut
                 const int a = 2 * a2;
                 {
                     const int cp = P.arc_cp[a], c = cp >> 10, pos = cp & 1023;
-                    atomicMin(&w.up[c], ((int)u2.x << HB) | pos);
-                    atomicMax(&w.lo[c], ((int)l2.x << HB) | pos);
+                    atomicMin(&SI(w.up + c), ((int)u2.x << HB) | pos);
+                    atomicMax(&SI(w.lo + c), ((int)l2.x << HB) | pos);
                 }
                 if (a + 1 < m) {
                     const int cp = P.arc_cp[a + 1], c = cp >> 10, pos = cp & 1023;
-                    atomicMin(&w.up[c], ((int)u2.y << HB) | pos);
-                    atomicMax(&w.lo[c], ((int)l2.y << HB) | pos);
+                    atomicMin(&SI(w.up + c), ((int)u2.y << HB) | pos);
+                    atomicMax(&SI(w.lo + c), ((int)l2.y << HB) | pos);
                 }
             }
         }
         T.sync();
         bool bad = false, forced = false;
         for (int c = T.tl; c < nch; c += TILE) {
-            const int lo = w.lo[c] >> HB;
+            const int lo = SI(w.lo + c) >> HB;
             if (c < nopen) {
-                const int up = w.up[c] >> HB;
-                w.x[c] = lo; bad |= lo > up; forced |= lo > 0;
-                w.res[c] = lo < up ? 1 : 0;          // x == lo: forward residual only
+                const int up = SI(w.up + c) >> HB;
+                SI(w.x + c) = lo; bad |= lo > up; forced |= lo > 0;
+                SI(w.res + c) = lo < up ? 1 : 0;          // x == lo: forward residual only
             } else bad |= lo > 0;
         }
         T.sync();
@@ -544,7 +550,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 4 : NW == 4 ? 8 : 1) k1_cut
         for (bool warm = false; fuel > 0; warm = true) {
             if (warm) shortest_paths<TILE, false, true>(0, P, nopen, nc, T, w, fuel);
             else shortest_paths<TILE, false, false>(0, P, nopen, nc, T, w, fuel);
-            const int lt = w.lab[nc];
+            const int lt = SI(w.lab + nc);
             if (lt == LAB_INF || lt >= 0) break;
             TP.prepare();
             while (--fuel > 0 && TP.augment(0, nc, INT_MAX) > 0) {}   // until the search fails: it leaves the reached set for the warm start
@@ -560,11 +566,11 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 4 : NW == 4 ? 8 : 1) k1_cut
         long long rhs = 0, objv = 0;
         for (int c = T.tl; c < nopen; c += TILE) {
             const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1, r = P.ch_r[c];
-            const int dp = w.pot[ev] - w.pot[sv];
-            const int g = r - dp, up = w.up[c] >> HB, lo = w.lo[c] >> HB;
-            objv += (long long)r * w.x[c];
+            const int dp = SI(w.pot + ev) - SI(w.pot + sv);
+            const int g = r - dp, up = SI(w.up + c) >> HB, lo = SI(w.lo + c) >> HB;
+            objv += (long long)r * SI(w.x + c);
             if (g > 0) {
-                const int a = P.ch_arcs[P.ch_ptr[c] + (w.up[c] & 1023)];
+                const int a = P.ch_arcs[P.ch_ptr[c] + (SI(w.up + c) & 1023)];
                 const int info = P.arc_info[a];
                 const long long v = (long long)up * g;
                 if ((info & 3) == KIND_GAMMA) rhs += v; else atomicAdd(sums + 1 + p.L + a, (unsigned long long)v);
@@ -594,11 +600,11 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 4 : NW == 4 ? 8 : 1) k1_cut
                 bool found = false;
                 for (int t = P.fb_ptr[i]; t < P.fb_ptr[i + 1]; t++) {
                     const int c = P.fb_ch[t], ev = (P.ch_ends[c] >> 16) - 1;
-                    const int cand = w.pot[ev] - P.ch_r[c];
+                    const int cand = SI(w.pot + ev) - P.ch_r[c];
                     if (!found || cand < alpha) { alpha = cand; found = true; }
                 }
             }
-            w.aq[i] = alpha;
+            SI(w.aq + i) = alpha;
         }
         T.sync();
         for (int c = nopen + T.tl; c < nch; c += TILE) {
@@ -607,23 +613,23 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 4 : NW == 4 ? 8 : 1) k1_cut
             const int q = P.ch_q[c], qs = (q & 0xffff) - 1, qe = (q >> 16) - 1;
             const int rfirst = P.arc_pre[first];
             if (qs >= 0 && qe >= 0 && b1 - b0 == 1) {
-                const int v = rfirst - (w.aq[qe] - w.aq[qs]);
+                const int v = rfirst - (SI(w.aq + qe) - SI(w.aq + qs));
                 if (v > 0) atomicAdd(sums + 1 + p.L + first, (unsigned long long)((long long)(int)row_u[first] * v));
                 continue;
             }
             if (qs >= 0) {
-                const int phf = ev >= 0 ? w.pot[ev] - (P.ch_r[c] - rfirst) : rfirst;
-                const int v = rfirst - (phf - w.aq[qs]);
+                const int phf = ev >= 0 ? SI(w.pot + ev) - (P.ch_r[c] - rfirst) : rfirst;
+                const int v = rfirst - (phf - SI(w.aq + qs));
                 if (v > 0) atomicAdd(sums + 1 + p.L + first, (unsigned long long)((long long)(int)row_u[first] * v));
             }
             if (qe >= 0) {
                 int pt, rlast;
                 if (b1 - b0 > 1) {
                     const int prev = P.ch_arcs[b1 - 2];
-                    pt = (sv >= 0 ? w.pot[sv] : 0) + P.arc_pre[prev];
+                    pt = (sv >= 0 ? SI(w.pot + sv) : 0) + P.arc_pre[prev];
                     rlast = P.ch_r[c] - P.arc_pre[prev];
-                } else { pt = w.pot[sv]; rlast = P.ch_r[c]; }
-                const int v = rlast - (w.aq[qe] - pt);
+                } else { pt = SI(w.pot + sv); rlast = P.ch_r[c]; }
+                const int v = rlast - (SI(w.aq + qe) - pt);
                 if (v > 0) atomicAdd(sums + 1 + p.L + last, (unsigned long long)((long long)(int)row_u[last] * v));
             }
         }
@@ -1164,13 +1170,13 @@ static cudaError_t launch_lane(const K1Launch &p, cudaStream_t st, int sm_count)
 // which variant: the warp-per-scenario kernel unless SGUFP_K1_MODE=lane asks for the lane-per-scenario
 // one (measured slower on C2 and C4, profiles/r01_k1_variants.md; kept as an independently written
 // second implementation that the parity tests also run)
+bool k1_lane_mode_requested() {
+    const char *e = getenv("SGUFP_K1_MODE");
+    return e && e[0] == 'l';
+}
+
 bool k1_use_lane_variant(const K1Launch &p) {
-    const bool fits = p.max_cap < 65536 && lane_bytes_per_warp(p) <= 200 * 1024;
-    if (const char *e = getenv("SGUFP_K1_MODE")) {
-        if (e[0] == 'l') return fits;
-        if (e[0] == 'w') return false;
-    }
-    return false;
+    return k1_lane_mode_requested() && p.max_cap < 65536 && lane_bytes_per_warp(p) <= 200 * 1024;
 }
 
 cudaError_t k1_launch(const K1Launch &p, cudaStream_t st, int sm_count, int *launches) {

@@ -20,6 +20,9 @@ struct K1Launch {
     int max_cap;                  // largest capacity of the instance (the lane variant keeps 16-bit state)
 };
 
+// whether SGUFP_K1_MODE asks for the lane-per-scenario kernel (its plans carry extra tables)
+bool k1_lane_mode_requested();
+
 // Returns cudaSuccess or the launch error.  *launches is incremented by the kernels launched.
 cudaError_t k1_launch(const K1Launch &p, cudaStream_t st, int sm_count, int *launches);
 

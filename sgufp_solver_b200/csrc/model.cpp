@@ -147,7 +147,7 @@ int Model::build(int n_, int m_, const int32_t *tail_, const int32_t *head_, con
     return 0;
 }
 
-int build_plan(const Model &M, const int16_t *path, int plen, Plan &P, std::string &err) {
+int build_plan(const Model &M, const int16_t *path, int plen, Plan &P, std::string &err, bool lane_tables) {
     const int m = M.m;
     if (!path || plen < 0 || plen > M.L) { err = "path must have at most L entries"; return SGUFP_ERR_ARG; }
     P.match_out.assign(m, -1); P.match_in.assign(m, -1);
@@ -246,8 +246,8 @@ int build_plan(const Model &M, const int16_t *path, int plen, Plan &P, std::stri
     // residual slots of the contracted graph, sorted by head node
     struct Slot { int tail, head, cs, ch; };
     std::vector<Slot> slots;
-    slots.reserve(2 * nopen);
-    for (int c = 0; c < nopen; c++) {
+    slots.reserve(lane_tables ? 2 * nopen : 0);
+    for (int c = 0; lane_tables && c < nopen; c++) {
         const Ch &ch = chains[c];
         slots.push_back({ch.sv, ch.ev == 0 ? M.nc : ch.ev, -ch.r * 1024 + 1, 2 * c});
         slots.push_back({ch.ev, ch.sv == 0 ? M.nc : ch.sv, ch.r * 1024 + 1, 2 * c + 1});
@@ -260,6 +260,8 @@ int build_plan(const Model &M, const int16_t *path, int plen, Plan &P, std::stri
     PlanHeader H{};
     H.nch = nch; H.nopen = nopen; H.nc = M.nc; H.nav = M.nav; H.m = m; H.L = M.L;
     std::vector<int32_t> &W = P.words;
+    W.clear();
+    W.reserve(sizeof(PlanHeader) / 4 + 4 * (size_t)m + 10 * (size_t)nch + 4 * (size_t)M.nav + 3 * (size_t)M.nc + (lane_tables ? 6 * (size_t)nopen + 8 * (size_t)M.nc : 0) + 64);
     W.assign(sizeof(PlanHeader) / 4, 0);
     auto put = [&](const std::vector<int32_t> &v) { int32_t off = (int32_t)W.size(); W.insert(W.end(), v.begin(), v.end()); if (W.size() & 1) W.push_back(0); return off; };
     H.o_arc_cp = put(arc_cp); H.o_arc_info = put(arc_info); H.o_arc_pre = put(arc_pre);

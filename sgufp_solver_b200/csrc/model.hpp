@@ -75,7 +75,8 @@ struct Plan {
 };
 
 // returns 0 / SGUFP_ERR_ARG / SGUFP_ERR_MATCHING / SGUFP_ERR_CYCLIC
-int build_plan(const Model &M, const int16_t *path, int plen, Plan &P, std::string &err);
+// lane_tables: also emit the head-sorted slot tables that only the lane-per-scenario kernel reads
+int build_plan(const Model &M, const int16_t *path, int plen, Plan &P, std::string &err, bool lane_tables = true);
 
 void ray_arrays(const Model &M, const Plan &P, std::vector<int32_t> &ts, std::vector<int32_t> &hs, std::vector<int32_t> &info,
                 std::vector<int32_t> &pair_layer, std::vector<int32_t> &next, std::vector<int32_t> &aq, std::vector<int32_t> &first_wire, int &nn);

@@ -26,7 +26,7 @@ def main():
         build()
         return
     from sgufp_solver_b200 import _lib
-    _lib.LIB_PATH = STATS_LIB
+    _lib.LIB_PATH = os.environ.get("SGUFP_STATS_LIB", STATS_LIB)
     import numpy as np
     from sgufp_solver_b200 import instances as I
     from sgufp_solver_b200.solver import GuroSolver
