@@ -29,6 +29,9 @@ def main():
     ap.add_argument("--C", type=int, default=64)
     ap.add_argument("--reps", type=int, default=7)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--sequential", action="store_true",
+                    help="one diagram, one cut at a time + getSolution after each (the Benders inner loop, NodeExplorer.cpp:949-971): "
+                         "wall time per iteration through the host API, device-side cut application (SURVEY 8f-2)")
     args = ap.parse_args()
     import torch
     from sgufp_solver_b200 import instances as I
@@ -49,6 +52,38 @@ def main():
         except Exception:
             ref_net = None
     points = [("restricted", int(w)) for w in args.widths.split(",")] + [("relaxed", 120)]
+    if args.sequential:
+        for kind, w in points:
+            d = RestrictedDDNew(solver, w) if kind == "restricted" else RelaxedDDNew(solver)
+            d.compile() if kind == "restricted" else d.buildTree()
+            nodes1, arcs1 = d.counts()
+            apply = (lambda c: d.applyOptimalityCut(c)) if kind == "restricted" else (lambda c: d.applyOptimalityCut(c, -1e300, 1e300))
+            sol = d.getMaxPath if kind == "restricted" else d.getSolution
+            for c in cuts[:3]:
+                apply(c); sol()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for c in cuts:
+                apply(c); sol()
+            dt = time.perf_counter() - t0
+            line = {"metric": "dd_sequential_cut_ms", "value": dt / len(cuts) * 1e3, "unit": "ms per (applyOptimalityCut + getSolution)",
+                    "higher_is_better": False, "kind": kind, "width": w, "arcs_per_diagram": arcs1, "nodes_per_diagram": nodes1,
+                    "arcs_per_sec": arcs1 * len(cuts) / dt, "cuts": len(cuts),
+                    "note": "host API wall time; longest path, terminal weights, pruning and path extraction run on the device, "
+                            "only the bound and the path come back"}
+            if ref_net is not None:
+                r = ref_dd.RefRestrictedDD(ref_net, w) if kind == "restricted" else ref_dd.RefRelaxedDD(ref_net)
+                r.compile() if kind == "restricted" else r.build()
+                t0 = time.perf_counter()
+                for c in cuts:
+                    r.apply_opt(c.RHS, c.keys, c.vals) if kind == "restricted" else r.apply_opt(c.RHS, c.keys, c.vals, -1e300, 1e300)
+                    r.solution()
+                dtr = time.perf_counter() - t0
+                line["cpu_reference"] = {"value": dtr / len(cuts) * 1e3, "unit": line["unit"], "cores": 1, "kind": "reference",
+                                         "sample": f"the same {len(cuts)} cuts on the unmodified reference class (oracle/_ref)"}
+            print(json.dumps(line), flush=True)
+            d.close()
+        return
     for kind, w in points:
         dds = []
         for _ in range(args.B):

@@ -36,26 +36,31 @@ int sgufp_dd_is_exact(const sgufp_dd *dd); /* isTreeExact(): 1 / 0 */
  * terminal arcs.  dump: nodes in tree order; per in-arc the POSITION of its tail in the previous
  * layer and its decision, in stored in-arc order (node_inptr has nodes+1 entries). */
 int sgufp_dd_num_layers(const sgufp_dd *dd);
-int sgufp_dd_layer_sizes(const sgufp_dd *dd, int32_t *sizes /*[num_layers]*/);
-int sgufp_dd_counts(const sgufp_dd *dd, int64_t *nodes, int64_t *arcs);
+int sgufp_dd_layer_sizes(sgufp_dd *dd, int32_t *sizes /*[num_layers]*/);
+int sgufp_dd_counts(sgufp_dd *dd, int64_t *nodes, int64_t *arcs);
 int sgufp_dd_dump(sgufp_dd *dd, int32_t *node_layer, double *node_state, int64_t *node_inptr, int32_t *arc_tailpos,
                   int32_t *arc_decision, double *terminal_weight /*[last layer]*/);
 
 /* applyOptimalityCut(cut, optimal, upperbound) -> bound (DD.cpp:3932-4023, 3425-3505) and
  * applyFeasibilityCut(cut) -> feasible (DD.cpp:3842-3930, 3340-3423).  The cut is an Inavap::Cut:
  * RHS + nnz (key,value) pairs.  `optimal`/`upperbound` are ignored by the restricted DD, whose
- * reference signature has none. */
+ * reference signature has none.
+ * The whole call runs on the device: longest path, terminal weights, removal of
+ * last-layer nodes with its bottom-up cascade, bound-based arc pruning of non-exact diagrams.  Only
+ * the bound / the flag come back; removed arcs and nodes are flagged in the device image and the
+ * host mirror replays them when layer_sizes / counts / dump / cutset / the batch call ask for it. */
 int sgufp_dd_apply_optimality(sgufp_dd *dd, double rhs, const uint64_t *keys, const double *vals, int nnz,
                               double optimal, double upperbound, double *bound);
 int sgufp_dd_apply_feasibility(sgufp_dd *dd, double rhs, const uint64_t *keys, const double *vals, int nnz,
                                int *feasible);
 
-/* getSolution() / getMaxPath() (DD.cpp:3825-3840, 3290-3305): returns the path length. */
-int sgufp_dd_solution(const sgufp_dd *dd, int16_t *path, int capacity);
+/* getSolution() / getMaxPath() (DD.cpp:3825-3840, 3290-3305): returns the path length.  After a
+ * single-cut apply the path is extracted on the device; only its L int16 decisions come back. */
+int sgufp_dd_solution(sgufp_dd *dd, int16_t *path, int capacity);
 /* getCutset(ub) (DD.cpp:4179-4218) for the relaxed DD; the cut-set of the last compile for the
  * restricted DD.  Nodes are flattened as (globalLayer, #states, states..., #solution, solution...);
  * returns the number of int32 words written or SGUFP_ERR_ARG if `capacity` is too small. */
-int sgufp_dd_cutset(const sgufp_dd *dd, double ub, int32_t *words, int capacity);
+int sgufp_dd_cutset(sgufp_dd *dd, double ub, int32_t *words, int capacity);
 
 /* Batched K2: apply the same C optimality cuts to B diagrams in ONE launch pair.
  * cut c is rhs[c] + (keys,vals)[cut_ptr[c] .. cut_ptr[c+1]).  For every diagram the terminal arc

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsgufp_b200.so")
+LIB_PATH = os.environ.get("SGUFP_B200_LIB") or os.path.join(_HERE, "libsgufp_b200.so")   # the override is for A/B timing of builds
 _LIB = None
 
 ERR = {0: "OK", -1: "ERR_ARG", -2: "ERR_MATCHING", -3: "ERR_CYCLIC", -4: "ERR_INSTANCE", -5: "ERR_LIMITS", -6: "ERR_CUDA"}

@@ -299,6 +299,46 @@ void HostDD::remove_last_layer_nodes(const std::vector<int32_t> &ids) {
     dirty_ = true; version_++;
 }
 
+void HostDD::absorb_device(const std::vector<double> &states, const std::vector<uint8_t> &arc_dead, const std::vector<uint8_t> &node_dead,
+                           const std::vector<double> &term, const std::vector<double> &coef) {
+    const DDCsr &C = csr_;   // the image the device worked on
+    last_coef_ = coef;
+    for (int v = 0; v < C.nnodes; v++) nodes_[C.node_id[v]].state2 = states[v];
+    for (int e = 0; e < C.narcs; e++)
+        if (C.arc_slot[e] >= 0 || arcs_[C.arc_id[e]].decision != -1) arcs_[C.arc_id[e]].weight = C.arc_slot[e] >= 0 ? coef[C.arc_slot[e]] : 0.0;
+    term_ = term;
+    bool changed = false;
+    std::vector<uint8_t> gone(arcs_.size(), 0), touched(nodes_.size(), 0);
+    for (int e = 0; e < C.narcs; e++)
+        if (arc_dead[e]) { const int a = C.arc_id[e]; gone[a] = 1; touched[arcs_[a].head] = 1; touched[arcs_[a].tail] = 1; changed = true; }
+    if (changed)
+        for (size_t id = 0; id < nodes_.size(); id++)
+            if (touched[id]) {
+                auto dead = [&](int a) { return gone[a] != 0; };
+                auto &in = nodes_[id].in; in.erase(std::remove_if(in.begin(), in.end(), dead), in.end());
+                auto &out = nodes_[id].out; out.erase(std::remove_if(out.begin(), out.end(), dead), out.end());
+            }
+    std::vector<uint8_t> dead_id(nodes_.size(), 0);
+    bool nodes_gone = false;
+    for (int v = 0; v < C.nnodes; v++) if (node_dead[v]) { dead_id[C.node_id[v]] = 1; nodes_gone = true; }
+    if (nodes_gone) {
+        for (size_t l = 0; l < tree_.size(); l++) {
+            const bool is_last = l + 1 == tree_.size();
+            std::vector<int32_t> keep;
+            std::vector<double> keep_term;
+            for (size_t i = 0; i < tree_[l].size(); i++) {
+                const int id = tree_[l][i];
+                if (!dead_id[id]) { keep.push_back(id); if (is_last) keep_term.push_back(term_[i]); }
+                else if (is_last) nodes_[id].out.clear();   // its arc to the terminal
+            }
+            tree_[l].swap(keep);
+            if (is_last) term_.swap(keep_term);
+        }
+        changed = true;
+    }
+    if (changed) { dirty_ = true; version_++; }
+}
+
 int HostDD::finish_feasibility(const std::vector<double> &coef, const std::vector<double> &states) {
     const DDCsr &C = flatten();
     last_coef_ = coef;

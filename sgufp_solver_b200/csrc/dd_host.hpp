@@ -6,8 +6,10 @@
 // The structure (layers, node order, in-arc order, states) is built on the host exactly as the
 // reference builds it; the layer-wise longest path with cut-adjusted arc weights — the hot loop of
 // applyOptimalityCut / applyFeasibilityCut (DD.cpp:3951-3973, 3860-3882, 3454-3470) — runs on the
-// GPU (k2_dd.cu); the sequential cut semantics around it (terminal min over cuts, node removal,
-// bound-based arc pruning, path extraction, cut-sets) stay on the host as SURVEY.md §7.2 prescribes.
+// GPU (k2_dd.cu).  The sequential cut semantics around it (terminal min over cuts, node removal,
+// bound-based arc pruning, path extraction) exist twice: here, for the batch entry point and as the
+// statement of the semantics, and on the device (k2_finish / k2_extract) for the one-cut-at-a-time
+// calls, whose flags absorb_device() replays into this mirror on demand.  Cut-sets stay on the host.
 #pragma once
 #include <cstdint>
 #include <limits>
@@ -74,6 +76,11 @@ public:
     double finish_optimality(const std::vector<double> &coef, const std::vector<double> &states, double optimal, double ub);
     int finish_feasibility(const std::vector<double> &coef, const std::vector<double> &states);
     std::vector<double> &terminal_weights() { return term_; }   // one per node of the last layer, in layer order
+    // Replay what the device did to its image of THIS flatten() (k2_finish): node
+    // states and terminal weights of the last cut, arcs and nodes it removed (flags in CSR order).
+    // The result is the structure finish_optimality / finish_feasibility would have left.
+    void absorb_device(const std::vector<double> &states, const std::vector<uint8_t> &arc_dead, const std::vector<uint8_t> &node_dead,
+                       const std::vector<double> &term, const std::vector<double> &coef);
 
     std::vector<int16_t> solution() const;                       // getSolution / getMaxPath
     std::vector<NodeSpec> cutset(double ub) const;                // RelaxedDDNew::getCutset (DD.cpp:4179-4218)

@@ -16,6 +16,7 @@
 #include "k2_dd.cuh"
 
 #include <cfloat>
+#include <climits>
 
 namespace sgufp {
 namespace {
@@ -39,7 +40,9 @@ __device__ __forceinline__ double block_max(double v, double *red) {
 
 // SMEM_STATES: states ping-pong in shared memory (width <= maxw); otherwise they live in the
 // global scratch block of this (diagram, cut) — `gstate` then has C blocks per diagram.
-template <bool SMEM_STATES>
+// DEADS: the diagram carries flags of arcs removed on the device (single-cut path); a flagged arc
+// contributes nothing, exactly as if it had been erased from the in-arc list.
+template <bool SMEM_STATES, bool DEADS>
 __global__ void __launch_bounds__(K2_THREADS) k2_longest_path(const K2DD *__restrict__ dds, const double *__restrict__ coef,
                                                                const double *__restrict__ rhs, int C, int Tpad, int maxw,
                                                                double *__restrict__ gstate, double *__restrict__ glast) {
@@ -73,6 +76,7 @@ __global__ void __launch_bounds__(K2_THREADS) k2_longest_path(const K2DD *__rest
             const int e1 = d.in_ptr[v0 + 1];
             double s = -DBL_MAX;
             for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+                if (DEADS && d.arc_dead[e]) continue;
                 const int2 ts = d.arc_ts[e];
                 const double p = prev[ts.x];
                 const double cand = ts.y >= 0 ? p + cf[ts.y] : p;
@@ -91,6 +95,7 @@ __global__ void __launch_bounds__(K2_THREADS) k2_longest_path(const K2DD *__rest
                 const double p = prev[ts.x];
                 double s = ts.y >= 0 ? p + cf[ts.y] : p;
                 s = -DBL_MAX < s ? s : -DBL_MAX;   // max(DOUBLE_MIN, .) of DD.cpp:3958
+                if (DEADS && d.arc_dead[e0 + i]) s = -DBL_MAX;
                 cur[i] = s;
                 if (SMEM_STATES && keep_all) all[v0 + i] = s;
                 if (is_last) lastp[i] = s;
@@ -99,6 +104,7 @@ __global__ void __launch_bounds__(K2_THREADS) k2_longest_path(const K2DD *__rest
             for (int i = threadIdx.x; i < width; i += blockDim.x) {
                 double s = -DBL_MAX;
                 for (int e = d.in_ptr[v0 + i]; e < d.in_ptr[v0 + i + 1]; e++) {
+                    if (DEADS && d.arc_dead[e]) continue;
                     const int2 ts = d.arc_ts[e];
                     const double p = prev[ts.x];
                     const double cand = ts.y >= 0 ? p + cf[ts.y] : p;
@@ -131,6 +137,260 @@ __global__ void __launch_bounds__(K2_THREADS) k2_terminal(const K2DD *__restrict
     if (threadIdx.x == 0) bound[blockIdx.x] = best;
 }
 
+
+// ---- single cut on a WIDE diagram: one launch per layer, the layer spread over the whole GPU ------
+// (one CTA per diagram would leave 147 SMs idle: the one-cut-at-a-time calls have no batch to fill
+// the grid with.)  States live in the diagram's global state block; arcs flagged dead are skipped.
+__global__ void __launch_bounds__(K2_THREADS) k2_layer(K2DD d, const double *__restrict__ coef, int l, double *__restrict__ state) {
+    const int4 li = d.layer_info[l];
+    const int v0 = li.x, e0 = li.y, width = li.z, prev0 = d.layer_info[l - 1].x;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= width) return;
+    double s = -DBL_MAX;
+    if (li.w) {
+        const int2 ts = d.arc_ts[e0 + i];
+        if (!d.arc_dead[e0 + i]) {
+            const double p = state[prev0 + ts.x];
+            s = ts.y >= 0 ? p + coef[ts.y] : p;
+            s = -DBL_MAX < s ? s : -DBL_MAX;
+        }
+    } else {
+        for (int e = d.in_ptr[v0 + i]; e < d.in_ptr[v0 + i + 1]; e++) {
+            if (d.arc_dead[e]) continue;
+            const int2 ts = d.arc_ts[e];
+            const double p = state[prev0 + ts.x];
+            const double cand = ts.y >= 0 ? p + coef[ts.y] : p;
+            s = s < cand ? cand : s;
+        }
+    }
+    state[v0 + i] = s;
+}
+
+// a collapsed layer (one node, many in-arcs) of the layered path: one CTA reduces it
+__global__ void __launch_bounds__(K2_THREADS) k2_layer_collapsed(K2DD d, const double *__restrict__ coef, int l, double *__restrict__ state) {
+    __shared__ double red[K2_THREADS / 32];
+    const int4 li = d.layer_info[l];
+    const int v0 = li.x, prev0 = d.layer_info[l - 1].x;
+    double s = -DBL_MAX;
+    for (int e = li.y + threadIdx.x; e < d.in_ptr[v0 + 1]; e += blockDim.x) {
+        if (d.arc_dead[e]) continue;
+        const int2 ts = d.arc_ts[e];
+        const double p = state[prev0 + ts.x];
+        const double cand = ts.y >= 0 ? p + coef[ts.y] : p;
+        s = s < cand ? cand : s;
+    }
+    s = block_max(s, red);
+    if (threadIdx.x == 0) state[v0] = s;
+}
+
+// ---- device-side cut application -----------------------------------------------------------------
+__device__ int block_sum(int v, int *red) {
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int x = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0;
+        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (threadIdx.x == 0) red[0] = x;
+    }
+    __syncthreads();
+    const int r = red[0];
+    __syncthreads();
+    return r;
+}
+
+// Bound-based pruning of the arcs that enter a collapsed (single-node) layer of a non-exact
+// diagram (DD.cpp:3995-4017 with threshold optimal - 0.01, layers 3 .. llayer-2; DD.cpp:3902-3926
+// with threshold -0.01, layers 1 .. llayer-1).  Candidates are flagged 2 and committed only if no
+// layer loses every arc; returns true if one did (the reference then returns without removing).
+__device__ bool prune_collapsed(const K2Apply &a, int first_layer, int end_layer, double max_state, double threshold,
+                                int *ired, int *sh) {
+    const K2DD &d = a.d;
+    bool abort = false;
+    for (int layer = first_layer; layer < end_layer && !abort; layer++) {
+        if (a.layer_alive[layer] != 1) continue;            // uniform: global memory, no writer in this loop
+        const int4 li = d.layer_info[layer];
+        if (threadIdx.x == 0) sh[0] = -1;
+        __syncthreads();
+        for (int i = threadIdx.x; i < li.z; i += blockDim.x) if (!a.node_dead[li.x + i]) sh[0] = li.x + i;   // the one node left
+        __syncthreads();
+        const int v = sh[0];
+        __syncthreads();
+        const double gain = max_state - a.state[v];
+        const int tail0 = d.layer_info[layer - 1].x;
+        int pruned = 0, total = 0;
+        for (int e = d.in_ptr[v] + threadIdx.x; e < d.in_ptr[v + 1]; e += blockDim.x) {
+            if (a.arc_dead[e]) continue;
+            const int2 ts = d.arc_ts[e];
+            const double w = ts.y >= 0 ? a.coef[ts.y] : 0.0;
+            total++;
+            if ((a.state[tail0 + ts.x] + w + gain) <= threshold) { a.arc_dead[e] = 2; pruned++; }
+        }
+        pruned = block_sum(pruned, ired);
+        total = block_sum(total, ired);
+        if (pruned == total) abort = true;
+    }
+    // commit or discard the candidates
+    const int narcs = d.in_ptr[d.nnodes];
+    int changed = 0;
+    for (int e = threadIdx.x; e < narcs; e += blockDim.x)
+        if (a.arc_dead[e] == 2) { a.arc_dead[e] = abort ? 0 : 1; changed |= abort ? 0 : 1; }
+    changed = block_sum(changed, ired);
+    if (threadIdx.x == 0 && changed) a.out->changed = 1;
+    __syncthreads();
+    return abort;
+}
+
+__global__ void __launch_bounds__(K2_THREADS) k2_finish(K2Apply a) {
+    __shared__ double red[K2_THREADS / 32];
+    __shared__ int ired[K2_THREADS / 32];
+    __shared__ int sh[2];
+    const K2DD &d = a.d;
+    const int nl = d.nlayers, llayer = nl - 1;
+    const int last0 = d.layer_info[llayer].x, nlast = d.nlast;
+    if (threadIdx.x == 0) { a.out->changed = 0; a.out->feasible = 1; a.out->bound = -DBL_MAX; }
+    __syncthreads();
+    if (a.mode == 0) {
+        // terminal arcs: weight = min(weight, parent state); bound = max over them (DD.cpp:3975-3984, 3495-3504)
+        double best = -DBL_MAX, ms = -DBL_MAX;
+        for (int i = threadIdx.x; i < nlast; i += blockDim.x) {
+            if (a.node_dead[last0 + i]) continue;
+            const double s = a.state[last0 + i];
+            double t = d.term[i];
+            t = s < t ? s : t;
+            d.term[i] = t;
+            best = best < t ? t : best;
+            ms = ms < s ? s : ms;
+        }
+        const double terminal = block_max(best, red);
+        const double max_state = block_max(ms, red);
+        if (a.restricted || terminal <= a.optimal || a.exact) { if (threadIdx.x == 0) a.out->bound = terminal; return; }
+        const bool abort = prune_collapsed(a, 3, llayer - 1, max_state, a.optimal - 0.01, ired, sh);   // layers 3 .. llayer-2
+        if (threadIdx.x == 0) a.out->bound = abort ? -DBL_MAX : terminal;
+        return;
+    }
+    // ---- feasibility ----
+    const double thr = a.restricted ? -0.5 : -0.01;            // DD.cpp:3398 / 3887
+    int alive = 0, drop = 0;
+    for (int i = threadIdx.x; i < nlast; i += blockDim.x) {
+        if (a.node_dead[last0 + i]) continue;
+        alive++;
+        if ((nl >= 2 || !a.restricted) && a.state[last0 + i] < thr) drop++;   // the restricted tree guards on size() >= 2 (DD.cpp:3376)
+    }
+    alive = block_sum(alive, ired);
+    drop = block_sum(drop, ired);
+    if (a.restricted) {
+        if (alive == 0) { if (threadIdx.x == 0) a.out->feasible = 0; return; }
+        if (drop) {
+            for (int i = threadIdx.x; i < nlast; i += blockDim.x)
+                if (!a.node_dead[last0 + i] && a.state[last0 + i] < thr) a.node_dead[last0 + i] = 1;
+            if (threadIdx.x == 0) { a.out->changed = 1; a.layer_alive[llayer] = alive - drop; a.out->feasible = alive - drop > 0 ? 1 : 0; }
+        }
+        return;
+    }
+    if (drop == alive) { if (threadIdx.x == 0) a.out->feasible = 0; return; }   // nothing is removed then (DD.cpp:3891)
+    if (drop) {
+        // batchRemoveNodes (DD.cpp:4040-4160): the nodes go, their in-arcs go, and a parent that LOSES its
+        // last out-arc this way goes too, layer by layer upwards.  node_dead == 2: dies in this sweep.
+        for (int i = threadIdx.x; i < nlast; i += blockDim.x)
+            if (!a.node_dead[last0 + i] && a.state[last0 + i] < thr) a.node_dead[last0 + i] = 2;
+        if (threadIdx.x == 0) { a.out->changed = 1; a.layer_alive[llayer] = alive - drop; }
+        __syncthreads();
+        for (int l = llayer; l >= 1; l--) {
+            const int4 li = d.layer_info[l], lp = d.layer_info[l - 1];
+            // in-arcs of the nodes that die in layer l
+            int any = 0;
+            for (int i = threadIdx.x; i < li.z; i += blockDim.x) {
+                const int v = li.x + i;
+                if (a.node_dead[v] != 2) continue;
+                any = 1;
+                for (int e = d.in_ptr[v]; e < d.in_ptr[v + 1]; e++)
+                    if (!a.arc_dead[e]) { a.arc_dead[e] = 1; a.lost[lp.x + d.arc_ts[e].x] = 1; }
+                a.node_dead[v] = 1;
+            }
+            any = block_sum(any, ired);
+            if (!any) break;
+            // live out-arcs of the parents that lost one
+            for (int i = threadIdx.x; i < lp.z; i += blockDim.x) a.cnt[lp.x + i] = 0;
+            __syncthreads();
+            const int e_end = d.in_ptr[li.x + li.z];
+            for (int e = li.y + threadIdx.x; e < e_end; e += blockDim.x)
+                if (!a.arc_dead[e]) { const int t = lp.x + d.arc_ts[e].x; if (a.lost[t]) atomicAdd(&a.cnt[t], 1); }
+            __syncthreads();
+            int died = 0;
+            for (int i = threadIdx.x; i < lp.z; i += blockDim.x) {
+                const int u = lp.x + i;
+                if (a.lost[u]) {
+                    a.lost[u] = 0;
+                    if (!a.node_dead[u] && a.cnt[u] == 0) { a.node_dead[u] = 2; died++; }
+                }
+            }
+            died = block_sum(died, ired);
+            if (threadIdx.x == 0 && died) a.layer_alive[l - 1] -= died;
+            __syncthreads();
+        }
+        // a root that died keeps flag 2 -> settle it
+        if (threadIdx.x == 0 && a.node_dead[0] == 2) a.node_dead[0] = 1;
+        __syncthreads();
+    }
+    if (!a.exact) {                                                               // DD.cpp:3895-3928
+        double ms = -DBL_MAX;
+        for (int i = threadIdx.x; i < nlast; i += blockDim.x)
+            if (!a.node_dead[last0 + i]) { const double s = a.state[last0 + i]; ms = ms < s ? s : ms; }
+        const double max_state = block_max(ms, red);
+        if (prune_collapsed(a, 1, llayer, max_state, -0.01, ired, sh)) { if (threadIdx.x == 0) a.out->feasible = 0; }
+    }
+}
+
+// getSolution (DD.cpp:3825-3840) / getMaxPath (DD.cpp:3290-3305) + getPathForNode (DD.cpp:3796-3820):
+// the first terminal arc of strictly greatest weight, then backwards over the first in-arc whose
+// parent state + weight EQUALS the node's state (exact fp compare); if none does, step to the first
+// in-arc's parent without recording a decision.  A restricted tree records its only in-arc always.
+__global__ void __launch_bounds__(K2_THREADS) k2_extract(K2Apply a) {
+    __shared__ double red[K2_THREADS / 32];
+    __shared__ int sh[2];
+    const K2DD &d = a.d;
+    const int llayer = d.nlayers - 1, last0 = d.layer_info[llayer].x;
+    // argmax with the lowest index among equals
+    double best = -DBL_MAX; int bi = INT_MAX;
+    for (int i = threadIdx.x; i < d.nlast; i += blockDim.x)
+        if (!a.node_dead[last0 + i] && d.term[i] > best) { best = d.term[i]; bi = i; }
+    const double gbest = block_max(best, red);
+    if (threadIdx.x == 0) sh[0] = INT_MAX;
+    __syncthreads();
+    if (bi != INT_MAX && best == gbest && gbest > -DBL_MAX) atomicMin(&sh[0], bi);
+    __syncthreads();
+    int cur = sh[0] == INT_MAX ? 0 : last0 + sh[0];
+    int l = sh[0] == INT_MAX ? 0 : llayer;
+    int n = 0;                                   // decisions recorded so far (leaf -> root), kept by every thread
+    __syncthreads();
+    while (l > 0) {
+        const int tail0 = d.layer_info[l - 1].x, e0 = d.in_ptr[cur], e1 = d.in_ptr[cur + 1];
+        if (threadIdx.x == 0) { sh[0] = INT_MAX; sh[1] = INT_MAX; }
+        __syncthreads();
+        const double sc = a.state[cur];
+        int first = INT_MAX, match = INT_MAX;
+        for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+            if (a.arc_dead[e]) continue;
+            if (e < first) first = e;
+            const int2 ts = d.arc_ts[e];
+            const double w = ts.y >= 0 ? a.coef[ts.y] : 0.0;
+            if (e < match && (a.restricted || (a.state[tail0 + ts.x] + w) == sc)) match = e;
+        }
+        if (first != INT_MAX) atomicMin(&sh[0], first);
+        if (match != INT_MAX) atomicMin(&sh[1], match);
+        __syncthreads();
+        const int f = sh[0], m = sh[1];
+        __syncthreads();
+        if (f == INT_MAX) break;                 // no in-arc left: the walk ends here
+        const int e = m != INT_MAX ? m : f;
+        if (m != INT_MAX) { if (threadIdx.x == 0) a.path[n] = (int16_t)a.arc_dec[e]; n++; }
+        cur = tail0 + d.arc_ts[e].x;
+        l--;
+    }
+    if (threadIdx.x == 0) a.out->path_len = n;
+}
+
 }  // namespace
 
 cudaError_t k2_launch(const K2DD *dds, int B, const double *coef, const double *rhs, int C, int Tpad, double *states, double *last,
@@ -142,14 +402,14 @@ cudaError_t k2_launch(const K2DD *dds, int B, const double *coef, const double *
     while (threads < K2_THREADS && threads < max_width_all) threads *= 2;
     const size_t smem = ((size_t)Tpad + 2 * (size_t)max_width_all) * sizeof(double);
     if (smem <= 200 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k2_longest_path<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k2_longest_path<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        k2_longest_path<true><<<grid, threads, smem, st>>>(dds, coef, rhs, C, Tpad, max_width_all, states, last);
+        k2_longest_path<true, false><<<grid, threads, smem, st>>>(dds, coef, rhs, C, Tpad, max_width_all, states, last);
     } else {
         const size_t sm2 = (size_t)Tpad * sizeof(double);
-        cudaError_t e = cudaFuncSetAttribute(k2_longest_path<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+        cudaError_t e = cudaFuncSetAttribute(k2_longest_path<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
         if (e != cudaSuccess) return e;
-        k2_longest_path<false><<<grid, threads, sm2, st>>>(dds, coef, rhs, C, Tpad, 0, states, last);
+        k2_longest_path<false, false><<<grid, threads, sm2, st>>>(dds, coef, rhs, C, Tpad, 0, states, last);
     }
     return cudaGetLastError();
 }
@@ -158,6 +418,47 @@ bool k2_states_in_smem(int Tpad, int max_width_all) { return ((size_t)Tpad + 2 *
 
 cudaError_t k2_terminal_launch(const K2DD *dds, int B, int C, const double *last, double *bound, cudaStream_t st, int *launches) {
     k2_terminal<<<B, K2_THREADS, 0, st>>>(dds, C, last, bound);
+    if (launches) (*launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t k2_single_launch(const K2DD *dd, const double *coef, const double *rhs, int Tpad, double *states, double *last,
+                             int max_width, cudaStream_t st, int *launches) {
+    if (launches) (*launches)++;
+    int threads = 64;
+    while (threads < K2_THREADS && threads < max_width) threads *= 2;
+    const size_t smem = ((size_t)Tpad + 2 * (size_t)max_width) * sizeof(double);
+    if (smem <= 200 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k2_longest_path<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k2_longest_path<true, true><<<dim3(1, 1), threads, smem, st>>>(dd, coef, rhs, 1, Tpad, max_width, states, last);
+    } else {
+        const size_t sm2 = (size_t)Tpad * sizeof(double);
+        cudaError_t e = cudaFuncSetAttribute(k2_longest_path<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+        if (e != cudaSuccess) return e;
+        k2_longest_path<false, true><<<dim3(1, 1), threads, sm2, st>>>(dd, coef, rhs, 1, Tpad, 0, states, last);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t k2_layered_launch(const K2DD &d, const int32_t *layer_width_host, const uint8_t *layer_collapsed_host, const double *coef,
+                              double *states, cudaStream_t st, int *launches) {
+    for (int l = 1; l < d.nlayers; l++) {
+        if (layer_collapsed_host[l]) k2_layer_collapsed<<<1, K2_THREADS, 0, st>>>(d, coef, l, states);
+        else k2_layer<<<(layer_width_host[l] + K2_THREADS - 1) / K2_THREADS, K2_THREADS, 0, st>>>(d, coef, l, states);
+        if (launches) (*launches)++;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t k2_finish_launch(const K2Apply &a, cudaStream_t st, int *launches) {
+    k2_finish<<<1, K2_THREADS, 0, st>>>(a);
+    if (launches) (*launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t k2_extract_launch(const K2Apply &a, cudaStream_t st, int *launches) {
+    k2_extract<<<1, K2_THREADS, 0, st>>>(a);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }

@@ -14,6 +14,7 @@ struct K2DD {   // device image of one decision diagram (CSR by layer, DESIGN.md
     long long state_off;        // offset of this DD's full-state block (states of the LAST cut of a batch), in doubles
     long long last_off;         // offset of this DD's [C][nlast] block of last-layer states, in doubles
     int nlayers, nroot, nnodes, nlast, max_width;
+    const uint8_t *arc_dead;    // [narcs] or null: arcs removed on the device since the last upload (k2_finish)
 };
 
 // One CTA per (cut c, diagram b).  Node states ping-pong between two shared-memory buffers (a layer
@@ -27,5 +28,43 @@ bool k2_states_in_smem(int Tpad, int max_width_all);
 // term[i] = min(term[i], min_c last[b][c][i]); bound[b] = max_i term[i]
 cudaError_t k2_terminal_launch(const K2DD *dds_device, int B, int C, const double *last_device, double *bound_device,
                                cudaStream_t st, int *launches);
+
+// ---- device-side cut application ----------------------------------------------
+// What follows the longest path in RelaxedDDNew / RestrictedDDNew::applyOptimalityCut and
+// applyFeasibilityCut (DD.cpp:3975-4021, 3884-3929, 3398-3422, 3493-3504), on the device image:
+// terminal weights, removal of last-layer nodes (with the bottom-up cascade of DD.cpp:4040-4160),
+// bound-based arc pruning of non-exact diagrams, and getSolution / getMaxPath (DD.cpp:3825-3840,
+// 3796-3820, 3290-3305).  Removed arcs and nodes are FLAGGED (the CSR stays as uploaded); the host
+// mirror replays the flags when somebody asks for the structure.
+struct K2Result {
+    double bound;        // optimality: the upper / lower bound returned by the reference
+    int feasible;        // feasibility: the uint8_t the reference returns
+    int changed;         // 1 if arcs or nodes were removed
+    int path_len;        // extract: decisions written
+};
+struct K2Apply {
+    K2DD d;                       // d.term, d.arc_dead: this diagram's persistent buffers
+    const double *state;          // [nnodes] states of the cut just applied
+    const double *coef;           // [Tpad]   its dense coefficient vector
+    const int32_t *arc_dec;       // [narcs]  decision of every arc (out-arc id or -1)
+    uint8_t *arc_dead, *node_dead;   // [narcs], [nnodes]
+    int32_t *layer_alive;         // [nlayers] nodes still in each layer
+    int32_t *cnt;                 // [nnodes] scratch
+    uint8_t *lost;                // [nnodes] scratch, zero on entry and on exit
+    K2Result *out;
+    int16_t *path;                // [nlayers] extract: decisions root -> leaf (after the fixed prefix)
+    double optimal;
+    int mode;                     // 0 optimality, 1 feasibility
+    int restricted, exact;
+};
+// single-cut longest path of ONE diagram that honours arc_dead; every node state goes to `states`
+cudaError_t k2_single_launch(const K2DD *dd_device, const double *coef_device, const double *rhs_device, int Tpad, double *states,
+                             double *last, int max_width, cudaStream_t st, int *launches);
+// the same for a WIDE diagram: one launch per layer over the whole GPU; states[0] (the root) must already be set.
+// layer_width_host / layer_collapsed_host: per layer, the node count and whether it is one node with several in-arcs.
+cudaError_t k2_layered_launch(const K2DD &d, const int32_t *layer_width_host, const uint8_t *layer_collapsed_host, const double *coef_device,
+                              double *states, cudaStream_t st, int *launches);
+cudaError_t k2_finish_launch(const K2Apply &a, cudaStream_t st, int *launches);
+cudaError_t k2_extract_launch(const K2Apply &a, cudaStream_t st, int *launches);
 
 }  // namespace sgufp

@@ -180,3 +180,79 @@ def test_real_cuts_drive_the_same_paths():
         else:
             assert ours.applyOptimalityCut(cut, -1e300, 1e300) == ref.apply_opt(cut.RHS, cut.keys, cut.vals, -1e300, 1e300)
     assert len(seen) >= 2
+
+
+@pytest.fixture(params=["one_cta", "layered"])
+def k2_path(request, monkeypatch):
+    """the single-cut longest path has two launch shapes: one CTA (narrow diagrams) or one launch per layer"""
+    monkeypatch.setenv("SGUFP_K2_LAYERED_MIN", "1" if request.param == "layered" else "1000000000")
+    return request.param
+
+
+@pytest.mark.parametrize("name", sorted(INSTANCES))
+@pytest.mark.parametrize("seed", [5, 17])
+def test_relaxed_device_resident_sequence(name, seed, k2_path):
+    """a whole sequence of cuts applied on the device image — terminal weights, node
+    removal with its cascade, bound-based arc pruning, getSolution — with NO structure query in
+    between (so removal flags accumulate on the device); only bounds, flags and paths are compared
+    per cut, the full structure once at the end, after the host mirror replays the flags."""
+    inst = INSTANCES[name]()
+    solver = sg.GuroSolver(inst)
+    rn = ref_dd.RefNetwork(inst)
+    ours, ref = RelaxedDDNew(solver), ref_dd.RefRelaxedDD(rn)
+    ours.buildTree(); ref.build()
+    rng = np.random.default_rng(seed)
+    ub = 1e300
+    arcs0 = ours.counts()[1]
+    alive = True
+    for it in range(40):
+        if it % 3 == 2:
+            cut = random_cut(solver, rng, cut_type=1)
+            cut = type(cut)(cut.RHS * 0.2, cut.keys, cut.vals)     # a tighter RHS: some last-layer nodes fall below -0.01
+            f_ref = ref.apply_feas(cut.RHS, cut.keys, cut.vals)
+            assert ours.applyFeasibilityCut(cut) == f_ref, it
+            if not f_ref:
+                alive = False
+                break
+        else:
+            cut = random_cut(solver, rng)
+            optimal = -1e300 if it % 2 == 0 else ub - rng.uniform(0, 300)
+            b_ref = ref.apply_opt(cut.RHS, cut.keys, cut.vals, optimal, ub)
+            assert ours.applyOptimalityCut(cut, optimal, ub) == b_ref, it
+            if b_ref == LOWEST:
+                alive = False
+                break
+            ub = min(ub, b_ref)
+        assert ours.getSolution().tolist() == ref.solution().tolist(), it
+    _same_state(ours, ref)
+    if alive:
+        assert ours.getSolution().tolist() == ref.solution().tolist()
+    test_relaxed_device_resident_sequence.removed = getattr(test_relaxed_device_resident_sequence, "removed", 0) + (arcs0 - ours.counts()[1])
+
+
+def test_device_resident_sequences_did_remove_something():
+    """the sequences above must have exercised the removal paths (runs after them in file order)"""
+    assert getattr(test_relaxed_device_resident_sequence, "removed", 0) > 0
+
+
+@pytest.mark.parametrize("width", [4, 64])
+def test_restricted_device_resident_sequence(width, k2_path):
+    inst = INSTANCES["c2"]()
+    solver = sg.GuroSolver(inst)
+    rn = ref_dd.RefNetwork(inst)
+    ours, ref = RestrictedDDNew(solver, width), ref_dd.RefRestrictedDD(rn, width)
+    ours.compile(); ref.compile()
+    rng = np.random.default_rng(29 + width)
+    for it in range(30):
+        if it % 3 == 2:
+            cut = random_cut(solver, rng, cut_type=1)
+            cut = type(cut)(cut.RHS * 0.2, cut.keys, cut.vals)
+            f_ref = ref.apply_feas(cut.RHS, cut.keys, cut.vals)
+            assert ours.applyFeasibilityCut(cut) == f_ref
+            if not f_ref:
+                break
+        else:
+            cut = random_cut(solver, rng)
+            assert ours.applyOptimalityCut(cut) == ref.apply_opt(cut.RHS, cut.keys, cut.vals)
+        assert ours.getMaxPath().tolist() == ref.solution().tolist()
+    _same_state(ours, ref, relaxed=False)
