@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--C", type=int, default=64)
     ap.add_argument("--reps", type=int, default=7)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--build", action="store_true",
+                    help="construction time of one diagram: k2_build on the device (SURVEY 8f-3) vs the host builder vs the reference class")
     ap.add_argument("--sequential", action="store_true",
                     help="one diagram, one cut at a time + getSolution after each (the Benders inner loop, NodeExplorer.cpp:949-971): "
                          "wall time per iteration through the host API, device-side cut application (SURVEY 8f-2)")
@@ -52,6 +54,32 @@ def main():
         except Exception:
             ref_net = None
     points = [("restricted", int(w)) for w in args.widths.split(",")] + [("relaxed", 120)]
+    if args.build:
+        for kind, w in points:
+            line = {"metric": "dd_build_ms", "unit": "ms per buildTree/compile", "higher_is_better": False, "kind": kind, "width": w}
+            for mode in ("device", "host"):
+                os.environ["SGUFP_DD_BUILD"] = mode
+                d = RestrictedDDNew(solver, w) if kind == "restricted" else RelaxedDDNew(solver)
+                build = d.compile if kind == "restricted" else d.buildTree
+                build(); torch.cuda.synchronize()
+                ts = []
+                for _ in range(5):
+                    t0 = time.perf_counter(); build(); ts.append(time.perf_counter() - t0)
+                line["value" if mode == "device" else "host_builder_ms"] = float(np.median(ts)) * 1e3
+                if mode == "device":
+                    line["built_on_device"] = bool(d.dump_device()["built_on_device"])
+                    line["nodes_per_diagram"], line["arcs_per_diagram"] = d.counts()
+                d.close()
+            os.environ.pop("SGUFP_DD_BUILD", None)
+            if ref_net is not None:
+                r = ref_dd.RefRestrictedDD(ref_net, w) if kind == "restricted" else ref_dd.RefRelaxedDD(ref_net)
+                rb = r.compile if kind == "restricted" else r.build
+                ts = []
+                for _ in range(3):
+                    t0 = time.perf_counter(); rb(); ts.append(time.perf_counter() - t0)
+                line["cpu_reference"] = {"value": float(np.median(ts)) * 1e3, "unit": line["unit"], "cores": 1, "kind": "reference"}
+            print(json.dumps(line), flush=True)
+        return
     if args.sequential:
         for kind, w in points:
             d = RestrictedDDNew(solver, w) if kind == "restricted" else RelaxedDDNew(solver)

@@ -28,6 +28,12 @@ void sgufp_dd_destroy(sgufp_dd *dd);
  * globalLayer) of `Inavap::Node` (DD.h:456-479); an empty node with globalLayer 0 is the root.
  * cutset_nodes (may be NULL): restricted DD only, the size of the exact cut-set, or -1 if the tree
  * is exact (DD.cpp:3157-3158); fetch it with sgufp_dd_cutset. */
+/* buildTree(node) (DD.cpp:3528-3600) / compile(node) (DD.cpp:3090-3159).  The diagram is built ON THE
+ * DEVICE (state sets as 32-bit masks, one prefix sum + one expansion per
+ * layer, CSR emitted in place) whenever the root is a cut-set node (solution length == globalLayer, states a
+ * subset of the layer's {-1} U outgoingArcs) and no V-bar node has more than 31 out-arcs; the host
+ * mirror is then constructed lazily, only if dump / cutset / layer_sizes / counts / the batch call need
+ * it.  SGUFP_DD_BUILD=host forces the host builder. */
 int sgufp_dd_build(sgufp_dd *dd, const int16_t *states, int nstates, const int16_t *solution, int nsolution,
                    int global_layer, int *cutset_nodes);
 int sgufp_dd_is_exact(const sgufp_dd *dd); /* isTreeExact(): 1 / 0 */
@@ -40,6 +46,12 @@ int sgufp_dd_layer_sizes(sgufp_dd *dd, int32_t *sizes /*[num_layers]*/);
 int sgufp_dd_counts(sgufp_dd *dd, int64_t *nodes, int64_t *arcs);
 int sgufp_dd_dump(sgufp_dd *dd, int32_t *node_layer, double *node_state, int64_t *node_inptr, int32_t *arc_tailpos,
                   int32_t *arc_decision, double *terminal_weight /*[last layer]*/);
+
+/* Test introspection: the CSR image as it sits on the device (built there by k2_build when the root is a
+ * cut-set node and state sets fit 32 bits, uploaded from the host mirror otherwise).  Sizes as for
+ * sgufp_dd_dump, which answers from the host mirror.  Returns 1 if the image was built on the device. */
+int sgufp_dd_dump_device(sgufp_dd *dd, int32_t *layer_sizes, int64_t *node_inptr, int32_t *arc_tailpos, int32_t *arc_decision,
+                         int32_t *arc_slot);
 
 /* applyOptimalityCut(cut, optimal, upperbound) -> bound (DD.cpp:3932-4023, 3425-3505) and
  * applyFeasibilityCut(cut) -> feasible (DD.cpp:3842-3930, 3340-3423).  The cut is an Inavap::Cut:

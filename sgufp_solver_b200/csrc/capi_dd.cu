@@ -38,6 +38,16 @@ struct sgufp_dd {
     std::vector<int32_t> layer_width;  // per layer of the uploaded image: nodes, and whether it is a collapsed node
     std::vector<uint8_t> layer_collapsed;
     std::vector<int32_t> root_slot;
+    // construction on the device (k2_build.cu): the host mirror is then built only when somebody needs it
+    NodeSpec root_spec;
+    std::vector<int16_t> root_solution;
+    bool host_built = true, device_built = false, exact_flag = true;
+    int nlayers_dev = 1, exact_layer_dev = 0;
+    DevBuf<int4> b_layer_info;
+    DevBuf<int2> b_arc_ts;
+    DevBuf<int32_t> b_in_ptr, b_off, b_widths, b_root_slot;
+    DevBuf<unsigned> b_mask;
+    DevBuf<K2BuildOut> b_out;
 };
 
 namespace {
@@ -46,6 +56,9 @@ int upload(sgufp_dd *d) {
     sgufp_ctx *c = d->ctx;
     if (c->device == SGUFP_DEVICE_NONE) return fail(c, SGUFP_ERR_CUDA, "handle was created with SGUFP_DEVICE_NONE: there is no CPU compute path for K2");
     CU(c, cudaSetDevice(c->device));
+    // an image built on the device stays as it is until the host mirror (if it exists at all) changes shape
+    if (d->device_built && (!d->host_built || d->uploaded_version == d->dd->version())) return 0;
+    d->device_built = false;
     const bool was_dirty = !d->uploaded || d->uploaded_version != d->dd->version();
     const DDCsr &C = d->dd->flatten();
     if (was_dirty) {
@@ -108,8 +121,18 @@ int upload(sgufp_dd *d) {
     return 0;
 }
 
+// the host mirror of a diagram that was built on the device: the same deterministic construction, on demand
+void ensure_host(sgufp_dd *d) {
+    if (d->host_built) return;
+    d->dd->build(d->root_spec, &d->compile_cutset);
+    d->dd->flatten();
+    d->uploaded_version = d->dd->version();   // same structure, same CSR order as the device image: no upload
+    d->host_built = true;
+}
+
 // bring the host mirror up to date with what the device did since the last upload
 int sync_host(sgufp_dd *d) {
+    ensure_host(d);
     if (!d->dev_ahead) return 0;
     sgufp_ctx *c = d->ctx;
     CU(c, cudaSetDevice(c->device));
@@ -138,7 +161,7 @@ K2Apply make_apply(sgufp_dd *d, int mode, double optimal) {
     a.state = d->d_state.p; a.coef = d->d_coef.p; a.arc_dec = d->d_arc_dec.p;
     a.arc_dead = d->d_arc_dead.p; a.node_dead = d->d_node_dead.p; a.layer_alive = d->d_layer_alive.p;
     a.cnt = d->d_cnt.p; a.lost = d->d_lost.p; a.out = d->d_res.p; a.path = d->d_path.p;
-    a.optimal = optimal; a.mode = mode; a.restricted = d->dd->restricted() ? 1 : 0; a.exact = d->dd->is_exact() ? 1 : 0;
+    a.optimal = optimal; a.mode = mode; a.restricted = d->dd->restricted() ? 1 : 0; a.exact = d->exact_flag ? 1 : 0;
     return a;
 }
 
@@ -177,9 +200,17 @@ int apply_on_device(sgufp_dd *d, double rhs, const uint64_t *keys, const double 
     return 0;
 }
 
-struct Scratch {   // per-context scratch for the batch call
+struct Scratch {   // per-context scratch for the batch call + the static tables of the device construction
     DevBuf<double> coef, rhs, states, last, bound;
     DevBuf<K2DD> dds;
+    bool tables_built = false, tables_ok = false;
+    DevBuf<int32_t> t_lay_tab, t_tab_ptr, t_slot_base;
+    DevBuf<uint8_t> t_lay_first;
+    DevBuf<int16_t> t_tab_dec, t_tab_k;
+    K2Tables tables{};
+    std::vector<int32_t> h_lay_tab, h_tab_ptr;
+    std::vector<int16_t> h_tab_dec;
+    std::vector<uint8_t> h_lay_first;
 };
 Scratch &scratch_of(sgufp_ctx *c) {
     if (!c->dd_scratch) {
@@ -187,10 +218,170 @@ Scratch &scratch_of(sgufp_ctx *c) {
         c->dd_scratch_free = [](void *p) {
             Scratch *s = static_cast<Scratch *>(p);
             s->coef.release(); s->rhs.release(); s->states.release(); s->last.release(); s->bound.release(); s->dds.release();
+            s->t_lay_tab.release(); s->t_tab_ptr.release(); s->t_slot_base.release(); s->t_lay_first.release(); s->t_tab_dec.release(); s->t_tab_k.release();
             delete s;
         };
     }
     return *static_cast<Scratch *>(c->dd_scratch);
+}
+
+
+// static tables of the device construction: per V-bar node the base state list {-1} U outgoingArcs (ascending,
+// Network.cpp:96-102) and, per entry, the coefficient slot of that decision relative to slot_base[layer]
+int ensure_tables(sgufp_ctx *c) {
+    Scratch &S = scratch_of(c);
+    if (S.tables_built) return 0;
+    const Model &M = c->M;
+    std::vector<int32_t> lay_tab(M.L), tab_ptr{0}, tab_of(M.n, -1);
+    std::vector<uint8_t> lay_first(M.L, 0);
+    std::vector<int16_t> tab_dec, tab_k;
+    bool ok = M.m <= 32767;
+    for (int g = 0; g < M.L; g++) {
+        const int q = M.head[M.layer_arc[g]];
+        lay_first[g] = (g == 0 || M.head[M.layer_arc[g - 1]] != q) ? 1 : 0;
+        if (tab_of[q] < 0) {
+            tab_of[q] = (int)tab_ptr.size() - 1;
+            std::vector<int32_t> outs(M.out_arc.begin() + M.out_ptr[q], M.out_arc.begin() + M.out_ptr[q + 1]);
+            std::sort(outs.begin(), outs.end());
+            tab_dec.push_back(-1); tab_k.push_back(-1);
+            for (int a : outs) {
+                int k = -1;
+                for (int i = 0; i < M.outdeg(q) && k < 0; i++) if (M.head[M.out_arc[M.out_ptr[q] + i]] == M.head[a]) k = i;
+                tab_dec.push_back((int16_t)a); tab_k.push_back((int16_t)k);
+            }
+            if (outs.size() + 1 > 32) ok = false;          // a state set is one 32-bit mask
+            tab_ptr.push_back((int32_t)tab_dec.size());
+        }
+        lay_tab[g] = tab_of[q];
+    }
+    S.tables_built = true; S.tables_ok = false;
+    if (!ok || M.L == 0 || c->device == SGUFP_DEVICE_NONE) return 0;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, S.t_lay_tab.reserve(M.L)); CU(c, S.t_lay_first.reserve(M.L)); CU(c, S.t_slot_base.reserve(M.L));
+    CU(c, S.t_tab_ptr.reserve(tab_ptr.size())); CU(c, S.t_tab_dec.reserve(tab_dec.size())); CU(c, S.t_tab_k.reserve(tab_k.size()));
+    CU(c, cudaMemcpy(S.t_lay_tab.p, lay_tab.data(), (size_t)M.L * 4, cudaMemcpyHostToDevice));
+    CU(c, cudaMemcpy(S.t_lay_first.p, lay_first.data(), (size_t)M.L, cudaMemcpyHostToDevice));
+    CU(c, cudaMemcpy(S.t_slot_base.p, M.slot_base.data(), (size_t)M.L * 4, cudaMemcpyHostToDevice));
+    CU(c, cudaMemcpy(S.t_tab_ptr.p, tab_ptr.data(), tab_ptr.size() * 4, cudaMemcpyHostToDevice));
+    CU(c, cudaMemcpy(S.t_tab_dec.p, tab_dec.data(), tab_dec.size() * 2, cudaMemcpyHostToDevice));
+    CU(c, cudaMemcpy(S.t_tab_k.p, tab_k.data(), tab_k.size() * 2, cudaMemcpyHostToDevice));
+    S.tables = K2Tables{S.t_lay_tab.p, S.t_lay_first.p, S.t_tab_ptr.p, S.t_tab_dec.p, S.t_tab_k.p, S.t_slot_base.p, M.L};
+    S.h_lay_tab = lay_tab; S.h_tab_ptr = tab_ptr; S.h_tab_dec = tab_dec; S.h_lay_first = lay_first;
+    S.tables_ok = true;
+    return 0;
+}
+
+bool device_build_enabled() { const char *e = getenv("SGUFP_DD_BUILD"); return !(e && e[0] == 'h'); }   // SGUFP_DD_BUILD=host forces the host builder
+
+// Build the diagram on the device (k2_build.cu).  Returns 1 if it did, 0 if this case is left to the
+// host builder (no device, state sets wider than 32, a root that is not a cut-set node, capacity), < 0 on error.
+int device_build(sgufp_dd *d, const NodeSpec &root, int *cutset_nodes) {
+    sgufp_ctx *c = d->ctx;
+    const Model &M = c->M;
+    if (c->device == SGUFP_DEVICE_NONE || !device_build_enabled()) return 0;
+    if (int rc = ensure_tables(c)) return rc;
+    Scratch &S = scratch_of(c);
+    const int start = root.global_layer;
+    if (!S.tables_ok || start >= M.L || (int)root.solution.size() != start) return 0;
+    const int tab = S.h_lay_tab[start], tp = S.h_tab_ptr[tab], nst = S.h_tab_ptr[tab + 1] - tp;
+    unsigned mask = 0;
+    if (!S.h_lay_first[start]) {                             // at the first layer of a V-bar node the states are reset anyway
+        for (int16_t s : root.states) {
+            int pos = -1;
+            for (int p = 0; p < nst && pos < 0; p++) if (S.h_tab_dec[tp + p] == s) pos = p;
+            if (pos < 0 || ((mask >> pos) & 1)) return 0;   // not a subset of the layer's base list (or a repeated state)
+            mask |= 1u << pos;
+        }
+        if (!(mask & 1u)) return 0;                          // every reference state set holds -1
+        for (size_t i = 1; i < root.states.size(); i++) if (root.states[i - 1] >= root.states[i]) return 0;   // set order
+    }
+    const bool restricted = d->dd->restricted();
+    const long long layers = M.L - start;
+    long long node_cap = restricted ? 1 + layers * (long long)d->dd->max_width() : (1LL << 21);
+    if (node_cap > (1LL << 26)) return 0;
+    const long long arc_cap = restricted ? node_cap : (1LL << 22);
+    CU(c, cudaSetDevice(c->device));
+    CU(c, d->b_layer_info.reserve(layers + 1)); CU(c, d->b_in_ptr.reserve(node_cap + 1)); CU(c, d->b_arc_ts.reserve(arc_cap));
+    CU(c, d->d_arc_dec.reserve(arc_cap)); CU(c, d->b_mask.reserve(node_cap)); CU(c, d->b_off.reserve(node_cap));
+    CU(c, d->b_widths.reserve(layers + 1)); CU(c, d->b_out.reserve(1));
+    K2Build b{};
+    b.t = S.tables; b.start = start; b.root_mask = mask; b.restricted = restricted ? 1 : 0; b.max_width = d->dd->max_width();
+    b.node_cap = (int)node_cap; b.arc_cap = (int)arc_cap;
+    b.layer_info = d->b_layer_info.p; b.in_ptr = d->b_in_ptr.p; b.arc_ts = d->b_arc_ts.p; b.arc_dec = d->d_arc_dec.p; b.mask = d->b_mask.p;
+    b.off = d->b_off.p; b.widths = d->b_widths.p; b.out = d->b_out.p;
+    K2BuildOut o{};
+    o.overflow = 1;
+    CU(c, cudaMemcpyAsync(d->b_out.p, &o, sizeof(o), cudaMemcpyHostToDevice, c->st));
+    c->dd_launches = 0;
+    CU(c, k2_build_launch(b, c->st, &c->dd_launches));
+    CU(c, cudaMemcpyAsync(&o, d->b_out.p, sizeof(o), cudaMemcpyDeviceToHost, c->st));
+    CU(c, cudaStreamSynchronize(c->st));
+    if (o.overflow) return 0;
+    std::vector<int4> li(o.nlayers);
+    d->layer_width.resize(o.nlayers);
+    CU(c, cudaMemcpyAsync(li.data(), d->b_layer_info.p, (size_t)o.nlayers * sizeof(int4), cudaMemcpyDeviceToHost, c->st));
+    CU(c, cudaMemcpyAsync(d->layer_width.data(), d->b_widths.p, (size_t)o.nlayers * 4, cudaMemcpyDeviceToHost, c->st));
+    // what the single-cut path keeps per diagram
+    const int T = std::max(1, M.T), Tpad = (T + 1) & ~1;
+    d->root_slot.clear();
+    for (int i = 0; i < start; i++) d->root_slot.push_back(d->dd->slot_of(i, root.solution[i]));
+    CU(c, d->b_root_slot.reserve(std::max(1, start)));
+    if (start) CU(c, cudaMemcpyAsync(d->b_root_slot.p, d->root_slot.data(), (size_t)start * 4, cudaMemcpyHostToDevice, c->st));
+    CU(c, d->d_term.reserve(o.nlast)); CU(c, d->d_layer_alive.reserve(o.nlayers));
+    CU(c, d->d_arc_dead.reserve(std::max(1, o.narcs))); CU(c, d->d_node_dead.reserve(o.nnodes)); CU(c, d->d_lost.reserve(o.nnodes));
+    CU(c, d->d_cnt.reserve(o.nnodes)); CU(c, d->d_state.reserve(o.nnodes)); CU(c, d->d_last.reserve(o.nlast)); CU(c, d->d_coef.reserve(Tpad));
+    CU(c, d->d_path.reserve(o.nlayers)); CU(c, d->d_self.reserve(1)); CU(c, d->d_res.reserve(1)); CU(c, d->d_rhs.reserve(1));
+    CU(c, cudaMemcpyAsync(d->d_layer_alive.p, d->b_widths.p, (size_t)o.nlayers * 4, cudaMemcpyDeviceToDevice, c->st));
+    CU(c, cudaMemsetAsync(d->d_arc_dead.p, 0, std::max(1, o.narcs), c->st));
+    CU(c, cudaMemsetAsync(d->d_node_dead.p, 0, o.nnodes, c->st));
+    CU(c, cudaMemsetAsync(d->d_lost.p, 0, o.nnodes, c->st));
+    CU(c, cudaMemsetAsync(d->d_coef.p, 0, (size_t)Tpad * 8, c->st));
+    CU(c, k2_fill_launch(d->d_term.p, DD_MAX, o.nlast, c->st));          // terminal arcs start at DOUBLE_MAX (DD.cpp:3145, 3595)
+    CU(c, k2_fill_launch(d->d_state.p, DD_LOWEST, o.nnodes, c->st));     // state2 of a fresh node (DD.h:453)
+    CU(c, cudaStreamSynchronize(c->st));
+    d->layer_collapsed.assign(o.nlayers, 0);
+    for (int l = 1; l < o.nlayers; l++) d->layer_collapsed[l] = (li[l].z == 1 && li[l].w == 0) ? 1 : 0;
+    K2DD dev{};
+    dev.layer_info = d->b_layer_info.p; dev.in_ptr = d->b_in_ptr.p; dev.arc_ts = d->b_arc_ts.p; dev.root_slot = d->b_root_slot.p;
+    dev.term = d->d_term.p; dev.nlayers = o.nlayers; dev.nroot = start; dev.nnodes = o.nnodes; dev.nlast = o.nlast; dev.max_width = o.max_width;
+    dev.arc_dead = d->d_arc_dead.p;
+    d->dev = dev;
+    d->narcs = o.narcs; d->nlayers_dev = o.nlayers; d->exact_flag = o.exact != 0; d->exact_layer_dev = o.exact_layer;
+    d->device_built = true; d->host_built = false; d->uploaded = true; d->term_dirty = false;
+    d->dev_ahead = false; d->dev_states_valid = true;     // fresh states: every walk takes the first in-arc, as on the host
+    d->last_coef.assign(T, 0.0);
+    d->has_cutset = restricted && !d->exact_flag;
+    d->compile_cutset.clear();
+    if (cutset_nodes) *cutset_nodes = d->has_cutset ? d->layer_width[o.exact_layer] : -1;
+    return 1;
+}
+
+// the exact cut-set of a restricted tree that was built on the device, without building the host mirror
+int device_cutset(sgufp_dd *d) {
+    sgufp_ctx *c = d->ctx;
+    Scratch &S = scratch_of(c);
+    const int el = d->exact_layer_dev, count = d->layer_width[el], start = d->root_spec.global_layer;
+    DevBuf<unsigned> om; DevBuf<int16_t> od;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, om.reserve(count)); CU(c, od.reserve((size_t)count * std::max(1, el)));
+    std::vector<unsigned> masks(count);
+    std::vector<int16_t> decs((size_t)count * std::max(1, el));
+    cudaError_t e = k2_cutset_launch(d->b_layer_info.p, d->b_in_ptr.p, d->b_arc_ts.p, d->d_arc_dec.p, d->b_mask.p, el, count, om.p, od.p, c->st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(masks.data(), om.p, (size_t)count * 4, cudaMemcpyDeviceToHost, c->st);
+    if (e == cudaSuccess && el) e = cudaMemcpyAsync(decs.data(), od.p, (size_t)count * el * 2, cudaMemcpyDeviceToHost, c->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->st);
+    om.release(); od.release();
+    CU(c, e);
+    const int g = start + el, tp = S.h_tab_ptr[S.h_lay_tab[g]];
+    d->compile_cutset.assign(count, NodeSpec());
+    for (int j = 0; j < count; j++) {
+        NodeSpec &n = d->compile_cutset[j];
+        n.global_layer = g;
+        for (unsigned m = masks[j]; m; m &= m - 1) n.states.push_back(S.h_tab_dec[tp + __builtin_ctz(m)]);
+        n.solution = d->root_spec.solution;
+        n.solution.insert(n.solution.end(), decs.begin() + (size_t)j * el, decs.begin() + (size_t)(j + 1) * el);
+    }
+    return 0;
 }
 
 // densify C cuts, run K2 over B diagrams, read back what the host semantics need
@@ -278,6 +469,8 @@ void sgufp_dd_destroy(sgufp_dd *d) {
     d->d_state.release(); d->d_last.release(); d->d_coef.release(); d->d_rhs.release(); d->d_arc_dead.release(); d->d_node_dead.release();
     d->d_lost.release(); d->d_layer_alive.release(); d->d_cnt.release(); d->d_arc_dec.release(); d->d_path.release(); d->d_self.release();
     d->d_res.release();
+    d->b_layer_info.release(); d->b_arc_ts.release(); d->b_in_ptr.release(); d->b_off.release(); d->b_widths.release(); d->b_root_slot.release();
+    d->b_mask.release(); d->b_out.release();
     delete d->dd;
     delete d;
 }
@@ -289,16 +482,23 @@ int sgufp_dd_build(sgufp_dd *d, const int16_t *states, int ns, const int16_t *so
     root.states.assign(states, states + ns);
     root.solution.assign(sol, sol + nsol);
     root.global_layer = global_layer;
+    d->root_spec = root;
+    d->root_solution = root.solution;
+    d->dev_ahead = false; d->dev_states_valid = false;   // a new tree: whatever the device held is void
+    const int built = device_build(d, root, cutset_nodes);
+    if (built < 0) return built;
+    if (built) return 0;
     d->dd->build(root, &d->compile_cutset);
+    d->host_built = true; d->device_built = false;
+    d->exact_flag = d->dd->is_exact();
     d->has_cutset = d->dd->restricted() && !d->dd->is_exact();
     d->uploaded = false; d->term_dirty = true;
-    d->dev_ahead = false; d->dev_states_valid = false;   // a new tree: whatever the device held is void
     if (cutset_nodes) *cutset_nodes = d->has_cutset ? (int)d->compile_cutset.size() : -1;
     return 0;
 }
 
-int sgufp_dd_is_exact(const sgufp_dd *d) { return d ? (d->dd->is_exact() ? 1 : 0) : SGUFP_ERR_ARG; }
-int sgufp_dd_num_layers(const sgufp_dd *d) { return d ? (int)d->dd->tree().size() : SGUFP_ERR_ARG; }
+int sgufp_dd_is_exact(const sgufp_dd *d) { return d ? (d->exact_flag ? 1 : 0) : SGUFP_ERR_ARG; }
+int sgufp_dd_num_layers(const sgufp_dd *d) { return d ? (d->host_built ? (int)d->dd->tree().size() : d->nlayers_dev) : SGUFP_ERR_ARG; }
 int sgufp_dd_layer_sizes(sgufp_dd *d, int32_t *sizes) {
     if (!d || !sizes) return SGUFP_ERR_ARG;
     if (int rc = sync_host(d)) return rc;
@@ -333,6 +533,29 @@ int sgufp_dd_dump(sgufp_dd *d, int32_t *node_layer, double *node_state, int64_t 
     if (node_inptr) node_inptr[C.nnodes] = C.narcs;
     if (terminal_weight) std::copy(d->dd->terminal_weights().begin(), d->dd->terminal_weights().end(), terminal_weight);
     return 0;
+}
+
+int sgufp_dd_dump_device(sgufp_dd *d, int32_t *layer_sizes, int64_t *node_inptr, int32_t *arc_tailpos, int32_t *arc_decision, int32_t *arc_slot) {
+    if (!d) return SGUFP_ERR_ARG;
+    sgufp_ctx *c = d->ctx;
+    if (int rc = upload(d)) return rc;
+    CU(c, cudaSetDevice(c->device));
+    const int nl = d->dev.nlayers, nn = d->dev.nnodes, na = d->narcs;
+    std::vector<int4> li(nl);
+    std::vector<int32_t> ip(nn + 1), dec(std::max(1, na));
+    std::vector<int2> ts(std::max(1, na));
+    CU(c, cudaMemcpy(li.data(), d->dev.layer_info, (size_t)nl * sizeof(int4), cudaMemcpyDeviceToHost));
+    CU(c, cudaMemcpy(ip.data(), d->dev.in_ptr, (size_t)(nn + 1) * 4, cudaMemcpyDeviceToHost));
+    if (na) CU(c, cudaMemcpy(ts.data(), d->dev.arc_ts, (size_t)na * sizeof(int2), cudaMemcpyDeviceToHost));
+    if (na) CU(c, cudaMemcpy(dec.data(), d->d_arc_dec.p, (size_t)na * 4, cudaMemcpyDeviceToHost));
+    for (int l = 0; l < nl; l++) if (layer_sizes) layer_sizes[l] = li[l].z;
+    for (int v = 0; v <= nn; v++) if (node_inptr) node_inptr[v] = ip[v];
+    for (int e = 0; e < na; e++) {
+        if (arc_tailpos) arc_tailpos[e] = ts[e].x;
+        if (arc_slot) arc_slot[e] = ts[e].y;
+        if (arc_decision) arc_decision[e] = dec[e];
+    }
+    return d->device_built ? 1 : 0;
 }
 
 int sgufp_dd_apply_optimality(sgufp_dd *d, double rhs, const uint64_t *keys, const double *vals, int nnz, double optimal, double ub,
@@ -389,9 +612,9 @@ int sgufp_dd_solution(sgufp_dd *d, int16_t *path, int capacity) {
         CU(c, cudaMemcpyAsync(&r, d->d_res.p, sizeof(K2Result), cudaMemcpyDeviceToHost, c->st));
         CU(c, cudaMemcpyAsync(rev.data(), d->d_path.p, (size_t)d->dev.nlayers * 2, cudaMemcpyDeviceToHost, c->st));
         CU(c, cudaStreamSynchronize(c->st));
-        p = d->dd->root_solution();
+        p = d->root_solution;
         for (int i = r.path_len - 1; i >= 0; i--) p.push_back(rev[i]);
-    } else p = d->dd->solution();
+    } else { ensure_host(d); p = d->dd->solution(); }
     if ((int)p.size() > capacity) return SGUFP_ERR_ARG;
     std::copy(p.begin(), p.end(), path);
     return (int)p.size();
@@ -399,8 +622,14 @@ int sgufp_dd_solution(sgufp_dd *d, int16_t *path, int capacity) {
 
 int sgufp_dd_cutset(sgufp_dd *d, double ub, int32_t *words, int capacity) {
     if (!d || !words) return SGUFP_ERR_ARG;
+    if (d->dd->restricted()) {
+        // the cut-set of the last compile: structure only, cuts applied since do not change it
+        if (!d->has_cutset) return 0;
+        if (d->compile_cutset.empty() && d->device_built && !d->host_built) { if (int rc = device_cutset(d)) return rc; }
+        else ensure_host(d);
+        return write_nodes(d->compile_cutset, words, capacity);
+    }
     if (int rc = sync_host(d)) return rc;
-    if (d->dd->restricted()) return d->has_cutset ? write_nodes(d->compile_cutset, words, capacity) : 0;
     return write_nodes(d->dd->cutset(ub), words, capacity);
 }
 

@@ -63,6 +63,8 @@ public:
     void build(const NodeSpec &root, std::vector<NodeSpec> *cutset);
     bool is_exact() const { return exact_; }
     bool restricted() const { return restricted_; }
+    int max_width() const { return max_width_; }
+    int slot_of(int global_layer, int decision) const;  // coefficient slot of (layer, decision) or -1
 
     // --- cut application, split around the device pass --------------------------------------
     // 1. flatten() -> upload -> K2 computes every node's state2 for the cut
@@ -111,7 +113,6 @@ private:
     int new_node() { nodes_.emplace_back(); return (int)nodes_.size() - 1; }
     int new_arc(int tail, int head, int16_t dec) { arcs_.push_back({tail, head, dec, 0.0}); return (int)arcs_.size() - 1; }
     std::vector<int16_t> layer_states(int g) const;     // stateUpdateMap[g] (Network.cpp:98-102) or empty
-    int slot_of(int global_layer, int decision) const;  // coefficient slot of (layer, decision) or -1
     void relaxed_next_layer(int index, unsigned &next_size);
     std::vector<int32_t> restricted_next_layer(const std::vector<int32_t> &cur, bool &exact);
     std::vector<int16_t> path_for_node(int id) const;

@@ -1,0 +1,180 @@
+// k2_build.cu — decision-diagram construction on the device, emitting the CSR image directly
+// (SURVEY.md §8f-3): RelaxedDDNew::buildTree / buildNextLayer (/root/reference/DD.cpp:3528-3694) and
+// RestrictedDDNew::compile / buildNextLayer / buildRestrictedLayer (DD.cpp:3090-3260).
+//
+// A node's state set is always a subset of {-1} U outgoingArcs(q) of the V-bar node q its layer
+// belongs to (stateUpdateMap, Network.cpp:96-102; a child only ever loses the decision that led to
+// it), so a state set is ONE 32-bit mask over that sorted base list: bit 0 is -1, iteration in set
+// order is ascending bit order, the union of a collapsed layer is an OR, max_element is the highest
+// bit.  One CTA builds the whole diagram layer by layer (a prefix sum over the children counts,
+// then every parent writes its children); nothing but the sizes goes back to the host.
+// The structure — layers, node order, in-arc order — is the reference's, node for node.
+#include "k2_dd.cuh"
+
+#include <algorithm>
+
+namespace sgufp {
+namespace {
+
+constexpr int KB_THREADS = 512;
+
+// exclusive prefix sum of cnt(i), i in [0, w), into off[]; returns the total (block-uniform)
+template <class F>
+__device__ int block_scan(int w, F cnt, int32_t *off, int *sh) {
+    int carry = 0;
+    for (int base = 0; base < w; base += KB_THREADS) {
+        const int i = base + threadIdx.x;
+        const int c = i < w ? cnt(i) : 0;
+        int x = c;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += t; }
+        if ((threadIdx.x & 31) == 31) sh[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int y = threadIdx.x < KB_THREADS / 32 ? sh[threadIdx.x] : 0;
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, y, o); if (threadIdx.x >= o) y += t; }
+            sh[32 + threadIdx.x] = y;                       // inclusive sums of the warp totals
+        }
+        __syncthreads();
+        const int warp_base = (threadIdx.x >> 5) ? sh[32 + (threadIdx.x >> 5) - 1] : 0;
+        if (i < w) off[i] = carry + warp_base + x - c;
+        carry += sh[32 + KB_THREADS / 32 - 1];
+        __syncthreads();
+    }
+    return carry;
+}
+
+__device__ unsigned block_or(unsigned v, unsigned *sh) {
+    v = __reduce_or_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    unsigned r = 0;
+    for (int i = 0; i < KB_THREADS / 32; i++) r |= sh[i];
+    __syncthreads();
+    return r;
+}
+
+__device__ unsigned block_addu(unsigned v, unsigned *sh) {
+    v = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    unsigned r = 0;
+    for (int i = 0; i < KB_THREADS / 32; i++) r += sh[i];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(KB_THREADS) k2_build(K2Build b) {
+    __shared__ int sh[64 + KB_THREADS / 32];
+    unsigned *shu = reinterpret_cast<unsigned *>(sh);
+    const K2Tables &t = b.t;
+    int v0 = 0, w = 1, n = 1, e_total = 0, nl = 1, exact = 1, exact_layer = 0, max_w = 1;
+    unsigned next_size = 0;
+    if (threadIdx.x == 0) { b.mask[0] = b.root_mask; b.layer_info[0] = make_int4(0, 0, 1, 0); b.in_ptr[0] = 0; b.widths[0] = 1; }
+    __syncthreads();
+    for (int g = b.start; g < t.L; g++) {
+        const int tab = t.lay_tab[g], tp = t.tab_ptr[tab], nst = t.tab_ptr[tab + 1] - tp;
+        const unsigned full = nst >= 32 ? 0xffffffffu : (1u << nst) - 1u;
+        const int sb = t.slot_base[g];
+        if (t.lay_first[g]) {                               // states reset at the first layer of a V-bar node (DD.cpp:3565-3571)
+            for (int i = threadIdx.x; i < w; i += KB_THREADS) b.mask[v0 + i] = full;
+            next_size = (unsigned)w * (unsigned)nst;
+            __syncthreads();
+        }
+        const bool collapse = !b.restricted && next_size >= 120u && (unsigned)g < (unsigned)t.L - 5u;   // DD.cpp:3614
+        const bool one_child = b.restricted && !exact;      // DD.cpp:3204: the greatest state only
+        auto cnt = [&](int i) { return one_child ? 1 : __popc(b.mask[v0 + i]); };
+        const int sum = block_scan(w, cnt, b.off, sh);
+        int total = sum;
+        if (b.restricted && exact && sum > b.max_width) total = b.max_width;   // the layer stops mid-node at max_width (DD.cpp:3238)
+        const int new_nodes = collapse ? 1 : total;
+        if (n + new_nodes > b.node_cap || e_total + (collapse ? sum : total) > b.arc_cap) { if (threadIdx.x == 0) b.out->overflow = 1; return; }
+        unsigned uni = 0, child_states = 0;
+        for (int i = threadIdx.x; i < w; i += KB_THREADS) {
+            const unsigned m = b.mask[v0 + i];
+            const int c = one_child ? 1 : __popc(m), o = b.off[i];
+            uni |= m;
+            for (int r = 0; r < c; r++) {
+                const int k = o + r;
+                if (k >= total) break;
+                // relaxed: states in set order; restricted: in REVERSE order (DD.cpp:3235); non-exact: the greatest
+                const int pos = one_child ? 31 - __clz(m) : (b.restricted ? __fns(m, 0, __popc(m) - r) : __fns(m, 0, r + 1));
+                const int dec = t.tab_dec[tp + pos], kk = t.tab_k[tp + pos];
+                const int e = e_total + k;
+                b.arc_ts[e] = make_int2(i, kk >= 0 ? sb + kk : -1);
+                b.arc_dec[e] = dec;
+                if (!collapse) {
+                    const unsigned cm = pos ? m & ~(1u << pos) : m;   // the child loses the decision taken, -1 is never removed
+                    b.mask[n + k] = cm;
+                    b.in_ptr[n + k] = e;
+                    child_states += (unsigned)__popc(cm);
+                }
+            }
+        }
+        if (collapse) {
+            uni = block_or(uni, shu);
+            if (threadIdx.x == 0) { b.mask[n] = uni; b.in_ptr[n] = e_total; b.layer_info[nl] = make_int4(n, e_total, 1, sum == 1 ? 1 : 0); b.widths[nl] = 1; }
+            next_size = (unsigned)__popc(uni);
+            exact = 0;
+            v0 = n; w = 1; n += 1; e_total += sum;
+        } else {
+            next_size = block_addu(child_states, shu);
+            if (threadIdx.x == 0) { b.layer_info[nl] = make_int4(n, e_total, total, 1); b.widths[nl] = total; }
+            if (b.restricted && exact && sum > b.max_width) exact = 0;
+            v0 = n; w = total; n += total; e_total += total;
+        }
+        if (b.restricted && exact) exact_layer++;
+        max_w = max(max_w, w);
+        nl++;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        b.in_ptr[n] = e_total;
+        K2BuildOut o;
+        o.nlayers = nl; o.nnodes = n; o.narcs = e_total; o.exact = exact; o.exact_layer = exact_layer; o.overflow = 0; o.max_width = max_w; o.nlast = w;
+        *b.out = o;
+    }
+}
+
+// getExactCutSet of a restricted tree (DD.cpp:3279-3288): for every node of the last exact layer its state
+// mask and the decisions of its single-parent chain, root first.
+__global__ void k2_cutset(const int4 *layer_info, const int32_t *in_ptr, const int2 *arc_ts, const int32_t *arc_dec, const unsigned *mask,
+                          int el, unsigned *out_mask, int16_t *out_dec) {
+    const int4 li = layer_info[el];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= li.z) return;
+    int v = li.x + j;
+    out_mask[j] = mask[v];
+    for (int l = el; l >= 1; l--) {
+        const int e = in_ptr[v];
+        out_dec[(size_t)j * el + (l - 1)] = (int16_t)arc_dec[e];
+        v = layer_info[l - 1].x + arc_ts[e].x;
+    }
+}
+
+__global__ void k2_fill(double *p, double v, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+}  // namespace
+
+cudaError_t k2_build_launch(const K2Build &b, cudaStream_t st, int *launches) {
+    k2_build<<<1, KB_THREADS, 0, st>>>(b);
+    if (launches) (*launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t k2_cutset_launch(const int4 *layer_info, const int32_t *in_ptr, const int2 *arc_ts, const int32_t *arc_dec, const unsigned *mask,
+                             int el, int count, unsigned *out_mask, int16_t *out_dec, cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+    k2_cutset<<<(count + 255) / 256, 256, 0, st>>>(layer_info, in_ptr, arc_ts, arc_dec, mask, el, out_mask, out_dec);
+    return cudaGetLastError();
+}
+
+cudaError_t k2_fill_launch(double *p, double v, long long n, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    const int blocks = (int)std::min<long long>((n + 255) / 256, 1184);
+    k2_fill<<<blocks, 256, 0, st>>>(p, v, n);
+    return cudaGetLastError();
+}
+
+}  // namespace sgufp

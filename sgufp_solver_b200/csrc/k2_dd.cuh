@@ -67,4 +67,31 @@ cudaError_t k2_layered_launch(const K2DD &d, const int32_t *layer_width_host, co
 cudaError_t k2_finish_launch(const K2Apply &a, cudaStream_t st, int *launches);
 cudaError_t k2_extract_launch(const K2Apply &a, cudaStream_t st, int *launches);
 
+// ---- construction on the device ---------------------------------------
+struct K2Tables {               // static per network, uploaded once per context
+    const int32_t *lay_tab;     // [L]      state table (V-bar node) of each global layer
+    const uint8_t *lay_first;   // [L]      1 at the first layer of a V-bar node: states reset (Network.cpp:96-102)
+    const int32_t *tab_ptr;     // [ntab+1]
+    const int16_t *tab_dec;     // base list of a table: -1, then the node's out-arcs ascending
+    const int16_t *tab_k;       // coefficient slot of that decision relative to slot_base[layer], -1 for none
+    const int32_t *slot_base;   // [L]
+    int L;
+};
+struct K2BuildOut { int nlayers, nnodes, narcs, exact, exact_layer, overflow, max_width, nlast; };
+struct K2Build {
+    K2Tables t;
+    int start;                  // global layer of the root (== number of fixed prefix decisions)
+    unsigned root_mask;         // the root's states over the base list of layer `start`
+    int restricted, max_width;
+    int node_cap, arc_cap;
+    int4 *layer_info; int32_t *in_ptr; int2 *arc_ts; int32_t *arc_dec; unsigned *mask; int32_t *off /*[node_cap] scratch*/;
+    int32_t *widths;            // [L - start + 1]
+    K2BuildOut *out;
+};
+cudaError_t k2_build_launch(const K2Build &b, cudaStream_t st, int *launches);
+cudaError_t k2_fill_launch(double *p, double v, long long n, cudaStream_t st);
+// restricted tree: state mask + decisions (root first, `el` per node) of every node of layer `el`
+cudaError_t k2_cutset_launch(const int4 *layer_info, const int32_t *in_ptr, const int2 *arc_ts, const int32_t *arc_dec, const unsigned *mask,
+                             int el, int count, unsigned *out_mask, int16_t *out_dec, cudaStream_t st);
+
 }  // namespace sgufp

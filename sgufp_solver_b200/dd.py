@@ -24,6 +24,7 @@ DD_SIGNATURES = {
     "sgufp_dd_layer_sizes": (C.c_int, [vp, ip]),
     "sgufp_dd_counts": (C.c_int, [vp, i64p, i64p]),
     "sgufp_dd_dump": (C.c_int, [vp, ip, dp, i64p, ip, ip, dp]),
+    "sgufp_dd_dump_device": (C.c_int, [vp, ip, i64p, ip, ip, ip]),
     "sgufp_dd_apply_optimality": (C.c_int, [vp, C.c_double, u64p, dp, C.c_int, C.c_double, C.c_double, dp]),
     "sgufp_dd_apply_feasibility": (C.c_int, [vp, C.c_double, u64p, dp, C.c_int, cip]),
     "sgufp_dd_solution": (C.c_int, [vp, i16p, C.c_int]),
@@ -135,6 +136,22 @@ class _DDBase:
                                                   tailpos.ctypes.data_as(ip), dec.ctypes.data_as(ip), term.ctypes.data_as(dp)))
         return dict(node_layer=node_layer, node_state=node_state, in_ptr=inptr, arc_tailpos=tailpos[:na_in], arc_decision=dec[:na_in],
                     terminal_weight=term[:nlast])
+
+    def dump_device(self):
+        """The CSR image as it sits on the device (test introspection).  `built_on_device` tells whether
+        k2_build made it or the host mirror was uploaded."""
+        nl = _lib_dd().sgufp_dd_num_layers(self.h)
+        sizes = np.zeros(nl, np.int32)
+        r = _lib_dd().sgufp_dd_dump_device(self.h, sizes.ctypes.data_as(ip), None, None, None, None)
+        if r < 0:
+            self.solver._check(r)
+        nn = int(sizes.sum()); na = nn - 1 if nn else 0
+        inptr = np.zeros(nn + 1, np.int64)
+        _lib_dd().sgufp_dd_dump_device(self.h, None, inptr.ctypes.data_as(i64p), None, None, None)
+        na = int(inptr[nn])
+        tailpos = np.zeros(max(1, na), np.int32); dec = np.zeros(max(1, na), np.int32); slot = np.zeros(max(1, na), np.int32)
+        r = _lib_dd().sgufp_dd_dump_device(self.h, None, None, tailpos.ctypes.data_as(ip), dec.ctypes.data_as(ip), slot.ctypes.data_as(ip))
+        return dict(layer_sizes=sizes, in_ptr=inptr, arc_tailpos=tailpos[:na], arc_decision=dec[:na], arc_slot=slot[:na], built_on_device=bool(r))
 
     def getSolution(self) -> np.ndarray:
         buf = np.zeros(self.solver.L + 8, np.int16)
