@@ -66,6 +66,18 @@ int sgufp_dd_apply_optimality(sgufp_dd *dd, double rhs, const uint64_t *keys, co
 int sgufp_dd_apply_feasibility(sgufp_dd *dd, double rhs, const uint64_t *keys, const double *vals, int nnz,
                                int *feasible);
 
+/* A RUN of cuts of one kind on one diagram, as the loops of NodeExplorer::process apply the global cuts to a
+ * fresh diagram (NodeExplorer.cpp:935-944, 975-983): mode 0 = applyOptimalityCut(cut, optimal, .) for every cut,
+ * mode 1 = applyFeasibilityCut(cut).  Stops after the first cut whose bound <= optimal (mode 0) or that is
+ * infeasible (mode 1) — where the caller's loop returns — and reports how many cuts were applied; bound[k] /
+ * feasible[k] are the values the reference's calls return (whichever array the mode fills; the other may be
+ * NULL).  The result is exactly that of the one-by-one calls: the longest paths of the cuts are computed side
+ * by side, the sequential part (terminal weights, removals, pruning) in order, and whenever a cut changes the
+ * structure the cuts behind it are recomputed on the new one. */
+int sgufp_dd_apply_sequence(sgufp_dd *dd, int mode, const double *rhs, const uint64_t *keys, const double *vals,
+                            const int32_t *cut_ptr, int C, double optimal, double *bound /*[C]*/, int *feasible /*[C]*/,
+                            int *applied);
+
 /* getSolution() / getMaxPath() (DD.cpp:3825-3840, 3290-3305): returns the path length.  After a
  * single-cut apply the path is extracted on the device; only its L int16 decisions come back. */
 int sgufp_dd_solution(sgufp_dd *dd, int16_t *path, int capacity);

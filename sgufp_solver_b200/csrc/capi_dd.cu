@@ -188,7 +188,7 @@ int apply_on_device(sgufp_dd *d, double rhs, const uint64_t *keys, const double 
         CU(c, cudaMemcpyAsync(d->d_state.p, &v, 8, cudaMemcpyHostToDevice, c->st));
         CU(c, k2_layered_launch(self, d->layer_width.data(), d->layer_collapsed.data(), d->d_coef.p, d->d_state.p, c->st, &c->dd_launches));
     } else
-        CU(c, k2_single_launch(d->d_self.p, d->d_coef.p, d->d_rhs.p, Tpad, d->d_state.p, d->d_last.p, d->dev.max_width, c->st, &c->dd_launches));
+        CU(c, k2_single_launch(d->d_self.p, d->d_coef.p, d->d_rhs.p, Tpad, d->d_state.p, d->d_last.p, d->dev.max_width, d->dev.nlayers, c->st, &c->dd_launches));
     CU(c, k2_finish_launch(make_apply(d, mode, optimal), c->st, &c->dd_launches));
     CU(c, cudaEventRecord(c->evk1, c->st));
     CU(c, cudaMemcpyAsync(&res, d->d_res.p, sizeof(K2Result), cudaMemcpyDeviceToHost, c->st));
@@ -392,11 +392,12 @@ int run_k2(sgufp_ctx *c, sgufp_dd **dds, int B, const std::vector<std::vector<do
     Scratch &S = scratch_of(c);
     std::vector<K2DD> hd(B);
     long long off = 0, loff = 0, arcs = 0;
-    int maxw = 1;
+    int maxw = 1, maxl = 1;
     for (int b = 0; b < B; b++) {
         if (dds[b]->ctx != c) return fail(c, SGUFP_ERR_ARG, "all diagrams of a batch must belong to one context");
         if (int rc = upload(dds[b])) return rc;
         maxw = std::max(maxw, dds[b]->dev.max_width);
+        maxl = std::max(maxl, dds[b]->dev.nlayers);
     }
     const bool in_smem = k2_states_in_smem(Tpad, maxw);   // else: one global state block per (diagram, cut)
     for (int b = 0; b < B; b++) {
@@ -414,7 +415,7 @@ int run_k2(sgufp_ctx *c, sgufp_dd **dds, int B, const std::vector<std::vector<do
     CU(c, cudaMemcpyAsync(S.dds.p, hd.data(), (size_t)B * sizeof(K2DD), cudaMemcpyHostToDevice, c->st));
     c->dd_launches = 0;
     CU(c, cudaEventRecord(c->evk0, c->st));
-    CU(c, k2_launch(S.dds.p, B, S.coef.p, S.rhs.p, C, Tpad, S.states.p, S.last.p, maxw, c->st, &c->dd_launches));
+    CU(c, k2_launch(S.dds.p, B, S.coef.p, S.rhs.p, C, Tpad, S.states.p, S.last.p, maxw, maxl, c->st, &c->dd_launches));
     if (update_terminal) CU(c, k2_terminal_launch(S.dds.p, B, C, S.last.p, S.bound.p, c->st, &c->dd_launches));
     CU(c, cudaEventRecord(c->evk1, c->st));
     if (states_last_cut) {
@@ -573,6 +574,65 @@ int sgufp_dd_apply_feasibility(sgufp_dd *d, double rhs, const uint64_t *keys, co
     K2Result r{};
     if (int rc = apply_on_device(d, rhs, keys, vals, nnz, 1, 0.0, r)) return rc;
     if (feasible) *feasible = r.feasible;
+    return 0;
+}
+
+int sgufp_dd_apply_sequence(sgufp_dd *d, int mode, const double *rhs, const uint64_t *keys, const double *vals, const int32_t *cut_ptr, int C,
+                            double optimal, double *bound, int *feasible, int *applied) {
+    if (!d || C < 1 || !rhs || !cut_ptr || (mode != 0 && mode != 1)) return SGUFP_ERR_ARG;
+    sgufp_ctx *c = d->ctx;
+    if (int rc = upload(d)) return rc;
+    Scratch &S = scratch_of(c);
+    const int T = std::max(1, c->M.T), Tpad = (T + 1) & ~1, nn = d->dev.nnodes, nlast = d->dev.nlast;
+    std::vector<double> cf((size_t)C * Tpad, 0.0), one;
+    for (int k = 0; k < C; k++) {
+        d->dd->densify(keys + cut_ptr[k], vals + cut_ptr[k], cut_ptr[k + 1] - cut_ptr[k], one);
+        std::copy(one.begin(), one.begin() + T, cf.begin() + (size_t)k * Tpad);
+    }
+    const int chunk = (int)std::max<long long>(1, std::min<long long>(C, (1LL << 27) / std::max(1, nn)));   // <= 1 GB of states
+    DevBuf<K2Result> res; DevBuf<int> ctl;
+    CU(c, S.coef.reserve(cf.size())); CU(c, S.rhs.reserve(C)); CU(c, S.states.reserve((size_t)chunk * nn)); CU(c, S.last.reserve((size_t)chunk * std::max(1, nlast)));
+    CU(c, res.reserve(C)); CU(c, ctl.reserve(2));
+    K2DD self = d->dev; self.state_off = 0; self.last_off = 0;
+    cudaError_t e = cudaMemcpyAsync(S.coef.p, cf.data(), cf.size() * 8, cudaMemcpyHostToDevice, c->st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(S.rhs.p, rhs, (size_t)C * 8, cudaMemcpyHostToDevice, c->st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d->d_self.p, &self, sizeof(K2DD), cudaMemcpyHostToDevice, c->st);
+    c->dd_launches = 0;
+    if (e == cudaSuccess) e = cudaEventRecord(c->evk0, c->st);
+    // Speculation window: the longest paths of `win` cuts are computed side by side on the current structure; a cut
+    // that changes it voids the ones behind it.  The window doubles after a clean run and restarts small after a change.
+    int k0 = 0, stopped = 0, last_base = 0, win = std::min(chunk, 8);
+    while (e == cudaSuccess && k0 < C && !stopped) {
+        K2Seq q{};
+        q.coef = S.coef.p; q.states = S.states.p; q.results = res.p; q.ctl = ctl.p; q.k0 = k0; q.k1 = std::min(C, k0 + win); q.Tpad = Tpad;
+        e = k2_sequence_launch(d->d_self.p, make_apply(d, mode, optimal), q, S.rhs.p, d->dev.max_width, S.last.p, c->st, &c->dd_launches);
+        int h[2] = {0, 0};
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h, ctl.p, 8, cudaMemcpyDeviceToHost, c->st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->st);
+        last_base = k0;
+        win = h[0] == q.k1 ? std::min(chunk, win * 2) : std::max(4, std::min(chunk, (h[0] - k0) * 2));
+        k0 = h[0]; stopped = h[1];
+    }
+    const int done = k0;   // cuts applied, the stopping one included
+    std::vector<K2Result> hr(std::max(1, done));
+    if (e == cudaSuccess && done > 0) {
+        // the diagram keeps the states and coefficients of the last cut applied (getSolution, the host mirror)
+        e = cudaMemcpyAsync(d->d_state.p, S.states.p + (size_t)(done - 1 - last_base) * nn, (size_t)nn * 8, cudaMemcpyDeviceToDevice, c->st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d->d_coef.p, S.coef.p + (size_t)(done - 1) * Tpad, (size_t)Tpad * 8, cudaMemcpyDeviceToDevice, c->st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hr.data(), res.p, (size_t)done * sizeof(K2Result), cudaMemcpyDeviceToHost, c->st);
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(c->evk1, c->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->st);
+    res.release(); ctl.release();
+    CU(c, e);
+    CU(c, cudaEventElapsedTime(&c->dd_kernel_ms, c->evk0, c->evk1));
+    c->dd_arcs = ((long long)d->narcs + nlast) * done;
+    for (int k = 0; k < done; k++) { if (bound) bound[k] = hr[k].bound; if (feasible) feasible[k] = hr[k].feasible; }
+    if (applied) *applied = done;
+    if (done > 0) {
+        d->last_coef.assign(cf.begin() + (size_t)(done - 1) * Tpad, cf.begin() + (size_t)(done - 1) * Tpad + T);
+        d->dev_ahead = true; d->dev_states_valid = true; d->term_dirty = false;
+    }
     return 0;
 }
 

@@ -200,12 +200,7 @@ void HostDD::densify(const uint64_t *keys, const double *vals, int nnz, std::vec
     const Model &M = *M_;
     coef.assign(std::max(1, M.T), 0.0);
     std::vector<uint8_t> seen(std::max(1, M.T), 0);
-    std::unordered_map<uint64_t, int> slot;   // key (48 bits) -> first slot with that (q,i,j)
-    slot.reserve(M.T * 2);
-    for (int s = 0; s < M.T; s++) {
-        const uint64_t i = (uint64_t)M.tail[M.slot_in[s]], q = (uint64_t)M.head[M.slot_in[s]], j = (uint64_t)M.head[M.slot_out[s]];
-        slot.emplace(q | (i << 16) | (j << 32), s);
-    }
+    const auto &slot = M.key_slot;            // key (48 bits) -> first slot with that (q,i,j), built once per model
     for (int k = 0; k < nnz; k++) {
         auto it = slot.find(keys[k] & 0xFFFFFFFFFFFFull);   // IQJ_MASK (Cut.h:197)
         if (it == slot.end() || seen[it->second]) continue;   // get() returns the FIRST match (Cut.h:275-282)

@@ -45,13 +45,18 @@ __device__ __forceinline__ double block_max(double v, double *red) {
 template <bool SMEM_STATES, bool DEADS>
 __global__ void __launch_bounds__(K2_THREADS) k2_longest_path(const K2DD *__restrict__ dds, const double *__restrict__ coef,
                                                                const double *__restrict__ rhs, int C, int Tpad, int maxw,
-                                                               double *__restrict__ gstate, double *__restrict__ glast) {
+                                                               double *__restrict__ gstate, double *__restrict__ glast, int li_cache) {
     extern __shared__ double sm[];
     __shared__ double red[K2_THREADS / 32];
     const K2DD d = dds[blockIdx.y];
     const int c = blockIdx.x;
     double *cf = sm;                       // [Tpad]
     double *buf0 = sm + Tpad, *buf1 = buf0 + (SMEM_STATES ? maxw : 0);
+    // the per-layer records, staged once: a layer is short, a dependent global load per layer is not
+    int4 *li_s = reinterpret_cast<int4 *>(buf1 + (SMEM_STATES ? maxw : 0));
+    const bool li_cached = d.nlayers <= li_cache;
+    if (li_cached) for (int i = threadIdx.x; i < d.nlayers; i += blockDim.x) li_s[i] = d.layer_info[i];
+    const int4 *layer_info = li_cached ? li_s : d.layer_info;
     for (int i = threadIdx.x; i < Tpad; i += blockDim.x) cf[i] = coef[(size_t)c * Tpad + i];
     const bool keep_all = c == C - 1;      // the host reads every node state of the last cut only
     double *all = gstate + d.state_off + (SMEM_STATES ? 0 : (size_t)c * d.nnodes);
@@ -65,9 +70,9 @@ __global__ void __launch_bounds__(K2_THREADS) k2_longest_path(const K2DD *__rest
     }
     __syncthreads();
     for (int l = 1; l < d.nlayers; l++) {
-        const int4 li = d.layer_info[l];
+        const int4 li = layer_info[l];
         const int v0 = li.x, e0 = li.y, width = li.z;
-        const double *prev = SMEM_STATES ? ((l & 1) ? buf0 : buf1) : all + d.layer_info[l - 1].x;
+        const double *prev = SMEM_STATES ? ((l & 1) ? buf0 : buf1) : all + layer_info[l - 1].x;
         double *cur = SMEM_STATES ? ((l & 1) ? buf1 : buf0) : all + v0;
         const bool is_last = l == d.nlayers - 1;
         double *lastp = glast + d.last_off + (size_t)c * d.nlast;
@@ -203,48 +208,78 @@ __device__ int block_sum(int v, int *red) {
 // diagram (DD.cpp:3995-4017 with threshold optimal - 0.01, layers 3 .. llayer-2; DD.cpp:3902-3926
 // with threshold -0.01, layers 1 .. llayer-1).  Candidates are flagged 2 and committed only if no
 // layer loses every arc; returns true if one did (the reference then returns without removing).
+constexpr int K2_MAX_COLLAPSED = 64;   // collapsed layers handled per call by the fast path of prune_collapsed
+
 __device__ bool prune_collapsed(const K2Apply &a, int first_layer, int end_layer, double max_state, double threshold,
                                 int *ired, int *sh) {
     const K2DD &d = a.d;
-    bool abort = false;
-    for (int layer = first_layer; layer < end_layer && !abort; layer++) {
-        if (a.layer_alive[layer] != 1) continue;            // uniform: global memory, no writer in this loop
+    // the collapsed layers (ONE live node) in range, found with one parallel sweep over the live layer sizes
+    // — a loop over the layers would pay one dependent global load each.  Their order does not matter: any layer
+    // that loses every arc aborts the whole call, otherwise all candidates are committed.
+    __shared__ int s_n, s_layer[K2_MAX_COLLAPSED];
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (int layer = first_layer + threadIdx.x; layer < end_layer; layer += blockDim.x)
+        if (a.layer_alive[layer] == 1) { const int k = atomicAdd(&s_n, 1); if (k < K2_MAX_COLLAPSED) s_layer[k] = layer; }
+    __syncthreads();
+    const int ncol = s_n;
+    const bool listed = ncol <= K2_MAX_COLLAPSED;
+    __shared__ int s_abort;
+    if (threadIdx.x == 0) s_abort = 0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    // one WARP per collapsed layer (they are independent): no block barrier, eight layers in flight
+    auto one_layer = [&](int layer, bool commit_only, bool keep) -> int {
         const int4 li = d.layer_info[layer];
-        if (threadIdx.x == 0) sh[0] = -1;
-        __syncthreads();
-        for (int i = threadIdx.x; i < li.z; i += blockDim.x) if (!a.node_dead[li.x + i]) sh[0] = li.x + i;   // the one node left
-        __syncthreads();
-        const int v = sh[0];
-        __syncthreads();
+        int v = -1;
+        for (int i = lane; i < li.z; i += 32) if (!a.node_dead[li.x + i]) v = li.x + i;      // the one node left
+        for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+        const int e0 = d.in_ptr[v], e1 = d.in_ptr[v + 1];
+        if (commit_only) {
+            int changed = 0;
+            for (int e = e0 + lane; e < e1; e += 32)
+                if (a.arc_dead[e] == 2) { a.arc_dead[e] = keep ? 1 : 0; changed |= keep ? 1 : 0; }
+            return changed;
+        }
         const double gain = max_state - a.state[v];
         const int tail0 = d.layer_info[layer - 1].x;
         int pruned = 0, total = 0;
-        for (int e = d.in_ptr[v] + threadIdx.x; e < d.in_ptr[v + 1]; e += blockDim.x) {
+        for (int e = e0 + lane; e < e1; e += 32) {
             if (a.arc_dead[e]) continue;
             const int2 ts = d.arc_ts[e];
             const double w = ts.y >= 0 ? a.coef[ts.y] : 0.0;
             total++;
             if ((a.state[tail0 + ts.x] + w + gain) <= threshold) { a.arc_dead[e] = 2; pruned++; }
         }
-        pruned = block_sum(pruned, ired);
-        total = block_sum(total, ired);
-        if (pruned == total) abort = true;
+        for (int o = 16; o; o >>= 1) { pruned += __shfl_xor_sync(0xffffffffu, pruned, o); total += __shfl_xor_sync(0xffffffffu, total, o); }
+        return pruned == total ? 1 : 0;
+    };
+    if (listed) {
+        for (int k = warp; k < ncol; k += nwarp) if (one_layer(s_layer[k], false, false) && lane == 0) atomicOr(&s_abort, 1);
+    } else {
+        for (int layer = first_layer + warp; layer < end_layer; layer += nwarp) {
+            if (a.layer_alive[layer] != 1) continue;
+            if (one_layer(layer, false, false) && lane == 0) atomicOr(&s_abort, 1);
+        }
     }
-    // commit or discard the candidates
-    const int narcs = d.in_ptr[d.nnodes];
+    __syncthreads();
+    const bool abort = s_abort != 0;
+    // commit or discard the candidates: they all sit among the in-arcs of the collapsed nodes
     int changed = 0;
-    for (int e = threadIdx.x; e < narcs; e += blockDim.x)
-        if (a.arc_dead[e] == 2) { a.arc_dead[e] = abort ? 0 : 1; changed |= abort ? 0 : 1; }
+    if (listed) {
+        for (int k = warp; k < ncol; k += nwarp) changed |= one_layer(s_layer[k], true, !abort);
+    } else {
+        const int narcs = d.in_ptr[d.nnodes];
+        for (int e = threadIdx.x; e < narcs; e += blockDim.x)
+            if (a.arc_dead[e] == 2) { a.arc_dead[e] = abort ? 0 : 1; changed |= abort ? 0 : 1; }
+    }
     changed = block_sum(changed, ired);
     if (threadIdx.x == 0 && changed) a.out->changed = 1;
     __syncthreads();
     return abort;
 }
 
-__global__ void __launch_bounds__(K2_THREADS) k2_finish(K2Apply a) {
-    __shared__ double red[K2_THREADS / 32];
-    __shared__ int ired[K2_THREADS / 32];
-    __shared__ int sh[2];
+__device__ void finish_body(const K2Apply &a, double *red, int *ired, int *sh) {
     const K2DD &d = a.d;
     const int nl = d.nlayers, llayer = nl - 1;
     const int last0 = d.layer_info[llayer].x, nlast = d.nlast;
@@ -342,6 +377,40 @@ __global__ void __launch_bounds__(K2_THREADS) k2_finish(K2Apply a) {
     }
 }
 
+__global__ void __launch_bounds__(K2_THREADS) k2_finish(K2Apply a) {
+    __shared__ double red[K2_THREADS / 32];
+    __shared__ int ired[K2_THREADS / 32];
+    __shared__ int sh[2];
+    finish_body(a, red, ired, sh);
+}
+
+// A run of cuts of one kind on one diagram.  Their longest paths were computed side by side on the
+// CURRENT structure (k2_longest_path, one CTA per cut); this kernel applies the sequential part cut
+// by cut and stops after the first cut that (a) ends the loop of the caller — bound <= optimal
+// (NodeExplorer.cpp:942, 982) or not feasible (:936, 977) — or (b) removed arcs or nodes: the states
+// of the cuts behind it were computed on a structure that no longer exists and are recomputed.
+__global__ void __launch_bounds__(K2_THREADS) k2_finish_seq(K2Apply a, K2Seq q) {
+    __shared__ double red[K2_THREADS / 32];
+    __shared__ int ired[K2_THREADS / 32];
+    __shared__ int sh[2];
+    for (int k = q.k0; k < q.k1; k++) {
+        K2Apply b = a;
+        b.state = q.states + (size_t)(k - q.k0) * a.d.nnodes;
+        b.coef = q.coef + (size_t)k * q.Tpad;
+        b.out = q.results + k;
+        finish_body(b, red, ired, sh);
+        __syncthreads();
+        const K2Result r = q.results[k];
+        const bool stop = a.mode == 0 ? r.bound <= a.optimal : r.feasible == 0;
+        if (r.changed || stop) {
+            if (threadIdx.x == 0) { q.ctl[0] = k + 1; q.ctl[1] = stop ? 1 : 0; }
+            return;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { q.ctl[0] = q.k1; q.ctl[1] = 0; }
+}
+
 // getSolution (DD.cpp:3825-3840) / getMaxPath (DD.cpp:3290-3305) + getPathForNode (DD.cpp:3796-3820):
 // the first terminal arc of strictly greatest weight, then backwards over the first in-arc whose
 // parent state + weight EQUALS the node's state (exact fp compare); if none does, step to the first
@@ -394,7 +463,8 @@ __global__ void __launch_bounds__(K2_THREADS) k2_extract(K2Apply a) {
 }  // namespace
 
 cudaError_t k2_launch(const K2DD *dds, int B, const double *coef, const double *rhs, int C, int Tpad, double *states, double *last,
-                      int max_width_all, cudaStream_t st, int *launches) {
+                      int max_width_all, int max_layers, cudaStream_t st, int *launches) {
+    const int K2_LI_CACHE = max_layers <= 640 ? max_layers : 0;   // shadows the constant: stage exactly what this batch needs
     dim3 grid(C, B);
     if (launches) (*launches)++;
     // narrow diagrams: smaller CTAs, more of them per SM (a layer is one barrier-separated step)
@@ -402,14 +472,15 @@ cudaError_t k2_launch(const K2DD *dds, int B, const double *coef, const double *
     while (threads < K2_THREADS && threads < max_width_all) threads *= 2;
     const size_t smem = ((size_t)Tpad + 2 * (size_t)max_width_all) * sizeof(double);
     if (smem <= 200 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k2_longest_path<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const size_t tot = smem + (size_t)K2_LI_CACHE * sizeof(int4);
+        cudaError_t e = cudaFuncSetAttribute(k2_longest_path<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tot);
         if (e != cudaSuccess) return e;
-        k2_longest_path<true, false><<<grid, threads, smem, st>>>(dds, coef, rhs, C, Tpad, max_width_all, states, last);
+        k2_longest_path<true, false><<<grid, threads, tot, st>>>(dds, coef, rhs, C, Tpad, max_width_all, states, last, K2_LI_CACHE);
     } else {
-        const size_t sm2 = (size_t)Tpad * sizeof(double);
+        const size_t sm2 = (size_t)Tpad * sizeof(double) + (size_t)K2_LI_CACHE * sizeof(int4);
         cudaError_t e = cudaFuncSetAttribute(k2_longest_path<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
         if (e != cudaSuccess) return e;
-        k2_longest_path<false, false><<<grid, threads, sm2, st>>>(dds, coef, rhs, C, Tpad, 0, states, last);
+        k2_longest_path<false, false><<<grid, threads, sm2, st>>>(dds, coef, rhs, C, Tpad, 0, states, last, K2_LI_CACHE);
     }
     return cudaGetLastError();
 }
@@ -423,20 +494,22 @@ cudaError_t k2_terminal_launch(const K2DD *dds, int B, int C, const double *last
 }
 
 cudaError_t k2_single_launch(const K2DD *dd, const double *coef, const double *rhs, int Tpad, double *states, double *last,
-                             int max_width, cudaStream_t st, int *launches) {
+                             int max_width, int max_layers, cudaStream_t st, int *launches) {
+    const int K2_LI_CACHE = max_layers <= 640 ? max_layers : 0;
     if (launches) (*launches)++;
     int threads = 64;
     while (threads < K2_THREADS && threads < max_width) threads *= 2;
     const size_t smem = ((size_t)Tpad + 2 * (size_t)max_width) * sizeof(double);
     if (smem <= 200 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k2_longest_path<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const size_t tot = smem + (size_t)K2_LI_CACHE * sizeof(int4);
+        cudaError_t e = cudaFuncSetAttribute(k2_longest_path<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tot);
         if (e != cudaSuccess) return e;
-        k2_longest_path<true, true><<<dim3(1, 1), threads, smem, st>>>(dd, coef, rhs, 1, Tpad, max_width, states, last);
+        k2_longest_path<true, true><<<dim3(1, 1), threads, tot, st>>>(dd, coef, rhs, 1, Tpad, max_width, states, last, K2_LI_CACHE);
     } else {
-        const size_t sm2 = (size_t)Tpad * sizeof(double);
+        const size_t sm2 = (size_t)Tpad * sizeof(double) + (size_t)K2_LI_CACHE * sizeof(int4);
         cudaError_t e = cudaFuncSetAttribute(k2_longest_path<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
         if (e != cudaSuccess) return e;
-        k2_longest_path<false, true><<<dim3(1, 1), threads, sm2, st>>>(dd, coef, rhs, 1, Tpad, 0, states, last);
+        k2_longest_path<false, true><<<dim3(1, 1), threads, sm2, st>>>(dd, coef, rhs, 1, Tpad, 0, states, last, K2_LI_CACHE);
     }
     return cudaGetLastError();
 }
@@ -454,6 +527,23 @@ cudaError_t k2_layered_launch(const K2DD &d, const int32_t *layer_width_host, co
 cudaError_t k2_finish_launch(const K2Apply &a, cudaStream_t st, int *launches) {
     k2_finish<<<1, K2_THREADS, 0, st>>>(a);
     if (launches) (*launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t k2_sequence_launch(const K2DD *dd_device, const K2Apply &a, const K2Seq &q, const double *rhs_device, int max_width,
+                               double *last_scratch, cudaStream_t st, int *launches) {
+    const int K2_LI_CACHE = a.d.nlayers <= 640 ? a.d.nlayers : 0;
+    // longest paths of cuts [k0, k1) side by side: global state blocks, one per cut, dead arcs honoured
+    const int n = q.k1 - q.k0;
+    int threads = 64;
+    while (threads < K2_THREADS && threads < max_width) threads *= 2;
+    const size_t sm2 = (size_t)q.Tpad * sizeof(double) + (size_t)K2_LI_CACHE * sizeof(int4);
+    cudaError_t e = cudaFuncSetAttribute(k2_longest_path<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+    if (e != cudaSuccess) return e;
+    k2_longest_path<false, true><<<dim3(n, 1), threads, sm2, st>>>(dd_device, q.coef + (size_t)q.k0 * q.Tpad, rhs_device + q.k0, n, q.Tpad, 0,
+                                                                     q.states, last_scratch, K2_LI_CACHE);
+    k2_finish_seq<<<1, K2_THREADS, 0, st>>>(a, q);
+    if (launches) (*launches) += 2;
     return cudaGetLastError();
 }
 

@@ -22,7 +22,8 @@ struct K2DD {   // device image of one decision diagram (CSR by layer, DESIGN.md
 // Only the last layer goes to global memory (last[b][c][i]); the states of every node are written
 // for cut C-1 alone, which is what the host semantics read back.
 cudaError_t k2_launch(const K2DD *dds_device, int B, const double *coef_device /*[C][Tpad]*/, const double *rhs_device /*[C]*/,
-                      int C, int Tpad, double *states_device, double *last_device, int max_width_all, cudaStream_t st, int *launches);
+                      int C, int Tpad, double *states_device, double *last_device, int max_width_all, int max_layers, cudaStream_t st,
+                      int *launches);   // max_layers: the per-layer records are staged in shared memory when <= 640
 // true if the widest layer fits the shared-memory state buffers (else: global state blocks, one per cut)
 bool k2_states_in_smem(int Tpad, int max_width_all);
 // term[i] = min(term[i], min_c last[b][c][i]); bound[b] = max_i term[i]
@@ -59,12 +60,22 @@ struct K2Apply {
 };
 // single-cut longest path of ONE diagram that honours arc_dead; every node state goes to `states`
 cudaError_t k2_single_launch(const K2DD *dd_device, const double *coef_device, const double *rhs_device, int Tpad, double *states,
-                             double *last, int max_width, cudaStream_t st, int *launches);
+                             double *last, int max_width, int max_layers, cudaStream_t st, int *launches);
 // the same for a WIDE diagram: one launch per layer over the whole GPU; states[0] (the root) must already be set.
 // layer_width_host / layer_collapsed_host: per layer, the node count and whether it is one node with several in-arcs.
 cudaError_t k2_layered_launch(const K2DD &d, const int32_t *layer_width_host, const uint8_t *layer_collapsed_host, const double *coef_device,
                               double *states, cudaStream_t st, int *launches);
 cudaError_t k2_finish_launch(const K2Apply &a, cudaStream_t st, int *launches);
+// a run of cuts on one diagram (k2_finish_seq)
+struct K2Seq {
+    const double *coef;     // [C][Tpad] all cuts of the call
+    double *states;         // [k1-k0][nnodes] states of cuts k0.., computed side by side on the current structure
+    K2Result *results;      // [C]
+    int *ctl;               // [2]: cuts consumed so far; 1 if the caller's loop ends there
+    int k0, k1, Tpad;
+};
+cudaError_t k2_sequence_launch(const K2DD *dd_device, const K2Apply &a, const K2Seq &q, const double *rhs_device, int max_width,
+                               double *last_scratch /*[(k1-k0)*nlast]*/, cudaStream_t st, int *launches);
 cudaError_t k2_extract_launch(const K2Apply &a, cudaStream_t st, int *launches);
 
 // ---- construction on the device ---------------------------------------

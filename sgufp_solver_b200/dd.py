@@ -30,6 +30,7 @@ DD_SIGNATURES = {
     "sgufp_dd_solution": (C.c_int, [vp, i16p, C.c_int]),
     "sgufp_dd_cutset": (C.c_int, [vp, C.c_double, ip, C.c_int]),
     "sgufp_dd_apply_optimality_batch": (C.c_int, [C.POINTER(vp), C.c_int, dp, u64p, dp, ip, C.c_int, dp]),
+    "sgufp_dd_apply_sequence": (C.c_int, [vp, C.c_int, dp, u64p, dp, ip, C.c_int, C.c_double, dp, cip, cip]),
     "sgufp_dd_last_stats": (C.c_int, [vp, C.POINTER(C.c_float), i64p, cip]),
 }
 _bound = False
@@ -137,6 +138,29 @@ class _DDBase:
         return dict(node_layer=node_layer, node_state=node_state, in_ptr=inptr, arc_tailpos=tailpos[:na_in], arc_decision=dec[:na_in],
                     terminal_weight=term[:nlast])
 
+    def _apply_sequence(self, mode: int, cuts, optimal: float):
+        """A run of cuts in ONE call (sgufp_dd_apply_sequence): returns (values, applied) where values[k] is what
+        the k-th applyOptimalityCut / applyFeasibilityCut of the reference's loop returns and `applied` counts the
+        cuts up to and including the one that ends that loop."""
+        Cn = len(cuts)
+        if Cn == 0:
+            return (np.zeros(0) if mode == 0 else np.zeros(0, np.int32)), 0
+        rhs, keys, vals, ptr = _pack_cuts(cuts)
+        bound = np.zeros(Cn); feas = np.zeros(Cn, np.int32); applied = C.c_int()
+        self.solver._check(_lib_dd().sgufp_dd_apply_sequence(self.h, mode, rhs.ctypes.data_as(dp), keys.ctypes.data_as(u64p), vals.ctypes.data_as(dp),
+                                                            ptr.ctypes.data_as(ip), Cn, float(optimal), bound.ctypes.data_as(dp),
+                                                            feas.ctypes.data_as(cip), C.byref(applied)))
+        n = applied.value
+        return (bound[:n] if mode == 0 else feas[:n]), n
+
+    def applyOptimalityCuts(self, cuts, optimal: float = DOUBLE_MIN):
+        """the loop `for cut: ub = applyOptimalityCut(cut, optimal, ub); if ub <= optimal: return` in one device call"""
+        return self._apply_sequence(0, cuts, optimal)
+
+    def applyFeasibilityCuts(self, cuts):
+        """the loop `for cut: if not applyFeasibilityCut(cut): return` in one device call"""
+        return self._apply_sequence(1, cuts, 0.0)
+
     def dump_device(self):
         """The CSR image as it sits on the device (test introspection).  `built_on_device` tells whether
         k2_build made it or the host mirror was uploaded."""
@@ -227,6 +251,17 @@ class RestrictedDDNew(_DDBase):
 
     def getMaxPath(self) -> np.ndarray:
         return self.getSolution()
+
+
+def _pack_cuts(cuts):
+    Cn = len(cuts)
+    rhs = np.array([c.RHS for c in cuts], np.float64)
+    ptr = np.zeros(Cn + 1, np.int32)
+    for i, c in enumerate(cuts):
+        ptr[i + 1] = ptr[i] + len(c.keys)
+    keys = np.concatenate([np.asarray(c.keys, np.uint64) for c in cuts]) if ptr[-1] else np.zeros(1, np.uint64)
+    vals = np.concatenate([np.asarray(c.vals, np.float64) for c in cuts]) if ptr[-1] else np.zeros(1, np.float64)
+    return rhs, np.ascontiguousarray(keys), np.ascontiguousarray(vals), ptr
 
 
 def apply_optimality_batch(dds: Sequence[_DDBase], cuts) -> np.ndarray:

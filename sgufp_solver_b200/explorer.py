@@ -42,7 +42,12 @@ class OutObject:
 
 
 class NodeExplorer:
-    def __init__(self, solver: GuroSolver, batch_global_cuts: bool = False):
+    def __init__(self, solver: GuroSolver, batch_global_cuts: bool = False, device_sequences: bool = True):
+        # device_sequences: every loop over the GLOBAL cuts (NodeExplorer.cpp:935-944,
+        # 975-983) is one device call (`sgufp_dd_apply_sequence`) that returns what the one-by-one calls
+        # return, stops where the loop returns, and works on non-exact diagrams and feasibility cuts too.
+        # False replays the reference's loop call by call.
+        self.device_sequences = device_sequences
         # batch_global_cuts: on an EXACT diagram the loop over the global optimality
         # cuts (NodeExplorer.cpp:940-944) has no side effect but the terminal minima, so all of them are
         # applied in ONE K2 launch pair; the bound and the prune decision are the sequential ones.
@@ -58,9 +63,22 @@ class NodeExplorer:
         feas = list(globalFeasCuts)
         opt = list(globalOptCuts)
         if dd.isTreeExact():                                                        # :931
-            for cut in feas:                                                        # :935-938
+            if self.device_sequences:
+                flags, n = dd.applyFeasibilityCuts(feas)                            # :935-938 in one call
+                if n and not flags[n - 1]:
+                    return OutObject(DOUBLE_MIN, DOUBLE_MIN, [], PRUNED_BY_FEASIBILITY_CUT)
+                feas_done = True
+            else:
+                feas_done = False
+            for cut in ([] if feas_done else feas):                                 # :935-938
                 if not dd.applyFeasibilityCut(cut):
                     return OutObject(DOUBLE_MIN, DOUBLE_MIN, [], PRUNED_BY_FEASIBILITY_CUT)
+            if self.device_sequences and opt:
+                bounds, n = dd.applyOptimalityCuts(opt, optimalLB)                  # :940-944 in one call
+                upperBound = float(bounds[n - 1])
+                if upperBound <= optimalLB:
+                    return OutObject(DOUBLE_MIN, DOUBLE_MIN, [], PRUNED_BY_OPTIMALITY_CUT)
+                opt = []
             if self.batch_global_cuts and len(opt) > 1:
                 from .dd import apply_optimality_batch
                 upperBound = float(apply_optimality_batch([dd], opt)[0])
@@ -88,6 +106,16 @@ class NodeExplorer:
                     upperBound = dd.applyOptimalityCut(cut, optimalLB, upperBound)  # (K2)
                     if upperBound <= optimalLB:
                         return OutObject(DOUBLE_MIN, DOUBLE_MIN, [], PRUNED_BY_OPTIMALITY_CUT)
+        if self.device_sequences:
+            flags, n = dd.applyFeasibilityCuts(feas)                                # :975-978 in one call
+            if n and not flags[n - 1]:
+                return OutObject(DOUBLE_MIN, DOUBLE_MIN, [], PRUNED_BY_FEASIBILITY_CUT)
+            bounds, n = dd.applyOptimalityCuts(opt, optimalLB)                      # :980-983 in one call
+            if n:
+                upperBound = min(upperBound, float(bounds.min()))
+                if upperBound <= optimalLB:
+                    return OutObject(DOUBLE_MIN, DOUBLE_MIN, [], PRUNED_BY_OPTIMALITY_CUT)
+            feas, opt = [], []
         for cut in feas:                                                            # :975-978
             if not dd.applyFeasibilityCut(cut):
                 return OutObject(DOUBLE_MIN, DOUBLE_MIN, [], PRUNED_BY_FEASIBILITY_CUT)
@@ -98,11 +126,12 @@ class NodeExplorer:
         return OutObject(DOUBLE_MIN, upperBound, dd.getCutset(upperBound), SUCCESS)  # :985
 
 
-def solve(solver: GuroSolver, known_lb: float = DOUBLE_MIN, max_nodes: int = 100000, batch_global_cuts: bool = False):
+def solve(solver: GuroSolver, known_lb: float = DOUBLE_MIN, max_nodes: int = 100000, batch_global_cuts: bool = False,
+          device_sequences: bool = True):
     """Sequential depth-first branch and bound over cut-set nodes (stand-in for DDSolver.cpp:658-776:
     pop a node, prune on ub <= incumbent, process, raise the incumbent, push the children).
     Returns (optimum, nodes processed, cuts generated)."""
-    explorer = NodeExplorer(solver, batch_global_cuts)
+    explorer = NodeExplorer(solver, batch_global_cuts, device_sequences)
     feas, opt = Container(), Container()
     best = known_lb
     root = Node(ub=DOUBLE_MAX)

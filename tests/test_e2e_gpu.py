@@ -50,8 +50,8 @@ def test_batched_global_cuts_give_the_same_node_result():
     feas, opt = Container(), Container()
     first = warm.process(Node(ub=1e300), -1e300, feas, opt)           # fills the global cut lists
     assert len(opt) >= 2
-    a = NodeExplorer(solver, batch_global_cuts=False).process(Node(ub=1e300), -1e300, Container(), _copy(opt))
-    b = NodeExplorer(solver, batch_global_cuts=True).process(Node(ub=1e300), -1e300, Container(), _copy(opt))
+    a = NodeExplorer(solver, batch_global_cuts=False, device_sequences=False).process(Node(ub=1e300), -1e300, Container(), _copy(opt))
+    b = NodeExplorer(solver, batch_global_cuts=True, device_sequences=False).process(Node(ub=1e300), -1e300, Container(), _copy(opt))
     assert (a.lb, a.ub, a.status) == (b.lb, b.ub, b.status) == (first.lb, first.ub, first.status)
 
 
@@ -61,3 +61,17 @@ def _copy(container):
     for cut in reversed(list(container)):
         c.add(cut)
     return c
+
+
+def test_device_sequences_replay_the_loop_call_by_call():
+    """the loops over the global cuts as ONE device call each must leave the search exactly
+    where the call-by-call loops of NodeExplorer.cpp:935-944, 975-983 leave it — same incumbent, same number
+    of nodes and cuts — on an instance whose root diagram is not exact (pruning, node removal, branching)."""
+    inst = I.make_layered([4, 5, 5, 4], 48, 12, 123, 0.7, 0.0, "mid")
+    a = solve(sg.GuroSolver(inst), max_nodes=60, device_sequences=False)
+    b = solve(sg.GuroSolver(inst), max_nodes=60, device_sequences=True)
+    assert a == b
+    inst = I.config1(S=20, lower_prob=0.15)                     # feasibility cuts in the global list
+    a = solve(sg.GuroSolver(inst), device_sequences=False)
+    b = solve(sg.GuroSolver(inst), device_sequences=True)
+    assert a == b

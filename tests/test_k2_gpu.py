@@ -256,3 +256,61 @@ def test_restricted_device_resident_sequence(width, k2_path):
             assert ours.applyOptimalityCut(cut) == ref.apply_opt(cut.RHS, cut.keys, cut.vals)
         assert ours.getMaxPath().tolist() == ref.solution().tolist()
     _same_state(ours, ref, relaxed=False)
+
+
+@pytest.mark.parametrize("name", sorted(INSTANCES))
+@pytest.mark.parametrize("seed", [3, 23])
+def test_sequence_call_equals_the_reference_loop(name, seed):
+    """sgufp_dd_apply_sequence: a run of cuts in one device call (longest paths side by side, the
+    sequential part in order, recomputation after every structural change) against the reference's
+    one-by-one loop with its early return — bounds, the stopping index, the final structure."""
+    inst = INSTANCES[name]()
+    solver = sg.GuroSolver(inst)
+    rn = ref_dd.RefNetwork(inst)
+    ours, ref = RelaxedDDNew(solver), ref_dd.RefRelaxedDD(rn)
+    ours.buildTree(); ref.build()
+    rng = np.random.default_rng(seed)
+    # 1. feasibility run (RHS tightened so that some last-layer nodes go)
+    fc = [random_cut(solver, rng, cut_type=1) for _ in range(6)]
+    fc = [type(c)(c.RHS * 0.25, c.keys, c.vals) for c in fc]
+    want = []
+    for c in fc:
+        want.append(ref.apply_feas(c.RHS, c.keys, c.vals))
+        if not want[-1]:
+            break
+    flags, n = ours.applyFeasibilityCuts(fc)
+    assert n == len(want) and flags.tolist() == want
+    if not want[-1]:
+        return
+    assert ours.getSolution().tolist() == ref.solution().tolist()
+    # 2. optimality run with a threshold that prunes arcs along the way and may end the loop
+    first = random_cut(solver, rng)
+    ub = ref.apply_opt(first.RHS, first.keys, first.vals, -1e300, 1e300)
+    assert ours.applyOptimalityCut(first, -1e300, 1e300) == ub
+    oc = [random_cut(solver, rng) for _ in range(25)]
+    optimal = ub - 250.0
+    want = []
+    for c in oc:
+        want.append(ref.apply_opt(c.RHS, c.keys, c.vals, optimal, ub))
+        if want[-1] <= optimal:
+            break
+    bounds, n = ours.applyOptimalityCuts(oc, optimal)
+    assert n == len(want) and bounds.tolist() == want
+    if want[-1] != LOWEST:
+        _same_state(ours, ref)
+        assert ours.getSolution().tolist() == ref.solution().tolist()
+
+
+def test_sequence_call_on_a_restricted_tree():
+    inst = INSTANCES["c2"]()
+    solver = sg.GuroSolver(inst)
+    rn = ref_dd.RefNetwork(inst)
+    ours, ref = RestrictedDDNew(solver, 64), ref_dd.RefRestrictedDD(rn, 64)
+    ours.compile(); ref.compile()
+    rng = np.random.default_rng(41)
+    oc = [random_cut(solver, rng) for _ in range(12)]
+    want = [ref.apply_opt(c.RHS, c.keys, c.vals) for c in oc]
+    bounds, n = ours.applyOptimalityCuts(oc)               # optimal = DOUBLE_MIN: never stops
+    assert n == 12 and bounds.tolist() == want
+    _same_state(ours, ref, relaxed=False)
+    assert ours.getMaxPath().tolist() == ref.solution().tolist()
