@@ -33,6 +33,18 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# The contract is ONE JSON line on stdout.  Libraries chat on file descriptor 1 (NCCL prints its version there
+# when NCCL_DEBUG is set in the environment), so fd 1 is pointed at stderr for the whole run and the JSON line
+# goes to a private duplicate of the real stdout.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+sys.stdout.flush()
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
 WORKLOADS = {
     # name: (config fn name, per-GPU scenarios, candidates per step, description)
     "c2": ("config2", 1000, 64, "C2: n=50 m=200 S=1000/GPU, K=64 candidate paths per step (BASELINE.json configs[1])"),
@@ -159,7 +171,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -301,7 +313,7 @@ def main():
             line["dd"] = dd_bench(local)
         except Exception as e:  # the DD half is reported beside the headline, never instead of it
             line["dd"] = {"error": str(e)[:200]}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
