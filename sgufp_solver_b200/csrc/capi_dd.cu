@@ -590,9 +590,10 @@ int sgufp_dd_apply_sequence(sgufp_dd *d, int mode, const double *rhs, const uint
         std::copy(one.begin(), one.begin() + T, cf.begin() + (size_t)k * Tpad);
     }
     const int chunk = (int)std::max<long long>(1, std::min<long long>(C, (1LL << 27) / std::max(1, nn)));   // <= 1 GB of states
-    DevBuf<K2Result> res; DevBuf<int> ctl;
+    DevBuf<K2Result> res; DevBuf<int> ctl, probe;
+    const bool probing = mode == 0 && !d->exact_flag && !d->dd->restricted();   // only there does an optimality cut prune arcs
     CU(c, S.coef.reserve(cf.size())); CU(c, S.rhs.reserve(C)); CU(c, S.states.reserve((size_t)chunk * nn)); CU(c, S.last.reserve((size_t)chunk * std::max(1, nlast)));
-    CU(c, res.reserve(C)); CU(c, ctl.reserve(2));
+    CU(c, res.reserve(C)); CU(c, ctl.reserve(2)); CU(c, probe.reserve(chunk));
     K2DD self = d->dev; self.state_off = 0; self.last_off = 0;
     cudaError_t e = cudaMemcpyAsync(S.coef.p, cf.data(), cf.size() * 8, cudaMemcpyHostToDevice, c->st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(S.rhs.p, rhs, (size_t)C * 8, cudaMemcpyHostToDevice, c->st);
@@ -604,7 +605,7 @@ int sgufp_dd_apply_sequence(sgufp_dd *d, int mode, const double *rhs, const uint
     int k0 = 0, stopped = 0, last_base = 0, win = std::min(chunk, 8);
     while (e == cudaSuccess && k0 < C && !stopped) {
         K2Seq q{};
-        q.coef = S.coef.p; q.states = S.states.p; q.results = res.p; q.ctl = ctl.p; q.k0 = k0; q.k1 = std::min(C, k0 + win); q.Tpad = Tpad;
+        q.coef = S.coef.p; q.states = S.states.p; q.results = res.p; q.ctl = ctl.p; q.k0 = k0; q.k1 = std::min(C, k0 + win); q.Tpad = Tpad; q.probe = probing ? probe.p : nullptr;
         e = k2_sequence_launch(d->d_self.p, make_apply(d, mode, optimal), q, S.rhs.p, d->dev.max_width, S.last.p, c->st, &c->dd_launches);
         int h[2] = {0, 0};
         if (e == cudaSuccess) e = cudaMemcpyAsync(h, ctl.p, 8, cudaMemcpyDeviceToHost, c->st);
@@ -623,7 +624,7 @@ int sgufp_dd_apply_sequence(sgufp_dd *d, int mode, const double *rhs, const uint
     }
     if (e == cudaSuccess) e = cudaEventRecord(c->evk1, c->st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->st);
-    res.release(); ctl.release();
+    res.release(); ctl.release(); probe.release();
     CU(c, e);
     CU(c, cudaEventElapsedTime(&c->dd_kernel_ms, c->evk0, c->evk1));
     c->dd_arcs = ((long long)d->narcs + nlast) * done;

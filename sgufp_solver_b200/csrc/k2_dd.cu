@@ -210,8 +210,9 @@ __device__ int block_sum(int v, int *red) {
 // layer loses every arc; returns true if one did (the reference then returns without removing).
 constexpr int K2_MAX_COLLAPSED = 64;   // collapsed layers handled per call by the fast path of prune_collapsed
 
+// probe != nullptr: nothing is written to the diagram; *probe = 1 if the call WOULD flag an arc or abort.
 __device__ bool prune_collapsed(const K2Apply &a, int first_layer, int end_layer, double max_state, double threshold,
-                                int *ired, int *sh) {
+                                int *ired, int *sh, int *probe = nullptr) {
     const K2DD &d = a.d;
     // the collapsed layers (ONE live node) in range, found with one parallel sweep over the live layer sizes
     // — a loop over the layers would pay one dependent global load each.  Their order does not matter: any layer
@@ -224,8 +225,8 @@ __device__ bool prune_collapsed(const K2Apply &a, int first_layer, int end_layer
     __syncthreads();
     const int ncol = s_n;
     const bool listed = ncol <= K2_MAX_COLLAPSED;
-    __shared__ int s_abort;
-    if (threadIdx.x == 0) s_abort = 0;
+    __shared__ int s_abort, s_any;
+    if (threadIdx.x == 0) { s_abort = 0; s_any = 0; }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     // one WARP per collapsed layer (they are independent): no block barrier, eight layers in flight
@@ -249,9 +250,10 @@ __device__ bool prune_collapsed(const K2Apply &a, int first_layer, int end_layer
             const int2 ts = d.arc_ts[e];
             const double w = ts.y >= 0 ? a.coef[ts.y] : 0.0;
             total++;
-            if ((a.state[tail0 + ts.x] + w + gain) <= threshold) { a.arc_dead[e] = 2; pruned++; }
+            if ((a.state[tail0 + ts.x] + w + gain) <= threshold) { if (!probe) a.arc_dead[e] = 2; pruned++; }
         }
         for (int o = 16; o; o >>= 1) { pruned += __shfl_xor_sync(0xffffffffu, pruned, o); total += __shfl_xor_sync(0xffffffffu, total, o); }
+        if (probe && pruned && lane == 0) atomicOr(&s_any, 1);
         return pruned == total ? 1 : 0;
     };
     if (listed) {
@@ -264,6 +266,7 @@ __device__ bool prune_collapsed(const K2Apply &a, int first_layer, int end_layer
     }
     __syncthreads();
     const bool abort = s_abort != 0;
+    if (probe) { if (threadIdx.x == 0) *probe = (s_any || s_abort) ? 1 : 0; __syncthreads(); return abort; }
     // commit or discard the candidates: they all sit among the in-arcs of the collapsed nodes
     int changed = 0;
     if (listed) {
@@ -279,7 +282,8 @@ __device__ bool prune_collapsed(const K2Apply &a, int first_layer, int end_layer
     return abort;
 }
 
-__device__ void finish_body(const K2Apply &a, double *red, int *ired, int *sh) {
+// quiet: a probe (k2_prune_probe) found that this cut flags nothing: the pruning pass is skipped
+__device__ void finish_body(const K2Apply &a, double *red, int *ired, int *sh, bool quiet = false) {
     const K2DD &d = a.d;
     const int nl = d.nlayers, llayer = nl - 1;
     const int last0 = d.layer_info[llayer].x, nlast = d.nlast;
@@ -299,7 +303,7 @@ __device__ void finish_body(const K2Apply &a, double *red, int *ired, int *sh) {
         }
         const double terminal = block_max(best, red);
         const double max_state = block_max(ms, red);
-        if (a.restricted || terminal <= a.optimal || a.exact) { if (threadIdx.x == 0) a.out->bound = terminal; return; }
+        if (a.restricted || terminal <= a.optimal || a.exact || quiet) { if (threadIdx.x == 0) a.out->bound = terminal; return; }
         const bool abort = prune_collapsed(a, 3, llayer - 1, max_state, a.optimal - 0.01, ired, sh);   // layers 3 .. llayer-2
         if (threadIdx.x == 0) a.out->bound = abort ? -DBL_MAX : terminal;
         return;
@@ -389,6 +393,25 @@ __global__ void __launch_bounds__(K2_THREADS) k2_finish(K2Apply a) {
 // by cut and stops after the first cut that (a) ends the loop of the caller — bound <= optimal
 // (NodeExplorer.cpp:942, 982) or not feasible (:936, 977) — or (b) removed arcs or nodes: the states
 // of the cuts behind it were computed on a structure that no longer exists and are recomputed.
+// One CTA per cut of the window: would the optimality pruning of this cut touch the diagram?  (It cannot
+// depend on the cuts before it except through the structure, which is the same for the whole window.)
+__global__ void __launch_bounds__(K2_THREADS) k2_prune_probe(K2Apply a, K2Seq q) {
+    __shared__ double red[K2_THREADS / 32];
+    __shared__ int ired[K2_THREADS / 32];
+    __shared__ int sh[2];
+    const int k = q.k0 + blockIdx.x;
+    K2Apply b = a;
+    b.state = q.states + (size_t)blockIdx.x * a.d.nnodes;
+    b.coef = q.coef + (size_t)k * q.Tpad;
+    const K2DD &d = a.d;
+    const int llayer = d.nlayers - 1, last0 = d.layer_info[llayer].x;
+    double ms = -DBL_MAX;
+    for (int i = threadIdx.x; i < d.nlast; i += blockDim.x)
+        if (!a.node_dead[last0 + i]) { const double s = b.state[last0 + i]; ms = ms < s ? s : ms; }
+    const double max_state = block_max(ms, red);
+    prune_collapsed(b, 3, llayer - 1, max_state, a.optimal - 0.01, ired, sh, q.probe + blockIdx.x);
+}
+
 __global__ void __launch_bounds__(K2_THREADS) k2_finish_seq(K2Apply a, K2Seq q) {
     __shared__ double red[K2_THREADS / 32];
     __shared__ int ired[K2_THREADS / 32];
@@ -398,7 +421,7 @@ __global__ void __launch_bounds__(K2_THREADS) k2_finish_seq(K2Apply a, K2Seq q) 
         b.state = q.states + (size_t)(k - q.k0) * a.d.nnodes;
         b.coef = q.coef + (size_t)k * q.Tpad;
         b.out = q.results + k;
-        finish_body(b, red, ired, sh);
+        finish_body(b, red, ired, sh, q.probe != nullptr && q.probe[k - q.k0] == 0);
         __syncthreads();
         const K2Result r = q.results[k];
         const bool stop = a.mode == 0 ? r.bound <= a.optimal : r.feasible == 0;
@@ -542,6 +565,7 @@ cudaError_t k2_sequence_launch(const K2DD *dd_device, const K2Apply &a, const K2
     if (e != cudaSuccess) return e;
     k2_longest_path<false, true><<<dim3(n, 1), threads, sm2, st>>>(dd_device, q.coef + (size_t)q.k0 * q.Tpad, rhs_device + q.k0, n, q.Tpad, 0,
                                                                      q.states, last_scratch, K2_LI_CACHE);
+    if (q.probe) { k2_prune_probe<<<n, K2_THREADS, 0, st>>>(a, q); if (launches) (*launches)++; }
     k2_finish_seq<<<1, K2_THREADS, 0, st>>>(a, q);
     if (launches) (*launches) += 2;
     return cudaGetLastError();

@@ -72,6 +72,7 @@ struct K2Seq {
     double *states;         // [k1-k0][nnodes] states of cuts k0.., computed side by side on the current structure
     K2Result *results;      // [C]
     int *ctl;               // [2]: cuts consumed so far; 1 if the caller's loop ends there
+    int *probe;             // [k1-k0] or null: per cut, 1 if its optimality pruning would touch the diagram (k2_prune_probe)
     int k0, k1, Tpad;
 };
 cudaError_t k2_sequence_launch(const K2DD *dd_device, const K2Apply &a, const K2Seq &q, const double *rhs_device, int max_width,
