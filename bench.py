@@ -36,14 +36,21 @@ sys.path.insert(0, ROOT)
 # The contract is ONE JSON line on stdout.  Libraries chat on file descriptor 1 (NCCL prints its version there
 # when NCCL_DEBUG is set in the environment), so fd 1 is pointed at stderr for the whole run and the JSON line
 # goes to a private duplicate of the real stdout.
-_REAL_STDOUT = os.fdopen(os.dup(1), "w")
-sys.stdout.flush()
-os.dup2(2, 1)
+_REAL_STDOUT = None
+
+
+def isolate_stdout() -> None:
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
 
 
 def emit(line: dict) -> None:
-    _REAL_STDOUT.write(json.dumps(line) + "\n")
-    _REAL_STDOUT.flush()
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 WORKLOADS = {
     # name: (config fn name, per-GPU scenarios, candidates per step, description)
@@ -183,6 +190,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    isolate_stdout()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
@@ -317,6 +325,46 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+class DDCpuBaseline:
+    """cpu_baseline leg of the DD benchmarks (bench_dd.py): Oracle A, the unmodified reference classes compiled into
+    oracle/_ref, timed on one host core.  Like `cpu_port_throughput` this is the only place a bench executes oracle/."""
+
+    def __init__(self, inst):
+        self.net = None
+        try:
+            from oracle import ref_dd
+            if ref_dd.available():
+                self.ref_dd = ref_dd
+                self.net = ref_dd.RefNetwork(inst)
+        except Exception:
+            self.net = None
+
+    def available(self):
+        return self.net is not None
+
+    def _new(self, kind, width):
+        return self.ref_dd.RefRestrictedDD(self.net, width) if kind == "restricted" else self.ref_dd.RefRelaxedDD(self.net)
+
+    def build_ms(self, kind, width, reps=3):
+        r = self._new(kind, width)
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            r.compile() if kind == "restricted" else r.build()
+            ts.append(time.perf_counter() - t0)
+        return float(np.median(ts)) * 1e3
+
+    def apply_seconds(self, kind, width, cuts, with_solution=False):
+        r = self._new(kind, width)
+        r.compile() if kind == "restricted" else r.build()
+        t0 = time.perf_counter()
+        for c in cuts:
+            r.apply_opt(c.RHS, c.keys, c.vals) if kind == "restricted" else r.apply_opt(c.RHS, c.keys, c.vals, -1e300, 1e300)
+            if with_solution:
+                r.solution()
+        return time.perf_counter() - t0
 
 
 def _plan_words(solver, path):

@@ -47,12 +47,9 @@ def main():
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
     ref_net = None
     if not args.no_cpu:
-        try:
-            from oracle import ref_dd
-            if ref_dd.available():
-                ref_net = ref_dd.RefNetwork(inst)
-        except Exception:
-            ref_net = None
+        import bench                                   # the CPU-baseline leg lives in bench.py (the one place that runs oracle/)
+        base = bench.DDCpuBaseline(inst)
+        ref_net = base if base.available() else None
     points = [("restricted", int(w)) for w in args.widths.split(",")] + [("relaxed", 120)]
     if args.build:
         for kind, w in points:
@@ -72,12 +69,7 @@ def main():
                 d.close()
             os.environ.pop("SGUFP_DD_BUILD", None)
             if ref_net is not None:
-                r = ref_dd.RefRestrictedDD(ref_net, w) if kind == "restricted" else ref_dd.RefRelaxedDD(ref_net)
-                rb = r.compile if kind == "restricted" else r.build
-                ts = []
-                for _ in range(3):
-                    t0 = time.perf_counter(); rb(); ts.append(time.perf_counter() - t0)
-                line["cpu_reference"] = {"value": float(np.median(ts)) * 1e3, "unit": line["unit"], "cores": 1, "kind": "reference"}
+                line["cpu_reference"] = {"value": ref_net.build_ms(kind, w), "unit": line["unit"], "cores": 1, "kind": "reference"}
             print(json.dumps(line), flush=True)
         return
     if args.sequential:
@@ -100,13 +92,7 @@ def main():
                     "note": "host API wall time; longest path, terminal weights, pruning and path extraction run on the device, "
                             "only the bound and the path come back"}
             if ref_net is not None:
-                r = ref_dd.RefRestrictedDD(ref_net, w) if kind == "restricted" else ref_dd.RefRelaxedDD(ref_net)
-                r.compile() if kind == "restricted" else r.build()
-                t0 = time.perf_counter()
-                for c in cuts:
-                    r.apply_opt(c.RHS, c.keys, c.vals) if kind == "restricted" else r.apply_opt(c.RHS, c.keys, c.vals, -1e300, 1e300)
-                    r.solution()
-                dtr = time.perf_counter() - t0
+                dtr = ref_net.apply_seconds(kind, w, cuts, with_solution=True)
                 line["cpu_reference"] = {"value": dtr / len(cuts) * 1e3, "unit": line["unit"], "cores": 1, "kind": "reference",
                                          "sample": f"the same {len(cuts)} cuts on the unmodified reference class (oracle/_ref)"}
             print(json.dumps(line), flush=True)
@@ -135,12 +121,7 @@ def main():
                              "frac": bytes_alg / (ms / 1e3) / 1e9 / peak, "bytes_per_launch": bytes_alg},
                 "l2": "flushed (512 MiB write) before every timed launch"}
         if ref_net is not None:
-            r = ref_dd.RefRestrictedDD(ref_net, w) if kind == "restricted" else ref_dd.RefRelaxedDD(ref_net)
-            r.compile() if kind == "restricted" else r.build()
-            t0 = time.perf_counter()
-            for c in cuts:
-                r.apply_opt(c.RHS, c.keys, c.vals) if kind == "restricted" else r.apply_opt(c.RHS, c.keys, c.vals, -1e300, 1e300)
-            dt = time.perf_counter() - t0
+            dt = ref_net.apply_seconds(kind, w, cuts)
             line["cpu_reference"] = {"value": arcs1 * args.C / dt, "unit": "arcs/s", "cores": 1, "kind": "reference",
                                      "sample": f"1 diagram x {args.C} cuts, unmodified reference class (oracle/_ref)"}
         print(json.dumps(line), flush=True)
