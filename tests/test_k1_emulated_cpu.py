@@ -96,3 +96,36 @@ def test_kernel_body_matches_oracle(emul, name, make, K, seed, unm, variant):
         assert (sums[k] == want).all(), np.nonzero(sums[k] != want)
         if first_bad is not None:
             assert (ray[k] == ray_wlayout(net, inst, paths[k], first_bad)).all()
+
+
+def _random_instance(rng, k):
+    nl = int(rng.integers(2, 5))
+    layers = [int(rng.integers(2, 7)) for _ in range(nl)]
+    n_int = sum(layers)
+    max_m = sum(a * b for a, b in zip(layers[:-1], layers[1:])) + layers[0] + layers[-1]
+    m = int(rng.integers(max(n_int + 2, max_m // 2), max_m + 1))
+    return I.make_layered(layers, m, int(rng.integers(2, 6)), 1000 + k, float(rng.uniform(0.3, 0.95)), float(rng.choice([0.0, 0.05, 0.3])), f"fz{k}")
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_kernel_body_fuzz(emul, block):
+    """Many small random networks (dense and sparse, few and many V-bar nodes, with and without lower
+    bounds): the kernel body's sums, first infeasible scenario and ray must equal Oracle B's."""
+    rng = np.random.default_rng(500 + block)
+    done = 0
+    for k in range(40):
+        try:
+            inst = _random_instance(rng, 100 * block + k)
+            net = OracleNet(inst)
+        except Exception:
+            continue                                   # the generator refused the shape (too few arcs for the layers)
+        paths = I.random_paths(net, 3, k, float(rng.choice([0.0, 0.2, 0.6])))
+        sums, finf, obj, st, ray = run_emul(emul, inst, net, paths)
+        for j in range(len(paths)):
+            want, first_bad = wlayout_partial(net, inst, paths[j], 0, inst.S)
+            assert (finf[j] if finf[j] != I64_MAX else -1) == (-1 if first_bad is None else first_bad), (inst.name, j)
+            assert (sums[j] == want).all(), (inst.name, j)
+            if first_bad is not None:
+                assert (ray[j] == ray_wlayout(net, inst, paths[j], first_bad)).all(), (inst.name, j)
+        done += 1
+    assert done >= 20

@@ -197,3 +197,27 @@ def test_lane_variant_gives_the_same_cuts(name, make, K, seed, unm, monkeypatch)
     assert (a.rhs == b.rhs).all() and (a.coef_dense == b.coef_dense).all()
     assert (a.status == b.status).all() and (a.obj == b.obj).all()
     _compare(inst, gs, net, paths, b)
+
+
+@pytest.mark.parametrize("block", range(3))
+def test_fuzz_small_networks(block):
+    """Random small networks (dense and sparse, few and many V-bar nodes, with and without lower bounds,
+    33-scenario blocks so that warps of one CTA sit on different candidates): every cut through the C
+    ABI against Oracle B.  The same generator drives the host emulation in test_k1_emulated_cpu.py."""
+    rng = np.random.default_rng(900 + block)
+    done = 0
+    for k in range(25):
+        nl = int(rng.integers(2, 5))
+        layers = [int(rng.integers(2, 7)) for _ in range(nl)]
+        max_m = sum(a * b for a, b in zip(layers[:-1], layers[1:])) + layers[0] + layers[-1]
+        m = int(rng.integers(max(sum(layers) + 2, max_m // 2), max_m + 1))
+        try:
+            inst = I.make_layered(layers, m, 33, 3000 + 100 * block + k, float(rng.uniform(0.3, 0.95)), float(rng.choice([0.0, 0.05, 0.3])), f"gfz{k}")
+            net = OracleNet(inst)
+        except Exception:
+            continue
+        gs = sg.GuroSolver(inst)
+        paths = I.random_paths(net, 5, k, float(rng.choice([0.0, 0.2, 0.6])))
+        _compare(inst, gs, net, paths, gs.solve_paths(paths))
+        done += 1
+    assert done >= 12
