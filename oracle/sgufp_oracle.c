@@ -100,7 +100,7 @@ static int shuffle_vbar(OrcNet *N) {
                 int p = N->tail[N->in_arc[e]];
                 if (!seen[p]) { seen[p] = 1; parents[np++] = p; }
             }
-        if (np == 0) { free(neworder); free(pending); free(seen); free(childs); free(parents); return -1; }
+        if (np <= 0) { free(neworder); free(pending); free(seen); free(childs); free(parents); return -1; }
         for (int i = 0; i < np; i++)
             if (pending[parents[i]]) { neworder[nn++] = parents[i]; pending[parents[i]] = 0; left--; }
         memcpy(childs, parents, (size_t)np * sizeof(int));
