@@ -149,10 +149,14 @@ int sync_host(sgufp_dd *d) {
     return 0;
 }
 
-// diagrams at least this wide run the single-cut longest path as one launch per layer over the whole GPU
-int layered_min_width() {
-    const char *e = getenv("SGUFP_K2_LAYERED_MIN");   // read per call: the tests force either path
-    return e ? std::max(1, atoi(e)) : 2048;
+// Single-cut longest path as one launch per layer over the whole GPU, or as one CTA walking all layers?  A launch
+// costs ~4 us, so the layered shape pays only when the AVERAGE layer is wide (a relaxed diagram has a few wide
+// layers at the end and dozens of narrow ones: one CTA wins there).  SGUFP_K2_LAYERED_MIN overrides the threshold
+// on the average width (read per call: the tests force either path).
+bool use_layered(const sgufp_dd *d) {
+    const char *e = getenv("SGUFP_K2_LAYERED_MIN");
+    const long long min_avg = e ? std::max(1, atoi(e)) : 1024;
+    return (long long)d->dev.nnodes >= min_avg * d->dev.nlayers;
 }
 
 K2Apply make_apply(sgufp_dd *d, int mode, double optimal) {
@@ -181,7 +185,7 @@ int apply_on_device(sgufp_dd *d, double rhs, const uint64_t *keys, const double 
     CU(c, cudaMemcpyAsync(d->d_self.p, &self, sizeof(K2DD), cudaMemcpyHostToDevice, c->st));
     c->dd_launches = 0;
     CU(c, cudaEventRecord(c->evk0, c->st));
-    if (d->dev.max_width >= layered_min_width()) {
+    if (use_layered(d)) {
         // wide diagram: the root state on the host (same additions in the same order), then one launch per layer
         double v = rhs;
         for (int s : d->root_slot) if (s >= 0) v = v + coef[s];
@@ -590,10 +594,10 @@ int sgufp_dd_apply_sequence(sgufp_dd *d, int mode, const double *rhs, const uint
         std::copy(one.begin(), one.begin() + T, cf.begin() + (size_t)k * Tpad);
     }
     const int chunk = (int)std::max<long long>(1, std::min<long long>(C, (1LL << 27) / std::max(1, nn)));   // <= 1 GB of states
-    DevBuf<K2Result> res; DevBuf<int> ctl, probe;
+    DevBuf<K2Result> res; DevBuf<int> ctl, probe; DevBuf<double> wb;
     const bool probing = mode == 0 && !d->exact_flag && !d->dd->restricted();   // only there does an optimality cut prune arcs
     CU(c, S.coef.reserve(cf.size())); CU(c, S.rhs.reserve(C)); CU(c, S.states.reserve((size_t)chunk * nn)); CU(c, S.last.reserve((size_t)chunk * std::max(1, nlast)));
-    CU(c, res.reserve(C)); CU(c, ctl.reserve(2)); CU(c, probe.reserve(chunk));
+    CU(c, res.reserve(C)); CU(c, ctl.reserve(2)); CU(c, probe.reserve(chunk)); CU(c, wb.reserve(chunk));
     K2DD self = d->dev; self.state_off = 0; self.last_off = 0;
     cudaError_t e = cudaMemcpyAsync(S.coef.p, cf.data(), cf.size() * 8, cudaMemcpyHostToDevice, c->st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(S.rhs.p, rhs, (size_t)C * 8, cudaMemcpyHostToDevice, c->st);
@@ -605,7 +609,7 @@ int sgufp_dd_apply_sequence(sgufp_dd *d, int mode, const double *rhs, const uint
     int k0 = 0, stopped = 0, last_base = 0, win = std::min(chunk, 8);
     while (e == cudaSuccess && k0 < C && !stopped) {
         K2Seq q{};
-        q.coef = S.coef.p; q.states = S.states.p; q.results = res.p; q.ctl = ctl.p; q.k0 = k0; q.k1 = std::min(C, k0 + win); q.Tpad = Tpad; q.probe = probing ? probe.p : nullptr;
+        q.coef = S.coef.p; q.states = S.states.p; q.results = res.p; q.ctl = ctl.p; q.k0 = k0; q.k1 = std::min(C, k0 + win); q.Tpad = Tpad; q.probe = probing ? probe.p : nullptr; q.last = S.last.p; q.bounds = mode == 0 ? wb.p : nullptr;
         e = k2_sequence_launch(d->d_self.p, make_apply(d, mode, optimal), q, S.rhs.p, d->dev.max_width, S.last.p, c->st, &c->dd_launches);
         int h[2] = {0, 0};
         if (e == cudaSuccess) e = cudaMemcpyAsync(h, ctl.p, 8, cudaMemcpyDeviceToHost, c->st);
@@ -624,7 +628,7 @@ int sgufp_dd_apply_sequence(sgufp_dd *d, int mode, const double *rhs, const uint
     }
     if (e == cudaSuccess) e = cudaEventRecord(c->evk1, c->st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->st);
-    res.release(); ctl.release(); probe.release();
+    res.release(); ctl.release(); probe.release(); wb.release();
     CU(c, e);
     CU(c, cudaEventElapsedTime(&c->dd_kernel_ms, c->evk0, c->evk1));
     c->dd_arcs = ((long long)d->narcs + nlast) * done;

@@ -22,6 +22,7 @@ namespace sgufp {
 namespace {
 
 constexpr int K2_THREADS = 256;
+constexpr int K2_FIN_THREADS = 1024;   // the one-CTA kernels that sweep a (possibly wide) last layer
 
 __device__ __forceinline__ double block_max(double v, double *red) {
     for (int o = 16; o; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, v, o); v = v < t ? t : v; }
@@ -381,9 +382,9 @@ __device__ void finish_body(const K2Apply &a, double *red, int *ired, int *sh, b
     }
 }
 
-__global__ void __launch_bounds__(K2_THREADS) k2_finish(K2Apply a) {
-    __shared__ double red[K2_THREADS / 32];
-    __shared__ int ired[K2_THREADS / 32];
+__global__ void __launch_bounds__(K2_FIN_THREADS) k2_finish(K2Apply a) {
+    __shared__ double red[K2_FIN_THREADS / 32];
+    __shared__ int ired[K2_FIN_THREADS / 32];
     __shared__ int sh[2];
     finish_body(a, red, ired, sh);
 }
@@ -412,13 +413,78 @@ __global__ void __launch_bounds__(K2_THREADS) k2_prune_probe(K2Apply a, K2Seq q)
     prune_collapsed(b, 3, llayer - 1, max_state, a.optimal - 0.01, ired, sh, q.probe + blockIdx.x);
 }
 
-__global__ void __launch_bounds__(K2_THREADS) k2_finish_seq(K2Apply a, K2Seq q) {
+constexpr int K2_SEQ_STAGE = 2048;   // window lengths whose probe flags are staged in shared memory
+
+// Terminal weights of a whole window, speculatively (valid up to the first cut that changes the structure):
+// q.last[c][i] becomes min(term[i], min over cuts <= c of the state of last-layer node i) ...
+__global__ void __launch_bounds__(K2_THREADS) k2_window_prefix_min(K2Apply a, K2Seq q) {
+    const K2DD &d = a.d;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, n = q.k1 - q.k0, nlast = d.nlast;
+    if (i >= nlast || a.node_dead[d.layer_info[d.nlayers - 1].x + i]) return;
+    double t = d.term[i];
+    for (int c = 0; c < n; c++) {
+        double *p = q.last + (size_t)c * nlast + i;
+        const double s = *p;
+        t = s < t ? s : t;                                   // arc.weight = min(arc.weight, parent.state2) (DD.cpp:3981)
+        *p = t;
+    }
+}
+// ... and q.bounds[c] = max over the live last-layer nodes: the bound the c-th call returns if nothing was removed before it.
+__global__ void __launch_bounds__(K2_THREADS) k2_window_bounds(K2Apply a, K2Seq q) {
     __shared__ double red[K2_THREADS / 32];
-    __shared__ int ired[K2_THREADS / 32];
+    const K2DD &d = a.d;
+    const int c = blockIdx.x, nlast = d.nlast, last0 = d.layer_info[d.nlayers - 1].x;
+    double m = -DBL_MAX;
+    for (int i = threadIdx.x; i < nlast; i += blockDim.x)
+        if (!a.node_dead[last0 + i]) { const double t = q.last[(size_t)c * nlast + i]; m = m < t ? t : m; }
+    m = block_max(m, red);
+    if (threadIdx.x == 0) q.bounds[c] = m;
+}
+
+__global__ void __launch_bounds__(K2_FIN_THREADS) k2_finish_seq(K2Apply a, K2Seq q) {
+    __shared__ double red[K2_FIN_THREADS / 32];
+    __shared__ int ired[K2_FIN_THREADS / 32];
     __shared__ int sh[2];
-    for (int k = q.k0; k < q.k1; k++) {
+    __shared__ unsigned char s_quiet[K2_SEQ_STAGE];
+    __shared__ int s_stop;
+    const K2DD &d = a.d;
+    const int n = q.k1 - q.k0, nlast = d.nlast, last0 = d.layer_info[d.nlayers - 1].x;
+    // A QUIET optimality cut changes nothing but the terminal weights: the diagram is exact or restricted (no
+    // pruning there, DD.cpp:3985-3987, 3493-3504), or the probe found nothing to prune.  For a run of quiet cuts
+    // the prefix minima and the bounds are already there (k2_window_prefix_min / k2_window_bounds): the run is
+    // scanned for the first bound <= optimal, and the terminal weights are taken from its last cut.
+    const bool all_quiet = a.mode == 0 && (a.exact || a.restricted);
+    const bool staged = a.mode == 0 && n <= K2_SEQ_STAGE && q.bounds != nullptr && (all_quiet || q.probe != nullptr);
+    if (staged) for (int i = threadIdx.x; i < n; i += blockDim.x) s_quiet[i] = all_quiet || q.probe[i] == 0;
+    __syncthreads();
+    int k = q.k0;
+    while (k < q.k1) {
+        if (staged && s_quiet[k - q.k0]) {
+            int r = k;
+            while (r < q.k1 && s_quiet[r - q.k0]) r++;
+            if (threadIdx.x == 0) s_stop = INT_MAX;
+            __syncthreads();
+            for (int c = k + threadIdx.x; c < r; c += blockDim.x) {
+                K2Result res; res.bound = q.bounds[c - q.k0]; res.feasible = 1; res.changed = 0; res.path_len = 0;
+                q.results[c] = res;
+                if (res.bound <= a.optimal) atomicMin(&s_stop, c);   // the caller's loop returns at the first such cut
+            }
+            __syncthreads();
+            const int stop = s_stop, upto = stop == INT_MAX ? r - 1 : stop;
+            for (int i = threadIdx.x; i < nlast; i += blockDim.x)
+                if (!a.node_dead[last0 + i]) d.term[i] = q.last[(size_t)(upto - q.k0) * nlast + i];
+            if (stop != INT_MAX) {
+                if (threadIdx.x == 0) { q.ctl[0] = stop + 1; q.ctl[1] = 1; }
+                return;
+            }
+            k = r;
+            __syncthreads();
+            continue;
+        }
+        // a cut that prunes (or a feasibility cut): the full sequential step on ITS OWN states; the terminal weights
+        // it starts from were just written above (or by the previous step)
         K2Apply b = a;
-        b.state = q.states + (size_t)(k - q.k0) * a.d.nnodes;
+        b.state = q.states + (size_t)(k - q.k0) * d.nnodes;
         b.coef = q.coef + (size_t)k * q.Tpad;
         b.out = q.results + k;
         finish_body(b, red, ired, sh, q.probe != nullptr && q.probe[k - q.k0] == 0);
@@ -430,6 +496,9 @@ __global__ void __launch_bounds__(K2_THREADS) k2_finish_seq(K2Apply a, K2Seq q) 
             return;
         }
         __syncthreads();
+        // the speculative prefix minima behind this cut did not see it: the window ends here, the rest is recomputed
+        if (staged) { if (threadIdx.x == 0) { q.ctl[0] = k + 1; q.ctl[1] = 0; } return; }
+        k++;
     }
     if (threadIdx.x == 0) { q.ctl[0] = q.k1; q.ctl[1] = 0; }
 }
@@ -548,7 +617,7 @@ cudaError_t k2_layered_launch(const K2DD &d, const int32_t *layer_width_host, co
 }
 
 cudaError_t k2_finish_launch(const K2Apply &a, cudaStream_t st, int *launches) {
-    k2_finish<<<1, K2_THREADS, 0, st>>>(a);
+    k2_finish<<<1, K2_FIN_THREADS, 0, st>>>(a);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }
@@ -566,7 +635,12 @@ cudaError_t k2_sequence_launch(const K2DD *dd_device, const K2Apply &a, const K2
     k2_longest_path<false, true><<<dim3(n, 1), threads, sm2, st>>>(dd_device, q.coef + (size_t)q.k0 * q.Tpad, rhs_device + q.k0, n, q.Tpad, 0,
                                                                      q.states, last_scratch, K2_LI_CACHE);
     if (q.probe) { k2_prune_probe<<<n, K2_THREADS, 0, st>>>(a, q); if (launches) (*launches)++; }
-    k2_finish_seq<<<1, K2_THREADS, 0, st>>>(a, q);
+    if (q.bounds && a.mode == 0 && a.d.nlast > 0) {
+        k2_window_prefix_min<<<(a.d.nlast + K2_THREADS - 1) / K2_THREADS, K2_THREADS, 0, st>>>(a, q);
+        k2_window_bounds<<<n, K2_THREADS, 0, st>>>(a, q);
+        if (launches) (*launches) += 2;
+    }
+    k2_finish_seq<<<1, K2_FIN_THREADS, 0, st>>>(a, q);
     if (launches) (*launches) += 2;
     return cudaGetLastError();
 }

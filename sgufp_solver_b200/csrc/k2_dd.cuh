@@ -72,6 +72,8 @@ struct K2Seq {
     double *states;         // [k1-k0][nnodes] states of cuts k0.., computed side by side on the current structure
     K2Result *results;      // [C]
     int *ctl;               // [2]: cuts consumed so far; 1 if the caller's loop ends there
+    double *last;           // [k1-k0][nlast] last-layer states of the window's cuts (written by the longest-path kernel)
+    double *bounds;         // [k1-k0] or null: speculative bound of every cut of the window (k2_window_bounds)
     int *probe;             // [k1-k0] or null: per cut, 1 if its optimality pruning would touch the diagram (k2_prune_probe)
     int k0, k1, Tpad;
 };
