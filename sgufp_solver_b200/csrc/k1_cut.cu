@@ -1104,12 +1104,18 @@ static cudaError_t launch_warp_nw(const K1Launch &p, cudaStream_t st, int sm_cou
     const int words = k1_words_per_tile(p);
     const size_t smem = (size_t)NW * words * sizeof(int);
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-    cudaError_t e = cudaFuncSetAttribute(k1_cut_eval<32, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_cut_eval<32, NW>, NW * 32, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    static thread_local int known_words = -1, known_per_sm = 0, known_dev = -1;   // per instantiation and device: attribute set, occupancy known
+    int per_sm = 1, dev = 0;
+    cudaGetDevice(&dev);
+    if (known_words == words && known_dev == dev) per_sm = known_per_sm;
+    else {
+        cudaError_t e = cudaFuncSetAttribute(k1_cut_eval<32, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_cut_eval<32, NW>, NW * 32, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorInvalidConfiguration;
+        known_words = words; known_per_sm = per_sm; known_dev = dev;
+    }
     *resident_warps = per_sm * NW;
     if (dry) return cudaSuccess;
     const long long items = (long long)p.K * p.S;
@@ -1133,16 +1139,22 @@ static cudaError_t launch_warp_dispatch(int nw, const K1Launch &p, cudaStream_t 
 // Warps per CTA: the count that keeps most warps resident per SM (shared memory per warp grows with
 // the network: 2.5 KB at C2, 12 KB at C4, tens of KB beyond); ties go to the larger CTA.
 static cudaError_t launch_warp(const K1Launch &p, cudaStream_t st, int sm_count) {
+    // the choice depends on the shared memory per warp alone: remember it (a one-candidate call is ~0.1 ms of kernel,
+    // eight occupancy queries per call would show)
+    static thread_local int cached_words = -1, cached_nw = 0, cached_dev = -1;
+    const int words = k1_words_per_tile(p);
+    int rw = 0, dev = 0;
+    cudaGetDevice(&dev);
+    if (cached_words == words && cached_dev == dev && cached_nw) return launch_warp_dispatch(cached_nw, p, st, sm_count, &rw, false);
     int best_nw = 0, best = 0;
     for (int nw = WARPS; nw >= 1; nw >>= 1) {
-        int rw = 0;
         const cudaError_t e = launch_warp_dispatch(nw, p, st, sm_count, &rw, true);
         if (e == cudaErrorInvalidConfiguration) { cudaGetLastError(); continue; }
         if (e != cudaSuccess) return e;
         if (rw > best) { best = rw; best_nw = nw; }
     }
     if (!best_nw) return cudaErrorInvalidConfiguration;
-    int rw = 0;
+    cached_words = words; cached_nw = best_nw; cached_dev = dev;
     return launch_warp_dispatch(best_nw, p, st, sm_count, &rw, false);
 }
 
