@@ -43,6 +43,8 @@ struct sgufp_dd {
     std::vector<int16_t> root_solution;
     bool host_built = true, device_built = false, exact_flag = true;
     int nlayers_dev = 1, exact_layer_dev = 0;
+    std::vector<int16_t> cached_path;  // getSolution of the state left by the last one-cut call (extracted in the same call)
+    bool cached_path_valid = false;
     DevBuf<int4> b_layer_info;
     DevBuf<int2> b_arc_ts;
     DevBuf<int32_t> b_in_ptr, b_off, b_widths, b_root_slot;
@@ -194,9 +196,21 @@ int apply_on_device(sgufp_dd *d, double rhs, const uint64_t *keys, const double 
     } else
         CU(c, k2_single_launch(d->d_self.p, d->d_coef.p, d->d_rhs.p, Tpad, d->d_state.p, d->d_last.p, d->dev.max_width, d->dev.nlayers, c->st, &c->dd_launches));
     CU(c, k2_finish_launch(make_apply(d, mode, optimal), c->st, &c->dd_launches));
+    // the Benders loop asks for the path right after every cut (NodeExplorer.cpp:950): extract it in the same call
+    const char *fe = getenv("SGUFP_DD_FUSED_PATH");
+    const bool fused = !(fe && fe[0] == '0');
+    if (fused) CU(c, k2_extract_launch(make_apply(d, mode, optimal), c->st, &c->dd_launches));
     CU(c, cudaEventRecord(c->evk1, c->st));
+    std::vector<int16_t> rev(d->dev.nlayers);
     CU(c, cudaMemcpyAsync(&res, d->d_res.p, sizeof(K2Result), cudaMemcpyDeviceToHost, c->st));
+    if (fused) CU(c, cudaMemcpyAsync(rev.data(), d->d_path.p, (size_t)d->dev.nlayers * 2, cudaMemcpyDeviceToHost, c->st));
     CU(c, cudaStreamSynchronize(c->st));   // also covers the pageable `coef`, `rhs`, `self`
+    d->cached_path_valid = false;
+    if (fused) {
+        d->cached_path = d->root_solution;
+        for (int i = res.path_len - 1; i >= 0; i--) d->cached_path.push_back(rev[i]);
+        d->cached_path_valid = true;
+    }
     CU(c, cudaEventElapsedTime(&c->dd_kernel_ms, c->evk0, c->evk1));
     c->dd_arcs = (long long)d->narcs + d->dev.nlast;   // in-arcs + terminal arcs of the uploaded image
     d->dev_ahead = true; d->dev_states_valid = true;
@@ -205,8 +219,10 @@ int apply_on_device(sgufp_dd *d, double rhs, const uint64_t *keys, const double 
 }
 
 struct Scratch {   // per-context scratch for the batch call + the static tables of the device construction
-    DevBuf<double> coef, rhs, states, last, bound;
+    DevBuf<double> coef, rhs, states, last, bound, wbounds;
     DevBuf<K2DD> dds;
+    DevBuf<K2Result> seq_res;
+    DevBuf<int> seq_ctl, seq_probe;
     bool tables_built = false, tables_ok = false;
     DevBuf<int32_t> t_lay_tab, t_tab_ptr, t_slot_base;
     DevBuf<uint8_t> t_lay_first;
@@ -222,6 +238,7 @@ Scratch &scratch_of(sgufp_ctx *c) {
         c->dd_scratch_free = [](void *p) {
             Scratch *s = static_cast<Scratch *>(p);
             s->coef.release(); s->rhs.release(); s->states.release(); s->last.release(); s->bound.release(); s->dds.release();
+            s->wbounds.release(); s->seq_res.release(); s->seq_ctl.release(); s->seq_probe.release();
             s->t_lay_tab.release(); s->t_tab_ptr.release(); s->t_slot_base.release(); s->t_lay_first.release(); s->t_tab_dec.release(); s->t_tab_k.release();
             delete s;
         };
@@ -490,6 +507,7 @@ int sgufp_dd_build(sgufp_dd *d, const int16_t *states, int ns, const int16_t *so
     d->root_spec = root;
     d->root_solution = root.solution;
     d->dev_ahead = false; d->dev_states_valid = false;   // a new tree: whatever the device held is void
+    d->cached_path_valid = false;
     const int built = device_build(d, root, cutset_nodes);
     if (built < 0) return built;
     if (built) return 0;
@@ -593,8 +611,9 @@ int sgufp_dd_apply_sequence(sgufp_dd *d, int mode, const double *rhs, const uint
         d->dd->densify(keys + cut_ptr[k], vals + cut_ptr[k], cut_ptr[k + 1] - cut_ptr[k], one);
         std::copy(one.begin(), one.begin() + T, cf.begin() + (size_t)k * Tpad);
     }
-    const int chunk = (int)std::max<long long>(1, std::min<long long>(C, (1LL << 27) / std::max(1, nn)));   // <= 1 GB of states
-    DevBuf<K2Result> res; DevBuf<int> ctl, probe; DevBuf<double> wb;
+    // widest window: 256 cuts, and at most 1 GB of node states (the scratch is kept between calls, it only grows)
+    const int chunk = (int)std::max<long long>(1, std::min<long long>(std::min(C, 256), (1LL << 27) / std::max(1, nn)));
+    DevBuf<K2Result> &res = S.seq_res; DevBuf<int> &ctl = S.seq_ctl, &probe = S.seq_probe; DevBuf<double> &wb = S.wbounds;
     const bool probing = mode == 0 && !d->exact_flag && !d->dd->restricted();   // only there does an optimality cut prune arcs
     CU(c, S.coef.reserve(cf.size())); CU(c, S.rhs.reserve(C)); CU(c, S.states.reserve((size_t)chunk * nn)); CU(c, S.last.reserve((size_t)chunk * std::max(1, nlast)));
     CU(c, res.reserve(C)); CU(c, ctl.reserve(2)); CU(c, probe.reserve(chunk)); CU(c, wb.reserve(chunk));
@@ -628,7 +647,6 @@ int sgufp_dd_apply_sequence(sgufp_dd *d, int mode, const double *rhs, const uint
     }
     if (e == cudaSuccess) e = cudaEventRecord(c->evk1, c->st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->st);
-    res.release(); ctl.release(); probe.release(); wb.release();
     CU(c, e);
     CU(c, cudaEventElapsedTime(&c->dd_kernel_ms, c->evk0, c->evk1));
     c->dd_arcs = ((long long)d->narcs + nlast) * done;
@@ -637,6 +655,7 @@ int sgufp_dd_apply_sequence(sgufp_dd *d, int mode, const double *rhs, const uint
     if (done > 0) {
         d->last_coef.assign(cf.begin() + (size_t)(done - 1) * Tpad, cf.begin() + (size_t)(done - 1) * Tpad + T);
         d->dev_ahead = true; d->dev_states_valid = true; d->term_dirty = false;
+        d->cached_path_valid = false;
     }
     return 0;
 }
@@ -659,6 +678,7 @@ int sgufp_dd_apply_optimality_batch(sgufp_dd **dds, int B, const double *rhs, co
         t = keep;   // finish_optimality folded cut C-1 once more; min is idempotent, keep the device values anyway
         dds[b]->term_dirty = false;
         dds[b]->dev_states_valid = false;   // the batch keeps its states in the shared scratch: paths come from the host mirror
+        dds[b]->cached_path_valid = false;
     }
     if (bound) std::copy(bnd.begin(), bnd.end(), bound);
     return 0;
@@ -667,7 +687,8 @@ int sgufp_dd_apply_optimality_batch(sgufp_dd **dds, int B, const double *rhs, co
 int sgufp_dd_solution(sgufp_dd *d, int16_t *path, int capacity) {
     if (!d || !path) return SGUFP_ERR_ARG;
     std::vector<int16_t> p;
-    if (d->dev_states_valid) {
+    if (d->cached_path_valid) p = d->cached_path;
+    else if (d->dev_states_valid) {
         // getSolution on the device image: only the path comes back
         sgufp_ctx *c = d->ctx;
         CU(c, cudaSetDevice(c->device));
