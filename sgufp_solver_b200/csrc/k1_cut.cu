@@ -97,7 +97,7 @@ __host__ __device__ inline int k1_search_words(int nc, int max_nopen) {   // bit
     return nc <= SMALL_NC ? 32 + 32 + 34 + 34 + 32 * 32 / 2 : max_nopen;
 }
 __host__ __device__ inline int k1_words_per_tile(const K1Launch &p) {
-    return 2 * p.max_nch + 2 * p.max_nopen + 4 * (p.nc + 2) + p.nav + 2 + 2 * reach_words(p.nc) + k1_search_words(p.nc, p.max_nopen);
+    return 4 * p.max_nopen + 3 * (p.nc + 2) + p.nav + 2 + 2 * reach_words(p.nc) + k1_search_words(p.nc, p.max_nopen);
 }
 
 template <int TILE>
@@ -476,14 +476,13 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         w.tin = base; w.tout = base + 32; w.hist = base + 64; w.path = base + 98; w.tab = base + 132;
         w.tc = base; base += k1_search_words(p.nc, p.max_nopen);
         w.rw = base; base += 2 * reach_words(p.nc);
-        w.up = base; base += p.max_nch;
-        w.lo = base; base += p.max_nch;
+        w.up = base; base += p.max_nopen;
+        w.lo = base; base += p.max_nopen;
         w.x = base; base += p.max_nopen;
         w.res = base; base += p.max_nopen;
         w.lab = base; base += p.nc + 2;
         w.pred = base; base += p.nc + 2;
-        w.pot = base; base += p.nc + 2;
-        w.exc = base; base += p.nc + 2;
+        w.pot = base; w.exc = base; base += p.nc + 2;   // excesses (lower-bound routing) and potentials are never live together
         w.aq = base;
     }
     const long long items = (long long)p.K * p.S;
@@ -497,9 +496,11 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         unsigned long long *sums = p.sums + (size_t)k * p.W;
         const double *row_u = p.cap_u + (size_t)s * p.m_pad, *row_l = p.cap_l + (size_t)s * p.m_pad;
 
-        // 1. chain capacities
-        for (int c = T.tl; c < nch; c += TILE) { SI(w.up + c) = INT_MAX; SI(w.lo + c) = 0; }
+        // 1. chain capacities (open chains only: a closed chain carries no flow, it is infeasible iff one of its
+        //    arcs has a positive lower bound, and its multipliers are read from the capacity row directly)
+        for (int c = T.tl; c < nopen; c += TILE) { SI(w.up + c) = INT_MAX; SI(w.lo + c) = 0; }
         T.sync();
+        bool bad = false, forced = false;
         {
             const double2 *ru = reinterpret_cast<const double2 *>(row_u), *rl = reinterpret_cast<const double2 *>(row_l);
             for (int a2 = T.tl; a2 < p.m_pad / 2; a2 += TILE) {
@@ -507,25 +508,21 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
                 const int a = 2 * a2;
                 {
                     const int cp = P.arc_cp[a], c = cp >> 10, pos = cp & 1023;
-                    atomicMin(&SI(w.up + c), ((int)u2.x << HB) | pos);
-                    atomicMax(&SI(w.lo + c), ((int)l2.x << HB) | pos);
+                    if (c < nopen) { atomicMin(&SI(w.up + c), ((int)u2.x << HB) | pos); atomicMax(&SI(w.lo + c), ((int)l2.x << HB) | pos); }
+                    else bad |= (int)l2.x > 0;
                 }
                 if (a + 1 < m) {
                     const int cp = P.arc_cp[a + 1], c = cp >> 10, pos = cp & 1023;
-                    atomicMin(&SI(w.up + c), ((int)u2.y << HB) | pos);
-                    atomicMax(&SI(w.lo + c), ((int)l2.y << HB) | pos);
+                    if (c < nopen) { atomicMin(&SI(w.up + c), ((int)u2.y << HB) | pos); atomicMax(&SI(w.lo + c), ((int)l2.y << HB) | pos); }
+                    else bad |= (int)l2.y > 0;
                 }
             }
         }
         T.sync();
-        bool bad = false, forced = false;
-        for (int c = T.tl; c < nch; c += TILE) {
-            const int lo = SI(w.lo + c) >> HB;
-            if (c < nopen) {
-                const int up = SI(w.up + c) >> HB;
-                SI(w.x + c) = lo; bad |= lo > up; forced |= lo > 0;
-                SI(w.res + c) = lo < up ? 1 : 0;          // x == lo: forward residual only
-            } else bad |= lo > 0;
+        for (int c = T.tl; c < nopen; c += TILE) {
+            const int lo = SI(w.lo + c) >> HB, up = SI(w.up + c) >> HB;
+            SI(w.x + c) = lo; bad |= lo > up; forced |= lo > 0;
+            SI(w.res + c) = lo < up ? 1 : 0;              // x == lo: forward residual only
         }
         T.sync();
         bad = T.any(bad);
