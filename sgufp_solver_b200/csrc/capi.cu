@@ -8,6 +8,7 @@
 #include <climits>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <thread>
 #include <vector>
@@ -24,12 +25,13 @@ thread_local std::string g_create_error;
 // ---- helpers shared by the one-GPU and the sharded entry points --------------------------------
 struct Batch {
     std::vector<Plan> plans;
-    std::vector<int32_t> words, off;
+    std::vector<int32_t> off;
+    size_t total_words = 0;          // the plans are gathered into the handle's pinned staging buffer at launch
     int max_nch = 0, max_nopen = 0;
 };
 
-// Host threads that build plans of one batch side by side (a plan is ~35 us of host work at C2,
-// ~140 us at C4: serial construction of 64 plans would cost as much as the kernel itself).
+// Host threads that build plans of one batch side by side (a plan is ~15 us of host work at C2, ~65 us at C4:
+// serial construction of 64 plans would cost a third of the kernel).  The threads persist in the handle.
 static int host_threads(int K) {
     int cap = 8;
     if (const char *e = getenv("SGUFP_HOST_THREADS")) cap = std::max(1, atoi(e));
@@ -44,43 +46,50 @@ static int make_batch(sgufp_ctx *c, const int16_t *paths, int K, int L, Batch &B
     const bool lane_tables = k1_lane_mode_requested();
     std::vector<int> rc(K, 0);
     std::vector<std::string> errs(K);
-    auto work = [&](int t, int nt) {
+    const std::function<void(int, int)> work = [&](int t, int nt) {
         for (int k = t; k < K; k += nt) rc[k] = build_plan(c->M, paths + (size_t)k * L, L, B.plans[k], errs[k], lane_tables);
     };
     const int nt = host_threads(K);
     if (nt > 1) {
-        std::vector<std::thread> pool;
-        for (int t = 1; t < nt; t++) pool.emplace_back(work, t, nt);
-        work(0, nt);
-        for (auto &th : pool) th.join();
+        if (!c->pool || c->pool->size() < nt) { delete c->pool; c->pool = new HostPool(nt - 1); }
+        c->pool->run(nt, work);
     } else work(0, 1);
     size_t total = 0;
     for (int k = 0; k < K; k++) {
         if (rc[k]) return fail(c, rc[k], "path " + std::to_string(k) + ": " + errs[k]);   // the lowest failing index, as a serial loop would report
+        B.off[k] = (int32_t)total;
         total += B.plans[k].words.size();
-    }
-    B.words.resize(total);
-    size_t at = 0;
-    for (int k = 0; k < K; k++) {
-        B.off[k] = (int32_t)at;
-        std::memcpy(B.words.data() + at, B.plans[k].words.data(), B.plans[k].words.size() * 4);
-        at += B.plans[k].words.size();
         B.max_nch = std::max(B.max_nch, B.plans[k].nch);
         B.max_nopen = std::max(B.max_nopen, B.plans[k].nopen);
     }
+    B.total_words = total;
     return 0;
 }
 
 static int launch_batch(sgufp_ctx *c, const Batch &B, int K, unsigned long long *d_sums, long long *d_finf, double *d_obj,
                         uint8_t *d_status, cudaStream_t st) {
-    CU(c, c->d_plans.reserve(B.words.size()));
+    CU(c, c->d_plans.reserve(B.total_words));
     CU(c, c->d_plan_off.reserve(K));
-    CU(c, cudaMemcpyAsync(c->d_plans.p, B.words.data(), B.words.size() * 4, cudaMemcpyHostToDevice, st));
-    CU(c, cudaMemcpyAsync(c->d_plan_off.p, B.off.data(), (size_t)K * 4, cudaMemcpyHostToDevice, st));
+    // gather the plans (+ offsets + the initial "no infeasible scenario" marks) into pinned memory: the uploads are then
+    // true asynchronous copies.  The staging buffer is reused by the next call: an event tells when the copies left it.
+    const size_t o_off = B.total_words, o_inf = (o_off + (size_t)K + 1) & ~(size_t)1, need = o_inf + 2 * (size_t)K;
+    if (c->h2d_pending) { CU(c, cudaEventSynchronize(c->ev_h2d)); c->h2d_pending = false; }
+    if (c->h_words_cap < need) {
+        if (c->h_words) cudaFreeHost(c->h_words);
+        c->h_words = nullptr; c->h_words_cap = 0;
+        CU(c, cudaHostAlloc(reinterpret_cast<void **>(&c->h_words), need * 2 * sizeof(int32_t), cudaHostAllocDefault));
+        c->h_words_cap = need * 2;
+    }
+    for (int k = 0; k < K; k++) std::memcpy(c->h_words + B.off[k], B.plans[k].words.data(), B.plans[k].words.size() * 4);
+    std::memcpy(c->h_words + o_off, B.off.data(), (size_t)K * 4);
+    long long *inf = reinterpret_cast<long long *>(c->h_words + o_inf);
+    for (int k = 0; k < K; k++) inf[k] = LLONG_MAX;
+    CU(c, cudaMemcpyAsync(c->d_plans.p, c->h_words, B.total_words * 4, cudaMemcpyHostToDevice, st));
+    CU(c, cudaMemcpyAsync(c->d_plan_off.p, c->h_words + o_off, (size_t)K * 4, cudaMemcpyHostToDevice, st));
+    CU(c, cudaMemcpyAsync(d_finf, inf, (size_t)K * 8, cudaMemcpyHostToDevice, st));
+    CU(c, cudaEventRecord(c->ev_h2d, st));
+    c->h2d_pending = true;
     CU(c, cudaMemsetAsync(d_sums, 0, (size_t)K * c->W() * 8, st));
-    std::vector<long long> inf(K, LLONG_MAX);
-    CU(c, cudaMemcpyAsync(d_finf, inf.data(), (size_t)K * 8, cudaMemcpyHostToDevice, st));
-    // B.words and `inf` are pageable host temporaries: cudaMemcpyAsync has staged them before it returns
     K1Launch p{};
     p.cap_u = c->d_u; p.cap_l = c->d_l; p.S = c->S; p.m = c->M.m; p.m_pad = c->m_pad; p.scen_offset = c->scen_off;
     p.plans = c->d_plans.p; p.plan_off = c->d_plan_off.p; p.K = K; p.W = c->W(); p.L = c->M.L;
@@ -202,6 +211,7 @@ int sgufp_create(sgufp_ctx **out, int n, int m, int S, const int32_t *tail, cons
     CUC(cudaEventCreate(&c->ev1));
     CUC(cudaEventCreate(&c->evk0));
     CUC(cudaEventCreate(&c->evk1));
+    CUC(cudaEventCreateWithFlags(&c->ev_h2d, cudaEventDisableTiming));
     if (S > 0) {
         const size_t cells = (size_t)S * c->m_pad;
         CUC(cudaMalloc(&c->d_u, cells * sizeof(double)));
@@ -225,6 +235,9 @@ int sgufp_create(sgufp_ctx **out, int n, int m, int S, const int32_t *tail, cons
 void sgufp_destroy(sgufp_ctx *c) {
     if (!c) return;
     if (c->dd_scratch && c->dd_scratch_free) c->dd_scratch_free(c->dd_scratch);
+    delete c->pool;
+    if (c->h_words) cudaFreeHost(c->h_words);
+    if (c->ev_h2d) cudaEventDestroy(c->ev_h2d);
     if (c->d_u) cudaFree(c->d_u);
     if (c->d_l) cudaFree(c->d_l);
     c->d_plans.release(); c->d_plan_off.release(); c->d_ray_i32.release(); c->d_sums.release(); c->d_finf.release();

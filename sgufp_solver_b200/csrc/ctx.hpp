@@ -5,6 +5,7 @@
 #include <string>
 
 #include "../../include/sgufp_b200.h"
+#include "host_pool.hpp"
 #include "model.hpp"
 
 template <typename T>
@@ -35,6 +36,11 @@ struct sgufp_ctx {
     DevBuf<double> d_obj;
     DevBuf<uint8_t> d_status;
     std::string err;
+    sgufp::HostPool *pool = nullptr;            // persistent host threads for the plans of a batch (created on first use)
+    int32_t *h_words = nullptr;                 // pinned staging of a batch's plans (cudaHostAlloc), h_words_cap int32 words
+    size_t h_words_cap = 0;
+    cudaEvent_t ev_h2d = nullptr;               // recorded after the uploads out of h_words
+    bool h2d_pending = false;
     int last_launches = 0;
     float last_ms = 0.f;
     bool kernel_timed = false;
