@@ -237,6 +237,7 @@ void sgufp_destroy(sgufp_ctx *c) {
     if (c->dd_scratch && c->dd_scratch_free) c->dd_scratch_free(c->dd_scratch);
     delete c->pool;
     if (c->h_words) cudaFreeHost(c->h_words);
+    if (c->h_out) cudaFreeHost(c->h_out);
     if (c->ev_h2d) cudaEventDestroy(c->ev_h2d);
     if (c->d_u) cudaFree(c->d_u);
     if (c->d_l) cudaFree(c->d_l);
@@ -333,9 +334,16 @@ int sgufp_solve_paths(sgufp_ctx *c, const int16_t *paths, int K, int L, int *cut
     if (status) CU(c, c->d_status.reserve(KS));
     CU(c, cudaEventRecord(c->ev0, c->st));
     if (int rc = launch_batch(c, B, K, c->d_sums.p, c->d_finf.p, obj ? c->d_obj.p : nullptr, status ? c->d_status.p : nullptr, c->st)) return rc;
-    std::vector<long long> sums((size_t)K * W), finf(K);
-    CU(c, cudaMemcpyAsync(sums.data(), c->d_sums.p, sums.size() * 8, cudaMemcpyDeviceToHost, c->st));
-    CU(c, cudaMemcpyAsync(finf.data(), c->d_finf.p, (size_t)K * 8, cudaMemcpyDeviceToHost, c->st));
+    const size_t n_out = (size_t)K * W + (size_t)K;
+    if (c->h_out_cap < n_out) {
+        if (c->h_out) cudaFreeHost(c->h_out);
+        c->h_out = nullptr; c->h_out_cap = 0;
+        CU(c, cudaHostAlloc(reinterpret_cast<void **>(&c->h_out), n_out * 2 * sizeof(long long), cudaHostAllocDefault));
+        c->h_out_cap = n_out * 2;
+    }
+    long long *sums = c->h_out, *finf = c->h_out + (size_t)K * W;     // pinned: the copies run at link speed, no staging
+    CU(c, cudaMemcpyAsync(sums, c->d_sums.p, (size_t)K * W * 8, cudaMemcpyDeviceToHost, c->st));
+    CU(c, cudaMemcpyAsync(finf, c->d_finf.p, (size_t)K * 8, cudaMemcpyDeviceToHost, c->st));
     if (obj) CU(c, cudaMemcpyAsync(obj, c->d_obj.p, KS * sizeof(double), cudaMemcpyDeviceToHost, c->st));
     if (status) CU(c, cudaMemcpyAsync(status, c->d_status.p, KS, cudaMemcpyDeviceToHost, c->st));
     CU(c, cudaStreamSynchronize(c->st));
@@ -343,19 +351,23 @@ int sgufp_solve_paths(sgufp_ctx *c, const int16_t *paths, int K, int L, int *cut
         if (finf[k] == LLONG_MAX) continue;
         // the lowest-index infeasible scenario alone defines the cut (grb.cpp:284-351)
         if (int rc = run_ray(c, B.plans[k], finf[k], c->d_sums.p + (size_t)k * W, c->st)) return rc;
-        CU(c, cudaMemcpyAsync(sums.data() + (size_t)k * W, c->d_sums.p + (size_t)k * W, (size_t)W * 8, cudaMemcpyDeviceToHost, c->st));
+        CU(c, cudaMemcpyAsync(sums + (size_t)k * W, c->d_sums.p + (size_t)k * W, (size_t)W * 8, cudaMemcpyDeviceToHost, c->st));
         CU(c, cudaStreamSynchronize(c->st));
     }
     CU(c, cudaEventRecord(c->ev1, c->st));
     CU(c, cudaEventSynchronize(c->ev1));
     CU(c, cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
-    for (int k = 0; k < K; k++) {
-        const bool feas = finf[k] != LLONG_MAX;
-        finalize_one(c, B.plans[k], sums.data() + (size_t)k * W, feas, cut_type ? cut_type + k : nullptr, rhs ? rhs + k : nullptr,
-                     keys ? keys + (size_t)k * T : nullptr, vals ? vals + (size_t)k * T : nullptr, nnz ? nnz + k : nullptr,
-                     coef_dense ? coef_dense + (size_t)k * T : nullptr);
-        if (first_infeasible) first_infeasible[k] = feas ? finf[k] : -1;
-    }
+    const std::function<void(int, int)> fin = [&](int t, int nt) {
+        for (int k = t; k < K; k += nt) {
+            const bool feas = finf[k] != LLONG_MAX;
+            finalize_one(c, B.plans[k], sums + (size_t)k * W, feas, cut_type ? cut_type + k : nullptr, rhs ? rhs + k : nullptr,
+                         keys ? keys + (size_t)k * T : nullptr, vals ? vals + (size_t)k * T : nullptr, nnz ? nnz + k : nullptr,
+                         coef_dense ? coef_dense + (size_t)k * T : nullptr);
+            if (first_infeasible) first_infeasible[k] = feas ? finf[k] : -1;
+        }
+    };
+    const int nt = host_threads(K);
+    if (nt > 1 && c->pool) c->pool->run(nt, fin); else fin(0, 1);
     return SGUFP_OK;
 }
 

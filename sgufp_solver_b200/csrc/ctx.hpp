@@ -39,6 +39,8 @@ struct sgufp_ctx {
     sgufp::HostPool *pool = nullptr;            // persistent host threads for the plans of a batch (created on first use)
     int32_t *h_words = nullptr;                 // pinned staging of a batch's plans (cudaHostAlloc), h_words_cap int32 words
     size_t h_words_cap = 0;
+    long long *h_out = nullptr;                 // pinned landing buffer of a batch's sums + first-infeasible marks
+    size_t h_out_cap = 0;
     cudaEvent_t ev_h2d = nullptr;               // recorded after the uploads out of h_words
     bool h2d_pending = false;
     int last_launches = 0;
