@@ -405,6 +405,62 @@ int device_cutset(sgufp_dd *d) {
     return 0;
 }
 
+// RelaxedDDNew::getCutset on a diagram that was built on the device and whose states are there: no host mirror.
+// Returns 1 and fills `out`, or 0 if this diagram is not in that situation.
+int device_relaxed_cutset(sgufp_dd *d, std::vector<NodeSpec> &out) {
+    sgufp_ctx *c = d->ctx;
+    if (!d->device_built || !d->dev_states_valid || d->dd->restricted()) return 0;
+    Scratch &S = scratch_of(c);
+    CU(c, cudaSetDevice(c->device));
+    const K2Apply a = make_apply(d, 0, 0.0);
+    DevBuf<int> d4; DevBuf<unsigned> om; DevBuf<int32_t> ol; DevBuf<int16_t> od;
+    CU(c, d4.reserve(4));
+    int h4[4] = {-1, -1, 0, 0};
+    cudaError_t e = k2_first_collapsed_launch(a, d4.p, c->st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h4, d4.p, 16, cudaMemcpyDeviceToHost, c->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->st);
+    d4.release();
+    CU(c, e);
+    out.clear();
+    const int layer = h4[0], count = h4[3] - h4[2];
+    if (layer < 0 || count <= 0) return 1;                       // no collapsed layer: the reference returns nothing useful either
+    const int stride = layer;                                    // at most one decision per layer 1..layer
+    std::vector<unsigned> masks(count); std::vector<int32_t> lens(count); std::vector<int16_t> decs((size_t)count * stride);
+    e = om.reserve(count);
+    if (e == cudaSuccess) e = ol.reserve(count);
+    if (e == cudaSuccess) e = od.reserve((size_t)count * stride);
+    if (e == cudaSuccess) e = k2_relaxed_cutset_launch(a, d->b_mask.p, layer, h4[1], h4[2], count, stride, om.p, ol.p, od.p, c->st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(masks.data(), om.p, (size_t)count * 4, cudaMemcpyDeviceToHost, c->st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(lens.data(), ol.p, (size_t)count * 4, cudaMemcpyDeviceToHost, c->st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(decs.data(), od.p, (size_t)count * stride * 2, cudaMemcpyDeviceToHost, c->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->st);
+    om.release(); ol.release(); od.release();
+    CU(c, e);
+    const Model &M = c->M;
+    const int start = d->root_spec.global_layer, gl = start + layer;
+    const bool fresh = gl < M.L && S.h_lay_first[gl];            // hasStateChanged[gl] (DD.cpp:4189)
+    const int tp_tail = S.h_tab_ptr[S.h_lay_tab[gl - 1]];        // the tail's states are over the list of ITS layer
+    for (int j = 0; j < count; j++) {
+        if (lens[j] < 0) continue;                               // arc removed by a cut
+        NodeSpec n;
+        n.global_layer = gl;
+        const int16_t dec = decs[(size_t)j * stride];
+        n.solution = d->root_spec.solution;
+        for (int k = lens[j] - 1; k >= 0; k--) n.solution.push_back(decs[(size_t)j * stride + k]);
+        if (fresh) {
+            const int tp = S.h_tab_ptr[S.h_lay_tab[gl]], nst = S.h_tab_ptr[S.h_lay_tab[gl] + 1] - tp;
+            for (int p = 0; p < nst; p++) n.states.push_back(S.h_tab_dec[tp + p]);
+        } else {
+            for (unsigned m = masks[j]; m; m &= m - 1) {
+                const int16_t s = S.h_tab_dec[tp_tail + __builtin_ctz(m)];
+                if (dec == -1 || s != dec) n.states.push_back(s);
+            }
+        }
+        out.push_back(std::move(n));
+    }
+    return 1;
+}
+
 // densify C cuts, run K2 over B diagrams, read back what the host semantics need
 int run_k2(sgufp_ctx *c, sgufp_dd **dds, int B, const std::vector<std::vector<double>> &coefs, const double *rhs, int C,
            std::vector<std::vector<double>> *states_last_cut /* per diagram, states of cut C-1, or null */, double *bound,
@@ -714,6 +770,12 @@ int sgufp_dd_cutset(sgufp_dd *d, double ub, int32_t *words, int capacity) {
         if (d->compile_cutset.empty() && d->device_built && !d->host_built) { if (int rc = device_cutset(d)) return rc; }
         else ensure_host(d);
         return write_nodes(d->compile_cutset, words, capacity);
+    }
+    {
+        std::vector<NodeSpec> cs;
+        const int got = device_relaxed_cutset(d, cs);
+        if (got < 0) return got;
+        if (got) return write_nodes(cs, words, capacity);
     }
     if (int rc = sync_host(d)) return rc;
     return write_nodes(d->dd->cutset(ub), words, capacity);

@@ -151,6 +151,52 @@ __global__ void k2_cutset(const int4 *layer_info, const int32_t *in_ptr, const i
     }
 }
 
+// RelaxedDDNew::getCutset (DD.cpp:4179-4218) on the device image: the cut-set is the set of arcs that enter the first
+// layer (from layer 3 on) with ONE live node; one thread per such arc writes the state mask of its tail, its decision
+// and the tail's path (getPathForNode, DD.cpp:3796-3820: upwards over the first live in-arc whose parent state + weight
+// EQUALS the node's state, recorded; otherwise the first live in-arc, not recorded), leaf first.
+__global__ void k2_relaxed_cutset(K2Apply a, const unsigned *mask, int layer, int v, int e0, int stride, unsigned *out_mask, int32_t *out_len,
+                                  int16_t *out_dec) {
+    const K2DD &d = a.d;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, e = e0 + j;
+    if (e >= d.in_ptr[v + 1]) return;
+    if (a.arc_dead[e]) { out_len[j] = -1; return; }
+    int cur = d.layer_info[layer - 1].x + d.arc_ts[e].x, n = 0;
+    out_mask[j] = mask[cur];
+    out_dec[(size_t)j * stride + n++] = (int16_t)a.arc_dec[e];
+    for (int l = layer - 1; l > 0; l--) {
+        const int tail0 = d.layer_info[l - 1].x;
+        const double sc = a.state[cur];
+        int first = -1, match = -1;
+        for (int x = d.in_ptr[cur]; x < d.in_ptr[cur + 1] && match < 0; x++) {
+            if (a.arc_dead[x]) continue;
+            if (first < 0) first = x;
+            const int2 ts = d.arc_ts[x];
+            const double w = ts.y >= 0 ? a.coef[ts.y] : 0.0;
+            if ((a.state[tail0 + ts.x] + w) == sc) match = x;
+        }
+        if (first < 0) break;
+        const int x = match >= 0 ? match : first;
+        if (match >= 0) out_dec[(size_t)j * stride + n++] = (int16_t)a.arc_dec[x];
+        cur = tail0 + d.arc_ts[x].x;
+    }
+    out_len[j] = n;
+}
+
+// the first layer >= 3 with one live node, and that node (result: {layer, node} or {-1, -1})
+__global__ void k2_first_collapsed(K2Apply a, int *out2) {
+    const K2DD &d = a.d;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    out2[0] = -1; out2[1] = -1; out2[2] = 0; out2[3] = 0;
+    for (int layer = 3; layer < d.nlayers; layer++)
+        if (a.layer_alive[layer] == 1) {
+            const int4 li = d.layer_info[layer];
+            for (int i = 0; i < li.z; i++)
+                if (!a.node_dead[li.x + i]) { out2[0] = layer; out2[1] = li.x + i; out2[2] = d.in_ptr[li.x + i]; out2[3] = d.in_ptr[li.x + i + 1]; return; }
+            return;
+        }
+}
+
 __global__ void k2_fill(double *p, double v, long long n) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -167,6 +213,18 @@ cudaError_t k2_cutset_launch(const int4 *layer_info, const int32_t *in_ptr, cons
                              int el, int count, unsigned *out_mask, int16_t *out_dec, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
     k2_cutset<<<(count + 255) / 256, 256, 0, st>>>(layer_info, in_ptr, arc_ts, arc_dec, mask, el, out_mask, out_dec);
+    return cudaGetLastError();
+}
+
+cudaError_t k2_first_collapsed_launch(const K2Apply &a, int *out4, cudaStream_t st) {
+    k2_first_collapsed<<<1, 32, 0, st>>>(a, out4);
+    return cudaGetLastError();
+}
+
+cudaError_t k2_relaxed_cutset_launch(const K2Apply &a, const unsigned *mask, int layer, int v, int e0, int count, int stride, unsigned *out_mask,
+                                     int32_t *out_len, int16_t *out_dec, cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+    k2_relaxed_cutset<<<(count + 127) / 128, 128, 0, st>>>(a, mask, layer, v, e0, stride, out_mask, out_len, out_dec);
     return cudaGetLastError();
 }
 

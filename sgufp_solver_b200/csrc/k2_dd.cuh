@@ -104,6 +104,11 @@ struct K2Build {
 };
 cudaError_t k2_build_launch(const K2Build &b, cudaStream_t st, int *launches);
 cudaError_t k2_fill_launch(double *p, double v, long long n, cudaStream_t st);
+// relaxed cut-set on the device image: out4 = {layer, node, first in-arc, end in-arc} of the first layer >= 3 with one live node
+cudaError_t k2_first_collapsed_launch(const K2Apply &a, int *out4, cudaStream_t st);
+// per in-arc j of that node: tail's state mask, number of decisions (-1: arc removed) and the decisions leaf first
+cudaError_t k2_relaxed_cutset_launch(const K2Apply &a, const unsigned *mask, int layer, int v, int e0, int count, int stride, unsigned *out_mask,
+                                     int32_t *out_len, int16_t *out_dec, cudaStream_t st);
 // restricted tree: state mask + decisions (root first, `el` per node) of every node of layer `el`
 cudaError_t k2_cutset_launch(const int4 *layer_info, const int32_t *in_ptr, const int2 *arc_ts, const int32_t *arc_dec, const unsigned *mask,
                              int el, int count, unsigned *out_mask, int16_t *out_dec, cudaStream_t st);
