@@ -469,12 +469,13 @@ int run_k2(sgufp_ctx *c, sgufp_dd **dds, int B, const std::vector<std::vector<do
     Scratch &S = scratch_of(c);
     std::vector<K2DD> hd(B);
     long long off = 0, loff = 0, arcs = 0;
-    int maxw = 1, maxl = 1;
+    int maxw = 1, maxl = 1, avgw = 1;
     for (int b = 0; b < B; b++) {
         if (dds[b]->ctx != c) return fail(c, SGUFP_ERR_ARG, "all diagrams of a batch must belong to one context");
         if (int rc = upload(dds[b])) return rc;
         maxw = std::max(maxw, dds[b]->dev.max_width);
         maxl = std::max(maxl, dds[b]->dev.nlayers);
+        avgw = std::max(avgw, dds[b]->dev.nnodes / std::max(1, dds[b]->dev.nlayers));
     }
     const bool in_smem = k2_states_in_smem(Tpad, maxw);   // else: one global state block per (diagram, cut)
     for (int b = 0; b < B; b++) {
@@ -492,7 +493,7 @@ int run_k2(sgufp_ctx *c, sgufp_dd **dds, int B, const std::vector<std::vector<do
     CU(c, cudaMemcpyAsync(S.dds.p, hd.data(), (size_t)B * sizeof(K2DD), cudaMemcpyHostToDevice, c->st));
     c->dd_launches = 0;
     CU(c, cudaEventRecord(c->evk0, c->st));
-    CU(c, k2_launch(S.dds.p, B, S.coef.p, S.rhs.p, C, Tpad, S.states.p, S.last.p, maxw, maxl, c->st, &c->dd_launches));
+    CU(c, k2_launch(S.dds.p, B, S.coef.p, S.rhs.p, C, Tpad, S.states.p, S.last.p, maxw, maxl, avgw, c->st, &c->dd_launches));
     if (update_terminal) CU(c, k2_terminal_launch(S.dds.p, B, C, S.last.p, S.bound.p, c->st, &c->dd_launches));
     CU(c, cudaEventRecord(c->evk1, c->st));
     if (states_last_cut) {

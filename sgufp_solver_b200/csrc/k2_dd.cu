@@ -17,6 +17,7 @@
 
 #include <cfloat>
 #include <climits>
+#include <cstdlib>
 
 namespace sgufp {
 namespace {
@@ -44,11 +45,11 @@ __device__ __forceinline__ double block_max(double v, double *red) {
 // DEADS: the diagram carries flags of arcs removed on the device (single-cut path); a flagged arc
 // contributes nothing, exactly as if it had been erased from the in-arc list.
 template <bool SMEM_STATES, bool DEADS>
-__global__ void __launch_bounds__(K2_THREADS) k2_longest_path(const K2DD *__restrict__ dds, const double *__restrict__ coef,
+__global__ void __launch_bounds__(K2_FIN_THREADS) k2_longest_path(const K2DD *__restrict__ dds, const double *__restrict__ coef,
                                                                const double *__restrict__ rhs, int C, int Tpad, int maxw,
                                                                double *__restrict__ gstate, double *__restrict__ glast, int li_cache) {
     extern __shared__ double sm[];
-    __shared__ double red[K2_THREADS / 32];
+    __shared__ double red[K2_FIN_THREADS / 32];
     const K2DD d = dds[blockIdx.y];
     const int c = blockIdx.x;
     double *cf = sm;                       // [Tpad]
@@ -555,13 +556,18 @@ __global__ void __launch_bounds__(K2_THREADS) k2_extract(K2Apply a) {
 }  // namespace
 
 cudaError_t k2_launch(const K2DD *dds, int B, const double *coef, const double *rhs, int C, int Tpad, double *states, double *last,
-                      int max_width_all, int max_layers, cudaStream_t st, int *launches) {
+                      int max_width_all, int max_layers, int avg_width, cudaStream_t st, int *launches) {
     const int K2_LI_CACHE = max_layers <= 640 ? max_layers : 0;   // shadows the constant: stage exactly what this batch needs
     dim3 grid(C, B);
     if (launches) (*launches)++;
-    // narrow diagrams: smaller CTAs, more of them per SM (a layer is one barrier-separated step)
+    // narrow diagrams: smaller CTAs, more of them per SM (a layer is one barrier-separated step); wide ones (few CTAs
+    // fit an SM: two state buffers of the full width each) get more threads per CTA instead
+    // (measured, width 4096: 2.2e11 arcs/s at 256 threads, 3.7e11 at 512, 4.7e11 at 1024; width 1024 and the relaxed
+    // diagram — wide only in its last layers — are fastest at 256: the AVERAGE width decides)
+    int cap = avg_width >= 2048 ? K2_FIN_THREADS : avg_width >= 1200 ? 512 : K2_THREADS;
+    if (const char *e = getenv("SGUFP_K2_THREADS")) { const int t = atoi(e); if (t >= 64 && t <= K2_FIN_THREADS) cap = t; }
     int threads = 64;
-    while (threads < K2_THREADS && threads < max_width_all) threads *= 2;
+    while (threads < cap && threads < max_width_all) threads *= 2;
     const size_t smem = ((size_t)Tpad + 2 * (size_t)max_width_all) * sizeof(double);
     if (smem <= 200 * 1024) {
         const size_t tot = smem + (size_t)K2_LI_CACHE * sizeof(int4);

@@ -22,8 +22,9 @@ struct K2DD {   // device image of one decision diagram (CSR by layer, DESIGN.md
 // Only the last layer goes to global memory (last[b][c][i]); the states of every node are written
 // for cut C-1 alone, which is what the host semantics read back.
 cudaError_t k2_launch(const K2DD *dds_device, int B, const double *coef_device /*[C][Tpad]*/, const double *rhs_device /*[C]*/,
-                      int C, int Tpad, double *states_device, double *last_device, int max_width_all, int max_layers, cudaStream_t st,
-                      int *launches);   // max_layers: the per-layer records are staged in shared memory when <= 640
+                      int C, int Tpad, double *states_device, double *last_device, int max_width_all, int max_layers, int avg_width, cudaStream_t st,
+                      int *launches);   // max_layers: the per-layer records are staged in shared memory when <= 640;
+                                        // avg_width (nodes per layer of the widest diagram) picks the threads per CTA
 // true if the widest layer fits the shared-memory state buffers (else: global state blocks, one per cut)
 bool k2_states_in_smem(int Tpad, int max_width_all);
 // term[i] = min(term[i], min_c last[b][c][i]); bound[b] = max_i term[i]
