@@ -477,7 +477,7 @@ int run_k2(sgufp_ctx *c, sgufp_dd **dds, int B, const std::vector<std::vector<do
         maxl = std::max(maxl, dds[b]->dev.nlayers);
         avgw = std::max(avgw, dds[b]->dev.nnodes / std::max(1, dds[b]->dev.nlayers));
     }
-    const bool in_smem = k2_states_in_smem(Tpad, maxw);   // else: one global state block per (diagram, cut)
+    const bool in_smem = k2_states_in_smem(Tpad, maxw, avgw);   // else: one global state block per (diagram, cut)
     for (int b = 0; b < B; b++) {
         hd[b] = dds[b]->dev;
         hd[b].state_off = off; hd[b].last_off = loff;
@@ -494,7 +494,12 @@ int run_k2(sgufp_ctx *c, sgufp_dd **dds, int B, const std::vector<std::vector<do
     c->dd_launches = 0;
     CU(c, cudaEventRecord(c->evk0, c->st));
     CU(c, k2_launch(S.dds.p, B, S.coef.p, S.rhs.p, C, Tpad, S.states.p, S.last.p, maxw, maxl, avgw, c->st, &c->dd_launches));
-    if (update_terminal) CU(c, k2_terminal_launch(S.dds.p, B, C, S.last.p, S.bound.p, c->st, &c->dd_launches));
+    if (update_terminal) {
+        int max_last = 1;
+        for (int b = 0; b < B; b++) max_last = std::max(max_last, hd[b].nlast);
+        CU(c, S.wbounds.reserve((size_t)B * 64));
+        CU(c, k2_terminal_launch(S.dds.p, B, C, S.last.p, S.bound.p, S.wbounds.p, max_last, c->st, &c->dd_launches));
+    }
     CU(c, cudaEventRecord(c->evk1, c->st));
     if (states_last_cut) {
         states_last_cut->resize(B);

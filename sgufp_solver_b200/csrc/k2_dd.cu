@@ -15,6 +15,7 @@
 // Diagrams wider than the shared-memory budget fall back to a global-state variant.
 #include "k2_dd.cuh"
 
+#include <algorithm>
 #include <cfloat>
 #include <climits>
 #include <cstdlib>
@@ -23,6 +24,7 @@ namespace sgufp {
 namespace {
 
 constexpr int K2_THREADS = 256;
+constexpr int K2_TERM_SLICES = 64;     // CTAs per diagram in k2_terminal (scratch: B x 64 partial maxima)
 constexpr int K2_FIN_THREADS = 1024;   // the one-CTA kernels that sweep a (possibly wide) last layer
 
 __device__ __forceinline__ double block_max(double v, double *red) {
@@ -126,12 +128,14 @@ __global__ void __launch_bounds__(K2_FIN_THREADS) k2_longest_path(const K2DD *__
     }
 }
 
+// term[i] = min(term[i], min_c last[b][c][i]); partial maxima per slice of the last layer (a wide last layer — the
+// relaxed diagram ends with ~10 k nodes — is spread over several CTAs), reduced by k2_terminal_bound
 __global__ void __launch_bounds__(K2_THREADS) k2_terminal(const K2DD *__restrict__ dds, int C, const double *__restrict__ glast,
-                                                           double *__restrict__ bound) {
+                                                           double *__restrict__ partial, int slices, double *__restrict__ bound) {
     __shared__ double red[K2_THREADS / 32];
     const K2DD d = dds[blockIdx.x];
     double best = -DBL_MAX;
-    for (int i = threadIdx.x; i < d.nlast; i += blockDim.x) {
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < d.nlast; i += slices * blockDim.x) {
         double t = d.term[i];
         for (int c = 0; c < C; c++) {
             const double s = glast[d.last_off + (size_t)c * d.nlast + i];
@@ -141,9 +145,15 @@ __global__ void __launch_bounds__(K2_THREADS) k2_terminal(const K2DD *__restrict
         best = best < t ? t : best;            // terminalState = max(terminalState, arc.weight)
     }
     best = block_max(best, red);
-    if (threadIdx.x == 0) bound[blockIdx.x] = best;
+    if (threadIdx.x == 0) { if (slices == 1) bound[blockIdx.x] = best; else partial[(size_t)blockIdx.x * slices + blockIdx.y] = best; }
 }
 
+__global__ void k2_terminal_bound(const double *__restrict__ partial, int slices, double *__restrict__ bound) {
+    double best = -DBL_MAX;
+    for (int i = threadIdx.x; i < slices; i += 32) { const double t = partial[(size_t)blockIdx.x * slices + i]; best = best < t ? t : best; }
+    for (int o = 16; o; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, best, o); best = best < t ? t : best; }
+    if (threadIdx.x == 0) bound[blockIdx.x] = best;
+}
 
 // ---- single cut on a WIDE diagram: one launch per layer, the layer spread over the whole GPU ------
 // (one CTA per diagram would leave 147 SMs idle: the one-cut-at-a-time calls have no batch to fill
@@ -569,7 +579,7 @@ cudaError_t k2_launch(const K2DD *dds, int B, const double *coef, const double *
     int threads = 64;
     while (threads < cap && threads < max_width_all) threads *= 2;
     const size_t smem = ((size_t)Tpad + 2 * (size_t)max_width_all) * sizeof(double);
-    if (smem <= 200 * 1024) {
+    if (k2_states_in_smem(Tpad, max_width_all, avg_width)) {
         const size_t tot = smem + (size_t)K2_LI_CACHE * sizeof(int4);
         cudaError_t e = cudaFuncSetAttribute(k2_longest_path<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tot);
         if (e != cudaSuccess) return e;
@@ -583,11 +593,24 @@ cudaError_t k2_launch(const K2DD *dds, int B, const double *coef, const double *
     return cudaGetLastError();
 }
 
-bool k2_states_in_smem(int Tpad, int max_width_all) { return ((size_t)Tpad + 2 * (size_t)max_width_all) * sizeof(double) <= 200 * 1024; }
+bool k2_states_in_smem(int Tpad, int max_width_all, int avg_width) {
+    const size_t bytes = ((size_t)Tpad + 2 * (size_t)max_width_all) * sizeof(double);
+    if (bytes > 200 * 1024) return false;
+    if (const char *e = getenv("SGUFP_K2_STATES")) { if (e[0] == 'g') return false; if (e[0] == 's') return true; }
+    // A diagram that is narrow almost everywhere but very wide somewhere (the relaxed diagram: dozens of layers of a
+    // few hundred nodes, then 10 k in the last ones) would pin one CTA per SM with two full-width buffers: its states
+    // go to the global block instead and the SM stays full.
+    if (bytes > 64 * 1024 && (long long)avg_width * 8 <= max_width_all) return false;
+    return true;
+}
 
-cudaError_t k2_terminal_launch(const K2DD *dds, int B, int C, const double *last, double *bound, cudaStream_t st, int *launches) {
-    k2_terminal<<<B, K2_THREADS, 0, st>>>(dds, C, last, bound);
-    if (launches) (*launches)++;
+cudaError_t k2_terminal_launch(const K2DD *dds, int B, int C, const double *last, double *bound, double *partial, int max_last, cudaStream_t st,
+                               int *launches) {
+    int slices = (max_last + 4 * K2_THREADS - 1) / (4 * K2_THREADS);      // ~4 nodes per thread
+    slices = std::max(1, std::min(slices, K2_TERM_SLICES));
+    k2_terminal<<<dim3(B, slices), K2_THREADS, 0, st>>>(dds, C, last, partial, slices, bound);
+    if (slices > 1) k2_terminal_bound<<<B, 32, 0, st>>>(partial, slices, bound);
+    if (launches) (*launches)++;           // counted as one step of the launch pair (longest path + terminal)
     return cudaGetLastError();
 }
 

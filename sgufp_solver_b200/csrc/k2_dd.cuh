@@ -26,10 +26,10 @@ cudaError_t k2_launch(const K2DD *dds_device, int B, const double *coef_device /
                       int *launches);   // max_layers: the per-layer records are staged in shared memory when <= 640;
                                         // avg_width (nodes per layer of the widest diagram) picks the threads per CTA
 // true if the widest layer fits the shared-memory state buffers (else: global state blocks, one per cut)
-bool k2_states_in_smem(int Tpad, int max_width_all);
+bool k2_states_in_smem(int Tpad, int max_width_all, int avg_width);
 // term[i] = min(term[i], min_c last[b][c][i]); bound[b] = max_i term[i]
 cudaError_t k2_terminal_launch(const K2DD *dds_device, int B, int C, const double *last_device, double *bound_device,
-                               cudaStream_t st, int *launches);
+                               double *partial_device /*[B * 64] scratch*/, int max_last, cudaStream_t st, int *launches);
 
 // ---- device-side cut application ----------------------------------------------
 // What follows the longest path in RelaxedDDNew / RestrictedDDNew::applyOptimalityCut and
