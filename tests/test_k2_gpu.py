@@ -314,3 +314,72 @@ def test_sequence_call_on_a_restricted_tree():
     assert n == 12 and bounds.tolist() == want
     _same_state(ours, ref, relaxed=False)
     assert ours.getMaxPath().tolist() == ref.solution().tolist()
+
+
+@pytest.mark.parametrize("block", range(3))
+def test_fuzz_random_networks(block):
+    """Random small networks: construction on the device, runs of cuts (feasibility and optimality, with thresholds
+    that prune), one-cut calls, paths and cut-sets against the unmodified reference classes."""
+    rng = np.random.default_rng(7000 + block)
+    done = 0
+    for k in range(10):
+        nl = int(rng.integers(2, 5))
+        layers = [int(rng.integers(2, 7)) for _ in range(nl)]
+        max_m = sum(a * b for a, b in zip(layers[:-1], layers[1:])) + layers[0] + layers[-1]
+        m = int(rng.integers(max(sum(layers) + 2, max_m // 2), max_m + 1))
+        try:
+            inst = I.make_layered(layers, m, 1, 5000 + 100 * block + k, float(rng.uniform(0.4, 0.95)), 0.0, f"dfz{k}")
+            rn = ref_dd.RefNetwork(inst)
+        except Exception:
+            continue
+        solver = sg.GuroSolver(inst)
+        # relaxed
+        ours, ref = RelaxedDDNew(solver), ref_dd.RefRelaxedDD(rn)
+        ours.buildTree(); ref.build()
+        assert ours.isTreeExact() == ref.is_exact()
+        assert ours.dump_device()["built_on_device"]
+        assert ours.getSolution().tolist() == ref.solution().tolist()
+        alive = True
+        fc = [random_cut(solver, rng, cut_type=1) for _ in range(3)]
+        fc = [type(c)(c.RHS * 0.3, c.keys, c.vals) for c in fc]
+        want = []
+        for c in fc:
+            want.append(ref.apply_feas(c.RHS, c.keys, c.vals))
+            if not want[-1]:
+                break
+        flags, n = ours.applyFeasibilityCuts(fc)
+        assert n == len(want) and flags.tolist() == want, inst.name
+        alive = bool(want[-1])
+        if alive:
+            c0 = random_cut(solver, rng)
+            ub = ref.apply_opt(c0.RHS, c0.keys, c0.vals, -1e300, 1e300)
+            assert ours.applyOptimalityCut(c0, -1e300, 1e300) == ub
+            assert ours.getSolution().tolist() == ref.solution().tolist()
+            oc = [random_cut(solver, rng) for _ in range(12)]
+            optimal = ub - float(rng.uniform(50, 400))
+            want = []
+            for c in oc:
+                want.append(ref.apply_opt(c.RHS, c.keys, c.vals, optimal, ub))
+                if want[-1] <= optimal:
+                    break
+            bounds, n = ours.applyOptimalityCuts(oc, optimal)
+            assert n == len(want) and bounds.tolist() == want, inst.name
+            if want[-1] != LOWEST:
+                assert ours.getSolution().tolist() == ref.solution().tolist()
+                if not ours.isTreeExact():
+                    assert [(x.globalLayer, x.states, x.solutionVector) for x in ours.getCutset(1e300)] == ref.cutset(1e300)
+                _same_state(ours, ref)
+        # restricted
+        width = int(rng.choice([1, 3, 16, 200]))
+        ro, rr = RestrictedDDNew(solver, width), ref_dd.RefRestrictedDD(rn, width)
+        cs = ro.compile(); rr.compile()
+        assert ro.isTreeExact() == rr.is_exact()
+        if not ro.isTreeExact():
+            assert [(x.globalLayer, x.states, x.solutionVector) for x in cs] == rr.cutset()
+        oc = [random_cut(solver, rng) for _ in range(5)]
+        bounds, n = ro.applyOptimalityCuts(oc)
+        assert bounds.tolist() == [rr.apply_opt(c.RHS, c.keys, c.vals) for c in oc]
+        assert ro.getMaxPath().tolist() == rr.solution().tolist()
+        _same_state(ro, rr, relaxed=False)
+        done += 1
+    assert done >= 5
