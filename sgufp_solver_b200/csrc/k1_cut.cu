@@ -498,7 +498,9 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
 
         // 1. chain capacities (open chains only: a closed chain carries no flow, it is infeasible iff one of its
         //    arcs has a positive lower bound, and its multipliers are read from the capacity row directly)
-        for (int c = T.tl; c < nopen; c += TILE) { SI(w.up + c) = INT_MAX; SI(w.lo + c) = 0; }
+        // lo[c] packs (greatest lower bound << 10 | position of its LAST arc): with no positive lower bound on the chain
+        // that is (0, last position), known up front, so only positive lower bounds (rare) need the atomic
+        for (int c = T.tl; c < nopen; c += TILE) { SI(w.up + c) = INT_MAX; SI(w.lo + c) = P.ch_ptr[c + 1] - P.ch_ptr[c] - 1; }
         T.sync();
         bool bad = false, forced = false;
         {
@@ -508,12 +510,12 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
                 const int a = 2 * a2;
                 {
                     const int cp = P.arc_cp[a], c = cp >> 10, pos = cp & 1023;
-                    if (c < nopen) { atomicMin(&SI(w.up + c), ((int)u2.x << HB) | pos); atomicMax(&SI(w.lo + c), ((int)l2.x << HB) | pos); }
+                    if (c < nopen) { atomicMin(&SI(w.up + c), ((int)u2.x << HB) | pos); if ((int)l2.x > 0) atomicMax(&SI(w.lo + c), ((int)l2.x << HB) | pos); }
                     else bad |= (int)l2.x > 0;
                 }
                 if (a + 1 < m) {
                     const int cp = P.arc_cp[a + 1], c = cp >> 10, pos = cp & 1023;
-                    if (c < nopen) { atomicMin(&SI(w.up + c), ((int)u2.y << HB) | pos); atomicMax(&SI(w.lo + c), ((int)l2.y << HB) | pos); }
+                    if (c < nopen) { atomicMin(&SI(w.up + c), ((int)u2.y << HB) | pos); if ((int)l2.y > 0) atomicMax(&SI(w.lo + c), ((int)l2.y << HB) | pos); }
                     else bad |= (int)l2.y > 0;
                 }
             }
