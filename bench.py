@@ -347,6 +347,9 @@ class DDCpuBaseline:
     def _new(self, kind, width):
         return self.ref_dd.RefRestrictedDD(self.net, width) if kind == "restricted" else self.ref_dd.RefRelaxedDD(self.net)
 
+    def supports(self, kind, width):
+        return kind == "restricted" or width == 120          # the reference's relaxed threshold is a compile-time 120
+
     def build_ms(self, kind, width, reps=3):
         r = self._new(kind, width)
         ts = []

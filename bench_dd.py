@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--C", type=int, default=64)
     ap.add_argument("--reps", type=int, default=7)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--relaxed-thresholds", default="120",
+                    help="collapse thresholds of the RelaxedDDNew points (the reference's compile-time constant is 120)")
     ap.add_argument("--build", action="store_true",
                     help="construction time of one diagram: k2_build on the device (SURVEY 8f-3) vs the host builder vs the reference class")
     ap.add_argument("--sequential", action="store_true",
@@ -50,13 +52,13 @@ def main():
         import bench                                   # the CPU-baseline leg lives in bench.py (the one place that runs oracle/)
         base = bench.DDCpuBaseline(inst)
         ref_net = base if base.available() else None
-    points = [("restricted", int(w)) for w in args.widths.split(",")] + [("relaxed", 120)]
+    points = [("restricted", int(w)) for w in args.widths.split(",") if w] + [("relaxed", int(t)) for t in args.relaxed_thresholds.split(",") if t]
     if args.build:
         for kind, w in points:
             line = {"metric": "dd_build_ms", "unit": "ms per buildTree/compile", "higher_is_better": False, "kind": kind, "width": w}
             for mode in ("device", "host"):
                 os.environ["SGUFP_DD_BUILD"] = mode
-                d = RestrictedDDNew(solver, w) if kind == "restricted" else RelaxedDDNew(solver)
+                d = RestrictedDDNew(solver, w) if kind == "restricted" else RelaxedDDNew(solver, w)
                 build = d.compile if kind == "restricted" else d.buildTree
                 build(); torch.cuda.synchronize()
                 ts = []
@@ -68,13 +70,13 @@ def main():
                     line["nodes_per_diagram"], line["arcs_per_diagram"] = d.counts()
                 d.close()
             os.environ.pop("SGUFP_DD_BUILD", None)
-            if ref_net is not None:
+            if ref_net is not None and ref_net.supports(kind, w):
                 line["cpu_reference"] = {"value": ref_net.build_ms(kind, w), "unit": line["unit"], "cores": 1, "kind": "reference"}
             print(json.dumps(line), flush=True)
         return
     if args.sequential:
         for kind, w in points:
-            d = RestrictedDDNew(solver, w) if kind == "restricted" else RelaxedDDNew(solver)
+            d = RestrictedDDNew(solver, w) if kind == "restricted" else RelaxedDDNew(solver, w)
             d.compile() if kind == "restricted" else d.buildTree()
             nodes1, arcs1 = d.counts()
             apply = (lambda c: d.applyOptimalityCut(c)) if kind == "restricted" else (lambda c: d.applyOptimalityCut(c, -1e300, 1e300))
@@ -91,7 +93,7 @@ def main():
                     "arcs_per_sec": arcs1 * len(cuts) / dt, "cuts": len(cuts),
                     "note": "host API wall time; longest path, terminal weights, pruning and path extraction run on the device, "
                             "only the bound and the path come back"}
-            if ref_net is not None:
+            if ref_net is not None and ref_net.supports(kind, w):
                 dtr = ref_net.apply_seconds(kind, w, cuts, with_solution=True)
                 line["cpu_reference"] = {"value": dtr / len(cuts) * 1e3, "unit": line["unit"], "cores": 1, "kind": "reference",
                                          "sample": f"the same {len(cuts)} cuts on the unmodified reference class (oracle/_ref)"}
@@ -101,7 +103,7 @@ def main():
     for kind, w in points:
         dds = []
         for _ in range(args.B):
-            d = RestrictedDDNew(solver, w) if kind == "restricted" else RelaxedDDNew(solver)
+            d = RestrictedDDNew(solver, w) if kind == "restricted" else RelaxedDDNew(solver, w)
             d.compile() if kind == "restricted" else d.buildTree()
             dds.append(d)
         for _ in range(3):
@@ -120,7 +122,7 @@ def main():
                 "roofline": {"bound": "hbm", "achieved": bytes_alg / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": bytes_alg / (ms / 1e3) / 1e9 / peak, "bytes_per_launch": bytes_alg},
                 "l2": "flushed (512 MiB write) before every timed launch"}
-        if ref_net is not None:
+        if ref_net is not None and ref_net.supports(kind, w):
             dt = ref_net.apply_seconds(kind, w, cuts)
             line["cpu_reference"] = {"value": arcs1 * args.C / dt, "unit": "arcs/s", "cores": 1, "kind": "reference",
                                      "sample": f"1 diagram x {args.C} cuts, unmodified reference class (oracle/_ref)"}

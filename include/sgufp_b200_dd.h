@@ -16,7 +16,7 @@
 extern "C" {
 #endif
 
-#define SGUFP_DD_RELAXED 0    /* RelaxedDDNew: collapse threshold RELAXED_MAX_WIDTH = 120 (DD.h:732) */
+#define SGUFP_DD_RELAXED 0    /* RelaxedDDNew: collapse threshold = max_width, or RELAXED_MAX_WIDTH = 120 (DD.h:732) if max_width <= 0 */
 #define SGUFP_DD_RESTRICTED 1 /* RestrictedDDNew(max_width) (DD.h:710) */
 
 typedef struct sgufp_dd sgufp_dd;

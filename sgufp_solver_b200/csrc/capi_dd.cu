@@ -326,7 +326,7 @@ int device_build(sgufp_dd *d, const NodeSpec &root, int *cutset_nodes) {
     CU(c, d->d_arc_dec.reserve(arc_cap)); CU(c, d->b_mask.reserve(node_cap)); CU(c, d->b_off.reserve(node_cap));
     CU(c, d->b_widths.reserve(layers + 1)); CU(c, d->b_out.reserve(1));
     K2Build b{};
-    b.t = S.tables; b.start = start; b.root_mask = mask; b.restricted = restricted ? 1 : 0; b.max_width = d->dd->max_width();
+    b.t = S.tables; b.start = start; b.root_mask = mask; b.restricted = restricted ? 1 : 0; b.max_width = restricted ? d->dd->max_width() : (d->dd->max_width() > 0 ? d->dd->max_width() : 120);
     b.node_cap = (int)node_cap; b.arc_cap = (int)arc_cap;
     b.layer_info = d->b_layer_info.p; b.in_ptr = d->b_in_ptr.p; b.arc_ts = d->b_arc_ts.p; b.arc_dec = d->d_arc_dec.p; b.mask = d->b_mask.p;
     b.off = d->b_off.p; b.widths = d->b_widths.p; b.out = d->b_out.p;

@@ -80,7 +80,8 @@ void HostDD::relaxed_next_layer(int index, unsigned &next_size) {
     const Model &M = *M_;
     const std::vector<int32_t> cur = tree_[index];
     const unsigned gl = (unsigned)nodes_[cur.front()].global_layer;
-    if (next_size >= 120u /* RELAXED_MAX_WIDTH, DD.h:732 */ && gl < (unsigned)M.L - 5u) {
+    const unsigned threshold = max_width_ > 0 ? (unsigned)max_width_ : 120u;   // RELAXED_MAX_WIDTH = 120 (DD.h:732), a runtime parameter here
+    if (next_size >= threshold && gl < (unsigned)M.L - 5u) {
         exact_ = false;
         const int nn = new_node();
         std::set<int16_t> all;

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(KB_THREADS) k2_build(K2Build b) {
             next_size = (unsigned)w * (unsigned)nst;
             __syncthreads();
         }
-        const bool collapse = !b.restricted && next_size >= 120u && (unsigned)g < (unsigned)t.L - 5u;   // DD.cpp:3614
+        const bool collapse = !b.restricted && next_size >= (unsigned)b.max_width && (unsigned)g < (unsigned)t.L - 5u;   // DD.cpp:3614, threshold 120 in the reference
         const bool one_child = b.restricted && !exact;      // DD.cpp:3204: the greatest state only
         auto cnt = [&](int i) { return one_child ? 1 : __popc(b.mask[v0 + i]); };
         const int sum = block_scan(w, cnt, b.off, sh);

@@ -198,8 +198,12 @@ class _DDBase:
 
 
 class RelaxedDDNew(_DDBase):
-    """`Inavap::RelaxedDDNew` (DD.h:734-810)."""
+    """`Inavap::RelaxedDDNew` (DD.h:734-810).  `threshold` is the collapse threshold: the reference's compile-time
+    RELAXED_MAX_WIDTH = 120 (DD.h:732) by default, a runtime parameter here for the width sweep of config C3."""
     KIND = 0
+
+    def __init__(self, solver, threshold: int = 0):
+        super().__init__(solver, threshold)
 
     def buildTree(self, node: Node = None) -> None:
         self._build(node or Node())

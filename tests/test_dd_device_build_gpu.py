@@ -99,3 +99,31 @@ def test_host_builder_still_reachable(monkeypatch):
     d = RelaxedDDNew(solver)
     d.buildTree()
     assert not d.dump_device()["built_on_device"]
+
+
+@pytest.mark.parametrize("threshold", [12, 500])
+def test_relaxed_threshold_is_a_runtime_parameter(threshold, monkeypatch):
+    """Config C3 sweeps the collapse threshold, a compile-time 120 in the reference (DD.h:732): other values cannot be
+    compared with the reference binary, so the device construction is checked against the host statement of the same
+    algorithm (which IS the reference's at 120, test above), structure and results."""
+    inst = INSTANCES["c2"]()
+    solver = sg.GuroSolver(inst)
+    dev_dd = RelaxedDDNew(solver, threshold)
+    dev_dd.buildTree()
+    img = dev_dd.dump_device()
+    assert img["built_on_device"]
+    monkeypatch.setenv("SGUFP_DD_BUILD", "host")
+    host_dd = RelaxedDDNew(solver, threshold)
+    host_dd.buildTree()
+    himg = host_dd.dump_device()
+    assert not himg["built_on_device"]
+    for k in ("layer_sizes", "in_ptr", "arc_tailpos", "arc_decision", "arc_slot"):
+        assert img[k].tolist() == himg[k].tolist(), k
+    ref120 = RelaxedDDNew(solver)                      # default threshold: a different diagram
+    ref120.buildTree()
+    assert ref120.layer_sizes().tolist() != dev_dd.layer_sizes().tolist()
+    rng = np.random.default_rng(threshold)
+    for _ in range(5):
+        cut = random_cut(solver, rng)
+        assert dev_dd.applyOptimalityCut(cut, -1e300, 1e300) == host_dd.applyOptimalityCut(cut, -1e300, 1e300)
+        assert dev_dd.getSolution().tolist() == host_dd.getSolution().tolist()
