@@ -318,26 +318,35 @@ int device_build(sgufp_dd *d, const NodeSpec &root, int *cutset_nodes) {
     }
     const bool restricted = d->dd->restricted();
     const long long layers = M.L - start;
-    long long node_cap = restricted ? 1 + layers * (long long)d->dd->max_width() : (1LL << 21);
-    if (node_cap > (1LL << 26)) return 0;
-    const long long arc_cap = restricted ? node_cap : (1LL << 22);
     CU(c, cudaSetDevice(c->device));
-    CU(c, d->b_layer_info.reserve(layers + 1)); CU(c, d->b_in_ptr.reserve(node_cap + 1)); CU(c, d->b_arc_ts.reserve(arc_cap));
-    CU(c, d->d_arc_dec.reserve(arc_cap)); CU(c, d->b_mask.reserve(node_cap)); CU(c, d->b_off.reserve(node_cap));
-    CU(c, d->b_widths.reserve(layers + 1)); CU(c, d->b_out.reserve(1));
-    K2Build b{};
-    b.t = S.tables; b.start = start; b.root_mask = mask; b.restricted = restricted ? 1 : 0; b.max_width = restricted ? d->dd->max_width() : (d->dd->max_width() > 0 ? d->dd->max_width() : 120);
-    b.node_cap = (int)node_cap; b.arc_cap = (int)arc_cap;
-    b.layer_info = d->b_layer_info.p; b.in_ptr = d->b_in_ptr.p; b.arc_ts = d->b_arc_ts.p; b.arc_dec = d->d_arc_dec.p; b.mask = d->b_mask.p;
-    b.off = d->b_off.p; b.widths = d->b_widths.p; b.out = d->b_out.p;
+    // capacity: exact for a restricted tree (a layer never exceeds max_width); a relaxed diagram starts with room for
+    // 256 k nodes and is rebuilt with 8x more when it runs out (up to 16 M nodes), so that the usual diagram of a few
+    // ten thousand nodes does not pin hundreds of megabytes
+    long long node_cap = restricted ? 1 + layers * (long long)d->dd->max_width() : std::max<long long>(1LL << 18, (long long)d->b_mask.cap);
+    if (node_cap > (1LL << 26)) return 0;
     K2BuildOut o{};
-    o.overflow = 1;
-    CU(c, cudaMemcpyAsync(d->b_out.p, &o, sizeof(o), cudaMemcpyHostToDevice, c->st));
-    c->dd_launches = 0;
-    CU(c, k2_build_launch(b, c->st, &c->dd_launches));
-    CU(c, cudaMemcpyAsync(&o, d->b_out.p, sizeof(o), cudaMemcpyDeviceToHost, c->st));
-    CU(c, cudaStreamSynchronize(c->st));
-    if (o.overflow) return 0;
+    for (;;) {
+        const long long arc_cap = restricted ? node_cap : 2 * node_cap;
+        CU(c, d->b_layer_info.reserve(layers + 1)); CU(c, d->b_in_ptr.reserve(node_cap + 1)); CU(c, d->b_arc_ts.reserve(arc_cap));
+        CU(c, d->d_arc_dec.reserve(arc_cap)); CU(c, d->b_mask.reserve(node_cap)); CU(c, d->b_off.reserve(node_cap));
+        CU(c, d->b_widths.reserve(layers + 1)); CU(c, d->b_out.reserve(1));
+        K2Build b{};
+        b.t = S.tables; b.start = start; b.root_mask = mask; b.restricted = restricted ? 1 : 0;
+        b.max_width = restricted ? d->dd->max_width() : (d->dd->max_width() > 0 ? d->dd->max_width() : 120);
+        b.node_cap = (int)node_cap; b.arc_cap = (int)arc_cap;
+        b.layer_info = d->b_layer_info.p; b.in_ptr = d->b_in_ptr.p; b.arc_ts = d->b_arc_ts.p; b.arc_dec = d->d_arc_dec.p; b.mask = d->b_mask.p;
+        b.off = d->b_off.p; b.widths = d->b_widths.p; b.out = d->b_out.p;
+        o = K2BuildOut{};
+        o.overflow = 1;
+        CU(c, cudaMemcpyAsync(d->b_out.p, &o, sizeof(o), cudaMemcpyHostToDevice, c->st));
+        c->dd_launches = 0;
+        CU(c, k2_build_launch(b, c->st, &c->dd_launches));
+        CU(c, cudaMemcpyAsync(&o, d->b_out.p, sizeof(o), cudaMemcpyDeviceToHost, c->st));
+        CU(c, cudaStreamSynchronize(c->st));
+        if (!o.overflow) break;
+        if (restricted || node_cap >= (1LL << 24)) return 0;    // leave it to the host builder
+        node_cap *= 8;
+    }
     std::vector<int4> li(o.nlayers);
     d->layer_width.resize(o.nlayers);
     CU(c, cudaMemcpyAsync(li.data(), d->b_layer_info.p, (size_t)o.nlayers * sizeof(int4), cudaMemcpyDeviceToHost, c->st));
