@@ -75,6 +75,21 @@ def measured_traffic(workload):
     return None
 
 
+def issue_roofline(workload, kernel_ms, sm_mhz, sms):
+    """Second roofline of K1 (the binding one): warp instructions per launch (ncu smsp__inst_executed.sum of
+    the seeded workload, committed in profiles/k1_traffic.json) / live kernel time, against 4 issue slots per SM and clock."""
+    p = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if not os.path.exists(p) or not sm_mhz:
+        return None
+    n = json.load(open(p)).get("warp_instructions", {}).get(workload)
+    if not n:
+        return None
+    achieved = n / (kernel_ms * 1e-3) / 1e9
+    peak = sms * 4 * sm_mhz * 1e6 / 1e9
+    return {"bound": "issue", "achieved": achieved, "peak": peak, "unit": "G warp-inst/s", "frac": achieved / peak,
+            "warp_instructions_per_launch": n, "peak_source": "%d SMs x 4 schedulers x %.0f MHz (sampled under load)" % (sms, sm_mhz)}
+
+
 class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -311,6 +326,8 @@ def main():
             "clocks": clocks,
             "dd": None,
         }
+        line["roofline"]["issue"] = issue_roofline(args.workload, k_ms, (clocks or {}).get("sm_mhz"),
+                                                   torch.cuda.get_device_properties(local).multi_processor_count)
         if not args.no_cpu_baseline and world == 1:
             threads = 1
             v, evals, dt, sample = cpu_port_throughput(inst, paths, 12.0, threads)

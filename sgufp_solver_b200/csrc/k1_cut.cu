@@ -273,30 +273,33 @@ __device__ int tight_list(const PlanView &P, int nopen, const Lanes<TILE> &T, Ti
     return n;
 }
 
-// list variant of the search, level synchronous: a node joins with a predecessor
-// (tail | (2*chain+dir) << 10) from an EARLIER level, so the predecessors form a tree rooted at src.
-// If dst is not reached, w.rw holds the complete reached set.
+// list variant of the search: sweeps over the tight-chain list that mark heads IN PLACE, so one sweep carries the
+// reached set along every run of list entries whose tails come before their heads (a level-synchronous scan needs one
+// sweep per level: 59 % of K1's instructions on C4, profiles/r01c_k1_c4_ncu.md).  The lane whose atomicOr sets a
+// node's bit is the only one to write its predecessor (tail | (2*chain+dir) << 10), and that tail's bit was set
+// before: the predecessors form a tree rooted at src.  Any tight path will do — the duals do not depend on which
+// optimal flow is found.  If dst is not reached, w.rw holds the complete reached set.
 template <int TILE>
 __device__ bool reach_list(int src, int dst, const PlanView &P, int ntc, int nword, const Lanes<TILE> &T, TileMem &w) {
-    const int R = w.rw, N = w.rw + nword;   // offsets of the reached set and of this level's joiners
-    for (int i = T.tl; i < nword; i += TILE) { SU(R + (i)) = i == (src >> 5) ? 1u << (src & 31) : 0u; SU(N + (i)) = 0u; }
+    const int R = w.rw;
+    for (int i = T.tl; i < nword; i += TILE) SU(R + (i)) = i == (src >> 5) ? 1u << (src & 31) : 0u;
     T.sync();
     for (;;) {
+        bool grew = false;
         for (int i = T.tl; i < ntc; i += TILE) {
             const int en = SI(w.tc + i), c = en & 0xffff, f = SI(w.res + c) & (en >> 16);
             if (f) {
                 const ChainEnds e(P.ch_st[c]);
                 if ((f & 1) && ((SU(R + (e.sv >> 5)) >> (e.sv & 31)) & 1) && !((SU(R + (e.hf >> 5)) >> (e.hf & 31)) & 1)) {
-                    atomicOr(&SU(N + (e.hf >> 5)), 1u << (e.hf & 31)); SI(w.pred + e.hf) = e.sv | ((2 * c) << 10);
+                    const unsigned bit = 1u << (e.hf & 31);
+                    if (!(atomicOr(&SU(R + (e.hf >> 5)), bit) & bit)) { SI(w.pred + e.hf) = e.sv | ((2 * c) << 10); grew = true; }
                 }
                 if ((f & 2) && ((SU(R + (e.ev >> 5)) >> (e.ev & 31)) & 1) && !((SU(R + (e.hb >> 5)) >> (e.hb & 31)) & 1)) {
-                    atomicOr(&SU(N + (e.hb >> 5)), 1u << (e.hb & 31)); SI(w.pred + e.hb) = e.ev | ((2 * c + 1) << 10);
+                    const unsigned bit = 1u << (e.hb & 31);
+                    if (!(atomicOr(&SU(R + (e.hb >> 5)), bit) & bit)) { SI(w.pred + e.hb) = e.ev | ((2 * c + 1) << 10); grew = true; }
                 }
             }
         }
-        T.sync();
-        bool grew = false;
-        for (int i = T.tl; i < nword; i += TILE) { const unsigned nb = SU(N + (i)); if (nb) { SU(R + (i)) |= nb; SU(N + (i)) = 0u; grew = true; } }
         T.sync();
         if ((SU(R + (dst >> 5)) >> (dst & 31)) & 1) return true;
         if (!T.any(grew)) return false;
