@@ -32,7 +32,7 @@
 namespace sgufp {
 
 #ifdef SGUFP_K1_STATS
-__device__ unsigned long long g_k1_stats[4];   // relaxation passes, label computations, breadth-first searches, work items
+__device__ unsigned long long g_k1_stats[8];   // relaxation passes, label computations, searches, work items, list sweeps, list entries swept, searches that reached dst, chains per pass
 #endif
 
 namespace {
@@ -163,7 +163,7 @@ __device__ void shortest_paths(int src, const PlanView &P, int nopen, int nc, co
         T.sync();
         changed = T.any(changed) && --fuel > 0;
 #ifdef SGUFP_K1_STATS
-        if (T.tl == 0) atomicAdd(&g_k1_stats[0], 1ull);
+        if (T.tl == 0) { atomicAdd(&g_k1_stats[0], 1ull); atomicAdd(&g_k1_stats[7], (unsigned long long)nopen); }
 #endif
     } while (changed);
 #ifdef SGUFP_K1_STATS
@@ -286,22 +286,41 @@ __device__ bool reach_list(int src, int dst, const PlanView &P, int ntc, int nwo
     T.sync();
     for (;;) {
         bool grew = false;
-        for (int i = T.tl; i < ntc; i += TILE) {
-            const int en = SI(w.tc + i), c = en & 0xffff, f = SI(w.res + c) & (en >> 16);
-            if (f) {
-                const ChainEnds e(P.ch_st[c]);
-                if ((f & 1) && ((SU(R + (e.sv >> 5)) >> (e.sv & 31)) & 1) && !((SU(R + (e.hf >> 5)) >> (e.hf & 31)) & 1)) {
+        for (int i0 = 0; i0 < ntc; i0 += TILE) {           // tile-uniform trip count
+            const int i = i0 + T.tl;
+            int c = 0, f = 0;
+            if (i < ntc) { const int en = SI(w.tc + i); c = en & 0xffff; f = SI(w.res + c) & (en >> 16); }
+            const ChainEnds e(f ? P.ch_st[c] : make_int2(0, 0));
+            // the 32 entries of a chunk stay in registers until none of them can grow the set any more: entries of one
+            // chunk feed each other (the list is in topological order of the tails), and a re-test is two loads per direction
+            bool again;
+            do {
+                bool g = false;
+                if ((f & 1) && ((SU(R + (e.sv >> 5)) >> (e.sv & 31)) & 1)) {
                     const unsigned bit = 1u << (e.hf & 31);
-                    if (!(atomicOr(&SU(R + (e.hf >> 5)), bit) & bit)) { SI(w.pred + e.hf) = e.sv | ((2 * c) << 10); grew = true; }
+                    if (!((SU(R + (e.hf >> 5)) & bit)) && !(atomicOr(&SU(R + (e.hf >> 5)), bit) & bit)) { SI(w.pred + e.hf) = e.sv | ((2 * c) << 10); g = true; }
+                    f &= ~1;
                 }
-                if ((f & 2) && ((SU(R + (e.ev >> 5)) >> (e.ev & 31)) & 1) && !((SU(R + (e.hb >> 5)) >> (e.hb & 31)) & 1)) {
+                if ((f & 2) && ((SU(R + (e.ev >> 5)) >> (e.ev & 31)) & 1)) {
                     const unsigned bit = 1u << (e.hb & 31);
-                    if (!(atomicOr(&SU(R + (e.hb >> 5)), bit) & bit)) { SI(w.pred + e.hb) = e.ev | ((2 * c + 1) << 10); grew = true; }
+                    if (!((SU(R + (e.hb >> 5)) & bit)) && !(atomicOr(&SU(R + (e.hb >> 5)), bit) & bit)) { SI(w.pred + e.hb) = e.ev | ((2 * c + 1) << 10); g = true; }
+                    f &= ~2;
                 }
-            }
+                T.sync();
+                again = T.any(g);
+                grew |= again;
+            } while (again);
         }
         T.sync();
-        if ((SU(R + (dst >> 5)) >> (dst & 31)) & 1) return true;
+#ifdef SGUFP_K1_STATS
+        if (T.tl == 0) { atomicAdd(&g_k1_stats[4], 1ull); atomicAdd(&g_k1_stats[5], (unsigned long long)ntc); }
+#endif
+        if ((SU(R + (dst >> 5)) >> (dst & 31)) & 1) {
+#ifdef SGUFP_K1_STATS
+            if (T.tl == 0) atomicAdd(&g_k1_stats[6], 1ull);
+#endif
+            return true;
+        }
         if (!T.any(grew)) return false;
     }
 }
@@ -1218,9 +1237,9 @@ cudaError_t relayout_launch(const int32_t *src, double *dst, int m, int S, int m
 
 #if defined(SGUFP_K1_STATS) && !defined(SGUFP_K1_EMULATE)
 // debug build only (-DSGUFP_K1_STATS): relaxation passes / label computations since the last call
-extern "C" int sgufp_debug_k1_stats(unsigned long long *out4) {
-    unsigned long long z[4] = {0, 0, 0, 0};
-    cudaError_t e = cudaMemcpyFromSymbol(out4, sgufp::g_k1_stats, sizeof(z));
+extern "C" int sgufp_debug_k1_stats(unsigned long long *out8) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaError_t e = cudaMemcpyFromSymbol(out8, sgufp::g_k1_stats, sizeof(z));
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(sgufp::g_k1_stats, z, sizeof(z));
     return e == cudaSuccess ? 0 : -6;
 }

@@ -16,6 +16,7 @@ typedef int cudaError_t;
 typedef void *cudaStream_t;
 struct double2 { double x, y; };
 struct int2 { int x, y; };
+static inline int2 make_int2(int x, int y) { return int2{x, y}; }
 struct int4 { int x, y, z, w; };
 struct EmulIdx { int x = 0, y = 0; };
 static EmulIdx threadIdx, blockIdx;

@@ -33,7 +33,7 @@ def main():
     L = _lib.lib()
     L.sgufp_debug_k1_stats.restype = C.c_int
     L.sgufp_debug_k1_stats.argtypes = [C.POINTER(C.c_ulonglong)]
-    out = (C.c_ulonglong * 4)()
+    out = (C.c_ulonglong * 8)()
     for name in [a for a in sys.argv[1:] if not a.startswith("-")]:
         inst, K = {"c2": (lambda: (I.config2(S=1000), 64)), "c4": (lambda: (I.config4(S=2000), 8))}[name]()
         solver = GuroSolver(inst)
@@ -43,6 +43,8 @@ def main():
         L.sgufp_debug_k1_stats(out)
         ev = max(1, out[3])
         print(f"{name}: evals {out[3]}  passes/eval {out[0] / ev:.1f}  label computations/eval {out[1] / ev:.1f}  searches/eval {out[2] / ev:.1f}  ms {solver.last_kernel_ms():.3f}")
+        if out[4]:
+            print(f"    list searches: sweeps/search {out[4] / max(1, out[2]):.2f}  entries/sweep {out[5] / out[4]:.0f}  reached dst {100.0 * out[6] / max(1, out[2]):.0f} %  open chains/pass {out[7] / max(1, out[0]):.0f}")
 
 
 if __name__ == "__main__":
