@@ -25,6 +25,7 @@
 #include "k1_cut.cuh"
 
 #include <climits>
+#include <type_traits>
 #include <cstdlib>
 
 #include "model.hpp"
@@ -74,7 +75,9 @@ struct ChainEnds {
 // This tile's slice of shared memory, as word OFFSETS into the CTA's buffer: indexing the
 // __shared__ symbol directly keeps every access a plain LDS/STS/ATOMS with a register + immediate
 // address (pointers kept in a struct are generic and cost an address computation per use).
-struct TileMem {
+template <bool BIG_>
+struct TileMemT {
+    static constexpr bool BIG = BIG_;     // contracted graph of more than SMALL_NC nodes (compile time: each kernel carries one search)
     int tin, tout, hist, path, tab;       // small graphs: bit sets of the tight residual graph, search levels, path, pair table
     int tc;                               // larger graphs: the tight-chain list (same place)
     int rw;                               // reached set (+ a scratch row for the list search)
@@ -88,16 +91,22 @@ extern __shared__ int k1_smem[];
 #define SI(off) (k1_smem[off])
 #define SU(off) (reinterpret_cast<unsigned *>(k1_smem)[off])
 #define SH(off) (reinterpret_cast<unsigned short *>(k1_smem)[off])
+#define SB(off) (reinterpret_cast<unsigned char *>(k1_smem)[off])
+// residual / tight flags of chain c: one byte each for the larger graphs (shared memory decides how many tiles an SM
+// holds: 3 -> 4 CTAs of 8 warps on C4), one word each for the small ones (byte accesses cost C2 7 %)
+#define TM_BIG(w) (std::remove_cv_t<std::remove_reference_t<decltype(w)>>::BIG)
+#define RGET(c) (TM_BIG(w) ? (int)SB(4 * w.res + (c)) : SI(w.res + (c)))
+#define RSET(c, v) do { if (TM_BIG(w)) SB(4 * w.res + (c)) = (unsigned char)(v); else SI(w.res + (c)) = (v); } while (0)
 
 __host__ __device__ inline int reach_words(int nc) { return (nc + 1 + 31) >> 5; }   // bit sets over the label indices 0..nc
 
 // int32 words of shared memory per tile (the launcher and the host emulation size the buffer with it)
 constexpr int SMALL_NC = 31;              // label indices 0..nc fit one 32-bit set
 __host__ __device__ inline int k1_search_words(int nc, int max_nopen) {   // bit sets + levels + path + pair table, or the tight-chain list
-    return nc <= SMALL_NC ? 32 + 32 + 34 + 34 + 32 * 32 / 2 : max_nopen;
+    return nc <= SMALL_NC ? 32 + 32 + 34 + 34 + 32 * 32 / 2 : (max_nopen + 1) / 2;   // list entries are 16 bits
 }
 __host__ __device__ inline int k1_words_per_tile(const K1Launch &p) {
-    return 4 * p.max_nopen + 3 * (p.nc + 2) + p.nav + 2 + 2 * reach_words(p.nc) + k1_search_words(p.nc, p.max_nopen);
+    return 3 * p.max_nopen + (p.nc <= SMALL_NC ? p.max_nopen : (p.max_nopen + 3) / 4) + 3 * (p.nc + 2) + p.nav + 2 + 2 * reach_words(p.nc) + k1_search_words(p.nc, p.max_nopen);
 }
 
 template <int TILE>
@@ -137,8 +146,8 @@ __device__ __forceinline__ int lab_dist(int lab) { return (lab >> HB) - LAB_BIAS
 // root end at index nc.
 // WARM: the nodes of the set w.rw (those a failed search could still reach over tight residual
 // arcs) keep their labels — they are still exact, see reach_* — and only the others start over.
-template <int TILE, bool MERGED, bool WARM>
-__device__ void shortest_paths(int src, const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TileMem &w, int &fuel) {
+template <int TILE, bool MERGED, bool WARM, class TM>
+__device__ void shortest_paths(int src, const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TM &w, int &fuel) {
     for (int v = T.tl; v <= nc; v += TILE)
         if (!WARM || !((SU(w.rw + (v >> 5)) >> (v & 31)) & 1)) SI(w.lab + v) = LAB_INF;
     T.sync();
@@ -148,7 +157,7 @@ __device__ void shortest_paths(int src, const PlanView &P, int nopen, int nc, co
     do {
         changed = false;
         for (int c = T.tl; c < nopen; c += TILE) {
-            const int f = SI(w.res + c);                // bit 0 forward residual, bit 1 backward residual
+            const int f = RGET(c);                // bit 0 forward residual, bit 1 backward residual
             const ChainEnds e(P.ch_st[c]);
             const int ls = SI(w.lab + e.sv), le = SI(w.lab + e.ev);
             if ((f & 1) && ls != LAB_INF && !(MERGED && e.hf == nc)) {
@@ -184,17 +193,17 @@ __device__ void shortest_paths(int src, const PlanView &P, int nopen, int nc, co
 // warp, the path is read back one level per hop, and the hops are updated in parallel.
 // Larger graphs: a compacted list of the tight chains, scanned once per level.
 
-template <int TILE>
-__device__ void tight_small(const PlanView &P, int nopen, const Lanes<TILE> &T, TileMem &w) {
+template <int TILE, class TM>
+__device__ void tight_small(const PlanView &P, int nopen, const Lanes<TILE> &T, TM &w) {
     for (int i = T.tl; i < 64; i += TILE) SU(w.tin + i) = 0u;    // tin[32] and tout[32] are adjacent
     T.sync();
     for (int c = T.tl; c < nopen; c += TILE) {
         const ChainEnds e(P.ch_st[c]);
-        const int ls = SI(w.lab + e.sv), le = SI(w.lab + e.ev), f = SI(w.res + c) & 3;
+        const int ls = SI(w.lab + e.sv), le = SI(w.lab + e.ev), f = RGET(c) & 3;
         int tf = 0;
         if (ls != LAB_INF && ls - e.r == SI(w.lab + e.hf)) tf |= 1;
         if (le != LAB_INF && le + e.r == SI(w.lab + e.hb)) tf |= 2;
-        SI(w.res + c) = f | (tf << 2);
+        RSET(c, f | (tf << 2));
         if (f & tf & 1) { atomicOr(&SU(w.tin + e.hf), 1u << e.sv); atomicOr(&SU(w.tout + e.sv), 1u << e.hf); SH(2 * w.tab + e.hf * 32 + e.sv) = (unsigned short)(2 * c); }
         if (f & tf & 2) { atomicOr(&SU(w.tin + e.hb), 1u << e.ev); atomicOr(&SU(w.tout + e.ev), 1u << e.hb); SH(2 * w.tab + e.hb * 32 + e.ev) = (unsigned short)(2 * c + 1); }
     }
@@ -203,8 +212,8 @@ __device__ void tight_small(const PlanView &P, int nopen, const Lanes<TILE> &T, 
 
 // Breadth-first search src -> dst; hist[l] = the nodes first reached at level l.  Returns the level
 // of dst, or 0 if it cannot be reached — then SU(w.rw + 0) holds the complete reached set.
-template <int TILE>
-__device__ int reach_small(int src, int dst, int nc, const Lanes<TILE> &T, TileMem &w) {
+template <int TILE, class TM>
+__device__ int reach_small(int src, int dst, int nc, const Lanes<TILE> &T, TM &w) {
     unsigned R = 1u << src, F = R;
     int lev = 0;
     if (T.tl == 0) SU(w.hist + 0) = F;
@@ -222,8 +231,8 @@ __device__ int reach_small(int src, int dst, int nc, const Lanes<TILE> &T, TileM
 
 // Push along a path dst -> src that drops one level per hop.  Every lane walks it (broadcast
 // loads) for the bottleneck; then one lane per hop moves the flow and updates the bit sets.
-template <int TILE>
-__device__ int push_small(int dst, int limit, int lev, int nc, const Lanes<TILE> &T, TileMem &w) {
+template <int TILE, class TM>
+__device__ int push_small(int dst, int limit, int lev, int nc, const Lanes<TILE> &T, TM &w) {
     int v = dst, d = limit, h = 0;
     for (int l = lev; l > 0; l--, h++) {
         const unsigned m = SU(w.tin + v) & SU(w.hist + l - 1);
@@ -239,8 +248,8 @@ __device__ int push_small(int dst, int limit, int lev, int nc, const Lanes<TILE>
         const int rec = SI(w.path + i), s = rec & 0xffff, u = (rec >> 16) & 31, vv = (rec >> 21) & 31, c = s >> 1, dir = s & 1;
         const int xc = SI(w.x + c) + (dir ? -d : d);
         SI(w.x + c) = xc;
-        const int nf = (xc < (SI(w.up + c) >> HB) ? 1 : 0) | (xc > (SI(w.lo + c) >> HB) ? 2 : 0) | (SI(w.res + c) & 12);
-        SI(w.res + c) = nf;
+        const int nf = (xc < (SI(w.up + c) >> HB) ? 1 : 0) | (xc > (SI(w.lo + c) >> HB) ? 2 : 0) | (RGET(c) & 12);
+        RSET(c, nf);
         if (!((nf >> dir) & 1)) { atomicAnd(&SU(w.tin + vv), ~(1u << u)); atomicAnd(&SU(w.tout + u), ~(1u << vv)); }   // saturated
         if ((nf >> (2 + (dir ^ 1))) & 1) {     // the reverse arc has residual capacity now and is tight
             const int rt = vv == nc ? 0 : vv, rh = u == 0 ? nc : u;
@@ -252,9 +261,10 @@ __device__ int push_small(int dst, int limit, int lev, int nc, const Lanes<TILE>
     return d;
 }
 
-// list variant: the tight chains compacted into w.tc as chain | flags << 16
-template <int TILE>
-__device__ int tight_list(const PlanView &P, int nopen, const Lanes<TILE> &T, TileMem &w) {
+// list variant: the tight chains compacted into w.tc as 16-bit entries chain | flags << 14 (a tile whose chains
+// fit shared memory has far fewer than 16 384 of them)
+template <int TILE, class TM>
+__device__ int tight_list(const PlanView &P, int nopen, const Lanes<TILE> &T, TM &w) {
     int n = 0;
     for (int c0 = 0; c0 < nopen; c0 += TILE) {     // tile-uniform trip count
         const int c = c0 + T.tl;
@@ -266,7 +276,7 @@ __device__ int tight_list(const PlanView &P, int nopen, const Lanes<TILE> &T, Ti
             if (le != LAB_INF && le + e.r == SI(w.lab + e.hb)) tf |= 2;
         }
         const unsigned b = T.ballot(tf != 0);
-        if (tf) SI(w.tc + n + __popc(b & T.lt)) = c | (tf << 16);
+        if (tf) SH(2 * w.tc + n + __popc(b & T.lt)) = (unsigned short)(c | (tf << 14));
         n += __popc(b);
     }
     T.sync();
@@ -279,8 +289,8 @@ __device__ int tight_list(const PlanView &P, int nopen, const Lanes<TILE> &T, Ti
 // node's bit is the only one to write its predecessor (tail | (2*chain+dir) << 10), and that tail's bit was set
 // before: the predecessors form a tree rooted at src.  Any tight path will do — the duals do not depend on which
 // optimal flow is found.  If dst is not reached, w.rw holds the complete reached set.
-template <int TILE>
-__device__ bool reach_list(int src, int dst, const PlanView &P, int ntc, int nword, const Lanes<TILE> &T, TileMem &w) {
+template <int TILE, class TM>
+__device__ bool reach_list(int src, int dst, const PlanView &P, int ntc, int nword, const Lanes<TILE> &T, TM &w) {
     const int R = w.rw;
     for (int i = T.tl; i < nword; i += TILE) SU(R + (i)) = i == (src >> 5) ? 1u << (src & 31) : 0u;
     T.sync();
@@ -289,7 +299,7 @@ __device__ bool reach_list(int src, int dst, const PlanView &P, int ntc, int nwo
         for (int i0 = 0; i0 < ntc; i0 += TILE) {           // tile-uniform trip count
             const int i = i0 + T.tl;
             int c = 0, f = 0;
-            if (i < ntc) { const int en = SI(w.tc + i); c = en & 0xffff; f = SI(w.res + c) & (en >> 16); }
+            if (i < ntc) { const int en = SH(2 * w.tc + i); c = en & 0x3fff; f = RGET(c) & (en >> 14); }
             const ChainEnds e(f ? P.ch_st[c] : make_int2(0, 0));
             // the 32 entries of a chunk stay in registers until none of them can grow the set any more: entries of one
             // chunk feed each other (the list is in topological order of the tails), and a re-test is two loads per direction
@@ -326,8 +336,8 @@ __device__ bool reach_list(int src, int dst, const PlanView &P, int ntc, int nwo
 }
 
 // list variant of the push: every lane walks the predecessor tree dst -> src, lane 0 writes
-template <int TILE>
-__device__ int push_list(int src, int dst, int limit, int nc, const Lanes<TILE> &T, TileMem &w) {
+template <int TILE, class TM>
+__device__ int push_list(int src, int dst, int limit, int nc, const Lanes<TILE> &T, TM &w) {
     int v = dst, d = limit, hops = 0;
     while (v != src) {
         const int p = SI(w.pred + v), s = p >> 10, c = s >> 1, xc = SI(w.x + c);
@@ -343,7 +353,7 @@ __device__ int push_list(int src, int dst, int limit, int nc, const Lanes<TILE> 
         if (T.tl == 0) {
             const int xc = SI(w.x + c) + ((s & 1) ? -d : d);
             SI(w.x + c) = xc;
-            SI(w.res + c) = (xc < (SI(w.up + c) >> HB) ? 1 : 0) | (xc > (SI(w.lo + c) >> HB) ? 2 : 0);
+            RSET(c, (xc < (SI(w.up + c) >> HB) ? 1 : 0) | (xc > (SI(w.lo + c) >> HB) ? 2 : 0));
         }
         v = p & 1023;
     }
@@ -352,33 +362,33 @@ __device__ int push_list(int src, int dst, int limit, int nc, const Lanes<TILE> 
 }
 
 // What one label computation allows: search + push over its tight arcs, until none is left.
-template <int TILE>
+template <int TILE, class TM>
 struct TightPaths {
     const PlanView &P;
     const Lanes<TILE> &T;
-    TileMem &w;
+    TM &w;
     int nopen, nc, nword, ntc;
-    bool small;
-    __device__ TightPaths(const PlanView &P_, const Lanes<TILE> &T_, TileMem &w_, int nopen_, int nc_)
-        : P(P_), T(T_), w(w_), nopen(nopen_), nc(nc_), nword(reach_words(nc_)), ntc(0), small(nc_ <= SMALL_NC) {}
-    __device__ void prepare() { if (small) tight_small<TILE>(P, nopen, T, w); else ntc = tight_list<TILE>(P, nopen, T, w); }
+    static constexpr bool small = !TM::BIG;
+    __device__ TightPaths(const PlanView &P_, const Lanes<TILE> &T_, TM &w_, int nopen_, int nc_)
+        : P(P_), T(T_), w(w_), nopen(nopen_), nc(nc_), nword(reach_words(nc_)), ntc(0) {}
+    __device__ void prepare() { if constexpr (small) tight_small<TILE>(P, nopen, T, w); else ntc = tight_list<TILE>(P, nopen, T, w); }
     // one search and, if dst is reachable, one push of at most `limit`; returns the amount pushed (0: not reachable)
     __device__ int augment(int src, int dst, int limit) {
 #ifdef SGUFP_K1_STATS
         if (T.tl == 0) atomicAdd(&g_k1_stats[2], 1ull);
 #endif
-        if (small) {
+        if constexpr (small) {
             const int lev = reach_small<TILE>(src, dst, nc, T, w);
             return lev ? push_small<TILE>(dst, limit, lev, nc, T, w) : 0;
-        }
+        } else
         return reach_list<TILE>(src, dst, P, ntc, nword, T, w) ? push_list<TILE>(src, dst, limit, nc, T, w) : 0;
     }
 };
 
 // Forced flow from lower bounds (rare): route every excess / deficit along shortest residual
 // paths.  Returns false if some forced flow cannot be routed (scenario infeasible).
-template <int TILE>
-__device__ bool route_lower_bounds(const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TileMem &w, TightPaths<TILE> &TP, int &fuel) {
+template <int TILE, class TM>
+__device__ bool route_lower_bounds(const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TM &w, TightPaths<TILE, TM> &TP, int &fuel) {
     for (int v = T.tl; v <= nc; v += TILE) SI(w.exc + v) = 0;
     T.sync();
     for (int c = T.tl; c < nopen; c += TILE) {
@@ -428,8 +438,8 @@ __device__ bool route_lower_bounds(const PlanView &P, int nopen, int nc, const L
 // SPEC-LP potentials: pot[v] = -(shortest residual distance from the root);
 // nodes the root cannot reach get the least labels consistent with the labelled ones; nodes cut
 // off both ways get a zero-rooted completion.
-template <int TILE>
-__device__ void canonical_potentials(const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TileMem &w, int &fuel) {
+template <int TILE, class TM>
+__device__ void canonical_potentials(const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TM &w, int &fuel) {
     shortest_paths<TILE, true, false>(0, P, nopen, nc, T, w, fuel);
     bool missing = false;
     for (int v = T.tl; v < nc; v += TILE) {
@@ -474,7 +484,8 @@ __device__ void canonical_potentials(const PlanView &P, int nopen, int nc, const
 }
 
 // wire potential at the HEAD of arc a (a matched in-arc, or any arc of a chain)
-__device__ __forceinline__ int head_potential(int a, const PlanView &P, int nopen, const TileMem &w) {
+template <class TM>
+__device__ __forceinline__ int head_potential(int a, const PlanView &P, int nopen, const TM &w) {
     const int cp = P.arc_cp[a], c = cp >> 10, pos = cp & 1023, pre = P.arc_pre[a];
     const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1;
     if (c < nopen) {
@@ -487,12 +498,14 @@ __device__ __forceinline__ int head_potential(int a, const PlanView &P, int nope
     return pre;
 }
 
-template <int TILE, int NW>
+// BIG: the contracted graph has more than SMALL_NC nodes (list searches, flag bytes); the launcher picks the instantiation.
+template <int TILE, int NW, bool BIG>
 __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 4 ? 2 * SGUFP_K1_MINBLOCKS : 1) k1_cut_eval(K1Launch p, int words_per_tile) {
     const Lanes<TILE> T;
     constexpr int TILES_PER_CTA = NW * 32 / TILE;
     const int tile_in_cta = threadIdx.x / TILE;
-    TileMem w;
+    using TM = TileMemT<BIG>;
+    TM w;
     {
         int base = tile_in_cta * words_per_tile;   // the fixed-size arrays first: constant offsets from the tile base
         w.tin = base; w.tout = base + 32; w.hist = base + 64; w.path = base + 98; w.tab = base + 132;
@@ -501,7 +514,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         w.up = base; base += p.max_nopen;
         w.lo = base; base += p.max_nopen;
         w.x = base; base += p.max_nopen;
-        w.res = base; base += p.max_nopen;
+        w.res = base; base += BIG ? (p.max_nopen + 3) / 4 : p.max_nopen;
         w.lab = base; base += p.nc + 2;
         w.pred = base; base += p.nc + 2;
         w.pot = base; w.exc = base; base += p.nc + 2;   // excesses (lower-bound routing) and potentials are never live together
@@ -546,13 +559,13 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         for (int c = T.tl; c < nopen; c += TILE) {
             const int lo = SI(w.lo + c) >> HB, up = SI(w.up + c) >> HB;
             SI(w.x + c) = lo; bad |= lo > up; forced |= lo > 0;
-            SI(w.res + c) = lo < up ? 1 : 0;              // x == lo: forward residual only
+            RSET(c, lo < up ? 1 : 0);              // x == lo: forward residual only
         }
         T.sync();
         bad = T.any(bad);
         forced = T.any(forced);
         // 2. optimal flow
-        TightPaths<TILE> TP(P, T, w, nopen, nc);
+        TightPaths<TILE, TM> TP(P, T, w, nopen, nc);
         if (!bad && forced) bad = !route_lower_bounds<TILE>(P, nopen, nc, T, w, TP, fuel);
         if (bad) {
             if (T.tl == 0) {
@@ -1120,7 +1133,7 @@ __global__ void relayout_caps(const int32_t *__restrict__ src, double *__restric
 }  // namespace
 
 #ifndef SGUFP_K1_EMULATE
-template <int NW>
+template <int NW, bool BIG>
 static cudaError_t launch_warp_nw(const K1Launch &p, cudaStream_t st, int sm_count, int *resident_warps, bool dry) {
     const int words = k1_words_per_tile(p);
     const size_t smem = (size_t)NW * words * sizeof(int);
@@ -1130,9 +1143,9 @@ static cudaError_t launch_warp_nw(const K1Launch &p, cudaStream_t st, int sm_cou
     cudaGetDevice(&dev);
     if (known_words == words && known_dev == dev) per_sm = known_per_sm;
     else {
-        cudaError_t e = cudaFuncSetAttribute(k1_cut_eval<32, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k1_cut_eval<32, NW, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_cut_eval<32, NW>, NW * 32, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_cut_eval<32, NW, BIG>, NW * 32, smem);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) return cudaErrorInvalidConfiguration;
         known_words = words; known_per_sm = per_sm; known_dev = dev;
@@ -1144,16 +1157,22 @@ static cudaError_t launch_warp_nw(const K1Launch &p, cudaStream_t st, int sm_cou
     long long grid = (long long)sm_count * per_sm;   // persistent: a whole number of CTAs per SM
     if (want < grid) grid = want;
     if (grid < 1) grid = 1;
-    k1_cut_eval<32, NW><<<(unsigned)grid, NW * 32, smem, st>>>(p, words);
+    k1_cut_eval<32, NW, BIG><<<(unsigned)grid, NW * 32, smem, st>>>(p, words);
     return cudaGetLastError();
 }
 
 static cudaError_t launch_warp_dispatch(int nw, const K1Launch &p, cudaStream_t st, int sm_count, int *rw, bool dry) {
+    if (p.nc <= SMALL_NC) switch (nw) {
+        case 8: return launch_warp_nw<8, false>(p, st, sm_count, rw, dry);
+        case 4: return launch_warp_nw<4, false>(p, st, sm_count, rw, dry);
+        case 2: return launch_warp_nw<2, false>(p, st, sm_count, rw, dry);
+        default: return launch_warp_nw<1, false>(p, st, sm_count, rw, dry);
+    }
     switch (nw) {
-        case 8: return launch_warp_nw<8>(p, st, sm_count, rw, dry);
-        case 4: return launch_warp_nw<4>(p, st, sm_count, rw, dry);
-        case 2: return launch_warp_nw<2>(p, st, sm_count, rw, dry);
-        default: return launch_warp_nw<1>(p, st, sm_count, rw, dry);
+        case 8: return launch_warp_nw<8, true>(p, st, sm_count, rw, dry);
+        case 4: return launch_warp_nw<4, true>(p, st, sm_count, rw, dry);
+        case 2: return launch_warp_nw<2, true>(p, st, sm_count, rw, dry);
+        default: return launch_warp_nw<1, true>(p, st, sm_count, rw, dry);
     }
 }
 

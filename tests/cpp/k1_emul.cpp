@@ -92,7 +92,7 @@ extern "C" int emul_paths(int n, int m, int S, const int32_t *tail, const int32_
         threadIdx.x = 0; blockIdx.x = 0; gridDim.x = 1;
         k1_lane_eval<1>(p, 0);
     } else
-    for (int t = 0; t < WARPS * 32; t++) { threadIdx.x = t; k1_cut_eval<1, WARPS>(p, wpt); }
+    for (int t = 0; t < WARPS * 32; t++) { threadIdx.x = t; if (p.nc <= SMALL_NC) k1_cut_eval<1, WARPS, false>(p, wpt); else k1_cut_eval<1, WARPS, true>(p, wpt); }
     for (int k = 0; k < K; k++) {
         if (first_inf[k] == LLONG_MAX || first_inf[k] < 0) continue;
         std::vector<int32_t> ts, hs, info, pl, nx, aq, fw;
