@@ -285,7 +285,7 @@ __device__ int tight_list(const PlanView &P, int nopen, const Lanes<TILE> &T, TM
 
 // list variant of the search: sweeps over the tight-chain list that mark heads IN PLACE, so one sweep carries the
 // reached set along every run of list entries whose tails come before their heads (a level-synchronous scan needs one
-// sweep per level: 59 % of K1's instructions on C4, profiles/r01c_k1_c4_ncu.md).  The lane whose atomicOr sets a
+// sweep per level: 59 % of K1's instructions on C4, profiles/r01c_summary.md).  The lane whose atomicOr sets a
 // node's bit is the only one to write its predecessor (tail | (2*chain+dir) << 10), and that tail's bit was set
 // before: the predecessors form a tree rooted at src.  Any tight path will do — the duals do not depend on which
 // optimal flow is found.  If dst is not reached, w.rw holds the complete reached set.
@@ -1177,7 +1177,7 @@ static cudaError_t launch_warp_dispatch(int nw, const K1Launch &p, cudaStream_t 
 }
 
 // Warps per CTA: the count that keeps most warps resident per SM (shared memory per warp grows with
-// the network: 2.5 KB at C2, 12 KB at C4, tens of KB beyond); ties go to the larger CTA.
+// the network: 4.7 KB at C2, 6.8 KB at C4, tens of KB beyond); ties go to the larger CTA.
 static cudaError_t launch_warp(const K1Launch &p, cudaStream_t st, int sm_count) {
     // the choice depends on the shared memory per warp alone: remember it (a one-candidate call is ~0.1 ms of kernel,
     // eight occupancy queries per call would show)
