@@ -80,7 +80,7 @@ struct TileMemT {
     static constexpr bool BIG = BIG_;     // contracted graph of more than SMALL_NC nodes (compile time: each kernel carries one search)
     int tin, tout, hist, path, tab;       // small graphs: bit sets of the tight residual graph, search levels, path, pair table
     int tc;                               // larger graphs: the tight-chain list (same place)
-    int rw;                               // reached set (+ a scratch row for the list search)
+    int rw;                               // reached set of the last search
     int up, lo, x, res, lab, pred, pot, exc, aq;
 };
 #ifdef SGUFP_K1_EMULATE
@@ -106,7 +106,7 @@ __host__ __device__ inline int k1_search_words(int nc, int max_nopen) {   // bit
     return nc <= SMALL_NC ? 32 + 32 + 34 + 34 + 32 * 32 / 2 : (max_nopen + 1) / 2;   // list entries are 16 bits
 }
 __host__ __device__ inline int k1_words_per_tile(const K1Launch &p) {
-    return 3 * p.max_nopen + (p.nc <= SMALL_NC ? p.max_nopen : (p.max_nopen + 3) / 4) + 3 * (p.nc + 2) + p.nav + 2 + 2 * reach_words(p.nc) + k1_search_words(p.nc, p.max_nopen);
+    return 3 * p.max_nopen + (p.nc <= SMALL_NC ? p.max_nopen : (p.max_nopen + 3) / 4) + 3 * (p.nc + 2) + p.nav + 2 + reach_words(p.nc) + k1_search_words(p.nc, p.max_nopen);
 }
 
 template <int TILE>
@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         int base = tile_in_cta * words_per_tile;   // the fixed-size arrays first: constant offsets from the tile base
         w.tin = base; w.tout = base + 32; w.hist = base + 64; w.path = base + 98; w.tab = base + 132;
         w.tc = base; base += k1_search_words(p.nc, p.max_nopen);
-        w.rw = base; base += 2 * reach_words(p.nc);
+        w.rw = base; base += reach_words(p.nc);
         w.up = base; base += p.max_nopen;
         w.lo = base; base += p.max_nopen;
         w.x = base; base += p.max_nopen;
