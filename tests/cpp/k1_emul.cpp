@@ -55,6 +55,9 @@ using namespace sgufp;
 
 // Same contract as sgufp_paths_partial + sgufp_ray_partial, on the host.  sums: [K][W] (W = 1+L+m),
 // first_inf: [K], obj/status: [K][S].  ray_sums[K][W]: filled for candidates with an infeasible scenario.
+static int g_last_nc = 0;
+extern "C" int emul_last_nc() { return g_last_nc; }   // contracted nodes of the last instance: which size class ran
+
 extern "C" int emul_paths(int n, int m, int S, const int32_t *tail, const int32_t *head, const int32_t *upper, const int32_t *lower,
                           const int32_t *rew0, const int32_t *vbar, int nvbar, const int16_t *paths, int K, int L,
                           long long *sums, long long *first_inf, double *obj, uint8_t *status, long long *ray_sums, int lane_variant) {
@@ -80,6 +83,7 @@ extern "C" int emul_paths(int n, int m, int S, const int32_t *tail, const int32_
     p.cap_u = cu.data(); p.cap_l = cl.data(); p.S = S; p.m = m; p.m_pad = m_pad; p.scen_offset = 0;
     p.plans = words.data(); p.plan_off = off.data(); p.K = K; p.W = W; p.L = M.L;
     p.sums = reinterpret_cast<unsigned long long *>(sums); p.first_inf = first_inf; p.obj = obj; p.status = status;
+    g_last_nc = M.nc;
     p.max_nch = max_nch; p.max_nopen = max_nopen; p.nc = M.nc; p.nav = M.nav; p.max_cap = 65535;
     const int wpt = k1_words_per_tile(p);
     std::vector<int> smem((size_t)WARPS * 32 * wpt, 0);

@@ -129,3 +129,38 @@ def test_kernel_body_fuzz(emul, block):
                 assert (ray[j] == ray_wlayout(net, inst, paths[j], first_bad)).all(), (inst.name, j)
         done += 1
     assert done >= 20
+
+
+def _random_larger_instance(rng, k):
+    nl = int(rng.integers(3, 7))
+    layers = [int(rng.integers(7, 16)) for _ in range(nl)]
+    n_int = sum(layers)
+    max_m = sum(a * b for a, b in zip(layers[:-1], layers[1:])) + layers[0] + layers[-1]
+    m = int(rng.integers(max(n_int + 2, max_m // 4), max(n_int + 3, max_m // 2)))
+    # few V-bar nodes: little contraction, so the contracted graph keeps more than 31 nodes
+    return I.make_layered(layers, m, int(rng.integers(2, 4)), 3000 + k, float(rng.uniform(0.05, 0.4)), float(rng.choice([0.0, 0.03, 0.2])), f"fzL{k}")
+
+
+@pytest.mark.parametrize("block", range(2))
+def test_kernel_body_fuzz_larger_graphs(emul, block):
+    """Random networks whose contracted graph has more than 31 nodes: the size class with the in-place list search,
+    flag bytes and 16-bit list entries (k1_cut_eval<.., BIG = true>)."""
+    rng = np.random.default_rng(900 + block)
+    done = big = 0
+    for k in range(12):
+        try:
+            inst = _random_larger_instance(rng, 100 * block + k)
+            net = OracleNet(inst)
+        except Exception:
+            continue
+        paths = I.random_paths(net, 2, k, float(rng.choice([0.0, 0.2, 0.6])))
+        sums, finf, obj, st, ray = run_emul(emul, inst, net, paths)
+        for j in range(len(paths)):
+            want, first_bad = wlayout_partial(net, inst, paths[j], 0, inst.S)
+            assert (finf[j] if finf[j] != I64_MAX else -1) == (-1 if first_bad is None else first_bad), (inst.name, j)
+            assert (sums[j] == want).all(), (inst.name, j)
+            if first_bad is not None:
+                assert (ray[j] == ray_wlayout(net, inst, paths[j], first_bad)).all(), (inst.name, j)
+        done += 1
+        big += emul.emul_last_nc() > 31
+    assert done >= 6 and big >= 4, (done, big)
