@@ -23,12 +23,7 @@ thread_local std::string g_create_error;
 }  // namespace
 
 // ---- helpers shared by the one-GPU and the sharded entry points --------------------------------
-struct Batch {
-    std::vector<Plan> plans;
-    std::vector<int32_t> off;
-    size_t total_words = 0;          // the plans are gathered into the handle's pinned staging buffer at launch
-    int max_nch = 0, max_nopen = 0;
-};
+using Batch = PlanBatch;            // ctx.hpp
 
 // Host threads that build plans of one batch side by side (a plan is ~15 us of host work at C2, ~65 us at C4:
 // serial construction of 64 plans would cost a third of the kernel).  The threads persist in the handle.
@@ -40,10 +35,18 @@ static int host_threads(int K) {
     return std::max(1, std::min(cap, K / 4));
 }
 
-static int make_batch(sgufp_ctx *c, const int16_t *paths, int K, int L, Batch &B) {
+// reuse: the caller is the second half of one operation on these paths (sgufp_finalize_paths after sgufp_paths_partial)
+// and may take the plans the first half built; every other entry point builds its plans anew, whatever the last call was.
+static int make_batch(sgufp_ctx *c, const int16_t *paths, int K, int L, Batch &B, bool reuse = false) {
     if (!paths || K < 1 || L < 0 || L > c->M.L) return fail(c, SGUFP_ERR_ARG, "paths: need K >= 1 and 0 <= L <= totalLayers");
-    B.plans.resize(K); B.off.resize(K);
     const bool lane_tables = k1_lane_mode_requested();
+    const size_t npath = (size_t)K * L;
+    if (reuse && B.key_K == K && B.key_L == L && B.key_lane == lane_tables && B.key_paths.size() == npath &&
+        (npath == 0 || memcmp(B.key_paths.data(), paths, npath * sizeof(int16_t)) == 0))
+        return 0;                    // the same paths as the first half of the operation: its plans stand
+    B.key_K = 0;
+    B.max_nch = B.max_nopen = 0;
+    B.plans.resize(K); B.off.resize(K);
     std::vector<int> rc(K, 0);
     std::vector<std::string> errs(K);
     const std::function<void(int, int)> work = [&](int t, int nt) {
@@ -63,6 +66,7 @@ static int make_batch(sgufp_ctx *c, const int16_t *paths, int K, int L, Batch &B
         B.max_nopen = std::max(B.max_nopen, B.plans[k].nopen);
     }
     B.total_words = total;
+    B.key_paths.assign(paths, paths + npath); B.key_K = K; B.key_L = L; B.key_lane = lane_tables;
     return 0;
 }
 
@@ -149,30 +153,32 @@ static void finalize_one(const sgufp_ctx *c, const Plan &P, const long long *sum
     };
     if (cut_type) *cut_type = feas ? SGUFP_CUT_FEASIBILITY : SGUFP_CUT_OPTIMALITY;
     if (rhs) *rhs = (double)sums[0] / div;
-    std::vector<double> coef(T);
+    static thread_local std::vector<double> scratch;
+    if (!coef_dense && (int)scratch.size() < T) scratch.resize(T);
+    double *coef = coef_dense ? coef_dense : scratch.data();      // slot order (the dense form the caller may ask for)
+    const int32_t *mo = P.match_out.data();
     for (int ell = 0; ell < L; ell++) {
-        const int a = M.layer_arc[ell];
-        const long long sig = kind(a) == KIND_SIGMA ? sums[1 + L + a] : 0;
+        const int a = M.layer_arc[ell], ma = mo[a];
+        const long long sig = kind(a) == KIND_SIGMA ? sums[1 + L + a] : 0, lam = sums[1 + ell];
         for (int s = M.slot_base[ell]; s < M.slot_base[ell + 1]; s++) {
             const int b = M.slot_out[s];
             long long v = sig;
-            if (P.match_out[a] == b) v -= sums[1 + ell];
+            if (ma == b) v -= lam;
             if (kind(b) == KIND_PHI) v += sums[1 + L + b];
             coef[s] = (double)v / div;
         }
     }
-    if (coef_dense) std::memcpy(coef_dense, coef.data(), T * sizeof(double));
     int k = 0;
-    for (int r = 0; r < T; r++) {
-        const int s = M.slot_sorted[r];
-        if (coef[s] == 0) continue;   // `if (v == 0) continue;` (Cut.h:412)
-        if (keys && vals) {
-            const uint64_t i = (uint64_t)M.tail[M.slot_in[s]], q = (uint64_t)M.head[M.slot_in[s]], j = (uint64_t)M.head[M.slot_out[s]];
-            keys[k] = q | (i << 16) | (j << 32);   // getKey (Cut.h:342-344)
-            vals[k] = coef[s];
+    if (keys && vals) {
+        for (int r = 0; r < T; r++) {
+            const double v = coef[M.slot_sorted[r]];
+            if (v == 0) continue;     // `if (v == 0) continue;` (Cut.h:412)
+            keys[k] = M.slot_key_sorted[r];   // getKey (Cut.h:342-344), (i,q,j)-lexicographic order
+            vals[k] = v;
+            k++;
         }
-        k++;
-    }
+    } else
+        for (int s = 0; s < T; s++) k += coef[s] != 0;
     if (nnz) *nnz = k;
 }
 
@@ -286,7 +292,7 @@ int sgufp_paths_partial(sgufp_ctx *c, const int16_t *paths, int K, int L, int64_
     if (c->device == SGUFP_DEVICE_NONE) return fail(c, SGUFP_ERR_CUDA, "handle was created with SGUFP_DEVICE_NONE: it holds the model only, there is no CPU compute path");
     CU(c, cudaSetDevice(c->device));
     c->last_launches = 0;
-    Batch B;
+    Batch &B = c->batch;
     if (int rc = make_batch(c, paths, K, L, B)) return rc;
     cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->st;
     return launch_batch(c, B, K, reinterpret_cast<unsigned long long *>(sums_device), reinterpret_cast<long long *>(first_inf_device),
@@ -306,13 +312,17 @@ int sgufp_ray_partial(sgufp_ctx *c, const int16_t *path, int L, int64_t global_s
 int sgufp_finalize_paths(sgufp_ctx *c, const int16_t *paths, int K, int L, const int64_t *sums_host, const int64_t *first_inf_host,
                          int *cut_type, double *rhs, uint64_t *keys, double *vals, int *nnz, double *coef_dense) {
     if (!c || !sums_host || !first_inf_host) return SGUFP_ERR_ARG;
-    Batch B;
-    if (int rc = make_batch(c, paths, K, L, B)) return rc;
+    Batch &B = c->batch;             // after sgufp_paths_partial with the same paths: no plan is built again
+    if (int rc = make_batch(c, paths, K, L, B, true)) return rc;
     const int T = c->M.T, W = c->W();
-    for (int k = 0; k < K; k++)
-        finalize_one(c, B.plans[k], reinterpret_cast<const long long *>(sums_host) + (size_t)k * W, first_inf_host[k] != LLONG_MAX,
-                     cut_type ? cut_type + k : nullptr, rhs ? rhs + k : nullptr, keys ? keys + (size_t)k * T : nullptr,
-                     vals ? vals + (size_t)k * T : nullptr, nnz ? nnz + k : nullptr, coef_dense ? coef_dense + (size_t)k * T : nullptr);
+    const std::function<void(int, int)> fin = [&](int t, int nt) {
+        for (int k = t; k < K; k += nt)
+            finalize_one(c, B.plans[k], reinterpret_cast<const long long *>(sums_host) + (size_t)k * W, first_inf_host[k] != LLONG_MAX,
+                         cut_type ? cut_type + k : nullptr, rhs ? rhs + k : nullptr, keys ? keys + (size_t)k * T : nullptr,
+                         vals ? vals + (size_t)k * T : nullptr, nnz ? nnz + k : nullptr, coef_dense ? coef_dense + (size_t)k * T : nullptr);
+    };
+    const int nt = host_threads(K);
+    if (nt > 1 && c->pool) c->pool->run(nt, fin); else fin(0, 1);   // the pool exists if the plans of this batch were built on it
     return 0;
 }
 
@@ -324,7 +334,7 @@ int sgufp_solve_paths(sgufp_ctx *c, const int16_t *paths, int K, int L, int *cut
     if (c->device == SGUFP_DEVICE_NONE) return fail(c, SGUFP_ERR_CUDA, "handle was created with SGUFP_DEVICE_NONE: it holds the model only, there is no CPU compute path");
     CU(c, cudaSetDevice(c->device));
     c->last_launches = 0;
-    Batch B;
+    Batch &B = c->batch;
     if (int rc = make_batch(c, paths, K, L, B)) return rc;
     const int W = c->W(), T = c->M.T;
     const size_t KS = (size_t)K * c->S;

@@ -23,6 +23,19 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// The plans of one batch of candidate paths (K1).  The handle keeps the last batch: the sharded sequence
+// sgufp_paths_partial -> all-reduce -> sgufp_finalize_paths hands the same paths to both calls, and a plan is 15 us (C2)
+// to 65 us (C4) of host work.
+struct PlanBatch {
+    std::vector<sgufp::Plan> plans;
+    std::vector<int32_t> off;
+    size_t total_words = 0;          // the plans are gathered into the handle's pinned staging buffer at launch
+    int max_nch = 0, max_nopen = 0;
+    std::vector<int16_t> key_paths;  // what the plans were built from (valid when key_K > 0)
+    int key_K = 0, key_L = -1;
+    bool key_lane = false;
+};
+
 struct sgufp_ctx {
     sgufp::Model M;
     int S = 0, m_pad = 0, device = 0, sm_count = 0, max_cap = 0;
@@ -36,6 +49,7 @@ struct sgufp_ctx {
     DevBuf<double> d_obj;
     DevBuf<uint8_t> d_status;
     std::string err;
+    PlanBatch batch;                            // plans of the last batch (reused when the next call brings the same paths)
     sgufp::HostPool *pool = nullptr;            // persistent host threads for the plans of a batch (created on first use)
     int32_t *h_words = nullptr;                 // pinned staging of a batch's plans (cudaHostAlloc), h_words_cap int32 words
     size_t h_words_cap = 0;

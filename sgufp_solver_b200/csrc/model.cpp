@@ -132,6 +132,12 @@ int Model::build(int n_, int m_, const int32_t *tail_, const int32_t *head_, con
     });
     slot_lex_rank.assign(T, 0);
     for (int r = 0; r < T; r++) slot_lex_rank[slot_sorted[r]] = r;
+    slot_key_sorted.resize(T);
+    for (int r = 0; r < T; r++) {
+        const int s = slot_sorted[r];
+        const uint64_t i = (uint64_t)tail[slot_in[s]], q = (uint64_t)head[slot_in[s]], j = (uint64_t)head[slot_out[s]];
+        slot_key_sorted[r] = q | (i << 16) | (j << 32);
+    }
     key_slot.clear();
     key_slot.reserve((size_t)T * 2);
     for (int s = 0; s < T; s++) {   // emplace keeps the FIRST slot of a key: Inavap::Cut::get returns the first match (Cut.h:275-282)

@@ -26,6 +26,7 @@ struct Model {
     std::vector<uint8_t> is_vbar, active, is_root;
     int L = 0, T = 0;
     std::vector<int32_t> layer_arc, arc_layer, slot_base, slot_in, slot_out, slot_lex_rank, slot_sorted;
+    std::vector<uint64_t> slot_key_sorted;   // getKey(q, i, j) of slot_sorted[r] (Cut.h:342-344)
     std::unordered_map<uint64_t, int32_t> key_slot;   // getKey(q,i,j) (Cut.h:342-344) -> first slot with those node ids
     int nc = 1;                              // contracted nodes, 0 = root
     std::vector<int32_t> cn;                 // node -> contracted id (0 root, -1 active V-bar)
