@@ -86,7 +86,8 @@ int sgufp_solve_paths(sgufp_ctx *ctx, const int16_t *paths, int K, int L, int *c
  *   first_inf[k] = lowest local infeasible GLOBAL scenario index or INT64_MAX
  * on `cuda_stream` (a cudaStream_t; NULL = the stream the handle owns, so pass a real non-default stream to order the call with your own work).  Step 2, caller: all-reduce `sums` (SUM, int64)
  * and `first_inf` (MIN, int64) across ranks — integers, so every rank count gives bit-identical
- * cuts.  Step 3: sgufp_finalize_paths on the reduced HOST copies.  If first_inf[k] is finite the
+ * cuts.  Step 3: sgufp_finalize_paths on the reduced HOST copies (given the paths of step 1 on the same
+ * handle it takes the plans step 1 built instead of building them again).  If first_inf[k] is finite the
  * owning rank (the one whose block contains it) must call sgufp_ray_partial for that path and
  * broadcast its sums before step 3. */
 int sgufp_partial_width(const sgufp_ctx *ctx);
