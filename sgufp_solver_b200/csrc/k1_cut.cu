@@ -296,6 +296,9 @@ __device__ bool reach_list(int src, int dst, const PlanView &P, int ntc, int nwo
     T.sync();
     for (;;) {
         bool grew = false;
+#ifdef SGUFP_K1_SKIP_CONFIRM
+        bool back = false;          // a backward arc fired, or a usable backward entry is still waiting for its tail
+#endif
         for (int i0 = 0; i0 < ntc; i0 += TILE) {           // tile-uniform trip count
             const int i = i0 + T.tl;
             int c = 0, f = 0;
@@ -313,13 +316,21 @@ __device__ bool reach_list(int src, int dst, const PlanView &P, int ntc, int nwo
                 }
                 if ((f & 2) && ((SU(R + (e.ev >> 5)) >> (e.ev & 31)) & 1)) {
                     const unsigned bit = 1u << (e.hb & 31);
-                    if (!((SU(R + (e.hb >> 5)) & bit)) && !(atomicOr(&SU(R + (e.hb >> 5)), bit) & bit)) { SI(w.pred + e.hb) = e.ev | ((2 * c + 1) << 10); g = true; }
+                    if (!((SU(R + (e.hb >> 5)) & bit)) && !(atomicOr(&SU(R + (e.hb >> 5)), bit) & bit)) {
+                        SI(w.pred + e.hb) = e.ev | ((2 * c + 1) << 10); g = true;
+#ifdef SGUFP_K1_SKIP_CONFIRM
+                        back = true;
+#endif
+                    }
                     f &= ~2;
                 }
                 T.sync();
                 again = T.any(g);
                 grew |= again;
             } while (again);
+#ifdef SGUFP_K1_SKIP_CONFIRM
+            back |= (f & 2) != 0;
+#endif
         }
         T.sync();
 #ifdef SGUFP_K1_STATS
@@ -332,6 +343,12 @@ __device__ bool reach_list(int src, int dst, const PlanView &P, int ntc, int nwo
             return true;
         }
         if (!T.any(grew)) return false;
+#ifdef SGUFP_K1_SKIP_CONFIRM
+        // Experiment (not measured yet, profiles/r01c_summary.md): the list is sorted by the depth of the tails
+        // (model.cpp: build_plan), so a forward entry can only be overtaken by a backward arc that fires after it, and a
+        // waiting backward entry by any later arc: without either, this sweep already reached the fixpoint.
+        if (!T.any(back)) return false;
+#endif
     }
 }
 
@@ -339,14 +356,34 @@ __device__ bool reach_list(int src, int dst, const PlanView &P, int ntc, int nwo
 template <int TILE, class TM>
 __device__ int push_list(int src, int dst, int limit, int nc, const Lanes<TILE> &T, TM &w) {
     int v = dst, d = limit, hops = 0;
+#ifdef SGUFP_K1_PUSH_PAR
+    int mine = -1;                         // the hop this lane will update (hop number == lane number)
+#endif
     while (v != src) {
         const int p = SI(w.pred + v), s = p >> 10, c = s >> 1, xc = SI(w.x + c);
         d = min(d, (s & 1) ? xc - (SI(w.lo + c) >> HB) : (SI(w.up + c) >> HB) - xc);
+#ifdef SGUFP_K1_PUSH_PAR
+        if (hops == T.tl) mine = p;
+#endif
         v = p & 1023;
         if (++hops > nc + 1) { d = 0; break; }
     }
     T.sync();                              // every lane has its bottleneck before lane 0 moves the flow
     if (d <= 0) return 0;
+#ifdef SGUFP_K1_PUSH_PAR
+    // Experiment (not measured yet, profiles/r01c_summary.md): a path of at most TILE hops is updated in one step, a hop
+    // per lane (the chains of a simple path are distinct), instead of a second walk.
+    if (hops <= TILE) {
+        if (mine >= 0) {
+            const int s = mine >> 10, c = s >> 1;
+            const int xc = SI(w.x + c) + ((s & 1) ? -d : d);
+            SI(w.x + c) = xc;
+            RSET(c, (xc < (SI(w.up + c) >> HB) ? 1 : 0) | (xc > (SI(w.lo + c) >> HB) ? 2 : 0));
+        }
+        T.sync();
+        return d;
+    }
+#endif
     v = dst;
     while (v != src) {
         const int p = SI(w.pred + v), s = p >> 10, c = s >> 1;

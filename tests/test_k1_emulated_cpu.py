@@ -21,9 +21,13 @@ I64_MAX = np.iinfo(np.int64).max
 
 @pytest.fixture(scope="module")
 def emul(tmp_path_factory):
+    return _build_emul(tmp_path_factory, [])
+
+
+def _build_emul(tmp_path_factory, defines):
     so = str(tmp_path_factory.mktemp("emul") / "libk1_emul.so")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-w", "-fPIC", "-shared", f"-I{ROOT}/tests/cpp/emul_stub", f"-I{ROOT}/include",
-                           f"{ROOT}/tests/cpp/k1_emul.cpp", "-o", so])
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-w", "-fPIC", "-shared", f"-I{ROOT}/tests/cpp/emul_stub", f"-I{ROOT}/include"] +
+                          [f"-D{d}" for d in defines] + [f"{ROOT}/tests/cpp/k1_emul.cpp", "-o", so])
     L = C.CDLL(so)
     ip, i16p = C.POINTER(C.c_int32), C.POINTER(C.c_int16)
     L.emul_paths.restype = C.c_int
@@ -164,3 +168,31 @@ def test_kernel_body_fuzz_larger_graphs(emul, block):
         done += 1
         big += emul.emul_last_nc() > 31
     assert done >= 6 and big >= 4, (done, big)
+
+
+@pytest.fixture(scope="module")
+def emul_experiments(tmp_path_factory):
+    return _build_emul(tmp_path_factory, ["SGUFP_K1_SKIP_CONFIRM", "SGUFP_K1_PUSH_PAR"])
+
+
+def test_experimental_switches_keep_parity(emul_experiments):
+    """The two search/push experiments that are compiled out by default (profiles/r01c_summary.md) must give Oracle B's
+    sums too, so that they can be A/B-timed on a GPU without a parity question."""
+    emul = emul_experiments
+    rng = np.random.default_rng(1234)
+    done = big = 0
+    for k in range(14):
+        try:
+            inst = _random_larger_instance(rng, 7000 + k) if k % 2 == 0 else _random_instance(rng, 7000 + k)
+            net = OracleNet(inst)
+        except Exception:
+            continue
+        paths = I.random_paths(net, 2, k, float(rng.choice([0.0, 0.2, 0.6])))
+        sums, finf, obj, st, ray = run_emul(emul, inst, net, paths)
+        for j in range(len(paths)):
+            want, first_bad = wlayout_partial(net, inst, paths[j], 0, inst.S)
+            assert (finf[j] if finf[j] != I64_MAX else -1) == (-1 if first_bad is None else first_bad), (inst.name, j)
+            assert (sums[j] == want).all(), (inst.name, j)
+        done += 1
+        big += emul.emul_last_nc() > 31
+    assert done >= 8 and big >= 3, (done, big)
