@@ -39,13 +39,13 @@ static int host_threads(int K) {
 // and may take the plans the first half built; every other entry point builds its plans anew, whatever the last call was.
 static int make_batch(sgufp_ctx *c, const int16_t *paths, int K, int L, Batch &B, bool reuse = false) {
     if (!paths || K < 1 || L < 0 || L > c->M.L) return fail(c, SGUFP_ERR_ARG, "paths: need K >= 1 and 0 <= L <= totalLayers");
-    const bool lane_tables = k1_lane_mode_requested();
+    const bool lane_tables = k1_lane_tables_wanted() && c->max_lower == 0;
     const size_t npath = (size_t)K * L;
     if (reuse && B.key_K == K && B.key_L == L && B.key_lane == lane_tables && B.key_paths.size() == npath &&
         (npath == 0 || memcmp(B.key_paths.data(), paths, npath * sizeof(int16_t)) == 0))
         return 0;                    // the same paths as the first half of the operation: its plans stand
     B.key_K = 0;
-    B.max_nch = B.max_nopen = 0;
+    B.max_nch = B.max_nopen = B.max_indeg = 0;
     B.plans.resize(K); B.off.resize(K);
     std::vector<int> rc(K, 0);
     std::vector<std::string> errs(K);
@@ -64,6 +64,7 @@ static int make_batch(sgufp_ctx *c, const int16_t *paths, int K, int L, Batch &B
         total += B.plans[k].words.size();
         B.max_nch = std::max(B.max_nch, B.plans[k].nch);
         B.max_nopen = std::max(B.max_nopen, B.plans[k].nopen);
+        B.max_indeg = std::max(B.max_indeg, B.plans[k].max_indeg);
     }
     B.total_words = total;
     B.key_paths.assign(paths, paths + npath); B.key_K = K; B.key_L = L; B.key_lane = lane_tables;
@@ -99,6 +100,7 @@ static int launch_batch(sgufp_ctx *c, const Batch &B, int K, unsigned long long 
     p.plans = c->d_plans.p; p.plan_off = c->d_plan_off.p; p.K = K; p.W = c->W(); p.L = c->M.L;
     p.sums = d_sums; p.first_inf = d_finf; p.obj = d_obj; p.status = d_status;
     p.max_nch = B.max_nch; p.max_nopen = B.max_nopen; p.nc = c->M.nc; p.nav = c->M.nav; p.max_cap = c->max_cap;
+    p.has_lower = c->max_lower > 0; p.lane_tables = B.key_lane; p.sum_abs_r = c->sum_abs_r; p.max_indeg = B.max_indeg;
     c->kernel_timed = false;
     if (c->S > 0) {
         CU(c, cudaEventRecord(c->evk0, st));
@@ -200,9 +202,11 @@ int sgufp_create(sgufp_ctx **out, int n, int m, int S, const int32_t *tail, cons
     if (int rc = c->M.build(n, m, tail, head, reward0, vbar, nvbar, e)) return bail(rc, e);
     for (size_t i = 0; upper && lower && i < (size_t)m * S; i++) {
         c->max_cap = std::max(c->max_cap, std::max(upper[i], lower[i]));
+        c->max_lower = std::max(c->max_lower, lower[i]);
         if (upper[i] < 0 || lower[i] < 0 || upper[i] >= (1 << 20) || lower[i] >= (1 << 20))
             return bail(SGUFP_ERR_LIMITS, "capacities must lie in [0, 2^20) (DESIGN.md §5)");
     }
+    { long long sa = 0; for (int a = 0; a < m; a++) sa += std::abs((long long)reward0[a]); c->sum_abs_r = (int)sa; }   // < 2^18 (Model::build)
     c->S = S; c->scen_off = scenario_offset; c->S_total = S_total; c->device = device;
     c->m_pad = (m + 1) & ~1;   // rows 16-byte aligned for 128-bit loads
 #define CUC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return bail(SGUFP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } while (0)

@@ -30,7 +30,7 @@ struct PlanBatch {
     std::vector<sgufp::Plan> plans;
     std::vector<int32_t> off;
     size_t total_words = 0;          // the plans are gathered into the handle's pinned staging buffer at launch
-    int max_nch = 0, max_nopen = 0;
+    int max_nch = 0, max_nopen = 0, max_indeg = 0;
     std::vector<int16_t> key_paths;  // what the plans were built from (valid when key_K > 0)
     int key_K = 0, key_L = -1;
     bool key_lane = false;
@@ -38,7 +38,7 @@ struct PlanBatch {
 
 struct sgufp_ctx {
     sgufp::Model M;
-    int S = 0, m_pad = 0, device = 0, sm_count = 0, max_cap = 0;
+    int S = 0, m_pad = 0, device = 0, sm_count = 0, max_cap = 0, max_lower = 0, sum_abs_r = 0;
     long long scen_off = 0, S_total = 0;
     double *d_u = nullptr, *d_l = nullptr;
     cudaStream_t st = nullptr;

@@ -29,6 +29,7 @@
 #include <cstdlib>
 
 #include "model.hpp"
+#include "k1_common.cuh"
 
 namespace sgufp {
 
@@ -37,40 +38,6 @@ __device__ unsigned long long g_k1_stats[8];   // relaxation passes, label compu
 #endif
 
 namespace {
-
-constexpr int HB = 10;                 // position bits packed under a chain capacity; hop bits of a lane-variant label
-constexpr int LAB_BIAS = 1 << 19;      // lane variant: |distance| < 2^18 (checked at create) => 0 < distance + bias < 2^20
-constexpr int LAB_INF = 0x3fffffff;    // "unreached"; label + increment never overflows an int
-constexpr int NEG_INF = INT_MIN / 4;
-constexpr int WARPS = 8;               // warps per CTA
-#ifndef SGUFP_K1_MINBLOCKS
-#define SGUFP_K1_MINBLOCKS 4            // resident CTAs per SM the register allocation aims at (64 registers per thread)
-#endif
-
-struct PlanView {
-    const PlanHeader *h;
-    const int32_t *arc_cp, *arc_info, *arc_pre, *ch_ends, *ch_r, *ch_ptr, *ch_arcs, *ch_q, *av_ptr, *av_arcs, *fb_ptr, *fb_ch;
-    const int2 *ch_st;             // static half of an open chain (model.hpp)
-    const int4 *slot_pk4;          // lane variant: padded residual slots, two per int4
-    const int32_t *node_in4;
-    __device__ explicit PlanView(const int32_t *base) {
-        h = reinterpret_cast<const PlanHeader *>(base);
-        arc_cp = base + h->o_arc_cp; arc_info = base + h->o_arc_info; arc_pre = base + h->o_arc_pre;
-        ch_ends = base + h->o_ch_ends; ch_r = base + h->o_ch_r; ch_ptr = base + h->o_ch_ptr; ch_arcs = base + h->o_ch_arcs;
-        ch_q = base + h->o_ch_q; av_ptr = base + h->o_av_ptr; av_arcs = base + h->o_av_arcs; fb_ptr = base + h->o_fb_ptr; fb_ch = base + h->o_fb_ch;
-        ch_st = reinterpret_cast<const int2 *>(base + h->o_ch_st);
-        slot_pk4 = reinterpret_cast<const int4 *>(base + h->o_slot_pk);
-        node_in4 = base + h->o_node_in4;
-    }
-};
-
-// the static half of an open chain, unpacked (model.hpp)
-struct ChainEnds {
-    int sv, ev, hf, hb, r;
-    __device__ __forceinline__ explicit ChainEnds(const int2 st) {
-        sv = st.x & 1023; ev = (st.x >> 10) & 1023; hf = (st.x >> 20) & 1023; hb = st.y & 1023; r = st.y >> 10;
-    }
-};
 
 // This tile's slice of shared memory, as word OFFSETS into the CTA's buffer: indexing the
 // __shared__ symbol directly keeps every access a plain LDS/STS/ATOMS with a register + immediate
@@ -136,8 +103,6 @@ struct Lanes {    // the TILE lanes that work on one scenario (32 on the GPU; 1 
         return v;
     }
 };
-
-__device__ __forceinline__ int lab_dist(int lab) { return (lab >> HB) - LAB_BIAS; }   // lane variant
 
 // Label-correcting shortest distances from `src` over the residual arcs of the contracted graph
 // (push style: every lane relaxes its chains, shared-memory atomicMin on the label).  One 64-bit
@@ -715,360 +680,6 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
     }
 }
 
-// =================================================================================================
-// Lane-per-scenario variant (small contracted graphs).
-//
-// One warp works on LW = 32 consecutive scenarios of ONE candidate: lane = scenario.  All lanes walk
-// the candidate's chains in the same order, so the static half of every chain (ends, reward) is
-// loaded once per warp-instruction and serves 32 scenarios, and every piece of per-scenario state
-// sits in shared memory as a column [index][lane] — each lane only ever touches its own bank:
-// no conflicts, no atomics, and label updates are sequential per lane (Gauss-Seidel in the
-// topological order of the chains, exact predecessors).  Lanes differ only in data, never in the
-// program counter, except for the per-lane path walks.  Same SPEC-LP results as the warp variant.
-// =================================================================================================
-struct LaneMem {   // column-major slices of this warp's shared memory, LW lanes wide
-    unsigned short *x, *up, *lo, *pred;   // [nopen], [nopen], [nopen], [nc+1]
-    unsigned char *res;                   // [nopen] residual flags: bit 0 forward, bit 1 backward
-    int *lab, *exc, *aq;                  // [nc+1], [nc+1], [nav]   (lab doubles as the potential after the flow phase)
-};
-
-template <int LW>
-struct LaneCtx {
-    int lane;
-    unsigned mask;
-    __device__ LaneCtx() { lane = LW == 1 ? 0 : (int)(threadIdx.x & 31); mask = 0xffffffffu; }
-    __device__ __forceinline__ bool any(bool p) const { return LW == 1 ? p : __any_sync(mask, p) != 0; }
-    __device__ __forceinline__ long long sum(long long v) const {
-        if (LW > 1) for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(mask, v, o);
-        return v;
-    }
-};
-
-#define LX(a, i) (a)[(i) * LW + L.lane]
-
-// Label correction from a per-lane source, PULL style and sequential per lane: nodes are visited in
-// topological order, each takes the minimum over its in-slots (the loads of one node are independent
-// of each other: that is the instruction-level parallelism of this kernel) and keeps the slot that
-// gave it as its exact predecessor.  Residual status comes from one flag byte per chain.
-template <int LW, bool MERGED>
-__device__ void lane_shortest_paths(int src, const PlanView &P, int nc, const LaneCtx<LW> &L, LaneMem &w, int &fuel) {
-    for (int v = 0; v <= nc + 1; v++) LX(w.lab, v) = LAB_INF;      // index nc+1: the tail of padding slots, never reached
-    LX(w.lab, src) = LAB_BIAS << HB;
-    const int vend = MERGED ? nc : nc + 1;
-    bool changed;
-    do {
-        changed = false;
-        for (int v = 1; v < vend; v++) {
-            const int s1 = P.node_in4[v + 1];
-            int best = LX(w.lab, v), bs = -1;
-            for (int sl = P.node_in4[v]; sl < s1; sl += 4) {          // slot lists are padded to a multiple of 4
-                const int4 q0 = P.slot_pk4[sl >> 1], q1 = P.slot_pk4[(sl >> 1) + 1];   // {tail | (2*chain+dir) << 16, increment} x 4
-                const int d0 = q0.x >> 16, d1 = q0.z >> 16, d2 = q1.x >> 16, d3 = q1.z >> 16;
-                const int f0 = LX(w.res, d0 >> 1), f1 = LX(w.res, d1 >> 1), f2 = LX(w.res, d2 >> 1), f3 = LX(w.res, d3 >> 1);
-                const int l0 = LX(w.lab, q0.x & 0xffff), l1 = LX(w.lab, q0.z & 0xffff), l2 = LX(w.lab, q1.x & 0xffff), l3 = LX(w.lab, q1.z & 0xffff);
-                const int c0 = l0 + q0.y, c1 = l1 + q0.w, c2 = l2 + q1.y, c3 = l3 + q1.w;
-                if (((f0 >> (d0 & 1)) & 1) && l0 != LAB_INF && c0 < best) { best = c0; bs = sl; }
-                if (((f1 >> (d1 & 1)) & 1) && l1 != LAB_INF && c1 < best) { best = c1; bs = sl + 1; }
-                if (((f2 >> (d2 & 1)) & 1) && l2 != LAB_INF && c2 < best) { best = c2; bs = sl + 2; }
-                if (((f3 >> (d3 & 1)) & 1) && l3 != LAB_INF && c3 < best) { best = c3; bs = sl + 3; }
-            }
-            if (bs >= 0) { LX(w.lab, v) = best; LX(w.pred, v) = (unsigned short)bs; changed = true; }
-        }
-        changed = L.any(changed) && --fuel > 0;
-    } while (changed);
-}
-
-// per-lane walk dst -> src along the exact predecessor slots, then push; lanes with go == false idle
-template <int LW>
-__device__ int lane_push(bool go, int src, int dst, int limit, const PlanView &P, const LaneCtx<LW> &L, LaneMem &w) {
-    int v = dst, d = limit;
-    while (L.any(go && v != src)) {
-        if (go && v != src) {
-            const int2 pk = reinterpret_cast<const int2 *>(P.slot_pk4)[LX(w.pred, v)];
-            const int cd = pk.x >> 16, c = cd >> 1;
-            d = min(d, (cd & 1) ? (int)LX(w.x, c) - (int)LX(w.lo, c) : (int)LX(w.up, c) - (int)LX(w.x, c));
-            v = pk.x & 0xffff;
-        }
-    }
-    v = dst;
-    while (L.any(go && v != src)) {
-        if (go && v != src) {
-            const int2 pk = reinterpret_cast<const int2 *>(P.slot_pk4)[LX(w.pred, v)];
-            const int cd = pk.x >> 16, c = cd >> 1;
-            const int xc = (int)LX(w.x, c) + ((cd & 1) ? -d : d);
-            LX(w.x, c) = (unsigned short)xc;
-            LX(w.res, c) = (unsigned char)((xc < (int)LX(w.up, c) ? 1 : 0) | (xc > (int)LX(w.lo, c) ? 2 : 0));
-            v = pk.x & 0xffff;
-        }
-    }
-    return go ? d : 0;
-}
-
-// potential at the HEAD of arc a for this lane's scenario (cf. head_potential of the warp variant);
-// the position tests "pos >= first least-capacity arc" / "pos >= last greatest-lower-bound arc" are
-// answered by re-reading the few capacities of the chain
-template <int LW>
-__device__ int lane_head_potential(int a, const PlanView &P, int nopen, const double *row_u, const double *row_l, const LaneCtx<LW> &L, const LaneMem &w) {
-    const int cp = P.arc_cp[a], c = cp >> 10, pos = cp & 1023, pre = P.arc_pre[a];
-    const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1;
-    if (c < nopen) {
-        const int r = P.ch_r[c], psv = LX(w.lab, sv), dp = LX(w.lab, ev) - psv;
-        const int g = max(0, r - dp), b = max(0, dp - r);
-        int val = psv + pre;
-        const int b0 = P.ch_ptr[c], b1 = P.ch_ptr[c + 1];
-        if (L.any(g > 0)) {
-            bool found = false;
-            const int up = LX(w.up, c);
-            for (int k = b0; k <= b0 + pos; k++) found |= (int)row_u[P.ch_arcs[k]] == up;
-            if (found) val -= g;
-        }
-        if (L.any(b > 0)) {
-            bool later = false;
-            const int lo = LX(w.lo, c);
-            for (int k = b0 + pos + 1; k < b1; k++) later |= (int)row_l[P.ch_arcs[k]] == lo;
-            if (!later) val += b;
-        }
-        return val;
-    }
-    if (sv >= 0) return LX(w.lab, sv) + pre;
-    if (ev >= 0) return LX(w.lab, ev) - (P.ch_r[c] - pre);
-    return pre;
-}
-
-template <int LW>
-__global__ void __launch_bounds__(32) k1_lane_eval(K1Launch p, int bytes_per_warp) {
-#ifdef SGUFP_K1_EMULATE
-    unsigned char *smem = reinterpret_cast<unsigned char *>(sgufp_emul_smem);
-#else
-    extern __shared__ unsigned char smem_l[];
-    unsigned char *smem = smem_l;
-#endif
-    const LaneCtx<LW> L;
-    const int nc_max = p.nc + 2;
-    LaneMem w;
-    {
-        unsigned char *base = smem;   // one warp per CTA
-        (void)bytes_per_warp;
-        w.lab = reinterpret_cast<int *>(base); base += (size_t)nc_max * LW * 4;
-        w.exc = reinterpret_cast<int *>(base); base += (size_t)nc_max * LW * 4;
-        w.aq = reinterpret_cast<int *>(base); base += (size_t)(p.nav + 1) * LW * 4;
-        w.x = reinterpret_cast<unsigned short *>(base); base += (size_t)p.max_nopen * LW * 2;
-        w.up = reinterpret_cast<unsigned short *>(base); base += (size_t)p.max_nopen * LW * 2;
-        w.lo = reinterpret_cast<unsigned short *>(base); base += (size_t)p.max_nopen * LW * 2;
-        w.pred = reinterpret_cast<unsigned short *>(base); base += (size_t)nc_max * LW * 2;
-        w.res = base;
-    }
-    const int bps = (p.S + LW - 1) / LW;                     // scenario blocks per candidate
-    const long long nblk = (long long)p.K * bps;
-    for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-        const int k = (int)(blk / bps), s_raw = (int)(blk - (long long)k * bps) * LW + L.lane;
-        const bool active = s_raw < p.S;
-        const int s = active ? s_raw : p.S - 1;             // idle lanes shadow the last scenario; they never write results
-        if (*reinterpret_cast<volatile long long *>(p.first_inf + k) < 0) continue;
-        int fuel = 1 << 20;
-        const PlanView P(p.plans + p.plan_off[k]);
-        const int nch = P.h->nch, nopen = P.h->nopen, nc = P.h->nc, nav = P.h->nav, m = p.m;
-        unsigned long long *sums = p.sums + (size_t)k * p.W;
-        const double *row_u = p.cap_u + (size_t)s * p.m_pad, *row_l = p.cap_l + (size_t)s * p.m_pad;
-
-        // 1. chain capacities, sequential per lane
-        for (int c = 0; c < nopen; c++) { LX(w.up, c) = 0xffff; LX(w.lo, c) = 0; }
-        bool bad = false;
-        for (int a = 0; a < m; a++) {
-            const int c = P.arc_cp[a] >> 10;
-            const int ua = (int)row_u[a], la = (int)row_l[a];
-            if (c < nopen) {
-                if (ua < (int)LX(w.up, c)) LX(w.up, c) = (unsigned short)ua;
-                if (la > (int)LX(w.lo, c)) LX(w.lo, c) = (unsigned short)la;
-            } else bad |= la > 0;
-        }
-        bool forced = false;
-        for (int c = 0; c < nopen; c++) {
-            const int lo = LX(w.lo, c), up = LX(w.up, c);
-            LX(w.x, c) = (unsigned short)lo;
-            LX(w.res, c) = (unsigned char)(lo < up ? 1 : 0);
-            bad |= lo > up; forced |= lo > 0;
-        }
-        // 2a. forced flow of the lower bounds (rare)
-        if (L.any(forced && !bad)) {
-            for (int v = 0; v <= nc; v++) LX(w.exc, v) = 0;
-            for (int c = 0; c < nopen; c++) {
-                const int lo = LX(w.lo, c), e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1;
-                if (lo > 0 && !bad) { if (ev > 0) LX(w.exc, ev) += lo; if (sv > 0) LX(w.exc, sv) -= lo; }
-            }
-            for (;;) {   // excess nodes: to the root or to a deficit node, whichever is nearer
-                int src = -1;
-                for (int v = 1; v < nc; v++) if (src < 0 && LX(w.exc, v) > 0) src = v;
-                const bool live = !bad && src >= 0;
-                if (!L.any(live) || fuel <= 0) break;
-                lane_shortest_paths<LW, false>(live ? src : 0, P, nc, L, w, fuel);
-                int best = -1, bl = LAB_INF;
-                for (int t = 1; t <= nc; t++) {
-                    const int lt = LX(w.lab, t);
-                    if ((t == nc || LX(w.exc, t) < 0) && lt < bl) { bl = lt; best = t; }
-                }
-                if (live && best < 0) bad = true;
-                const bool go = live && !bad;
-                int lim = go ? LX(w.exc, src) : 0;
-                if (go && best != nc) lim = min(lim, -LX(w.exc, best));
-                const int d = lane_push<LW>(go, src, best, lim, P, L, w);
-                if (go) { LX(w.exc, src) -= d; if (best != nc) LX(w.exc, best) += d; }
-                fuel--;
-            }
-            for (;;) {   // deficit nodes: from the root
-                int dst = -1;
-                for (int v = 1; v < nc; v++) if (dst < 0 && LX(w.exc, v) < 0) dst = v;
-                const bool live = !bad && dst >= 0;
-                if (!L.any(live) || fuel <= 0) break;
-                lane_shortest_paths<LW, false>(0, P, nc, L, w, fuel);
-                if (live && LX(w.lab, dst) == LAB_INF) bad = true;
-                const bool go = live && !bad;
-                const int d = lane_push<LW>(go, 0, go ? dst : 0, go ? -LX(w.exc, dst) : 0, P, L, w);
-                if (go) LX(w.exc, dst) += d;
-                fuel--;
-            }
-        }
-        // 2b. successive shortest paths, all lanes in step
-        while (fuel > 0) {
-            lane_shortest_paths<LW, false>(0, P, nc, L, w, fuel);
-            const int lt = LX(w.lab, nc);
-            const bool go = !bad && lt != LAB_INF && lab_dist(lt) < 0;
-            if (!L.any(go)) break;
-            lane_push<LW>(go, 0, nc, INT_MAX, P, L, w);
-            fuel--;
-        }
-        // 3. potentials (lab becomes the potential)
-        lane_shortest_paths<LW, true>(0, P, nc, L, w, fuel);
-        bool missing = false;
-        for (int v = 0; v < nc; v++) {
-            const int l = LX(w.lab, v);
-            if (l == LAB_INF) { missing = true; LX(w.lab, v) = NEG_INF; LX(w.pred, v) = 0; } else { LX(w.lab, v) = lab_dist(l); LX(w.pred, v) = 1; }
-        }
-        if (L.any(missing)) {
-            bool changed;
-            do {   // least labels consistent with the labelled nodes
-                changed = false;
-                for (int c = 0; c < nopen; c++) {
-                    const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1, r = P.ch_r[c];
-                    const int xc = LX(w.x, c), up = LX(w.up, c), lo = LX(w.lo, c);
-                    if (xc < up && LX(w.pred, sv) == 0) { const int db = LX(w.lab, ev); if (db > NEG_INF && db + r > LX(w.lab, sv)) { LX(w.lab, sv) = db + r; changed = true; } }
-                    if (xc > lo && LX(w.pred, ev) == 0) { const int da = LX(w.lab, sv); if (da > NEG_INF && da - r > LX(w.lab, ev)) { LX(w.lab, ev) = da - r; changed = true; } }
-                }
-                changed = L.any(changed) && --fuel > 0;
-            } while (changed);
-            bool iso = false;
-            for (int v = 0; v < nc; v++) if (LX(w.lab, v) == NEG_INF) { LX(w.lab, v) = 0; LX(w.pred, v) = 2; iso = true; }
-            if (L.any(iso)) {
-                do {   // zero-rooted completion of the nodes cut off both ways
-                    changed = false;
-                    for (int c = 0; c < nopen; c++) {
-                        const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1, r = P.ch_r[c];
-                        const int xc = LX(w.x, c), up = LX(w.up, c), lo = LX(w.lo, c);
-                        if (xc < up && LX(w.pred, ev) == 2) { const int cand = LX(w.lab, sv) - r; if (cand < LX(w.lab, ev)) { LX(w.lab, ev) = cand; changed = true; } }
-                        if (xc > lo && LX(w.pred, sv) == 2) { const int cand = LX(w.lab, ev) + r; if (cand < LX(w.lab, sv)) { LX(w.lab, sv) = cand; changed = true; } }
-                    }
-                    changed = L.any(changed) && --fuel > 0;
-                } while (changed);
-            }
-        }
-        for (int v = 0; v < nc; v++) LX(w.lab, v) = -LX(w.lab, v);
-        if (fuel <= 0) {
-            if (L.lane == 0) atomicMin(p.first_inf + k, -1LL);
-            continue;
-        }
-        const bool ok = active && !bad;      // lanes whose scenario contributes to the cut
-        // 4. lifting + folding: one reduction over the 32 scenarios per accumulator touched
-        long long rhs = 0, objv = 0;
-        for (int c = 0; c < nopen; c++) {
-            const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1, r = P.ch_r[c];
-            const int dp = LX(w.lab, ev) - LX(w.lab, sv), g = r - dp;
-            const int up = LX(w.up, c), lo = LX(w.lo, c);
-            objv += (long long)r * (int)LX(w.x, c);
-            if (ok && g < 0) rhs -= (long long)lo * (-g);
-            if (L.any(ok && g > 0)) {
-                bool found = false;
-                for (int kk = P.ch_ptr[c]; kk < P.ch_ptr[c + 1]; kk++) {   // the FIRST arc of least capacity carries the multiplier
-                    const int a = P.ch_arcs[kk];
-                    const bool hit = ok && g > 0 && !found && (int)row_u[a] == up;
-                    found |= hit;
-                    const long long tot = L.sum(hit ? (long long)up * g : 0);
-                    if (tot != 0 && L.lane == 0) {
-                        if ((P.arc_info[a] & 3) == KIND_GAMMA) atomicAdd(sums, (unsigned long long)tot);
-                        else atomicAdd(sums + 1 + p.L + a, (unsigned long long)tot);
-                    }
-                }
-            }
-        }
-        for (int i = 0; i < nav; i++) {
-            const int b0 = P.av_ptr[i], b1 = P.av_ptr[i + 1];
-            int alpha = 0;
-            if (b1 > b0) {
-                alpha = lane_head_potential<LW>(P.av_arcs[b0], P, nopen, row_u, row_l, L, w);
-                for (int t = b0 + 1; t < b1; t++) {
-                    const int a = P.av_arcs[t];
-                    const int dl = lane_head_potential<LW>(a, P, nopen, row_u, row_l, L, w) - alpha;
-                    if (L.any(ok && dl != 0)) {
-                        long long v = 0;
-                        if (ok && dl > 0) v = (long long)(int)row_u[a] * dl;
-                        else if (ok && dl < 0) {
-                            const int cp = P.arc_cp[a];
-                            v = (long long)(int)row_u[P.ch_arcs[P.ch_ptr[cp >> 10] + (cp & 1023) + 1]] * (-dl);
-                        }
-                        const long long tot = L.sum(v);
-                        rhs += v;
-                        if (tot != 0 && L.lane == 0) atomicAdd(sums + 1 + (P.arc_info[a] >> 2) - 1, (unsigned long long)tot);
-                    }
-                }
-            } else {
-                bool found = false;
-                for (int t = P.fb_ptr[i]; t < P.fb_ptr[i + 1]; t++) {
-                    const int c = P.fb_ch[t], ev = (P.ch_ends[c] >> 16) - 1;
-                    const int cand = LX(w.lab, ev) - P.ch_r[c];
-                    if (!found || cand < alpha) { alpha = cand; found = true; }
-                }
-            }
-            LX(w.aq, i) = alpha;
-        }
-        for (int c = nopen; c < nch; c++) {
-            const int b0 = P.ch_ptr[c], b1 = P.ch_ptr[c + 1], first = P.ch_arcs[b0], last = P.ch_arcs[b1 - 1];
-            const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1;
-            const int q = P.ch_q[c], qs = (q & 0xffff) - 1, qe = (q >> 16) - 1;
-            const int rfirst = P.arc_pre[first];
-            if (qs >= 0 && qe >= 0 && b1 - b0 == 1) {
-                const int v = rfirst - (LX(w.aq, qe) - LX(w.aq, qs));
-                const long long tot = L.sum(ok && v > 0 ? (long long)(int)row_u[first] * v : 0);
-                if (tot != 0 && L.lane == 0) atomicAdd(sums + 1 + p.L + first, (unsigned long long)tot);
-                continue;
-            }
-            if (qs >= 0) {
-                const int phf = ev >= 0 ? LX(w.lab, ev) - (P.ch_r[c] - rfirst) : rfirst;
-                const int v = rfirst - (phf - LX(w.aq, qs));
-                const long long tot = L.sum(ok && v > 0 ? (long long)(int)row_u[first] * v : 0);
-                if (tot != 0 && L.lane == 0) atomicAdd(sums + 1 + p.L + first, (unsigned long long)tot);
-            }
-            if (qe >= 0) {
-                int pt, rlast;
-                if (b1 - b0 > 1) {
-                    const int prev = P.ch_arcs[b1 - 2];
-                    pt = (sv >= 0 ? LX(w.lab, sv) : 0) + P.arc_pre[prev];
-                    rlast = P.ch_r[c] - P.arc_pre[prev];
-                } else { pt = LX(w.lab, sv); rlast = P.ch_r[c]; }
-                const int v = rlast - (LX(w.aq, qe) - pt);
-                const long long tot = L.sum(ok && v > 0 ? (long long)(int)row_u[last] * v : 0);
-                if (tot != 0 && L.lane == 0) atomicAdd(sums + 1 + p.L + last, (unsigned long long)tot);
-            }
-        }
-        const long long rtot = L.sum(ok ? rhs : 0);
-        if (rtot != 0 && L.lane == 0) atomicAdd(sums, (unsigned long long)rtot);
-        if (active) {
-            if (bad) atomicMin(p.first_inf + k, p.scen_offset + s);
-            if (p.status) p.status[(size_t)k * p.S + s] = bad ? 1 : 0;
-            if (p.obj) p.obj[(size_t)k * p.S + s] = bad ? 0.0 : (double)objv;
-        }
-    }
-}
-#undef LX
-
 // ---- feasibility ray of ONE scenario (replaces GRB_DoubleAttr_UnbdRay, grb.cpp:304-344) --------
 // Cold path: runs once per call that meets an infeasible scenario.  One thread, split graph
 // (DESIGN.md §3): minimal min-cut of the lower-bound feasibility network.
@@ -1235,42 +846,14 @@ static cudaError_t launch_warp(const K1Launch &p, cudaStream_t st, int sm_count)
     return launch_warp_dispatch(best_nw, p, st, sm_count, &rw, false);
 }
 
-static size_t lane_bytes_per_warp(const K1Launch &p) {
-    return ((size_t)2 * (p.nc + 2) * 4 + (size_t)(p.nav + 1) * 4 + (size_t)3 * p.max_nopen * 2 + (size_t)(p.nc + 2) * 2 + (size_t)p.max_nopen) * 32;
-}
-
-// lane-per-scenario variant: one warp per CTA, as many CTAs per SM as the shared memory allows
-static cudaError_t launch_lane(const K1Launch &p, cudaStream_t st, int sm_count) {
-    const size_t smem = lane_bytes_per_warp(p);
-    cudaError_t e = cudaFuncSetAttribute(k1_lane_eval<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_lane_eval<32>, 32, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
-    const long long nblk = (long long)p.K * ((p.S + 31) / 32);
-    long long grid = (long long)sm_count * per_sm;
-    if (nblk < grid) grid = nblk;
-    if (grid < 1) grid = 1;
-    k1_lane_eval<32><<<(unsigned)grid, 32, smem, st>>>(p, (int)smem);
-    return cudaGetLastError();
-}
-
-// which variant: the warp-per-scenario kernel unless SGUFP_K1_MODE=lane asks for the lane-per-scenario
-// one (measured slower on C2 and C4, profiles/r01_k1_variants.md; kept as an independently written
-// second implementation that the parity tests also run)
-bool k1_lane_mode_requested() {
-    const char *e = getenv("SGUFP_K1_MODE");
-    return e && e[0] == 'l';
-}
-
-bool k1_use_lane_variant(const K1Launch &p) {
-    return k1_lane_mode_requested() && p.max_cap < 65536 && lane_bytes_per_warp(p) <= 200 * 1024;
-}
-
+// which kernel: the lane-per-scenario one (k1_lane.cu) for batches it accepts, else the warp-per-scenario one
 cudaError_t k1_launch(const K1Launch &p, cudaStream_t st, int sm_count, int *launches) {
     if (launches) (*launches)++;
-    if (k1_use_lane_variant(p)) return launch_lane(p, st, sm_count);
+    if (k1_lane_eligible(p, sm_count)) {
+        const cudaError_t e = k1_lane_launch(p, st, sm_count);
+        if (e != cudaErrorInvalidConfiguration) return e;
+        cudaGetLastError();          // the state of this batch does not fit one SM's shared memory: the warp kernel takes it
+    }
     return launch_warp(p, st, sm_count);
 }
 

@@ -17,11 +17,19 @@ struct K1Launch {
     double *obj;                  // [K][S] or nullptr
     uint8_t *status;              // [K][S] or nullptr
     int max_nch, max_nopen, nc, nav;
-    int max_cap;                  // largest capacity of the instance (the lane variant keeps 16-bit state)
+    int max_cap;                  // largest capacity of this handle's scenarios (the lane kernel keeps 8- or 16-bit flow state)
+    // what decides whether the lane-per-scenario kernel (k1_lane.cu) takes the batch
+    int has_lower;                // some lower bound of this handle's scenarios is positive (then: warp kernel)
+    int lane_tables;              // the plans carry the head-sorted in-slot tables
+    int sum_abs_r;                // sum |reward| of the instance (bounds every label)
+    int max_indeg;                // largest in-degree of a contracted node over the batch
 };
 
-// whether SGUFP_K1_MODE asks for the lane-per-scenario kernel (its plans carry extra tables)
-bool k1_lane_mode_requested();
+// K1 dispatch: the warp-per-scenario kernel (k1_cut.cu) unless SGUFP_K1_MODE=lane asks for the lane-per-scenario kernel
+// (k1_lane.cu), which then takes every batch it accepts: no positive lower bounds, capacities < 65536, state fits shared memory.
+bool k1_lane_tables_wanted();                               // false when the mode rules the lane kernel out
+bool k1_lane_eligible(const K1Launch &p, int sm_count);
+cudaError_t k1_lane_launch(const K1Launch &p, cudaStream_t st, int sm_count);   // cudaErrorInvalidConfiguration: state too large
 
 // Returns cudaSuccess or the launch error.  *launches is incremented by the kernels launched.
 cudaError_t k1_launch(const K1Launch &p, cudaStream_t st, int sm_count, int *launches);

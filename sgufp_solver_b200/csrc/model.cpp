@@ -255,19 +255,19 @@ int build_plan(const Model &M, const int16_t *path, int plen, Plan &P, std::stri
     }
     av_ptr[M.nav] = (int)av_arcs.size(); fb_ptr[M.nav] = (int)fb_ch.size();
 
-    // residual slots of the contracted graph, sorted by head node
-    struct Slot { int tail, head, cs, ch; };
+    // residual slots of the contracted graph, sorted by head label index (lane kernel: backward searches from the sink)
+    struct Slot { int tail, head, cost, cd; };
     std::vector<Slot> slots;
     slots.reserve(lane_tables ? 2 * nopen : 0);
     for (int c = 0; lane_tables && c < nopen; c++) {
         const Ch &ch = chains[c];
-        slots.push_back({ch.sv, ch.ev == 0 ? M.nc : ch.ev, -ch.r * 1024 + 1, 2 * c});
-        slots.push_back({ch.ev, ch.sv == 0 ? M.nc : ch.sv, ch.r * 1024 + 1, 2 * c + 1});
+        slots.push_back({ch.sv, ch.ev == 0 ? M.nc : ch.ev, -ch.r, 2 * c});
+        slots.push_back({ch.ev, ch.sv == 0 ? M.nc : ch.sv, ch.r, 2 * c + 1});
     }
     std::sort(slots.begin(), slots.end(), [](const Slot &a, const Slot &b) {
         if (a.head != b.head) return a.head < b.head;
         if (a.tail != b.tail) return a.tail < b.tail;
-        return a.ch < b.ch;
+        return a.cd < b.cd;
     });
     PlanHeader H{};
     H.nch = nch; H.nopen = nopen; H.nc = M.nc; H.nav = M.nav; H.m = m; H.L = M.L;
@@ -288,17 +288,23 @@ int build_plan(const Model &M, const int16_t *path, int plen, Plan &P, std::stri
             st[2 * c + 1] = hb | (int32_t)((uint32_t)ch.r << 10);
         }
         H.o_ch_st = put(st);   // W.size() is even here (header even, every array padded to even)
-        std::vector<int32_t> pk, in4(M.nc + 2, 0);
+        std::vector<int32_t> pk, in_pd(M.nc + 2, 0);
         size_t s = 0;
+        int max_indeg = 0;
         for (int v = 0; v <= M.nc; v++) {
-            in4[v] = (int32_t)(pk.size() / 2);
-            for (; s < slots.size() && slots[s].head == v; s++) { pk.push_back(slots[s].tail | (slots[s].ch << 16)); pk.push_back(slots[s].cs); }
-            while ((pk.size() / 2) & 3) { pk.push_back(M.nc + 1); pk.push_back(0); }   // padding slot: tail nc+1 is never labelled
+            const int first = (int)(pk.size() / 2);
+            for (; s < slots.size() && slots[s].head == v; s++) {
+                pk.push_back(slots[s].tail | (slots[s].cd << 16));
+                pk.push_back((int32_t)((uint32_t)slots[s].cost << 12) | slots[s].head);
+            }
+            const int deg = (int)(pk.size() / 2) - first;
+            in_pd[v] = first | (deg << 16);
+            max_indeg = std::max(max_indeg, deg);
         }
-        in4[M.nc + 1] = (int32_t)(pk.size() / 2);
-        while (W.size() & 3) W.push_back(0);   // int4 loads: 16-byte aligned (plans start on 16-byte boundaries)
-        H.o_slot_pk = put(pk);
-        H.o_node_in4 = put(in4);
+        H.o_slots = put(pk);           // W.size() is even here: 8-byte aligned records
+        H.o_in_pd = put(in_pd);
+        H.max_indeg = max_indeg;
+        P.max_indeg = max_indeg;
     }
     while (W.size() & 3) W.push_back(0);  // keep every plan 16-byte aligned inside a batch
     H.total = (int32_t)W.size();

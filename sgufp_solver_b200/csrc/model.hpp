@@ -62,10 +62,13 @@ struct PlanHeader {
                            //            x = sv | ev << 10 | hf << 20,  y = hb | reward << 10, where hf / hb are the label
                            //            indices of the heads of the forward (sv->ev, cost -r) and backward (ev->sv, cost +r)
                            //            residual arcs: an arc entering the root ends at index nc (the root seen as a path END)
-    // residual slots of the lane-per-scenario variant: sorted by head node
-    int32_t o_slot_pk;     // int2 {tail | (2*chain+dir) << 16, label increment} per slot, every node's list padded to a multiple of 4
-                           // with slots whose tail is the never-labelled node nc+1; 16-byte aligned
-    int32_t o_node_in4;    // [nc+2]     ranges of the padded lists
+    // in-slots of the lane-per-scenario kernel (k1_lane.cu): the residual arcs of the contracted graph sorted by HEAD label
+    // index (1..nc; an arc entering the root ends at index nc, the root seen as a path END)
+    int32_t o_slots;       // int2 per slot, 8-byte aligned: x = tail | (2*chain+dir) << 16, y = cost << 12 | head
+                           //   (dir 0: the chain's forward arc sv->ev at cost -r; dir 1: its backward arc ev->sv at cost +r)
+    int32_t o_in_pd;       // [nc+2]     first slot | in-degree << 16 of every head index (index 0, the root as a source, has none)
+    int32_t max_indeg;     // largest in-degree (decides the cursor width of the lane kernel)
+    int32_t pad_;
     int32_t total;         // int32 words used by this plan, header included (the header is an even number of words)
 };
 
@@ -74,11 +77,11 @@ static_assert(sizeof(PlanHeader) % 8 == 0, "64-bit records follow the header");
 struct Plan {
     std::vector<int32_t> words;   // PlanHeader followed by the arrays
     std::vector<int32_t> match_out, match_in;
-    int nch = 0, nopen = 0;
+    int nch = 0, nopen = 0, max_indeg = 0;
 };
 
 // returns 0 / SGUFP_ERR_ARG / SGUFP_ERR_MATCHING / SGUFP_ERR_CYCLIC
-// lane_tables: also emit the head-sorted slot tables that only the lane-per-scenario kernel reads
+// lane_tables: also emit the head-sorted slot tables that only the lane-per-scenario kernel reads (k1_lane.cu)
 int build_plan(const Model &M, const int16_t *path, int plen, Plan &P, std::string &err, bool lane_tables = true);
 
 void ray_arrays(const Model &M, const Plan &P, std::vector<int32_t> &ts, std::vector<int32_t> &hs, std::vector<int32_t> &info,

@@ -49,6 +49,7 @@ template <class T> static inline T __shfl_sync(unsigned, T v, int, int = 32) { r
 static inline double2 __ldg(const double2 *p) { return *p; }
 
 #include "../../sgufp_solver_b200/csrc/k1_cut.cu"
+#include "../../sgufp_solver_b200/csrc/k1_lane.cu"
 #include "../../sgufp_solver_b200/csrc/model.cpp"
 
 using namespace sgufp;
@@ -90,11 +91,25 @@ extern "C" int emul_paths(int n, int m, int S, const int32_t *tail, const int32_
     sgufp_emul_smem = smem.data();
     threadIdx.x = 0; blockIdx.x = 0; gridDim.x = 1;
     // one "thread" walks all items: with TILE = 1 the tile stride is WARPS*32, so visit every tile slot of the CTA
-    if (lane_variant) {   // the lane-per-scenario kernel with one lane
-        std::vector<int> lsm(((size_t)2 * (M.nc + 2) * 4 + (size_t)(M.nav + 1) * 4 + (size_t)3 * max_nopen * 2 + (size_t)(M.nc + 2) * 2 + max_nopen) / 4 + 16, 0);
-        sgufp_emul_smem = lsm.data();
+    if (lane_variant) {   // the lane-per-scenario kernel (k1_lane.cu) with one lane; lane_variant 1/2/3 = state widths small/mid/wide
+        int max_lower = 0, max_cap = 0, max_indeg = 0;
+        long long sum_abs = 0;
+        for (size_t i = 0; i < (size_t)m * S; i++) { max_lower = std::max(max_lower, lower[i]); max_cap = std::max(max_cap, upper[i]); }
+        for (int a = 0; a < m; a++) sum_abs += std::abs((long long)rew0[a]);
+        for (int k = 0; k < K; k++) max_indeg = std::max(max_indeg, plans[k].max_indeg);
+        if (max_lower > 0) return 99;                 // the lane kernel does not take instances with positive lower bounds
+        p.max_cap = max_cap; p.has_lower = 0; p.lane_tables = 1; p.sum_abs_r = (int)sum_abs; p.max_indeg = max_indeg;
         threadIdx.x = 0; blockIdx.x = 0; gridDim.x = 1;
-        k1_lane_eval<1>(p, 0);
+        auto run = [&](auto cfg) -> int {
+            using Cfg = decltype(cfg);
+            if (!lane_cfg_fits<Cfg>(p)) return 98;
+            std::vector<int> lsm(lane_layout<Cfg>(max_nopen, M.nc, M.nav, 1).bytes / 4 + 16, 0);
+            sgufp_emul_smem = lsm.data();
+            k1_lane_pd<1, Cfg>(p);
+            return 0;
+        };
+        const int rc = lane_variant == 1 ? run(CfgSmall{}) : lane_variant == 2 ? run(CfgMid{}) : run(CfgWide{});
+        if (rc) return rc;
     } else
     for (int t = 0; t < WARPS * 32; t++) { threadIdx.x = t; if (p.nc <= SMALL_NC) k1_cut_eval<1, WARPS, false>(p, wpt); else k1_cut_eval<1, WARPS, true>(p, wpt); }
     for (int k = 0; k < K; k++) {

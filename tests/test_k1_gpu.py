@@ -180,11 +180,23 @@ def test_bad_path_is_rejected():
     assert e.value.code == -2
 
 
-@pytest.mark.parametrize("name,make,K,seed,unm", [c for c in CASES if c[0] in ("c1_lb", "c2", "c2_lb", "odd_m_single_scenario")],
-                         ids=["c1_lb", "c2", "c2_lb", "odd_m_single_scenario"])
-def test_lane_variant_gives_the_same_cuts(name, make, K, seed, unm, monkeypatch):
-    """The lane-per-scenario kernel (SGUFP_K1_MODE=lane) is a second, independently written K1: same
-    statuses, objectives and bit-identical cuts as the default warp-per-scenario kernel and as Oracle B."""
+LANE_CASES = [c for c in CASES if c[0] in ("c1", "c1_all_unmatched", "c2", "c4", "odd_m_single_scenario")] + [
+    ("c2_ragged", lambda: I.config2(S=77), 5, 23, 0.3),          # a last block of 13 scenarios: idle lanes shadow the last one
+    ("c4_two_blocks", lambda: I.config4(S=40), 2, 25, 0.0),
+    ("wide_caps", lambda: _scaled(I.config2(S=33), 300), 3, 27, 0.1),   # capacities up to 9000: the 16-bit state (CfgWide)
+]
+
+
+def _scaled(inst, f):
+    import dataclasses
+    return dataclasses.replace(inst, upper=inst.upper * f)
+
+
+@pytest.mark.parametrize("name,make,K,seed,unm", LANE_CASES, ids=[c[0] for c in LANE_CASES])
+def test_lane_kernel_gives_the_same_cuts(name, make, K, seed, unm, monkeypatch):
+    """The lane-per-scenario kernel (k1_lane.cu; SGUFP_K1_MODE=lane forces it on small batches too) and the
+    warp-per-scenario kernel (SGUFP_K1_MODE=warp) are two independently written K1s: same statuses, objectives and
+    bit-identical cuts as each other and as Oracle B."""
     inst = make()
     net = OracleNet(inst)
     gs = sg.GuroSolver(inst)
@@ -197,6 +209,39 @@ def test_lane_variant_gives_the_same_cuts(name, make, K, seed, unm, monkeypatch)
     assert (a.rhs == b.rhs).all() and (a.coef_dense == b.coef_dense).all()
     assert (a.status == b.status).all() and (a.obj == b.obj).all()
     _compare(inst, gs, net, paths, b)
+
+
+def test_lane_mode_leaves_lower_bounds_to_the_warp_kernel(monkeypatch):
+    """An instance with positive lower bounds is not for the lane kernel: forcing the mode must not change the answer."""
+    inst = I.config2(S=64, lower_prob=0.05)
+    net = OracleNet(inst)
+    gs = sg.GuroSolver(inst)
+    paths = I.random_paths(net, 4, 29, 0.2)
+    monkeypatch.setenv("SGUFP_K1_MODE", "lane")
+    _compare(inst, gs, net, paths, gs.solve_paths(paths))
+
+
+@pytest.mark.parametrize("block", range(2))
+def test_lane_kernel_fuzz(block, monkeypatch):
+    """Random networks without lower bounds, 45-scenario blocks (a full warp and a ragged one), forced lane kernel."""
+    monkeypatch.setenv("SGUFP_K1_MODE", "lane")
+    rng = np.random.default_rng(1700 + block)
+    done = 0
+    for k in range(25):
+        nl = int(rng.integers(2, 6))
+        layers = [int(rng.integers(2, 12)) for _ in range(nl)]
+        max_m = sum(a * b for a, b in zip(layers[:-1], layers[1:])) + layers[0] + layers[-1]
+        m = int(rng.integers(max(sum(layers) + 2, max_m // 3), max_m + 1))
+        try:
+            inst = I.make_layered(layers, m, 45, 5000 + 100 * block + k, float(rng.uniform(0.1, 0.95)), 0.0, f"lfz{k}")
+            net = OracleNet(inst)
+        except Exception:
+            continue
+        gs = sg.GuroSolver(inst)
+        paths = I.random_paths(net, 4, k, float(rng.choice([0.0, 0.2, 0.6])))
+        _compare(inst, gs, net, paths, gs.solve_paths(paths))
+        done += 1
+    assert done >= 12
 
 
 @pytest.mark.parametrize("block", range(3))

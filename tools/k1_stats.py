@@ -34,13 +34,22 @@ def main():
     L.sgufp_debug_k1_stats.restype = C.c_int
     L.sgufp_debug_k1_stats.argtypes = [C.POINTER(C.c_ulonglong)]
     out = (C.c_ulonglong * 8)()
+    L.sgufp_debug_k1_lane_stats.restype = C.c_int
+    L.sgufp_debug_k1_lane_stats.argtypes = [C.POINTER(C.c_ulonglong)]
+    lane = (C.c_ulonglong * 8)()
     for name in [a for a in sys.argv[1:] if not a.startswith("-")]:
         inst, K = {"c2": (lambda: (I.config2(S=1000), 64)), "c4": (lambda: (I.config4(S=2000), 8))}[name]()
         solver = GuroSolver(inst)
         paths = I.random_paths(solver, K, 31, 0.1)
         L.sgufp_debug_k1_stats(out)
+        L.sgufp_debug_k1_lane_stats(lane)
         solver.solve_paths(np.asarray(paths, dtype=np.int16))
         L.sgufp_debug_k1_stats(out)
+        L.sgufp_debug_k1_lane_stats(lane)
+        if lane[0]:      # the lane-per-scenario kernel ran: counters per block of 32 scenarios (warp level) and per scenario (lane level)
+            print(f"{name}: lane kernel, blocks {lane[0]}  sweeps/block {lane[1] / lane[0]:.1f}  steps/block {lane[2] / lane[0]:.0f}  "
+                  f"dual updates/scenario {lane[3] / max(1, lane[5]):.1f}  pushes/scenario {lane[4] / max(1, lane[5]):.1f}  ms {solver.last_kernel_ms():.3f}")
+            continue
         ev = max(1, out[3])
         print(f"{name}: evals {out[3]}  passes/eval {out[0] / ev:.1f}  label computations/eval {out[1] / ev:.1f}  searches/eval {out[2] / ev:.1f}  ms {solver.last_kernel_ms():.3f}")
         if out[4]:
