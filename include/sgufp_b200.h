@@ -100,6 +100,40 @@ int sgufp_finalize_paths(sgufp_ctx *ctx, const int16_t *paths, int K, int L, con
                          const int64_t *first_inf_host, int *cut_type, double *rhs, uint64_t *keys,
                          double *vals, int *nnz, double *coef_dense);
 
+/* ---- scenario partition across GPUs, exchange inside the library -------------------
+ * What is sharded is the scenario loop of GuroSolver::solveSubProblem (`for scenario`, grb.cpp:174); the
+ * coupling is the sum of grb.cpp:241-278 and the lowest-index-infeasible rule of grb.cpp:284-351.
+ * On a handle that belongs to a partition sgufp_solve_path(s) runs: K1 on every block -> ONE all-reduce
+ * (SUM, int64, K*W partial sums + K "met an infeasible scenario" flags, in place in the buffer K1 wrote)
+ * -> one device-to-host copy -> cuts.  Only a non-zero flag triggers the cold steps (MIN of the first
+ * infeasible index, the ray on the owning rank, all-reduce of that row).  Integer sums: the cuts are
+ * bit-identical for every number of GPUs.
+ *
+ * (1) One process, N devices (a C++ host with one GuroSolver per thread, grb.h:36 / NodeExplorer.h:115):
+ *     sgufp_create_sharded takes the whole instance as sgufp_create does, cuts the scenarios into N contiguous
+ *     blocks, puts block r on devices[r] and opens the communicator itself (ncclCommInitAll).  The returned
+ *     handle is used exactly like a one-GPU handle (obj/status: [K][S]).  Equal device ids (a one-GPU box) are
+ *     allowed: the blocks are then reduced by a kernel, no NCCL involved.
+ * (2) One process per GPU (torchrun, MPI): every rank creates its block with sgufp_create(..., scenario_offset,
+ *     S_total); rank 0 calls sgufp_comm_unique_id and the HOST hands the 128 bytes to the others (its own
+ *     launcher's channel); every rank calls sgufp_comm_init.  sgufp_solve_path(s) is then a collective call:
+ *     same paths on every rank, same cuts back on every rank (obj/status: this rank's block, [K][S_local]).
+ * NCCL is loaded at run time (dlopen "libnccl.so.2"); a one-GPU user needs none. */
+#define SGUFP_COMM_ID_BYTES 128
+int sgufp_create_sharded(sgufp_ctx **out, int n, int m, int S, const int32_t *tail, const int32_t *head,
+                         const int32_t *upper, const int32_t *lower, const int32_t *reward0, const int32_t *vbar,
+                         int nvbar, const int *devices, int device_count);
+int sgufp_comm_unique_id(void *id128);
+int sgufp_comm_init(sgufp_ctx *ctx, const void *id128, int rank, int world);
+int sgufp_comm_info(const sgufp_ctx *ctx, int *world, int *local_ranks, int *uses_nccl, int *exchanges_last_call);
+/* The device half of a partitioned call alone, asynchronous on the handle's stream (sgufp_stream): K1 on
+ * every local block + the one all-reduce.  *sums_device: [K*W] reduced sums followed by [K] flag counts;
+ * *first_inf_device: this rank's (not reduced) first infeasible indices.  For device-side timing. */
+int sgufp_paths_reduced(sgufp_ctx *ctx, const int16_t *paths, int K, int L, int64_t **sums_device,
+                        int64_t **first_inf_device);
+/* the cudaStream_t every call on this handle is enqueued on */
+void *sgufp_stream(const sgufp_ctx *ctx);
+
 /* `Inavap::Cut::Cut` hash (Cut.h:243-251) of a (key,value) list, so a host wrapper can rebuild the
  * reference object bit for bit. */
 uint64_t sgufp_cut_hash(const uint64_t *keys, const double *vals, int nnz);

@@ -11,6 +11,9 @@
 // against them unchanged apart from the two member types.  See INTEGRATION.md.
 #pragma once
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <limits>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -22,8 +25,19 @@
 
 namespace sgufp {
 
+// Error convention.  The reference has none: its Release build is -fno-exceptions (CMakeLists.txt:27), where a GRBException
+// terminates the process.  With exceptions enabled an SGUFP_ERR_* code becomes a std::runtime_error; without them
+// (-fno-exceptions: __cpp_exceptions is not defined) the message goes to stderr and the process aborts, as the reference's would.
+[[noreturn]] inline void raise(const std::string &msg) {
+#if defined(__cpp_exceptions) && !defined(SGUFP_B200_NO_EXCEPTIONS)
+    throw std::runtime_error(msg);
+#else
+    std::fprintf(stderr, "%s\n", msg.c_str());
+    std::abort();
+#endif
+}
 inline void check(int rc, const sgufp_ctx *ctx) {
-    if (rc < 0) throw std::runtime_error(std::string("sgufp_b200: ") + sgufp_last_error(ctx));
+    if (rc < 0) raise(std::string("sgufp_b200: ") + sgufp_last_error(ctx));
 }
 
 // One handle per host thread, like one GuroSolver per NodeExplorer (NodeExplorer.h:115).
@@ -41,7 +55,7 @@ public:
         // the handle applies shuffleVBarNodes itself; it is idempotent on an already shuffled list
         for (auto v : net->Vbar) vbar.push_back((int32_t)v);
         int rc = sgufp_create(&ctx_, n, m, S, tail.data(), head.data(), up.data(), lo.data(), r0.data(), vbar.data(), (int)vbar.size(), device, 0, S);
-        if (rc < 0) throw std::runtime_error(std::string("sgufp_create: ") + sgufp_last_error(nullptr));
+        if (rc < 0) raise(std::string("sgufp_create: ") + sgufp_last_error(nullptr));
         sgufp_dims(ctx_, &L_, &T_, nullptr);
     }
     ~GuroSolver() { sgufp_destroy(ctx_); }
@@ -64,7 +78,10 @@ public:
     std::vector<std::pair<CutType, Inavap::Cut>> solveSubProblems(const std::vector<std::vector<int16_t>> &paths) {
         const int K = (int)paths.size(), Tn = T_ > 0 ? T_ : 1;
         std::vector<int16_t> flat((size_t)K * L_, -1);
-        for (int k = 0; k < K; k++) std::copy(paths[k].begin(), paths[k].end(), flat.begin() + (size_t)k * L_);
+        for (int k = 0; k < K; k++) {
+            if ((int)paths[k].size() > L_) raise("sgufp_b200: path " + std::to_string(k) + " has more than totalLayers entries");
+            std::copy(paths[k].begin(), paths[k].end(), flat.begin() + (size_t)k * L_);
+        }
         std::vector<uint64_t> keys((size_t)K * Tn);
         std::vector<double> vals((size_t)K * Tn), rhs(K);
         std::vector<int> type(K), nnz(K);

@@ -29,6 +29,12 @@ SIGNATURES = {
     "sgufp_paths_partial": (C.c_int, [vp, i16p, C.c_int, C.c_int, vp, vp, vp, vp, vp]),
     "sgufp_ray_partial": (C.c_int, [vp, i16p, C.c_int, C.c_int64, vp, vp]),
     "sgufp_finalize_paths": (C.c_int, [vp, i16p, C.c_int, C.c_int, i64p, i64p, cip, dp, u64p, dp, cip, dp]),
+    "sgufp_create_sharded": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int, ip, ip, ip, ip, ip, ip, C.c_int, cip, C.c_int]),
+    "sgufp_comm_unique_id": (C.c_int, [vp]),
+    "sgufp_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),
+    "sgufp_comm_info": (C.c_int, [vp, cip, cip, cip, cip]),
+    "sgufp_paths_reduced": (C.c_int, [vp, i16p, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp)]),
+    "sgufp_stream": (vp, [vp]),
     "sgufp_cut_hash": (C.c_uint64, [u64p, dp, C.c_int]),
     "sgufp_last_stats": (C.c_int, [vp, cip, C.POINTER(C.c_float)]),
     "sgufp_last_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),

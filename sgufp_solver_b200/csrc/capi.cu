@@ -13,6 +13,7 @@
 #include <thread>
 #include <vector>
 
+#include "capi_internal.hpp"
 #include "ctx.hpp"
 #include "k1_cut.cuh"
 
@@ -22,12 +23,11 @@ namespace {
 thread_local std::string g_create_error;
 }  // namespace
 
-// ---- helpers shared by the one-GPU and the sharded entry points --------------------------------
-using Batch = PlanBatch;            // ctx.hpp
+// ---- helpers shared by the one-GPU and the sharded entry points (capi_internal.hpp) -------------
 
 // Host threads that build plans of one batch side by side (a plan is ~15 us of host work at C2, ~65 us at C4:
 // serial construction of 64 plans would cost a third of the kernel).  The threads persist in the handle.
-static int host_threads(int K) {
+int host_threads(int K) {
     int cap = 8;
     if (const char *e = getenv("SGUFP_HOST_THREADS")) cap = std::max(1, atoi(e));
     const int hw = (int)std::thread::hardware_concurrency();
@@ -37,7 +37,7 @@ static int host_threads(int K) {
 
 // reuse: the caller is the second half of one operation on these paths (sgufp_finalize_paths after sgufp_paths_partial)
 // and may take the plans the first half built; every other entry point builds its plans anew, whatever the last call was.
-static int make_batch(sgufp_ctx *c, const int16_t *paths, int K, int L, Batch &B, bool reuse = false) {
+int make_batch(sgufp_ctx *c, const int16_t *paths, int K, int L, Batch &B, bool reuse) {
     if (!paths || K < 1 || L < 0 || L > c->M.L) return fail(c, SGUFP_ERR_ARG, "paths: need K >= 1 and 0 <= L <= totalLayers");
     const bool lane_tables = k1_lane_tables_wanted() && c->max_lower == 0;
     const size_t npath = (size_t)K * L;
@@ -71,7 +71,7 @@ static int make_batch(sgufp_ctx *c, const int16_t *paths, int K, int L, Batch &B
     return 0;
 }
 
-static int launch_batch(sgufp_ctx *c, const Batch &B, int K, unsigned long long *d_sums, long long *d_finf, double *d_obj,
+int launch_batch(sgufp_ctx *c, const Batch &B, int K, unsigned long long *d_sums, long long *d_finf, double *d_obj,
                         uint8_t *d_status, cudaStream_t st) {
     CU(c, c->d_plans.reserve(B.total_words));
     CU(c, c->d_plan_off.reserve(K));
@@ -104,14 +104,18 @@ static int launch_batch(sgufp_ctx *c, const Batch &B, int K, unsigned long long 
     c->kernel_timed = false;
     if (c->S > 0) {
         CU(c, cudaEventRecord(c->evk0, st));
-        CU(c, k1_launch(p, st, c->sm_count, &c->last_launches));
+        {
+            const cudaError_t ek = k1_launch(p, st, c->sm_count, &c->last_launches);
+            if (ek == cudaErrorInvalidConfiguration) { cudaGetLastError(); return fail(c, SGUFP_ERR_LIMITS, "the per-scenario state of this network does not fit one SM's shared memory (227 KB) even with one warp per CTA"); }
+            CU(c, ek);
+        }
         CU(c, cudaEventRecord(c->evk1, st));
         c->kernel_timed = true;
     }
     return 0;
 }
 
-static int run_ray(sgufp_ctx *c, const Plan &P, long long global_s, unsigned long long *d_sums, cudaStream_t st) {
+int run_ray(sgufp_ctx *c, const Plan &P, long long global_s, unsigned long long *d_sums, cudaStream_t st) {
     const long long sl = global_s - c->scen_off;
     if (sl < 0 || sl >= c->S) return fail(c, SGUFP_ERR_ARG, "ray: scenario is not in this rank's block");
     std::vector<int32_t> ts, hs, info, pl, nx, aq, fw;
@@ -139,7 +143,7 @@ static int run_ray(sgufp_ctx *c, const Plan &P, long long global_s, unsigned lon
 }
 
 // exact integer sums -> Inavap::Cut (cutToCut, Cut.h:406-421)
-static void finalize_one(const sgufp_ctx *c, const Plan &P, const long long *sums, bool feas, int *cut_type, double *rhs,
+void finalize_one(const sgufp_ctx *c, const Plan &P, const long long *sums, bool feas, int *cut_type, double *rhs,
                          uint64_t *keys, double *vals, int *nnz, double *coef_dense) {
     const Model &M = c->M;
     const int L = M.L, T = M.T;
@@ -244,6 +248,7 @@ int sgufp_create(sgufp_ctx **out, int n, int m, int S, const int32_t *tail, cons
 
 void sgufp_destroy(sgufp_ctx *c) {
     if (!c) return;
+    partition_destroy(c);          // communicators and the peer handles of a single-process partition (capi_shard.cu)
     if (c->dd_scratch && c->dd_scratch_free) c->dd_scratch_free(c->dd_scratch);
     delete c->pool;
     if (c->h_words) cudaFreeHost(c->h_words);
@@ -316,6 +321,8 @@ int sgufp_ray_partial(sgufp_ctx *c, const int16_t *path, int L, int64_t global_s
 int sgufp_finalize_paths(sgufp_ctx *c, const int16_t *paths, int K, int L, const int64_t *sums_host, const int64_t *first_inf_host,
                          int *cut_type, double *rhs, uint64_t *keys, double *vals, int *nnz, double *coef_dense) {
     if (!c || !sums_host || !first_inf_host) return SGUFP_ERR_ARG;
+    for (int k = 0; k < K; k++)
+        if (first_inf_host[k] < 0) return fail(c, SGUFP_ERR_LIMITS, "path " + std::to_string(k) + ": the iteration guard of the subproblem solver was hit on some rank (k1_cut.cu: fuel)");
     Batch &B = c->batch;             // after sgufp_paths_partial with the same paths: no plan is built again
     if (int rc = make_batch(c, paths, K, L, B, true)) return rc;
     const int T = c->M.T, W = c->W();
@@ -333,8 +340,10 @@ int sgufp_finalize_paths(sgufp_ctx *c, const int16_t *paths, int K, int L, const
 int sgufp_solve_paths(sgufp_ctx *c, const int16_t *paths, int K, int L, int *cut_type, double *rhs, uint64_t *keys, double *vals,
                       int *nnz, double *coef_dense, double *obj, uint8_t *status, int64_t *first_infeasible) {
     if (!c) return SGUFP_ERR_ARG;
+    if (c->part)     // a scenario partition (sgufp_create_sharded / sgufp_comm_init): partial sums, ONE exchange, cuts (capi_shard.cu)
+        return solve_paths_partitioned(c, paths, K, L, cut_type, rhs, keys, vals, nnz, coef_dense, obj, status, first_infeasible);
     if (c->scen_off != 0 || c->S != c->S_total)
-        return fail(c, SGUFP_ERR_ARG, "handle holds a scenario shard: use sgufp_paths_partial + all-reduce + sgufp_finalize_paths");
+        return fail(c, SGUFP_ERR_ARG, "handle holds a scenario shard without a communicator: call sgufp_comm_init first, or use sgufp_paths_partial + your own all-reduce + sgufp_finalize_paths");
     if (c->device == SGUFP_DEVICE_NONE) return fail(c, SGUFP_ERR_CUDA, "handle was created with SGUFP_DEVICE_NONE: it holds the model only, there is no CPU compute path");
     CU(c, cudaSetDevice(c->device));
     c->last_launches = 0;
@@ -361,6 +370,8 @@ int sgufp_solve_paths(sgufp_ctx *c, const int16_t *paths, int K, int L, int *cut
     if (obj) CU(c, cudaMemcpyAsync(obj, c->d_obj.p, KS * sizeof(double), cudaMemcpyDeviceToHost, c->st));
     if (status) CU(c, cudaMemcpyAsync(status, c->d_status.p, KS, cudaMemcpyDeviceToHost, c->st));
     CU(c, cudaStreamSynchronize(c->st));
+    for (int k = 0; k < K; k++)
+        if (finf[k] < 0) return fail(c, SGUFP_ERR_LIMITS, "path " + std::to_string(k) + ": the iteration guard of the subproblem solver was hit (k1_cut.cu: fuel)");
     for (int k = 0; k < K; k++) {
         if (finf[k] == LLONG_MAX) continue;
         // the lowest-index infeasible scenario alone defines the cut (grb.cpp:284-351)

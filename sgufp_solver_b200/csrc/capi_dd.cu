@@ -525,11 +525,11 @@ int run_k2(sgufp_ctx *c, sgufp_dd **dds, int B, const std::vector<std::vector<do
     return 0;
 }
 
-int write_nodes(const std::vector<NodeSpec> &v, int32_t *words, int capacity) {
+int write_nodes(sgufp_ctx *c, const std::vector<NodeSpec> &v, int32_t *words, int capacity) {
     int k = 0;
     for (const NodeSpec &n : v) {
         const int need = 3 + (int)n.states.size() + (int)n.solution.size();
-        if (k + need > capacity) return SGUFP_ERR_ARG;
+        if (k + need > capacity) return fail(c, SGUFP_ERR_ARG, "cut-set buffer too small: " + std::to_string(v.size()) + " nodes do not fit " + std::to_string(capacity) + " words");
         words[k++] = n.global_layer;
         words[k++] = (int32_t)n.states.size();
         for (int16_t s : n.states) words[k++] = s;
@@ -688,6 +688,7 @@ int sgufp_dd_apply_sequence(sgufp_dd *d, int mode, const double *rhs, const uint
     const bool probing = mode == 0 && !d->exact_flag && !d->dd->restricted();   // only there does an optimality cut prune arcs
     CU(c, S.coef.reserve(cf.size())); CU(c, S.rhs.reserve(C)); CU(c, S.states.reserve((size_t)chunk * nn)); CU(c, S.last.reserve((size_t)chunk * std::max(1, nlast)));
     CU(c, res.reserve(C)); CU(c, ctl.reserve(2)); CU(c, probe.reserve(chunk)); CU(c, wb.reserve(chunk));
+    CU(c, d->d_coef.reserve(Tpad));   // a host-built diagram (SGUFP_DD_BUILD=host, the fallbacks) has none before its first single-cut apply
     K2DD self = d->dev; self.state_off = 0; self.last_off = 0;
     cudaError_t e = cudaMemcpyAsync(S.coef.p, cf.data(), cf.size() * 8, cudaMemcpyHostToDevice, c->st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(S.rhs.p, rhs, (size_t)C * 8, cudaMemcpyHostToDevice, c->st);
@@ -784,16 +785,16 @@ int sgufp_dd_cutset(sgufp_dd *d, double ub, int32_t *words, int capacity) {
         if (!d->has_cutset) return 0;
         if (d->compile_cutset.empty() && d->device_built && !d->host_built) { if (int rc = device_cutset(d)) return rc; }
         else ensure_host(d);
-        return write_nodes(d->compile_cutset, words, capacity);
+        return write_nodes(d->ctx, d->compile_cutset, words, capacity);
     }
     {
         std::vector<NodeSpec> cs;
         const int got = device_relaxed_cutset(d, cs);
         if (got < 0) return got;
-        if (got) return write_nodes(cs, words, capacity);
+        if (got) return write_nodes(d->ctx, cs, words, capacity);
     }
     if (int rc = sync_host(d)) return rc;
-    return write_nodes(d->dd->cutset(ub), words, capacity);
+    return write_nodes(d->ctx, d->dd->cutset(ub), words, capacity);
 }
 
 int sgufp_dd_last_stats(const sgufp_dd *d, float *kernel_ms, int64_t *arcs_touched, int *kernel_launches) {

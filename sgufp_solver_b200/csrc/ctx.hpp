@@ -36,8 +36,11 @@ struct PlanBatch {
     bool key_lane = false;
 };
 
+struct Partition;                     // capi_shard.cu: the communicator(s) and peer handles of a scenario partition
+
 struct sgufp_ctx {
     sgufp::Model M;
+    Partition *part = nullptr;
     int S = 0, m_pad = 0, device = 0, sm_count = 0, max_cap = 0, max_lower = 0, sum_abs_r = 0;
     long long scen_off = 0, S_total = 0;
     double *d_u = nullptr, *d_l = nullptr;

@@ -829,11 +829,15 @@ static cudaError_t launch_warp_dispatch(int nw, const K1Launch &p, cudaStream_t 
 static cudaError_t launch_warp(const K1Launch &p, cudaStream_t st, int sm_count) {
     // the choice depends on the shared memory per warp alone: remember it (a one-candidate call is ~0.1 ms of kernel,
     // eight occupancy queries per call would show)
-    static thread_local int cached_words = -1, cached_nw = 0, cached_dev = -1;
-    const int words = k1_words_per_tile(p);
+    static thread_local int cached_words = -1, cached_nw = 0, cached_dev = -1, cached_big = -1;
+    const int words = k1_words_per_tile(p), big = p.nc > SMALL_NC;   // the size class picks the kernel instantiation: part of the key
     int rw = 0, dev = 0;
     cudaGetDevice(&dev);
-    if (cached_words == words && cached_dev == dev && cached_nw) return launch_warp_dispatch(cached_nw, p, st, sm_count, &rw, false);
+    if (cached_words == words && cached_dev == dev && cached_big == big && cached_nw) {
+        const cudaError_t e = launch_warp_dispatch(cached_nw, p, st, sm_count, &rw, false);
+        if (e != cudaErrorInvalidConfiguration) return e;
+        cudaGetLastError(); cached_nw = 0;      // probe again below
+    }
     int best_nw = 0, best = 0;
     for (int nw = WARPS; nw >= 1; nw >>= 1) {
         const cudaError_t e = launch_warp_dispatch(nw, p, st, sm_count, &rw, true);
@@ -842,7 +846,7 @@ static cudaError_t launch_warp(const K1Launch &p, cudaStream_t st, int sm_count)
         if (rw > best) { best = rw; best_nw = nw; }
     }
     if (!best_nw) return cudaErrorInvalidConfiguration;
-    cached_words = words; cached_nw = best_nw; cached_dev = dev;
+    cached_words = words; cached_nw = best_nw; cached_dev = dev; cached_big = big;
     return launch_warp_dispatch(best_nw, p, st, sm_count, &rw, false);
 }
 

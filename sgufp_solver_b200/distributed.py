@@ -47,7 +47,11 @@ def owner_of(scenario: int, S_total: int, world: int) -> int:
 class ShardedGuroSolver:
     """`GuroSolver` over a scenario partition: same `solveSubProblem(path)` contract on every rank."""
 
-    def __init__(self, inst_full_or_shard, S_total: int, rank: int, world: int, device: int = 0, is_shard: bool = False, group=None):
+    def __init__(self, inst_full_or_shard, S_total: int, rank: int, world: int, device: int = 0, is_shard: bool = False, group=None,
+                 library_exchange: Optional[bool] = None):
+        """`library_exchange`: the all-reduce runs inside libsgufp_b200.so (`sgufp_comm_init`, NCCL loaded by the library) and
+        `solve_paths` is one C call; default: whenever the process group runs on NCCL.  Otherwise the exchange is
+        `torch.distributed` on the partial sums (what the CPU tests drive over gloo)."""
         import torch
         self.torch = torch
         self.rank, self.world, self.group = rank, world, group
@@ -63,6 +67,18 @@ class ShardedGuroSolver:
         self.stream = torch.cuda.Stream(self.device)
         self._sums = None
         self._finf = None
+        import torch.distributed as dist
+        if library_exchange is None:
+            library_exchange = world > 1 and dist.is_initialized() and dist.get_backend(group) == "nccl"
+        self.library_exchange = bool(library_exchange)
+        if self.library_exchange:
+            # the 128-byte NCCL id travels over the launcher's own channel (here: the torch process group)
+            idt = torch.zeros(128, dtype=torch.uint8, device=self.device)
+            if rank == 0:
+                idt.copy_(torch.frombuffer(bytearray(GuroSolver.comm_unique_id()), dtype=torch.uint8))
+            if world > 1:
+                dist.broadcast(idt, src=0, group=group)
+            self.solver.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
 
     def partial(self, paths):
         """Step 1: local scenarios -> device partial sums (no host round trip)."""
@@ -82,10 +98,14 @@ class ShardedGuroSolver:
         import torch.distributed as dist
         p = np.ascontiguousarray(paths, dtype=np.int16)
         K, plen = p.shape
+        if self.library_exchange:      # one C call: K1 -> ncclAllReduce -> cuts (capi_shard.cu); obj/status cover this rank's block
+            return self.solver.solve_paths(p, want_obj=False, want_status=False)
         with torch.cuda.stream(self.stream):
             sums, finf = self.partial(p)
             reduce_partials(sums, finf, self.group)
             finf_h = finf.cpu().numpy()
+            if (finf_h < 0).any():   # a rank's subproblem solver hit its iteration guard (k1_cut.cu: fuel): no cut can be built
+                raise _lib.SgufpError(-5, "the iteration guard of the subproblem solver was hit on some rank")
             # feasibility: the rank owning the lowest infeasible scenario builds the ray, everyone gets it
             for k in np.nonzero(finf_h != I64_MAX)[0]:
                 own = owner_of(int(finf_h[k]), self.S_total, self.world)

@@ -46,13 +46,18 @@ class Instance:
             f.write(" ".join(str(int(v)) for v in self.vbar) + "\n")
 
     def scenario_slice(self, lo: int, hi: int) -> "Instance":
-        """Contiguous scenario block [lo, hi) — the multi-GPU shard of SURVEY.md §8e."""
+        """Contiguous scenario block [lo, hi) — the multi-GPU shard of SURVEY.md §8e.  The rows of the dual LP use
+        `rewards[0]` of the FULL instance for every scenario (grb.cpp:53,71,89), so a shard keeps the full instance's
+        scenario-0 rewards in its own column 0 (an empty shard keeps one reward column and no capacities)."""
+        rew = np.ascontiguousarray(self.reward[:, lo:hi]) if hi > lo else np.ascontiguousarray(self.reward[:, :1])
+        rew = rew.copy()
+        rew[:, 0] = self.reward[:, 0]
         return dataclasses.replace(
             self,
             S=hi - lo,
             lower=np.ascontiguousarray(self.lower[:, lo:hi]),
             upper=np.ascontiguousarray(self.upper[:, lo:hi]),
-            reward=np.ascontiguousarray(self.reward[:, lo:hi]),
+            reward=rew,
         )
 
 

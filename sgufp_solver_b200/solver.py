@@ -73,7 +73,9 @@ class GuroSolver:
     Construct from an instance in the reference's data model (`Network`, Network.h:69-117);
     `solveSubProblem(path)` is grb.h:75.  `solve_paths` evaluates K candidates in one launch."""
 
-    def __init__(self, inst, device: int = 0, scenario_offset: int = 0, S_total=None):
+    def __init__(self, inst, device: int = 0, scenario_offset: int = 0, S_total=None, devices=None):
+        """`devices`: a list of CUDA device ids — ONE process drives them all: the scenarios are cut into len(devices)
+        contiguous blocks and the exchange runs inside the library (`sgufp_create_sharded`); otherwise one device."""
         L = _lib.lib()
         self.inst = inst
         self.n, self.m, self.S = int(inst.n), int(inst.m), int(inst.S)
@@ -86,9 +88,16 @@ class GuroSolver:
         r0 = np.ascontiguousarray(inst.reward[:, 0], dtype=np.int32)
         vb = np.ascontiguousarray(inst.vbar, dtype=np.int32)
         h = C.c_void_p()
-        rc = L.sgufp_create(C.byref(h), self.n, self.m, self.S, self.tail.ctypes.data_as(ip), self.head.ctypes.data_as(ip),
-                            u.ctypes.data_as(ip), lo.ctypes.data_as(ip), r0.ctypes.data_as(ip), vb.ctypes.data_as(ip), len(vb),
-                            int(device), self.scenario_offset, self.S_total)
+        if devices is not None:
+            assert scenario_offset == 0 and self.S_total == self.S, "a single-process partition takes the whole instance"
+            devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+            rc = L.sgufp_create_sharded(C.byref(h), self.n, self.m, self.S, self.tail.ctypes.data_as(ip), self.head.ctypes.data_as(ip),
+                                        u.ctypes.data_as(ip), lo.ctypes.data_as(ip), r0.ctypes.data_as(ip), vb.ctypes.data_as(ip), len(vb),
+                                        devs, len(devices))
+        else:
+            rc = L.sgufp_create(C.byref(h), self.n, self.m, self.S, self.tail.ctypes.data_as(ip), self.head.ctypes.data_as(ip),
+                                u.ctypes.data_as(ip), lo.ctypes.data_as(ip), r0.ctypes.data_as(ip), vb.ctypes.data_as(ip), len(vb),
+                                int(device), self.scenario_offset, self.S_total)
         if rc:
             raise SgufpError(rc, L.sgufp_last_error(None).decode())
         self.h = h
@@ -139,14 +148,45 @@ class GuroSolver:
         ct = np.zeros(K, np.int32); rhs = np.zeros(K); nnz = np.zeros(K, np.int32); fi = np.zeros(K, np.int64)
         keys = np.zeros((K, T1), np.uint64); vals = np.zeros((K, T1))
         dense = np.zeros((K, T1)) if want_dense else None
-        obj = np.zeros((K, self.S)) if want_obj else None
-        st = np.zeros((K, self.S), np.uint8) if want_status else None
+        obj = np.zeros((K, max(1, self.S))) if want_obj else None
+        st = np.zeros((K, max(1, self.S)), np.uint8) if want_status else None
         rc = L.sgufp_solve_paths(self.h, p.ctypes.data_as(i16p), K, plen, ct.ctypes.data_as(cip), rhs.ctypes.data_as(dp),
                                  keys.ctypes.data_as(u64p), vals.ctypes.data_as(dp), nnz.ctypes.data_as(cip),
                                  dense.ctypes.data_as(dp) if want_dense else None, obj.ctypes.data_as(dp) if want_obj else None,
                                  st.ctypes.data_as(u8p) if want_status else None, fi.ctypes.data_as(i64p))
         self._check(rc)
         return BatchResult(ct, rhs, keys, vals, nnz, dense, obj, st, fi)
+
+    # -- scenario partition with the exchange inside the library (include/sgufp_b200.h) -----------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """Rank 0: the 128 bytes every rank hands to `comm_init` (the host's launcher carries them)."""
+        buf = C.create_string_buffer(128)
+        rc = _lib.lib().sgufp_comm_unique_id(buf)
+        if rc:
+            raise SgufpError(rc, "sgufp_comm_unique_id: NCCL is not available")
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int) -> None:
+        """Joins this block (created with scenario_offset / S_total) to the partition: `solve_paths` becomes a collective call."""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(_lib.lib().sgufp_comm_init(self.h, buf, int(rank), int(world)))
+
+    def comm_info(self):
+        w, l, u, e = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _lib.lib().sgufp_comm_info(self.h, C.byref(w), C.byref(l), C.byref(u), C.byref(e))
+        return {"world": w.value, "local_ranks": l.value, "nccl": bool(u.value), "exchanges_last_call": e.value}
+
+    def paths_reduced(self, paths):
+        """Device half of a partitioned call (asynchronous on `stream_ptr()`): returns the device addresses of the reduced
+        sums [K*W + K flags] and of this rank's first-infeasible marks."""
+        p = np.ascontiguousarray(paths, dtype=np.int16)
+        a, b = C.c_void_p(), C.c_void_p()
+        self._check(_lib.lib().sgufp_paths_reduced(self.h, p.ctypes.data_as(i16p), p.shape[0], p.shape[1], C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def stream_ptr(self) -> int:
+        return int(_lib.lib().sgufp_stream(self.h))
 
     def last_stats(self):
         a, b = C.c_int(), C.c_float()
