@@ -327,6 +327,77 @@ def bench_longest_path(device: int = 0, B: int = 64, Cn: int = 64, width: int = 
             "achieved_GBps": bytes_alg / (ms / 1e3) / 1e9, "gpu_launches": launches}
 
 
+def frontier_nodes(solver, want: int) -> List[Node]:
+    """Distinct open nodes of one branch-and-bound frontier: the cut-set of the root's relaxed diagram, widened breadth-first
+    through the children's own cut-sets until `want` nodes are there (DDSolver.cpp:788-791 forms the initial frontier so)."""
+    dd = RelaxedDDNew(solver)
+    dd.buildTree()
+    frontier = dd.getCutset(DOUBLE_MAX) if not dd.isTreeExact() else []
+    guard = 0
+    while frontier and len(frontier) < want and guard < 64:
+        node = frontier.pop(0)
+        dd.buildTree(node)
+        kids = dd.getCutset(DOUBLE_MAX) if not dd.isTreeExact() else []
+        frontier.extend(kids if kids else [])
+        if not kids:
+            frontier.append(node)      # an exact sub-tree stays a frontier node itself
+        guard += 1
+    dd.close()
+    return frontier[:want] if frontier else [Node()]
+
+
+def bench_frontier(device: int = 0, widths=(64, 1024, 4096), B: int = 64, Cn: int = 64, reps: int = 5):
+    """DD arcs/s of K2 on config C3 (C2 network): B DISTINCT diagrams — the restricted / relaxed sub-trees of B nodes of one
+    branch-and-bound frontier — x Cn cuts per launch pair, L2 flushed before every timed launch.
+    The scope table's byte model (16 B per arc + 8 B per node through HBM) does not describe this kernel: the
+    node states never leave shared memory and a diagram's CSR is read once for its Cn cuts, so `model_GBps` is reported as
+    what it is — a model — next to the DRAM bytes ncu measured (profiles/k2_traffic.json), and what bounds the kernel is
+    stated there (issue slots and one barrier per layer), not an HBM fraction."""
+    import json as _json
+    import os as _os
+    import torch
+    from . import instances as I
+    from .solver import GuroSolver
+    inst = I.config2(S=1)
+    solver = GuroSolver(inst, device=device)
+    rng = np.random.default_rng(5)
+    nodes = frontier_nodes(solver, B)
+    cuts = [random_cut(solver, rng) for _ in range(Cn)]
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=f"cuda:{device}")
+    tf = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "profiles", "k2_traffic.json")
+    traffic = _json.load(open(tf)) if _os.path.exists(tf) else {}
+    points = []
+    for kind, w in [("restricted", int(x)) for x in widths] + [("relaxed", 120)]:
+        dds = []
+        for i in range(B):
+            d = RestrictedDDNew(solver, w) if kind == "restricted" else RelaxedDDNew(solver)
+            d.compile(nodes[i % len(nodes)]) if kind == "restricted" else d.buildTree(nodes[i % len(nodes)])
+            dds.append(d)
+        apply_optimality_batch(dds, cuts)
+        times, arcs, launches = [], 0, 0
+        for _ in range(reps):
+            flush.zero_(); torch.cuda.synchronize()
+            apply_optimality_batch(dds, cuts)
+            ms, arcs, launches = dds[0].last_stats()
+            times.append(ms)
+        ms = float(np.median(times))
+        cnt = [d.counts() for d in dds]
+        nn, na = sum(c[0] for c in cnt), sum(c[1] for c in cnt)
+        model = Cn * (na * 16 + nn * 8) + Cn * solver.T * 8
+        points.append({"kind": kind, "width": w, "value": arcs / (ms / 1e3), "unit": "arcs/s", "kernel_ms": ms, "arcs_per_launch": int(arcs),
+                       "diagrams": B, "distinct_roots": min(B, len(nodes)), "cuts": Cn, "nodes_all_diagrams": int(nn), "arcs_all_diagrams": int(na),
+                       "model_GBps": model / (ms / 1e3) / 1e9, "gpu_launches": launches,
+                       "ncu": traffic.get(f"{kind}_{w}")})
+        for d in dds:
+            d.close()
+    head = next(p for p in points if p["kind"] == "restricted" and p["width"] == 1024) if any(p["width"] == 1024 for p in points) else points[0]
+    del flush
+    return {"metric": "dd_arcs_per_sec", "value": head["value"], "unit": "arcs/s", "kernel_ms": head["kernel_ms"], "arcs_per_launch": head["arcs_per_launch"],
+            "config": f"C3: C2 network, {B} distinct diagrams of one B&B frontier x {Cn} cuts per launch pair, RestrictedDDNew widths {list(widths)} + RelaxedDDNew (threshold 120); headline = width 1024",
+            "l2": "flushed (512 MiB write) before every timed launch", "points": points,
+            "bound": traffic.get("bound", "node states stay in shared memory, the CSR of a diagram is read once for its cuts: not an HBM-bound kernel; see profiles/r02_k2_bound.md")}
+
+
 def smoke():
     from . import instances as I
     from .solver import GuroSolver

@@ -25,6 +25,29 @@ def test_reference_arm_prints_one_contract_line():
     assert d["value"] > 0 and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["kind"] in ("port", "reference")
     assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    # the headline workload and the config keys the GPU arm prints (the driver compares the two config objects)
+    assert d["scaling"] == "strong" and d["config"]["scenarios_total"] == 100000 and d["config"]["candidates_per_step"] == 8
+    for k in ("n", "m", "L", "T", "scenarios_per_gpu", "candidate_paths", "l2", "timing"):
+        assert k in d["config"], k
+
+
+def test_strong_scaling_data_do_not_depend_on_the_number_of_gpus():
+    """The C4 / C5 instance is drawn in 8 blocks: the shards of a 2- or 4-GPU run are slices of the 1-GPU instance."""
+    import numpy as np
+    import bench
+    from sgufp_solver_b200.distributed import shard_bounds
+    S = bench.totals("c4", 1)
+    full = bench.scenario_range("c4", 0, S)
+    assert full.S == S and full.upper.shape == (full.m, S)
+    for world in (2, 4):
+        for rank in (0, world - 1):
+            lo, hi = shard_bounds(S, world, rank)
+            part = bench.scenario_range("c4", lo, hi)
+            assert (part.upper == full.upper[:, lo:hi]).all() and (part.lower == full.lower[:, lo:hi]).all()
+            assert (part.tail == full.tail).all() and (part.reward[:, 0] == full.reward[:, 0]).all()
+    odd = bench.scenario_range("c4", 1000, 2777)          # a range that starts and ends inside blocks
+    assert (odd.upper == full.upper[:, 1000:2777]).all()
+    assert bench.totals("c2", 4) == 4000 and bench.totals("c5", 8) == 100000
 
 
 def test_roofline_helpers_read_the_committed_counts():

@@ -75,3 +75,18 @@ def test_device_sequences_replay_the_loop_call_by_call():
     a = solve(sg.GuroSolver(inst), device_sequences=False)
     b = solve(sg.GuroSolver(inst), device_sequences=True)
     assert a == b
+
+
+def test_committed_bench_candidates_are_the_dd_emission():
+    """bench.py evaluates the candidate paths of sgufp_solver_b200/data/bench_candidates.npz: they must be what the DD master
+    emits today (candidates.dd_emitted_paths on a 32-scenario copy of the network), path for path."""
+    import os
+    import bench
+    from sgufp_solver_b200 import instances as I
+    from sgufp_solver_b200.candidates import dd_emitted_paths
+    if not os.path.exists(bench.CANDIDATES_FILE):
+        pytest.skip("no committed emission: bench.py runs the master itself")
+    z = np.load(bench.CANDIDATES_FILE)
+    for net in z.files:
+        fresh, info = dd_emitted_paths(getattr(I, net)(S=32), z[net].shape[0], budget_s=120.0)
+        assert fresh.shape == z[net].shape and (fresh == z[net]).all(), (net, info)
