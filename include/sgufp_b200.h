@@ -57,6 +57,9 @@ const char *sgufp_last_error(const sgufp_ctx *ctx); /* ctx may be NULL: error of
 int sgufp_dims(const sgufp_ctx *ctx, int *L, int *T, int *nvbar);
 int sgufp_vbar_order(const sgufp_ctx *ctx, int32_t *vbar /*[nvbar]*/);
 int sgufp_processing_order(const sgufp_ctx *ctx, int32_t *layer_arc /*[L]*/); /* processingOrder[l].second */
+/* sizes and arcs of the network behind a handle (Network.h:69-117): what a handle made from a cache file knows */
+int sgufp_network(const sgufp_ctx *ctx, int *n, int *m, int *S_local, int64_t *scenario_offset, int64_t *S_total,
+                  int32_t *tail /*[m] or NULL*/, int32_t *head /*[m] or NULL*/);
 /* slot s in processingOrder-major / outgoingArcs-minor order -> node ids (i,q,j) and its
  * rank in the (i,q,j)-lexicographic order of std::map (Cut.h:75) */
 int sgufp_slots(const sgufp_ctx *ctx, int32_t *si, int32_t *sq, int32_t *sj, int32_t *lex_rank /*[T] each*/);
@@ -133,6 +136,24 @@ int sgufp_paths_reduced(sgufp_ctx *ctx, const int16_t *paths, int K, int L, int6
                         int64_t **first_inf_device);
 /* the cudaStream_t every call on this handle is enqueued on */
 void *sgufp_stream(const sgufp_ctx *ctx);
+
+/* ---- on-disk cache either side of the path and handles that share the capacities --------
+ * The reference parses `n m S`, then per arc `tail head (lb ub reward) x S` from text (Network::Network,
+ * Network.cpp:18-51): O(m*S) tokens.  The cache file holds the scenario-major fp64 arrays exactly as they lie in
+ * HBM (header + raw arrays, mmap-able); sgufp_create_from_cache streams the rows of one scenario block
+ * [scenario_offset, scenario_offset + S_local) (S_local < 0: to the end) to the device through pinned staging
+ * chunks.  The handle behaves like one made by sgufp_create(..., scenario_offset, S_total = S of the file).
+ * Errors of these three calls: sgufp_cache_last_error(). */
+int sgufp_cache_write(const char *path, int n, int m, int S, const int32_t *tail, const int32_t *head,
+                      const int32_t *upper /*[m][S]*/, const int32_t *lower, const int32_t *reward0,
+                      const int32_t *vbar, int nvbar);
+int sgufp_cache_dims(const char *path, int *n, int *m, int *S, int *nvbar, int64_t *file_bytes);
+int sgufp_create_from_cache(sgufp_ctx **out, const char *path, int device, int64_t scenario_offset, int64_t S_local);
+const char *sgufp_cache_last_error(void);
+/* Another handle on the SAME device-resident capacities (read-only, reference-counted): own stream, own plan and
+ * result buffers.  The reference runs N_WORKERS + 1 host threads, each with its own GuroSolver
+ * (NodeExplorer.h:115-116, DDSolver.cpp:583,675, main.cpp:20): one upload, one clone per thread. */
+int sgufp_clone(const sgufp_ctx *src, sgufp_ctx **out);
 
 /* `Inavap::Cut::Cut` hash (Cut.h:243-251) of a (key,value) list, so a host wrapper can rebuild the
  * reference object bit for bit. */

@@ -20,6 +20,7 @@ SIGNATURES = {
     "sgufp_destroy": (None, [vp]),
     "sgufp_last_error": (C.c_char_p, [vp]),
     "sgufp_dims": (C.c_int, [vp, cip, cip, cip]),
+    "sgufp_network": (C.c_int, [vp, cip, cip, cip, i64p, i64p, ip, ip]),
     "sgufp_vbar_order": (C.c_int, [vp, ip]),
     "sgufp_processing_order": (C.c_int, [vp, ip]),
     "sgufp_slots": (C.c_int, [vp, ip, ip, ip, ip]),
@@ -35,6 +36,11 @@ SIGNATURES = {
     "sgufp_comm_info": (C.c_int, [vp, cip, cip, cip, cip]),
     "sgufp_paths_reduced": (C.c_int, [vp, i16p, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp)]),
     "sgufp_stream": (vp, [vp]),
+    "sgufp_cache_write": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, ip, ip, ip, ip, ip, ip, C.c_int]),
+    "sgufp_cache_dims": (C.c_int, [C.c_char_p, cip, cip, cip, cip, i64p]),
+    "sgufp_create_from_cache": (C.c_int, [C.POINTER(vp), C.c_char_p, C.c_int, C.c_int64, C.c_int64]),
+    "sgufp_cache_last_error": (C.c_char_p, []),
+    "sgufp_clone": (C.c_int, [vp, C.POINTER(vp)]),
     "sgufp_cut_hash": (C.c_uint64, [u64p, dp, C.c_int]),
     "sgufp_last_stats": (C.c_int, [vp, cip, C.POINTER(C.c_float)]),
     "sgufp_last_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),

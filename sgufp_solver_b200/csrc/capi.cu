@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -188,6 +189,35 @@ void finalize_one(const sgufp_ctx *c, const Plan &P, const long long *sums, bool
     if (nnz) *nnz = k;
 }
 
+std::mutex &cap_store_mutex() { static std::mutex m; return m; }
+
+// stream, events, device properties of a handle (shared by sgufp_create, sgufp_create_from_cache and sgufp_clone)
+int init_device(sgufp_ctx *c, int device, std::string &err) {
+#define CUI(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e__); return SGUFP_ERR_CUDA; } } while (0)
+    CUI(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUI(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) { err = std::string("device ") + prop.name + " is not sm_100-class; the kernels are built for sm_100a only"; return SGUFP_ERR_CUDA; }
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    CUI(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    CUI(cudaEventCreate(&c->ev0));
+    CUI(cudaEventCreate(&c->ev1));
+    CUI(cudaEventCreate(&c->evk0));
+    CUI(cudaEventCreate(&c->evk1));
+    CUI(cudaEventCreateWithFlags(&c->ev_h2d, cudaEventDisableTiming));
+#undef CUI
+    return 0;
+}
+
+// rows are padded to an even number of arcs: the pad column of both arrays is zero
+cudaError_t zero_pad_column(sgufp_ctx *c) {
+    if (c->m_pad <= c->M.m || c->S == 0) return cudaSuccess;
+    cudaError_t e = cudaMemset2DAsync(c->d_u + c->M.m, (size_t)c->m_pad * 8, 0, 8, (size_t)c->S, c->st);
+    if (e == cudaSuccess) e = cudaMemset2DAsync(c->d_l + c->M.m, (size_t)c->m_pad * 8, 0, 8, (size_t)c->S, c->st);
+    return e;
+}
+
 extern "C" {
 
 const char *sgufp_last_error(const sgufp_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -215,28 +245,31 @@ int sgufp_create(sgufp_ctx **out, int n, int m, int S, const int32_t *tail, cons
     c->m_pad = (m + 1) & ~1;   // rows 16-byte aligned for 128-bit loads
 #define CUC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return bail(SGUFP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } while (0)
     if (device == SGUFP_DEVICE_NONE) { *out = c; return SGUFP_OK; }   // model only: no compute entry point will run
-    CUC(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CUC(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) return bail(SGUFP_ERR_CUDA, std::string("device ") + prop.name + " is not sm_100-class; the kernels are built for sm_100a only");
-    c->sm_count = prop.multiProcessorCount;
-    CUC(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
-    CUC(cudaEventCreate(&c->ev0));
-    CUC(cudaEventCreate(&c->ev1));
-    CUC(cudaEventCreate(&c->evk0));
-    CUC(cudaEventCreate(&c->evk1));
-    CUC(cudaEventCreateWithFlags(&c->ev_h2d, cudaEventDisableTiming));
+    { std::string de; if (int rc = init_device(c, device, de)) return bail(rc, de); }
     if (S > 0) {
         const size_t cells = (size_t)S * c->m_pad;
-        CUC(cudaMalloc(&c->d_u, cells * sizeof(double)));
-        CUC(cudaMalloc(&c->d_l, cells * sizeof(double)));
+        c->caps = new CapStore();
+        c->caps->device = device;
+        CUC(cudaMalloc(&c->caps->d_u, cells * sizeof(double)));
+        CUC(cudaMalloc(&c->caps->d_l, cells * sizeof(double)));
+        c->d_u = c->caps->d_u; c->d_l = c->caps->d_l;
+        // the reference's arc-major int32 vectors go up in slabs of arcs (at most 64 MiB of staging), each re-laid out on the device
+        const int slab = (int)std::max<size_t>(32, std::min<size_t>((size_t)m, ((size_t)64 << 20) / ((size_t)S * 4)) / 32 * 32);
         int32_t *tmp = nullptr;
-        CUC(cudaMalloc(&tmp, (size_t)m * S * 4));
+        CUC(cudaMalloc(&tmp, (size_t)std::min(slab, m) * S * 4));
         int launches = 0;
-        cudaError_t e1 = cudaMemcpyAsync(tmp, upper, (size_t)m * S * 4, cudaMemcpyHostToDevice, c->st);
-        if (e1 == cudaSuccess) e1 = relayout_launch(tmp, c->d_u, m, S, c->m_pad, c->st, &launches);
-        if (e1 == cudaSuccess) e1 = cudaMemcpyAsync(tmp, lower, (size_t)m * S * 4, cudaMemcpyHostToDevice, c->st);
-        if (e1 == cudaSuccess) e1 = relayout_launch(tmp, c->d_l, m, S, c->m_pad, c->st, &launches);
+        cudaError_t e1 = cudaSuccess;
+        for (int pass = 0; pass < 2 && e1 == cudaSuccess; pass++) {
+            const int32_t *src = pass == 0 ? upper : lower;
+            double *dst = pass == 0 ? c->d_u : c->d_l;
+            for (int a0 = 0; a0 < m && e1 == cudaSuccess; a0 += slab) {
+                const int na = std::min(slab, m - a0);
+                e1 = cudaMemcpyAsync(tmp, src + (size_t)a0 * S, (size_t)na * S * 4, cudaMemcpyHostToDevice, c->st);
+                if (e1 == cudaSuccess) e1 = relayout_launch(tmp, dst, na, S, c->m_pad, a0, c->st, &launches);
+                if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(c->st);      // the staging slab is reused
+            }
+        }
+        if (e1 == cudaSuccess && c->m_pad > m) e1 = zero_pad_column(c);
         if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(c->st);
         cudaFree(tmp);
         CUC(e1);
@@ -254,8 +287,12 @@ void sgufp_destroy(sgufp_ctx *c) {
     if (c->h_words) cudaFreeHost(c->h_words);
     if (c->h_out) cudaFreeHost(c->h_out);
     if (c->ev_h2d) cudaEventDestroy(c->ev_h2d);
-    if (c->d_u) cudaFree(c->d_u);
-    if (c->d_l) cudaFree(c->d_l);
+    if (c->caps) {      // the capacity arrays go with their last handle
+        bool last;
+        { std::lock_guard<std::mutex> g(cap_store_mutex()); last = --c->caps->refs == 0; }
+        if (last) { cudaSetDevice(c->caps->device); if (c->caps->d_u) cudaFree(c->caps->d_u); if (c->caps->d_l) cudaFree(c->caps->d_l); delete c->caps; }
+        c->caps = nullptr; c->d_u = c->d_l = nullptr;
+    }
     c->d_plans.release(); c->d_plan_off.release(); c->d_ray_i32.release(); c->d_sums.release(); c->d_finf.release();
     c->d_ray_scratch.release(); c->d_obj.release(); c->d_status.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -271,6 +308,17 @@ int sgufp_dims(const sgufp_ctx *c, int *L, int *T, int *nvbar) {
     if (L) *L = c->M.L;
     if (T) *T = c->M.T;
     if (nvbar) *nvbar = (int)c->M.vbar.size();
+    return 0;
+}
+int sgufp_network(const sgufp_ctx *c, int *n, int *m, int *S_local, int64_t *scenario_offset, int64_t *S_total, int32_t *tail, int32_t *head) {
+    if (!c) return SGUFP_ERR_ARG;
+    if (n) *n = c->M.n;
+    if (m) *m = c->M.m;
+    if (S_local) *S_local = c->S_view >= 0 ? (int)c->S_view : c->S;
+    if (scenario_offset) *scenario_offset = c->S_view >= 0 ? 0 : c->scen_off;
+    if (S_total) *S_total = c->S_total;
+    if (tail) std::memcpy(tail, c->M.tail.data(), (size_t)c->M.m * 4);
+    if (head) std::memcpy(head, c->M.head.data(), (size_t)c->M.m * 4);
     return 0;
 }
 int sgufp_vbar_order(const sgufp_ctx *c, int32_t *vbar) {

@@ -18,6 +18,12 @@ int run_ray(sgufp_ctx *c, const sgufp::Plan &P, long long global_s, unsigned lon
 void finalize_one(const sgufp_ctx *c, const sgufp::Plan &P, const long long *sums, bool feas, int *cut_type, double *rhs, uint64_t *keys,
                   double *vals, int *nnz, double *coef_dense);
 
+#include <mutex>
+#include <string>
+std::mutex &cap_store_mutex();
+int init_device(sgufp_ctx *c, int device, std::string &err);
+cudaError_t zero_pad_column(sgufp_ctx *c);
+
 // capi_shard.cu
 int solve_paths_partitioned(sgufp_ctx *c, const int16_t *paths, int K, int L, int *cut_type, double *rhs, uint64_t *keys, double *vals,
                             int *nnz, double *coef_dense, double *obj, uint8_t *status, int64_t *first_infeasible);

@@ -330,6 +330,7 @@ int sgufp_create_sharded(sgufp_ctx **out, int n, int m, int S, const int32_t *ta
         for (auto &e : P->ev) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail(SGUFP_ERR_CUDA);
     }
     lead->part = P;       // the peers only serve their block: the partition is driven through the leader
+    lead->S_view = S;
     *out = lead;
     return SGUFP_OK;
 }

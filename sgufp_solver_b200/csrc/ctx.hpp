@@ -38,12 +38,22 @@ struct PlanBatch {
 
 struct Partition;                     // capi_shard.cu: the communicator(s) and peer handles of a scenario partition
 
+// The scenario-major capacity arrays in HBM, shared read-only by every handle cloned from the one that uploaded them
+// (sgufp_clone: N_WORKERS + 1 host threads each own a GuroSolver, NodeExplorer.h:115-116 / DDSolver.cpp:583,675).
+struct CapStore {
+    double *d_u = nullptr, *d_l = nullptr;
+    int device = 0;
+    int refs = 1;                     // guarded by cap_store_mutex() (capi.cu)
+};
+
 struct sgufp_ctx {
     sgufp::Model M;
     Partition *part = nullptr;
     int S = 0, m_pad = 0, device = 0, sm_count = 0, max_cap = 0, max_lower = 0, sum_abs_r = 0;
     long long scen_off = 0, S_total = 0;
-    double *d_u = nullptr, *d_l = nullptr;
+    long long S_view = -1;                      // leader of a single-process partition: the scenarios the caller sees (all of them)
+    double *d_u = nullptr, *d_l = nullptr;      // aliases of caps->d_u / d_l
+    CapStore *caps = nullptr;
     cudaStream_t st = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
     DevBuf<int32_t> d_plans, d_plan_off, d_ray_i32;

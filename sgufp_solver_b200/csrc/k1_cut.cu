@@ -761,18 +761,18 @@ __global__ void k1_ray(RayLaunch p) {
 }
 
 #ifndef SGUFP_K1_EMULATE
-// [m][S] int32 (the reference's per-arc vectors) -> [S][m_pad] fp64, 32x32 tiles through shared memory
-__global__ void relayout_caps(const int32_t *__restrict__ src, double *__restrict__ dst, int m, int S, int m_pad) {
+// a slab of na arcs, [na][S] int32 (the reference's per-arc vectors) -> columns a0 .. a0+na of [S][m_pad] fp64, 32x32 tiles through shared memory
+__global__ void relayout_caps(const int32_t *__restrict__ src, double *__restrict__ dst, int na, int S, int m_pad, int a0) {
     __shared__ int tile[32][33];
-    const int a0 = blockIdx.y * 32, s0 = blockIdx.x * 32;
+    const int b0 = blockIdx.y * 32, s0 = blockIdx.x * 32;
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        const int a = a0 + r, s = s0 + threadIdx.x;
-        tile[r][threadIdx.x] = (a < m && s < S) ? src[(size_t)a * S + s] : 0;
+        const int a = b0 + r, s = s0 + threadIdx.x;
+        tile[r][threadIdx.x] = (a < na && s < S) ? src[(size_t)a * S + s] : 0;
     }
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        const int s = s0 + r, a = a0 + threadIdx.x;
-        if (s < S && a < m_pad) dst[(size_t)s * m_pad + a] = (double)tile[threadIdx.x][r];
+        const int s = s0 + r, a = b0 + threadIdx.x;
+        if (s < S && a < na) dst[(size_t)s * m_pad + a0 + a] = (double)tile[threadIdx.x][r];
     }
 }
 
@@ -867,9 +867,9 @@ cudaError_t ray_launch(const RayLaunch &p, cudaStream_t st, int *launches) {
     return cudaGetLastError();
 }
 
-cudaError_t relayout_launch(const int32_t *src, double *dst, int m, int S, int m_pad, cudaStream_t st, int *launches) {
-    dim3 grid((S + 31) / 32, (m_pad + 31) / 32), block(32, 8);
-    relayout_caps<<<grid, block, 0, st>>>(src, dst, m, S, m_pad);
+cudaError_t relayout_launch(const int32_t *src, double *dst, int na, int S, int m_pad, int a0, cudaStream_t st, int *launches) {
+    dim3 grid((S + 31) / 32, (na + 31) / 32), block(32, 8);
+    relayout_caps<<<grid, block, 0, st>>>(src, dst, na, S, m_pad, a0);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }

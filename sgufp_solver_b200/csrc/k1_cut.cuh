@@ -49,8 +49,8 @@ struct RayLaunch {
 };
 cudaError_t ray_launch(const RayLaunch &p, cudaStream_t st, int *launches);
 
-// scenario-major fp64 re-layout of the reference's arc-major int32 capacity arrays
-cudaError_t relayout_launch(const int32_t *src /*[m][S] device*/, double *dst /*[S][m_pad]*/, int m, int S, int m_pad,
+// scenario-major fp64 re-layout of a slab of the reference's arc-major int32 capacity arrays: arcs a0 .. a0+na
+cudaError_t relayout_launch(const int32_t *src /*[na][S] device*/, double *dst /*[S][m_pad]*/, int na, int S, int m_pad, int a0,
                             cudaStream_t st, int *launches);
 
 }  // namespace sgufp

@@ -14,6 +14,7 @@ rows, `Network.cpp:80`).
 from __future__ import annotations
 
 import dataclasses
+import os
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -218,6 +219,30 @@ def read_text(path: str, name: str = "file") -> Instance:
     vbar = np.array([int(x) for x in rest], dtype=np.int32)
     return Instance(n, m, S, tail, head, np.ascontiguousarray(trip[:, :, 0], dtype=np.int32),
                     np.ascontiguousarray(trip[:, :, 1], dtype=np.int32), np.ascontiguousarray(trip[:, :, 2], dtype=np.int32), vbar, name)
+
+
+def save_cache(inst: Instance, path: str) -> None:
+    """The scenario-major binary cache: header + the fp64 capacity arrays exactly as K1 reads them in HBM
+    (`sgufp_cache_write`, csrc/cache.cu).  `GuroSolver.from_cache(path, ...)` streams it — or one rank's block of it — to a device."""
+    import ctypes as C
+    from . import _lib
+    L = _lib.lib()
+    arr = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    t, h, u, lo, r0, vb = arr(inst.tail), arr(inst.head), arr(inst.upper), arr(inst.lower), arr(inst.reward[:, 0]), arr(inst.vbar)
+    p = lambda a: a.ctypes.data_as(_lib.ip)
+    rc = L.sgufp_cache_write(os.fsencode(path), inst.n, inst.m, inst.S, p(t), p(h), p(u), p(lo), p(r0), p(vb), len(vb))
+    if rc:
+        raise _lib.SgufpError(rc, L.sgufp_cache_last_error().decode())
+
+
+def cache_dims(path: str):
+    import ctypes as C
+    from . import _lib
+    n, m, S, nv, fb = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+    rc = _lib.lib().sgufp_cache_dims(os.fsencode(path), C.byref(n), C.byref(m), C.byref(S), C.byref(nv), C.byref(fb))
+    if rc:
+        raise _lib.SgufpError(rc, _lib.lib().sgufp_cache_last_error().decode())
+    return {"n": n.value, "m": m.value, "S": S.value, "nvbar": nv.value, "file_bytes": fb.value}
 
 
 def save_binary(inst: Instance, path: str) -> None:

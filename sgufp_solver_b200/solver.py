@@ -7,6 +7,7 @@ result format of `/root/reference/grb.h:75` / `grb.cpp:139-159`; `Cut` mirrors `
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Sequence, Tuple
 
 import numpy as np
@@ -100,7 +101,18 @@ class GuroSolver:
                                 int(device), self.scenario_offset, self.S_total)
         if rc:
             raise SgufpError(rc, L.sgufp_last_error(None).decode())
+        self._adopt(h)
+
+    def _adopt(self, h):
+        """Everything the wrapper knows about the network comes from the handle (also for handles made from a cache file)."""
+        L = _lib.lib()
         self.h = h
+        n, m, S = C.c_int(), C.c_int(), C.c_int()
+        off, tot = C.c_int64(), C.c_int64()
+        L.sgufp_network(h, C.byref(n), C.byref(m), C.byref(S), C.byref(off), C.byref(tot), None, None)
+        self.n, self.m, self.S, self.scenario_offset, self.S_total = n.value, m.value, S.value, off.value, tot.value
+        self.tail, self.head = np.zeros(self.m, np.int32), np.zeros(self.m, np.int32)
+        L.sgufp_network(h, None, None, None, None, None, self.tail.ctypes.data_as(ip), self.head.ctypes.data_as(ip))
         a, b, c = C.c_int(), C.c_int(), C.c_int()
         L.sgufp_dims(h, C.byref(a), C.byref(b), C.byref(c))
         self.L, self.T = a.value, b.value
@@ -114,6 +126,32 @@ class GuroSolver:
         self._out = [[] for _ in range(self.n)]
         for arc in range(self.m):
             self._out[int(self.tail[arc])].append(arc)
+
+    @classmethod
+    def from_cache(cls, path: str, device: int = 0, scenario_offset: int = 0, S_local: int = -1) -> "GuroSolver":
+        """A handle whose capacities stream from a cache file (`instances.save_cache`, `sgufp_create_from_cache`) straight into
+        the device layout; `scenario_offset` / `S_local` pick one rank's block of a partition."""
+        L = _lib.lib()
+        h = C.c_void_p()
+        rc = L.sgufp_create_from_cache(C.byref(h), os.fsencode(path), int(device), int(scenario_offset), int(S_local))
+        if rc:
+            raise SgufpError(rc, L.sgufp_cache_last_error().decode())
+        self = cls.__new__(cls)
+        self.inst = None
+        self._adopt(h)
+        return self
+
+    def clone(self) -> "GuroSolver":
+        """Another handle (own stream and buffers) on the same device-resident capacities: one per host thread."""
+        L = _lib.lib()
+        h = C.c_void_p()
+        rc = L.sgufp_clone(self.h, C.byref(h))
+        if rc:
+            raise SgufpError(rc, L.sgufp_cache_last_error().decode())
+        other = type(self).__new__(type(self))
+        other.inst = self.inst
+        other._adopt(h)
+        return other
 
     def out_arcs(self, q):
         return self._out[int(q)]
