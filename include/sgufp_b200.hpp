@@ -10,6 +10,7 @@
 // so that NodeExplorer (/root/reference/NodeExplorer.h:115-116, NodeExplorer.cpp:915-986) compiles
 // against them unchanged apart from the two member types.  See INTEGRATION.md.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -43,8 +44,10 @@ inline void check(int rc, const sgufp_ctx *ctx) {
 // One handle per host thread, like one GuroSolver per NodeExplorer (NodeExplorer.h:115).
 class GuroSolver {
 public:
-    // `GuroSolver(const shared_ptr<Network>&, const GRBEnv&)` (grb.h:36) minus the Gurobi environment
-    explicit GuroSolver(const std::shared_ptr<Network> &net, int device = 0) : net_(net) {
+    // `GuroSolver(const shared_ptr<Network>&, const GRBEnv&)` (grb.h:36) minus the Gurobi environment.
+    // device_count > 1: ONE host thread's solver spreads the scenarios over devices device .. device+device_count-1 and the
+    // all-reduce of the partial cuts runs inside the library (sgufp_create_sharded); solveSubProblem is unchanged.
+    explicit GuroSolver(const std::shared_ptr<Network> &net, int device = 0, int device_count = 1) : net_(net) {
         const int n = (int)net->n, m = (int)net->edges, S = (int)net->nScenarios;
         std::vector<int32_t> tail(m), head(m), r0(m), up((size_t)m * S), lo((size_t)m * S), vbar;
         for (int a = 0; a < m; a++) {
@@ -54,9 +57,20 @@ public:
         }
         // the handle applies shuffleVBarNodes itself; it is idempotent on an already shuffled list
         for (auto v : net->Vbar) vbar.push_back((int32_t)v);
-        int rc = sgufp_create(&ctx_, n, m, S, tail.data(), head.data(), up.data(), lo.data(), r0.data(), vbar.data(), (int)vbar.size(), device, 0, S);
+        int rc;
+        if (device_count > 1) {
+            std::vector<int> devs(device_count);
+            for (int i = 0; i < device_count; i++) devs[i] = device + i;
+            rc = sgufp_create_sharded(&ctx_, n, m, S, tail.data(), head.data(), up.data(), lo.data(), r0.data(), vbar.data(), (int)vbar.size(), devs.data(), device_count);
+        } else
+            rc = sgufp_create(&ctx_, n, m, S, tail.data(), head.data(), up.data(), lo.data(), r0.data(), vbar.data(), (int)vbar.size(), device, 0, S);
         if (rc < 0) raise(std::string("sgufp_create: ") + sgufp_last_error(nullptr));
         sgufp_dims(ctx_, &L_, &T_, nullptr);
+    }
+    // another solver on the SAME device-resident capacities (one per worker thread, NodeExplorer.h:115 / DDSolver.cpp:675)
+    struct CloneTag {};
+    GuroSolver(const GuroSolver &other, CloneTag) : net_(other.net_), L_(other.L_), T_(other.T_) {
+        if (sgufp_clone(other.ctx_, &ctx_) < 0) raise(std::string("sgufp_clone: ") + sgufp_cache_last_error());
     }
     ~GuroSolver() { sgufp_destroy(ctx_); }
     GuroSolver(const GuroSolver &) = delete;
@@ -155,6 +169,28 @@ public:
         check(sgufp_dd_apply_optimality(dd_, cut.RHS, f.keys.data(), f.vals.data(), (int)f.keys.size(), optimal, upperbound, &b), ctx_);
         return b;
     }
+    // The loops of NodeExplorer::process over the GLOBAL cuts (NodeExplorer.cpp:935-944, 975-983) as one device call each
+    // (sgufp_dd_apply_sequence): same results as the one-by-one calls, stops where the caller's loop returns.
+    // Returns false if some cut was infeasible (the loop `return PRUNED_BY_FEASIBILITY_CUT`).
+    bool applyFeasibilityCuts(const std::vector<const Inavap::Cut *> &cuts) {
+        if (cuts.empty()) return true;
+        Packed p(cuts);
+        std::vector<int> ok(cuts.size(), 1);
+        int applied = 0;
+        check(sgufp_dd_apply_sequence(dd_, 1, p.rhs.data(), p.keys.data(), p.vals.data(), p.ptr.data(), (int)cuts.size(), 0.0, nullptr, ok.data(), &applied), ctx_);
+        return applied == 0 || ok[applied - 1] != 0;
+    }
+    // Returns how many cuts were applied; `bound`: the upper bound the loop holds when it ends — on an exact diagram the last
+    // call's value (:941), on a non-exact one the minimum over the calls (:981).
+    int applyOptimalityCuts(const std::vector<const Inavap::Cut *> &cuts, double optimal, bool exact, double &bound) {
+        if (cuts.empty()) return 0;
+        Packed p(cuts);
+        std::vector<double> b(cuts.size(), 0.0);
+        int applied = 0;
+        check(sgufp_dd_apply_sequence(dd_, 0, p.rhs.data(), p.keys.data(), p.vals.data(), p.ptr.data(), (int)cuts.size(), optimal, b.data(), nullptr, &applied), ctx_);
+        if (applied > 0) bound = exact ? b[applied - 1] : *std::min_element(b.begin(), b.begin() + applied);
+        return applied;
+    }
     std::vector<NodeT> getCutset(double ub) {   // DD.h:807
         std::vector<int32_t> w(1 << 22);
         const int k = sgufp_dd_cutset(dd_, ub, w.data(), (int)w.size());
@@ -163,6 +199,19 @@ public:
     }
 
 private:
+    struct Packed {   // a run of cuts flattened for the C ABI
+        std::vector<double> rhs, vals;
+        std::vector<uint64_t> keys;
+        std::vector<int32_t> ptr;
+        explicit Packed(const std::vector<const Inavap::Cut *> &cuts) : ptr(cuts.size() + 1, 0) {
+            for (size_t i = 0; i < cuts.size(); i++) {
+                rhs.push_back(cuts[i]->RHS);
+                for (const auto &kv : cuts[i]->coeff) { keys.push_back(kv.first); vals.push_back(kv.second); }
+                ptr[i + 1] = (int32_t)keys.size();
+            }
+            if (keys.empty()) { keys.push_back(0); vals.push_back(0.0); }
+        }
+    };
     sgufp_ctx *ctx_;
     sgufp_dd *dd_ = nullptr;
 };

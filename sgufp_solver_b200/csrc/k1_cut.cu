@@ -24,6 +24,7 @@
 //      candidate's accumulators; write objective + status
 #include "k1_cut.cuh"
 
+#include <atomic>
 #include <climits>
 #include <type_traits>
 #include <cstdlib>
@@ -786,14 +787,21 @@ static cudaError_t launch_warp_nw(const K1Launch &p, cudaStream_t st, int sm_cou
     const int words = k1_words_per_tile(p);
     const size_t smem = (size_t)NW * words * sizeof(int);
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-    static thread_local int known_words = -1, known_per_sm = 0, known_dev = -1;   // per instantiation and device: attribute set, occupancy known
+    // The dynamic shared-memory limit of a kernel is PROCESS-wide state (per device): host threads with batches of different
+    // sizes must not lower it under each other (17 threads, one handle each: tests/test_cache_gpu.py).  It is raised once per
+    // device to the most an SM offers; a launch then asks for what its batch needs.
+    static std::atomic<unsigned long long> limit_raised{0};
+    static thread_local int known_words = -1, known_per_sm = 0, known_dev = -1;   // per instantiation, thread and device: occupancy known
     int per_sm = 1, dev = 0;
     cudaGetDevice(&dev);
+    if (!((limit_raised.load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) {
+        const cudaError_t e = cudaFuncSetAttribute(k1_cut_eval<32, NW, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        limit_raised.fetch_or(1ull << (dev & 63), std::memory_order_release);
+    }
     if (known_words == words && known_dev == dev) per_sm = known_per_sm;
     else {
-        cudaError_t e = cudaFuncSetAttribute(k1_cut_eval<32, NW, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_cut_eval<32, NW, BIG>, NW * 32, smem);
+        const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_cut_eval<32, NW, BIG>, NW * 32, smem);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) return cudaErrorInvalidConfiguration;
         known_words = words; known_per_sm = per_sm; known_dev = dev;

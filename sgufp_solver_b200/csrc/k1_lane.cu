@@ -28,6 +28,7 @@
 // against 2.4, C4 70 against 28) and runs only on request (SGUFP_K1_MODE=lane).  No tensor cores: integer graph work.
 #include "k1_cut.cuh"
 
+#include <atomic>
 #include <climits>
 #include <cstdlib>
 #include <type_traits>
@@ -464,14 +465,18 @@ template <class Cfg>
 static cudaError_t lane_launch_cfg(const K1Launch &p, cudaStream_t st, int sm_count) {
     const LaneLayout lay = lane_layout<Cfg>(p.max_nopen, p.nc, p.nav, 32);
     if (lay.bytes > 227 * 1024) return cudaErrorInvalidConfiguration;
-    static thread_local int known_bytes = -1, known_per_sm = 0, known_dev = -1;   // per instantiation and device
+    static std::atomic<unsigned long long> limit_raised{0};    // the shared-memory limit of a kernel is process-wide state: raised once per device (k1_cut.cu)
+    static thread_local int known_bytes = -1, known_per_sm = 0, known_dev = -1;   // per instantiation, thread and device
     int per_sm = 1, dev = 0;
     cudaGetDevice(&dev);
+    if (!((limit_raised.load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) {
+        const cudaError_t e = cudaFuncSetAttribute(k1_lane_pd<32, Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        limit_raised.fetch_or(1ull << (dev & 63), std::memory_order_release);
+    }
     if (known_bytes == lay.bytes && known_dev == dev) per_sm = known_per_sm;
     else {
-        cudaError_t e = cudaFuncSetAttribute(k1_lane_pd<32, Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.bytes);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_lane_pd<32, Cfg>, 32, (size_t)lay.bytes);
+        const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_lane_pd<32, Cfg>, 32, (size_t)lay.bytes);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) return cudaErrorInvalidConfiguration;
         known_bytes = lay.bytes; known_per_sm = per_sm; known_dev = dev;

@@ -126,6 +126,115 @@ class NodeExplorer:
         return OutObject(DOUBLE_MIN, upperBound, dd.getCutset(upperBound), SUCCESS)  # :985
 
 
+class FrontierExplorer:
+    """W explorers in lock step: `process_many` takes up to W branch-and-bound nodes, one diagram each, and
+    every round hands the current argmax path of every node still in its cut loop (NodeExplorer.cpp:949-971) to ONE
+    `solve_paths` call — K candidates per K1 launch instead of 1.  Per node nothing changes: it reads the global containers when
+    it starts (:928-929), applies ITS OWN new cut to its own diagram, takes its own prune / repeat decisions.  This is what the
+    reference's N_WORKERS explorers do on N nodes at the same time (DDSolver.cpp:701-712), in lock step.  The C++ form is
+    include/sgufp_b200_explorer.hpp."""
+
+    def __init__(self, solver: GuroSolver, width: int):
+        self.solver = solver
+        self.dds = [RelaxedDDNew(solver) for _ in range(max(1, width))]
+        self.cuts_generated = 0
+        self.k1_calls = 0
+
+    def process_many(self, nodes, optimalLB: float, globalFeasCuts: Container, globalOptCuts: Container) -> List[OutObject]:
+        import numpy as np
+        n = len(nodes)
+        assert n <= len(self.dds)
+        out: List[Optional[OutObject]] = [None] * n
+        ub = [nd.ub for nd in nodes]
+        looping = [False] * n
+        seen = [[] for _ in range(n)]
+        feas, opt = list(globalFeasCuts), list(globalOptCuts)
+        for i, node in enumerate(nodes):
+            dd = self.dds[i]
+            dd.buildTree(node)                                                      # :922
+            exact = dd.isTreeExact()                                                # :931
+            flags, k = dd.applyFeasibilityCuts(feas)                                # :935-938 / :975-978
+            if k and not flags[k - 1]:
+                out[i] = OutObject(DOUBLE_MIN, DOUBLE_MIN, [], PRUNED_BY_FEASIBILITY_CUT)
+                continue
+            bounds, k = dd.applyOptimalityCuts(opt, optimalLB)                      # :940-944 / :980-983
+            if k:
+                ub[i] = float(bounds[k - 1]) if exact else min(ub[i], float(bounds[:k].min()))
+                if ub[i] <= optimalLB:
+                    out[i] = OutObject(DOUBLE_MIN, DOUBLE_MIN, [], PRUNED_BY_OPTIMALITY_CUT)
+                    continue
+            if exact:
+                looping[i] = True
+            else:
+                out[i] = OutObject(DOUBLE_MIN, ub[i], dd.getCutset(ub[i]), SUCCESS)  # :985
+        while True:
+            who, paths = [], []
+            for i in range(n):
+                if not looping[i]:
+                    continue
+                path = self.dds[i].getSolution().tolist()                           # :950
+                if path in seen[i]:                                                 # :951-953
+                    out[i] = OutObject(ub[i], ub[i], [], SUCCESS)
+                    looping[i] = False
+                    continue
+                seen[i].append(path)
+                who.append(i)
+                paths.append(path)
+            if not who:
+                break
+            L = max(len(p) for p in paths)
+            batch = np.full((len(paths), L), -1, dtype=np.int16)
+            for k, p in enumerate(paths):
+                batch[k, :len(p)] = p
+            res = self.solver.solve_paths(batch, want_obj=False, want_status=False, want_dense=False)   # :957 for every node at once (K1)
+            self.k1_calls += 1
+            self.cuts_generated += len(who)
+            for k, i in enumerate(who):
+                cut = res.cut(k)
+                if int(res.cut_type[k]) == FEASIBILITY:
+                    globalFeasCuts.add(cut)
+                    if not self.dds[i].applyFeasibilityCut(cut):                    # :961-962
+                        out[i] = OutObject(DOUBLE_MIN, DOUBLE_MIN, [], PRUNED_BY_FEASIBILITY_CUT)
+                        looping[i] = False
+                else:
+                    globalOptCuts.add(cut)
+                    ub[i] = self.dds[i].applyOptimalityCut(cut, optimalLB, ub[i])   # :966
+                    if ub[i] <= optimalLB:                                          # :967-968
+                        out[i] = OutObject(DOUBLE_MIN, DOUBLE_MIN, [], PRUNED_BY_OPTIMALITY_CUT)
+                        looping[i] = False
+        return out
+
+
+def solve_frontier(solver: GuroSolver, width: int = 8, known_lb: float = DOUBLE_MIN, max_nodes: int = 100000):
+    """`solve` taking up to `width` nodes of the stack per round (FrontierExplorer.process_many).
+    Returns (optimum, nodes processed, cuts generated, K1 calls)."""
+    ex = FrontierExplorer(solver, width)
+    feas, opt = Container(), Container()
+    best = known_lb
+    stack = [Node(ub=DOUBLE_MAX)]
+    processed = 0
+    while stack and processed < max_nodes:
+        batch = []
+        while stack and len(batch) < width:
+            node = stack.pop()
+            if node.ub <= best:                                 # DDSolver.cpp:707-711
+                continue
+            batch.append(node)
+        if not batch:
+            break
+        outs = ex.process_many(batch, best, feas, opt)          # DDSolver.cpp:712
+        processed += len(outs)
+        for o in outs:
+            if o.status != SUCCESS:
+                continue
+            if o.lb > best:                                     # DDSolver.cpp:723-731
+                best = o.lb
+            for child in o.nodes:                               # DDSolver.cpp:744-748
+                if child.ub > best:
+                    stack.append(child)
+    return best, processed, ex.cuts_generated, ex.k1_calls
+
+
 def solve(solver: GuroSolver, known_lb: float = DOUBLE_MIN, max_nodes: int = 100000, batch_global_cuts: bool = False,
           device_sequences: bool = True):
     """Sequential depth-first branch and bound over cut-set nodes (stand-in for DDSolver.cpp:658-776:

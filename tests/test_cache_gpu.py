@@ -94,3 +94,27 @@ def test_seventeen_threads_on_clones_of_one_upload():
     base.close()                                    # the clones keep the capacities alive
     again = clones[3].solve_paths(batches[3])
     _same(serial[3], again)
+
+
+def test_seventeen_benders_loops_at_once():
+    """The whole caller side by side: 17 host threads, each running the Benders loop (K1 + K2, its own diagram) on its own clone."""
+    from sgufp_solver_b200.explorer import solve
+    inst = I.config1(S=40, lower_prob=0.1)
+    base = sg.GuroSolver(inst)
+    want = solve(base, max_nodes=300)
+    T = 17
+    clones = [base.clone() for _ in range(T)]
+    got, errs = [None] * T, []
+
+    def work(t):
+        try:
+            got[t] = solve(clones[t], max_nodes=300)
+        except Exception as e:                      # noqa: BLE001
+            errs.append((t, repr(e)))
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(T)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    assert not errs, errs
+    assert all(g == want for g in got), (want, got)

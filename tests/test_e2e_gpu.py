@@ -90,3 +90,19 @@ def test_committed_bench_candidates_are_the_dd_emission():
     for net in z.files:
         fresh, info = dd_emitted_paths(getattr(I, net)(S=32), z[net].shape[0], budget_s=120.0)
         assert fresh.shape == z[net].shape and (fresh == z[net]).all(), (net, info)
+
+
+@pytest.mark.parametrize("make", [lambda: I.config1(S=50), lambda: I.config1(S=50, lower_prob=0.1),
+                                  lambda: I.make_layered([4, 5, 5, 4], 48, 12, 123, 0.7, 0.0, "mid")], ids=["c1", "c1_lb", "mid"])
+def test_frontier_explorer_keeps_the_search_and_batches_k1(make):
+    """SURVEY.md 8f-1, K1 side: nodes side by side, one K1 call per round.  Width 1 IS the one-path loop (same optimum, nodes and
+    cuts as `solve`); wider frontiers reach the same optimum with several candidates per K1 call."""
+    from sgufp_solver_b200.explorer import solve_frontier
+    inst = make()
+    best, nodes, cuts = solve(sg.GuroSolver(inst), max_nodes=2000)
+    b1, n1, c1, k1 = solve_frontier(sg.GuroSolver(inst), width=1, max_nodes=2000)
+    assert (b1, n1, c1) == (best, nodes, cuts) and k1 == c1
+    for width in (4, 16):
+        bw, nw, cw, kw = solve_frontier(sg.GuroSolver(inst), width=width, max_nodes=2000)
+        assert bw == best
+        assert kw <= cw

@@ -26,3 +26,21 @@ pr.disable()
 dt = time.perf_counter() - t0
 print(f"{name}: {nodes} nodes, {cuts} cuts, best {best:.3f}, {dt * 1e3:.1f} ms  ({dt / max(1, nodes) * 1e3:.2f} ms per node)")
 pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
+# the same search budget with nodes side by side: K1 time = time inside solve_paths
+from sgufp_solver_b200.explorer import solve_frontier  # noqa: E402
+for width in (1, 8, 32):
+    s2 = sg.GuroSolver(inst)
+    k1_time = [0.0]
+    orig = s2.solve_paths
+
+    def timed(*a, **k):
+        t1 = time.perf_counter()
+        r = orig(*a, **k)
+        k1_time[0] += time.perf_counter() - t1
+        return r
+    s2.solve_paths = timed
+    t0 = time.perf_counter()
+    b, n, c, calls = solve_frontier(s2, width=width, max_nodes=max_nodes)
+    dt = time.perf_counter() - t0
+    print(f"frontier width {width:2d}: {n} nodes, {c} cuts in {calls} K1 calls ({c / max(1, calls):.1f} candidates per call), best {b:.3f}, "
+          f"total {dt * 1e3:.1f} ms, inside solve_paths {k1_time[0] * 1e3:.1f} ms ({k1_time[0] / max(1, c) * 1e6:.0f} us per cut)")
