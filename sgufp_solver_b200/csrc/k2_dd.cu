@@ -24,7 +24,13 @@ namespace sgufp {
 
 // The dynamic shared-memory limit of a kernel is process-wide state: it is always raised to the same value (the most an SM
 // offers), never to "what this launch needs" — host threads with diagrams of different widths would lower it under each other.
-constexpr int K2_SMEM_LIMIT = 227 * 1024;
+template <class F>
+static cudaError_t k2_raise_smem_limit(F *kernel) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes);   // static + dynamic <= 227 KB
+}
 
 namespace {
 
@@ -586,12 +592,12 @@ cudaError_t k2_launch(const K2DD *dds, int B, const double *coef, const double *
     const size_t smem = ((size_t)Tpad + 2 * (size_t)max_width_all) * sizeof(double);
     if (k2_states_in_smem(Tpad, max_width_all, avg_width)) {
         const size_t tot = smem + (size_t)K2_LI_CACHE * sizeof(int4);
-        cudaError_t e = cudaFuncSetAttribute(k2_longest_path<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_LIMIT);
+        cudaError_t e = k2_raise_smem_limit(k2_longest_path<true, false>);
         if (e != cudaSuccess) return e;
         k2_longest_path<true, false><<<grid, threads, tot, st>>>(dds, coef, rhs, C, Tpad, max_width_all, states, last, K2_LI_CACHE);
     } else {
         const size_t sm2 = (size_t)Tpad * sizeof(double) + (size_t)K2_LI_CACHE * sizeof(int4);
-        cudaError_t e = cudaFuncSetAttribute(k2_longest_path<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_LIMIT);
+        cudaError_t e = k2_raise_smem_limit(k2_longest_path<false, false>);
         if (e != cudaSuccess) return e;
         k2_longest_path<false, false><<<grid, threads, sm2, st>>>(dds, coef, rhs, C, Tpad, 0, states, last, K2_LI_CACHE);
     }
@@ -628,12 +634,12 @@ cudaError_t k2_single_launch(const K2DD *dd, const double *coef, const double *r
     const size_t smem = ((size_t)Tpad + 2 * (size_t)max_width) * sizeof(double);
     if (smem <= 200 * 1024) {
         const size_t tot = smem + (size_t)K2_LI_CACHE * sizeof(int4);
-        cudaError_t e = cudaFuncSetAttribute(k2_longest_path<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_LIMIT);
+        cudaError_t e = k2_raise_smem_limit(k2_longest_path<true, true>);
         if (e != cudaSuccess) return e;
         k2_longest_path<true, true><<<dim3(1, 1), threads, tot, st>>>(dd, coef, rhs, 1, Tpad, max_width, states, last, K2_LI_CACHE);
     } else {
         const size_t sm2 = (size_t)Tpad * sizeof(double) + (size_t)K2_LI_CACHE * sizeof(int4);
-        cudaError_t e = cudaFuncSetAttribute(k2_longest_path<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_LIMIT);
+        cudaError_t e = k2_raise_smem_limit(k2_longest_path<false, true>);
         if (e != cudaSuccess) return e;
         k2_longest_path<false, true><<<dim3(1, 1), threads, sm2, st>>>(dd, coef, rhs, 1, Tpad, 0, states, last, K2_LI_CACHE);
     }
@@ -664,7 +670,7 @@ cudaError_t k2_sequence_launch(const K2DD *dd_device, const K2Apply &a, const K2
     int threads = 64;
     while (threads < K2_THREADS && threads < max_width) threads *= 2;
     const size_t sm2 = (size_t)q.Tpad * sizeof(double) + (size_t)K2_LI_CACHE * sizeof(int4);
-    cudaError_t e = cudaFuncSetAttribute(k2_longest_path<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_LIMIT);
+    cudaError_t e = k2_raise_smem_limit(k2_longest_path<false, true>);
     if (e != cudaSuccess) return e;
     k2_longest_path<false, true><<<dim3(n, 1), threads, sm2, st>>>(dd_device, q.coef + (size_t)q.k0 * q.Tpad, rhs_device + q.k0, n, q.Tpad, 0,
                                                                      q.states, last_scratch, K2_LI_CACHE);
