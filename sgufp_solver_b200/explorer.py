@@ -205,15 +205,15 @@ class FrontierExplorer:
         return out
 
 
-def solve_frontier(solver: GuroSolver, width: int = 8, known_lb: float = DOUBLE_MIN, max_nodes: int = 100000):
+def solve_frontier(solver: GuroSolver, width: int = 8, known_lb: float = DOUBLE_MIN, max_nodes: int = 100000, max_cuts: Optional[int] = None):
     """`solve` taking up to `width` nodes of the stack per round (FrontierExplorer.process_many).
-    Returns (optimum, nodes processed, cuts generated, K1 calls)."""
+    Returns (optimum, nodes processed, cuts generated, K1 calls).  `max_cuts` ends the search early (profiling)."""
     ex = FrontierExplorer(solver, width)
     feas, opt = Container(), Container()
     best = known_lb
     stack = [Node(ub=DOUBLE_MAX)]
     processed = 0
-    while stack and processed < max_nodes:
+    while stack and processed < max_nodes and (max_cuts is None or ex.cuts_generated < max_cuts):
         batch = []
         while stack and len(batch) < width:
             node = stack.pop()

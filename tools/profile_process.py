@@ -40,7 +40,7 @@ for width in (1, 8, 32):
         return r
     s2.solve_paths = timed
     t0 = time.perf_counter()
-    b, n, c, calls = solve_frontier(s2, width=width, max_nodes=max_nodes)
+    b, n, c, calls = solve_frontier(s2, width=width, max_nodes=100000, max_cuts=cuts)      # the same number of cuts as the run above
     dt = time.perf_counter() - t0
     print(f"frontier width {width:2d}: {n} nodes, {c} cuts in {calls} K1 calls ({c / max(1, calls):.1f} candidates per call), best {b:.3f}, "
           f"total {dt * 1e3:.1f} ms, inside solve_paths {k1_time[0] * 1e3:.1f} ms ({k1_time[0] / max(1, c) * 1e6:.0f} us per cut)")
