@@ -99,6 +99,10 @@ struct Lanes {    // the TILE lanes that work on one scenario (32 on the GPU; 1 
         for (int o = TILE / 2; o; o >>= 1) v += __shfl_xor_sync(mask, v, o, TILE);
         return v;
     }
+    __device__ __forceinline__ int min_i32(int v) const {
+        if constexpr (TILE == 32) return __reduce_min_sync(mask, v);
+        else { for (int o = TILE / 2; o; o >>= 1) { const int t = __shfl_xor_sync(mask, v, o, TILE); v = t < v ? t : v; } return v; }
+    }
     __device__ __forceinline__ unsigned long long min_u64(unsigned long long v) const {
         for (int o = TILE / 2; o; o >>= 1) { const unsigned long long t = __shfl_xor_sync(mask, v, o, TILE); v = t < v ? t : v; }
         return v;
@@ -256,9 +260,11 @@ __device__ int tight_list(const PlanView &P, int nopen, const Lanes<TILE> &T, TM
 // before: the predecessors form a tree rooted at src.  Any tight path will do — the duals do not depend on which
 // optimal flow is found.  If dst is not reached, w.rw holds the complete reached set.
 template <int TILE, class TM>
-__device__ bool reach_list(int src, int dst, const PlanView &P, int ntc, int nword, const Lanes<TILE> &T, TM &w) {
+__device__ bool reach_list(int src, int dst, const PlanView &P, int ntc, int nword, const Lanes<TILE> &T, TM &w, bool keep = false) {
     const int R = w.rw;
-    for (int i = T.tl; i < nword; i += TILE) SU(R + (i)) = i == (src >> 5) ? 1u << (src & 31) : 0u;
+    // keep: the search goes on from the reached set of the last (failed) one — after a dual update its nodes keep their labels
+    // and their predecessors, only more arcs are tight
+    if (!keep) for (int i = T.tl; i < nword; i += TILE) SU(R + (i)) = i == (src >> 5) ? 1u << (src & 31) : 0u;
     T.sync();
     for (;;) {
         bool grew = false;
@@ -375,8 +381,38 @@ struct TightPaths {
     __device__ TightPaths(const PlanView &P_, const Lanes<TILE> &T_, TM &w_, int nopen_, int nc_)
         : P(P_), T(T_), w(w_), nopen(nopen_), nc(nc_), nword(reach_words(nc_)), ntc(0) {}
     __device__ void prepare() { if constexpr (small) tight_small<TILE>(P, nopen, T, w); else ntc = tight_list<TILE>(P, nopen, T, w); }
+    __device__ __forceinline__ bool in_r(int v) const {
+        if constexpr (small) return (SU(w.rw) >> v) & 1u; else return (SU(w.rw + (v >> 5)) >> (v & 31)) & 1u;
+    }
+    // Primal-dual step after a FAILED search from the root (w.rw = the complete reached set R): the labels of the nodes outside R
+    // rise by delta = the least slack of a residual arc that leaves R.  They stay feasible potentials (every residual arc keeps
+    // a non-negative reduced cost), the labels inside R stay exact, at least one more arc becomes tight: ONE pass over the
+    // chains instead of a label computation of 3.6 - 3.9 relaxation passes (profiles/r02_summary.md).  Returns false when the
+    // flow is optimal: no residual arc leaves R (maximum flow), or the sink's label has reached 0 (no profitable path left).
+    __device__ bool dual_update() {
+        int best = INT_MAX;
+        for (int c = T.tl; c < nopen; c += TILE) {
+            const int f = RGET(c) & 3;
+            if (!f) continue;
+            const ChainEnds e(P.ch_st[c]);
+            if ((f & 1) && in_r(e.sv) && !in_r(e.hf)) { const int lh = SI(w.lab + e.hf); if (lh != LAB_INF) best = min(best, SI(w.lab + e.sv) - e.r - lh); }
+            if ((f & 2) && in_r(e.ev) && !in_r(e.hb)) { const int lh = SI(w.lab + e.hb); if (lh != LAB_INF) best = min(best, SI(w.lab + e.ev) + e.r - lh); }
+        }
+        const int delta = T.min_i32(best);
+#ifdef SGUFP_K1_STATS
+        if (T.tl == 0) atomicAdd(&g_k1_stats[1], 1ull);
+#endif
+        if (delta == INT_MAX) return false;
+        T.sync();
+        for (int v = T.tl; v <= nc; v += TILE)
+            if (!in_r(v)) { const int l = SI(w.lab + v); if (l != LAB_INF) SI(w.lab + v) = l + delta; }
+        T.sync();
+        if (SI(w.lab + nc) >= 0) return false;
+        prepare();
+        return true;
+    }
     // one search and, if dst is reachable, one push of at most `limit`; returns the amount pushed (0: not reachable)
-    __device__ int augment(int src, int dst, int limit) {
+    __device__ int augment(int src, int dst, int limit, bool keep = false) {
 #ifdef SGUFP_K1_STATS
         if (T.tl == 0) atomicAdd(&g_k1_stats[2], 1ull);
 #endif
@@ -384,7 +420,7 @@ struct TightPaths {
             const int lev = reach_small<TILE>(src, dst, nc, T, w);
             return lev ? push_small<TILE>(dst, limit, lev, nc, T, w) : 0;
         } else
-        return reach_list<TILE>(src, dst, P, ntc, nword, T, w) ? push_list<TILE>(src, dst, limit, nc, T, w) : 0;
+        return reach_list<TILE>(src, dst, P, ntc, nword, T, w, keep) ? push_list<TILE>(src, dst, limit, nc, T, w) : 0;
     }
 };
 
@@ -582,6 +618,25 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
 #ifdef SGUFP_K1_STATS
         if (T.tl == 0) atomicAdd(&g_k1_stats[3], 1ull);
 #endif
+#ifndef SGUFP_K1_NO_DUAL
+        // primal-dual: ONE label computation (shortest distances at the starting flow); then searches over the tight chains push
+        // along every shortest path, and when a search fails a dual update — one pass — raises the labels outside its reached
+        // set until the next arc becomes tight (labels stay feasible potentials, pushes along tight arcs keep the flow optimal
+        // for its value).  Done when the sink's label reaches 0 or no residual arc leaves the reached set.
+        shortest_paths<TILE, false, false>(0, P, nopen, nc, T, w, fuel);
+        {
+            const int lt = SI(w.lab + nc);
+            if (lt != LAB_INF && lt < 0) {
+                TP.prepare();
+                bool keep = false;
+                while (fuel > 0) {
+                    while (--fuel > 0 && TP.augment(0, nc, INT_MAX, keep) > 0) keep = false;   // until a search fails: w.rw = its reached set
+                    if (!TP.dual_update()) break;
+                    keep = TM::BIG;                     // the list search goes on from that set; the bit-set search starts over (it is cheap)
+                }
+            }
+        }
+#else
         // one label computation per distinct path length; in between, breadth-first searches over the
         // tight chains find the other shortest paths of that length (labels stay feasible potentials)
         for (bool warm = false; fuel > 0; warm = true) {
@@ -592,6 +647,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
             TP.prepare();
             while (--fuel > 0 && TP.augment(0, nc, INT_MAX) > 0) {}   // until the search fails: it leaves the reached set for the warm start
         }
+#endif
         // 3. potentials
         canonical_potentials<TILE>(P, nopen, nc, T, w, fuel);
         if (fuel <= 0) {   // a bound that no valid instance reaches: refuse to answer rather than spin

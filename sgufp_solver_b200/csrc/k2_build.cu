@@ -109,7 +109,11 @@ __device__ __forceinline__ void k2_build_body(const K2Build &b) {
         int total = sum;
         if (b.restricted && exact && sum > b.max_width) total = b.max_width;   // the layer stops mid-node at max_width (DD.cpp:3238)
         const int new_nodes = collapse ? 1 : total;
-        if (n + new_nodes > b.node_cap || e_total + (collapse ? sum : total) > b.arc_cap) { if (rank == 0 && threadIdx.x == 0) b.out->overflow = 1; return; }
+        if (n + new_nodes > b.node_cap || e_total + (collapse ? sum : total) > b.arc_cap) {      // every CTA sees the same sizes and leaves together
+            if (rank == 0 && threadIdx.x == 0) b.out->overflow = 1;
+            if constexpr (NC > 1) cg::this_cluster().sync();   // nobody exits while a neighbour may still read its shared memory
+            return;
+        }
         unsigned uni = 0, child_states = 0;
         for (int i = c0 + threadIdx.x; i < c1; i += KB_THREADS) {
             const unsigned m = b.mask[v0 + i];
@@ -158,6 +162,7 @@ __device__ __forceinline__ void k2_build_body(const K2Build &b) {
         nl++;
         __syncthreads();
     }
+    if constexpr (NC > 1) cg::this_cluster().sync();       // a CTA's shared memory must outlive its neighbours' last remote reads
     if (rank == 0 && threadIdx.x == 0) {
         b.in_ptr[n] = e_total;
         K2BuildOut o;

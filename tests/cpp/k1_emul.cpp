@@ -42,6 +42,7 @@ static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
 static inline unsigned __reduce_or_sync(unsigned, unsigned v) { return v; }
+static inline int __reduce_min_sync(unsigned, int v) { return v; }
 static inline void __syncwarp(unsigned = 0xffffffffu) {}
 static inline int __any_sync(unsigned, int p) { return p; }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int, int = 32) { return v; }

@@ -70,6 +70,8 @@ def test_cpp_compute_path_on_the_gpu(tmp_path, make, device_count):
     assert len(ex) == 2
     o1 = float(ex[0].split("optimum ")[1].split()[0]); n1 = int(ex[0].split("nodes ")[1].split()[0]); c1 = int(ex[0].split("cuts ")[1].split()[0])
     ow = float(ex[1].split("optimum ")[1].split()[0]); kw = int(ex[1].split("k1_calls ")[1].split()[0]); cw = int(ex[1].split("cuts ")[1].split()[0])
-    assert o1 == best and ow == best                             # the same optimum as the Python loop, whatever the width
-    assert (n1, c1) == (nodes, ncuts)                            # one node at a time: the same search, node for node and cut for cut
+    nw = int(ex[1].split("nodes ")[1].split()[0])
+    assert o1 == best and (n1, c1) == (nodes, ncuts)             # one node at a time: the Python loop's search, node for node and cut for cut
+    if nodes < 400 and nw < 400:                                 # both searches ran to the end (not cut off by the node budget):
+        assert ow == best                                        # the same optimum whatever the width
     assert kw <= cw                                              # side by side: several candidates per K1 call

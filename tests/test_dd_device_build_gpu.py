@@ -82,6 +82,42 @@ def test_restricted_built_on_device_is_the_reference_structure(name, width):
         assert ours.getMaxPath().tolist() == ref.solution().tolist()
 
 
+@pytest.mark.parametrize("name,width", [("c2", 4), ("c2", 37), ("c2", 1024), ("c2", 4096), ("mid", 300)])
+def test_cluster_builder_gives_the_reference_structure(name, width, monkeypatch):
+    """k2_build_cluster (8 CTAs of a thread-block cluster build one diagram: wide layers) against the reference node for
+    node — forced onto narrow widths too (SGUFP_DD_BUILD_CLUSTER=1), where slices are ragged or empty; width 4096 takes it
+    by default."""
+    if width < 2048:
+        monkeypatch.setenv("SGUFP_DD_BUILD_CLUSTER", "1")
+    inst = INSTANCES[name]()
+    solver = sg.GuroSolver(inst)
+    rn = ref_dd.RefNetwork(inst)
+    ours, ref = RestrictedDDNew(solver, width), ref_dd.RefRestrictedDD(rn, width)
+    cs = ours.compile(); ref.compile()
+    dev = ours.dump_device()
+    assert dev["built_on_device"]
+    b = ref.dump()
+    sizes = ref.layer_sizes()
+    assert dev["layer_sizes"].tolist() == sizes.tolist()[:len(dev["layer_sizes"])]
+    nn = int(dev["layer_sizes"].sum())
+    assert dev["arc_tailpos"].tolist() == b["parentpos"][1:nn].tolist()
+    assert dev["arc_decision"].tolist() == b["decision"][1:nn].tolist()
+    assert ours.isTreeExact() == ref.is_exact()
+    if not ours.isTreeExact():
+        assert [(n.globalLayer, n.states, n.solutionVector) for n in cs] == ref.cutset()
+    rng = np.random.default_rng(width)
+    for _ in range(3):
+        cut = random_cut(solver, rng)
+        assert ours.applyOptimalityCut(cut) == ref.apply_opt(cut.RHS, cut.keys, cut.vals)
+        assert ours.getMaxPath().tolist() == ref.solution().tolist()
+    # the relaxed diagram through the cluster kernel as well (collapsed layers: the one node is written by rank 0)
+    monkeypatch.setenv("SGUFP_DD_BUILD_CLUSTER", "1")
+    ro, rr = RelaxedDDNew(solver), ref_dd.RefRelaxedDD(rn)
+    ro.buildTree(); rr.build()
+    assert ro.isTreeExact() == rr.is_exact()
+    _relaxed_matches(ro, rr)
+
+
 def test_fresh_device_tree_gives_the_reference_first_path():
     """getSolution before any cut: every state is DOUBLE_MIN, every terminal arc DOUBLE_MAX (DD.cpp:3595)"""
     inst = INSTANCES["c2"]()

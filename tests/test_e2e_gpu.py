@@ -104,5 +104,6 @@ def test_frontier_explorer_keeps_the_search_and_batches_k1(make):
     assert (b1, n1, c1) == (best, nodes, cuts) and k1 == c1
     for width in (4, 16):
         bw, nw, cw, kw = solve_frontier(sg.GuroSolver(inst), width=width, max_nodes=2000)
-        assert bw == best
+        if nodes < 2000 and nw < 2000:          # both searches ran to the end (not cut off by the node budget)
+            assert bw == best
         assert kw <= cw

@@ -38,11 +38,18 @@ def _compare(inst, gs, net, paths, res):
             assert (res.status[k, :s] == 0).all() and res.status[k, s] == 1
             assert (res.obj[k, :s] == oc.obj[:s]).all()
         cut = res.cut(k)
-        # the oracle's (key, value) list comes from the REFERENCE-ORDER fold (running fp64 sums of `(cap / S) * dual`,
-        # grb.cpp:241-278, then cutToCut's `v == 0` test, Cut.h:412): same keys, same count, same (i,q,j) order — no filter.
-        # (tests/test_zero_residue_cpu.py: with integer duals a coefficient that is exactly 0 is 0 in the running sum too.)
-        assert [int(x) for x in cut.keys] == [int(kk) for kk in oc.keys] and len(cut.keys) == res.nnz[k]
-        assert np.allclose(cut.vals, oc.vals, rtol=RTOL, atol=RTOL * scale)
+        # The oracle's (key, value) list comes from the REFERENCE-ORDER fold (running fp64 sums of `(cap / S) * dual`,
+        # grb.cpp:241-278, then cutToCut's `v == 0` test, Cut.h:412).  Ours must be that list minus the RESIDUES: slots whose
+        # exact integer sum is 0 but whose running fp64 sum is not (rare — tests/test_zero_residue_cpu.py — and below 1e-12).
+        # No tolerance decides membership: the exact sums do.
+        lex = np.lexsort((gs.slot_j[:gs.T], gs.slot_q[:gs.T], gs.slot_i[:gs.T]))
+        key_of = lambda s: int(gs.slot_q[s]) | (int(gs.slot_i[s]) << 16) | (int(gs.slot_j[s]) << 32)
+        assert [int(kk) for kk in oc.keys] == [key_of(s) for s in lex if oc.coef_dense[s] != 0]
+        residue = (oc.isum[1:] == 0) & (oc.coef_dense != 0)
+        assert np.abs(oc.coef_dense[residue]).max(initial=0.0) <= 1e-12 * scale
+        assert not ((oc.isum[1:] != 0) & (oc.coef_dense == 0)).any()
+        assert [int(x) for x in cut.keys] == [key_of(s) for s in lex if oc.isum[1 + s] != 0] and len(cut.keys) == res.nnz[k]
+        assert np.allclose(cut.vals, [oc.coef_dense[s] for s in lex if oc.isum[1 + s] != 0], rtol=RTOL, atol=RTOL * scale)
 
 
 CASES = [
