@@ -10,9 +10,11 @@ from sgufp_solver_b200.solver import GuroSolver  # noqa: E402
 
 wl = sys.argv[1]
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-inst, K = {"c2": lambda: (I.config2(S=1000), 64), "c4": lambda: (I.config4(S=10000), 8), "c5": lambda: (I.config4(S=100000), 8)}[wl]()
+import bench  # noqa: E402  (the bench's own instance blocks and DD-emitted candidate paths: what profiles/k1_traffic.json describes)
+K = bench.WORKLOADS[wl]["K"]
+inst = bench.scenario_range(wl, 0, bench.totals(wl, 1))
 solver = GuroSolver(inst)
-paths = np.asarray(I.random_paths(solver, K, 31, 0.1), dtype=np.int16)
+paths, _ = bench.candidate_paths(wl, K, 0)
 for _ in range(reps):
     solver.solve_paths(paths, want_obj=False, want_status=False, want_dense=False)
 print(wl, os.environ.get("SGUFP_K1_MODE", "auto"), "kernel ms", solver.last_kernel_ms())
