@@ -91,6 +91,9 @@ __global__ void __launch_bounds__(K2_FIN_THREADS) k2_longest_path(const K2DD *__
         double *cur = SMEM_STATES ? ((l & 1) ? buf1 : buf0) : all + v0;
         const bool is_last = l == d.nlayers - 1;
         double *lastp = glast + d.last_off + (size_t)c * d.nlast;
+        // the last layer's states go to `lastp`; nobody reads them from the state block unless the host wants every state
+        // (the global-state variant of a relaxed diagram would write its ~10 k-node last layer twice per cut)
+        const bool store = SMEM_STATES || !is_last || keep_all || DEADS;      // DEADS: the sequence path reads every cut's states afterwards
         if (width == 1 && !li.w) {
             // collapsed layer: one node, many in-arcs -> the whole CTA reduces it
             const int e1 = d.in_ptr[v0 + 1];
@@ -104,7 +107,7 @@ __global__ void __launch_bounds__(K2_FIN_THREADS) k2_longest_path(const K2DD *__
             }
             s = block_max(s, red);
             if (threadIdx.x == 0) {
-                cur[0] = s;
+                if (store) cur[0] = s;
                 if (SMEM_STATES && keep_all) all[v0] = s;
                 if (is_last) lastp[0] = s;
             }
@@ -116,7 +119,7 @@ __global__ void __launch_bounds__(K2_FIN_THREADS) k2_longest_path(const K2DD *__
                 double s = ts.y >= 0 ? p + cf[ts.y] : p;
                 s = -DBL_MAX < s ? s : -DBL_MAX;   // max(DOUBLE_MIN, .) of DD.cpp:3958
                 if (DEADS && d.arc_dead[e0 + i]) s = -DBL_MAX;
-                cur[i] = s;
+                if (store) cur[i] = s;
                 if (SMEM_STATES && keep_all) all[v0 + i] = s;
                 if (is_last) lastp[i] = s;
             }
@@ -130,7 +133,7 @@ __global__ void __launch_bounds__(K2_FIN_THREADS) k2_longest_path(const K2DD *__
                     const double cand = ts.y >= 0 ? p + cf[ts.y] : p;
                     s = s < cand ? cand : s;
                 }
-                cur[i] = s;
+                if (store) cur[i] = s;
                 if (SMEM_STATES && keep_all) all[v0 + i] = s;
                 if (is_last) lastp[i] = s;
             }
