@@ -52,11 +52,11 @@ def test_strong_scaling_data_do_not_depend_on_the_number_of_gpus():
 
 def test_roofline_helpers_read_the_committed_counts():
     import bench
-    for wl in ("c2", "c4"):
+    for wl in ("c2", "c4", "c5"):
         t = bench.measured_traffic(wl)
         assert isinstance(t, int) and t > 0
         r = bench.issue_roofline(wl, 10.0, 1965.0, 148)
         assert r["bound"] == "issue" and abs(r["peak"] - 148 * 4 * 1.965) < 1e-9
         assert abs(r["achieved"] - r["warp_instructions_per_launch"] / 10e-3 / 1e9) < 1e-6 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
-    assert bench.issue_roofline("c5", 10.0, 1965.0, 148) is None        # no committed count: no claim
+    assert bench.issue_roofline("c9", 10.0, 1965.0, 148) is None        # no committed count: no claim
     assert bench.issue_roofline("c2", 10.0, None, 148) is None           # no clock sample: no claim
