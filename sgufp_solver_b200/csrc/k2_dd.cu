@@ -35,6 +35,7 @@ static cudaError_t k2_raise_smem_limit(F *kernel) {
 namespace {
 
 constexpr int K2_THREADS = 256;
+constexpr int K2_HYBRID = 2048;        // global-state variant of the batch path: layers up to this width keep their states in shared memory
 constexpr int K2_TERM_SLICES = 64;     // CTAs per diagram in k2_terminal (scratch: B x 64 partial maxima)
 constexpr int K2_FIN_THREADS = 1024;   // the one-CTA kernels that sweep a (possibly wide) last layer
 
@@ -53,8 +54,10 @@ __device__ __forceinline__ double block_max(double v, double *red) {
     return r;
 }
 
-// SMEM_STATES: states ping-pong in shared memory (width <= maxw); otherwise they live in the
-// global scratch block of this (diagram, cut) — `gstate` then has C blocks per diagram.
+// SMEM_STATES: states ping-pong in shared memory (every layer is at most maxw wide); otherwise they live in the
+// global scratch block of this (diagram, cut) — `gstate` then has C blocks per diagram — except, in the batch path
+// (!DEADS), the layers of at most maxw nodes: those still ping-pong in two shared buffers of maxw states (a relaxed diagram
+// is dozens of narrow layers and a few very wide ones at the end: only the wide ones touch global memory).
 // DEADS: the diagram carries flags of arcs removed on the device (single-cut path); a flagged arc
 // contributes nothing, exactly as if it had been erased from the in-arc list.
 template <bool SMEM_STATES, bool DEADS>
@@ -65,35 +68,40 @@ __global__ void __launch_bounds__(K2_FIN_THREADS) k2_longest_path(const K2DD *__
     __shared__ double red[K2_FIN_THREADS / 32];
     const K2DD d = dds[blockIdx.y];
     const int c = blockIdx.x;
+    const int sw = (SMEM_STATES || !DEADS) ? maxw : 0;   // layers up to this width live in the two shared buffers
     double *cf = sm;                       // [Tpad]
-    double *buf0 = sm + Tpad, *buf1 = buf0 + (SMEM_STATES ? maxw : 0);
+    double *buf[2] = {sm + Tpad, sm + Tpad + sw};
     // the per-layer records, staged once: a layer is short, a dependent global load per layer is not
-    int4 *li_s = reinterpret_cast<int4 *>(buf1 + (SMEM_STATES ? maxw : 0));
+    int4 *li_s = reinterpret_cast<int4 *>(sm + Tpad + 2 * sw);
     const bool li_cached = d.nlayers <= li_cache;
     if (li_cached) for (int i = threadIdx.x; i < d.nlayers; i += blockDim.x) li_s[i] = d.layer_info[i];
     const int4 *layer_info = li_cached ? li_s : d.layer_info;
     for (int i = threadIdx.x; i < Tpad; i += blockDim.x) cf[i] = coef[(size_t)c * Tpad + i];
     const bool keep_all = c == C - 1;      // the host reads every node state of the last cut only
     double *all = gstate + d.state_off + (SMEM_STATES ? 0 : (size_t)c * d.nnodes);
+    const bool root_s = SMEM_STATES || sw >= 1;
     __syncthreads();
     if (threadIdx.x == 0) {
         double v = rhs[c];
         for (int k = 0; k < d.nroot; k++) { const int s = d.root_slot[k]; if (s >= 0) v = v + cf[s]; }
-        if (SMEM_STATES) buf0[0] = v;
-        if (!SMEM_STATES || keep_all) all[0] = v;
+        if (root_s) buf[0][0] = v;
+        if (!root_s || keep_all) all[0] = v;
         if (d.nlayers == 1) glast[d.last_off + (size_t)c * d.nlast] = v;
     }
     __syncthreads();
+    const double *prev = root_s ? buf[0] : all;
+    int which = 0;                         // the shared buffer written last
     for (int l = 1; l < d.nlayers; l++) {
         const int4 li = layer_info[l];
         const int v0 = li.x, e0 = li.y, width = li.z;
-        const double *prev = SMEM_STATES ? ((l & 1) ? buf0 : buf1) : all + layer_info[l - 1].x;
-        double *cur = SMEM_STATES ? ((l & 1) ? buf1 : buf0) : all + v0;
+        const bool cur_s = SMEM_STATES || width <= sw;
+        double *cur = cur_s ? buf[which ^ 1] : all + v0;
         const bool is_last = l == d.nlayers - 1;
         double *lastp = glast + d.last_off + (size_t)c * d.nlast;
         // the last layer's states go to `lastp`; nobody reads them from the state block unless the host wants every state
         // (the global-state variant of a relaxed diagram would write its ~10 k-node last layer twice per cut)
-        const bool store = SMEM_STATES || !is_last || keep_all || DEADS;      // DEADS: the sequence path reads every cut's states afterwards
+        const bool store = cur_s || !is_last || keep_all || DEADS;      // DEADS: the sequence path reads every cut's states afterwards
+        const bool mirror = cur_s && keep_all;                           // shared-memory states the host will read
         if (width == 1 && !li.w) {
             // collapsed layer: one node, many in-arcs -> the whole CTA reduces it
             const int e1 = d.in_ptr[v0 + 1];
@@ -108,7 +116,7 @@ __global__ void __launch_bounds__(K2_FIN_THREADS) k2_longest_path(const K2DD *__
             s = block_max(s, red);
             if (threadIdx.x == 0) {
                 if (store) cur[0] = s;
-                if (SMEM_STATES && keep_all) all[v0] = s;
+                if (mirror) all[v0] = s;
                 if (is_last) lastp[0] = s;
             }
         } else if (li.w) {
@@ -120,7 +128,7 @@ __global__ void __launch_bounds__(K2_FIN_THREADS) k2_longest_path(const K2DD *__
                 s = -DBL_MAX < s ? s : -DBL_MAX;   // max(DOUBLE_MIN, .) of DD.cpp:3958
                 if (DEADS && d.arc_dead[e0 + i]) s = -DBL_MAX;
                 if (store) cur[i] = s;
-                if (SMEM_STATES && keep_all) all[v0 + i] = s;
+                if (mirror) all[v0 + i] = s;
                 if (is_last) lastp[i] = s;
             }
         } else {
@@ -134,10 +142,12 @@ __global__ void __launch_bounds__(K2_FIN_THREADS) k2_longest_path(const K2DD *__
                     s = s < cand ? cand : s;
                 }
                 if (store) cur[i] = s;
-                if (SMEM_STATES && keep_all) all[v0 + i] = s;
+                if (mirror) all[v0 + i] = s;
                 if (is_last) lastp[i] = s;
             }
         }
+        prev = cur;
+        if (cur_s) which ^= 1;
         __syncthreads();
     }
 }
@@ -599,10 +609,12 @@ cudaError_t k2_launch(const K2DD *dds, int B, const double *coef, const double *
         if (e != cudaSuccess) return e;
         k2_longest_path<true, false><<<grid, threads, tot, st>>>(dds, coef, rhs, C, Tpad, max_width_all, states, last, K2_LI_CACHE);
     } else {
-        const size_t sm2 = (size_t)Tpad * sizeof(double) + (size_t)K2_LI_CACHE * sizeof(int4);
+        // global-state variant: layers of at most K2_HYBRID nodes keep their states in two shared buffers all the same
+        const int hyb = (std::min(K2_HYBRID, max_width_all) + 1) & ~1;      // even: the staged layer records behind the buffers are 16-byte aligned
+        const size_t sm2 = ((size_t)Tpad + 2 * (size_t)hyb) * sizeof(double) + (size_t)K2_LI_CACHE * sizeof(int4);
         cudaError_t e = k2_raise_smem_limit(k2_longest_path<false, false>);
         if (e != cudaSuccess) return e;
-        k2_longest_path<false, false><<<grid, threads, sm2, st>>>(dds, coef, rhs, C, Tpad, 0, states, last, K2_LI_CACHE);
+        k2_longest_path<false, false><<<grid, threads, sm2, st>>>(dds, coef, rhs, C, Tpad, hyb, states, last, K2_LI_CACHE);
     }
     return cudaGetLastError();
 }
