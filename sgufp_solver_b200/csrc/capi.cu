@@ -101,10 +101,12 @@ int launch_batch(sgufp_ctx *c, const Batch &B, int K, unsigned long long *d_sums
     CU(c, cudaEventRecord(c->ev_h2d, st));
     c->h2d_pending = true;
     CU(c, cudaMemsetAsync(d_sums, 0, (size_t)K * c->W() * 8, st));
+    CU(c, c->d_work.reserve(1));
+    CU(c, cudaMemsetAsync(c->d_work.p, 0, 8, st));
     K1Launch p{};
     p.cap_u = c->d_u; p.cap_l = c->d_l; p.S = c->S; p.m = c->M.m; p.m_pad = c->m_pad; p.scen_offset = c->scen_off;
     p.plans = c->d_plans.p; p.plan_off = c->d_plan_off.p; p.K = K; p.W = c->W(); p.L = c->M.L;
-    p.sums = d_sums; p.first_inf = d_finf; p.obj = d_obj; p.status = d_status;
+    p.sums = d_sums; p.first_inf = d_finf; p.obj = d_obj; p.status = d_status; p.work = c->d_work.p;
     p.max_nch = B.max_nch; p.max_nopen = B.max_nopen; p.nc = c->M.nc; p.nav = c->M.nav; p.max_cap = c->max_cap;
     p.has_lower = c->max_lower > 0; p.lane_tables = B.key_lane; p.sum_abs_r = c->sum_abs_r; p.max_indeg = B.max_indeg;
     c->kernel_timed = false;
@@ -298,7 +300,7 @@ void sgufp_destroy(sgufp_ctx *c) {
         if (last) { cudaSetDevice(c->caps->device); if (c->caps->d_u) cudaFree(c->caps->d_u); if (c->caps->d_l) cudaFree(c->caps->d_l); delete c->caps; }
         c->caps = nullptr; c->d_u = c->d_l = nullptr;
     }
-    c->d_plans.release(); c->d_plan_off.release(); c->d_ray_i32.release(); c->d_sums.release(); c->d_finf.release();
+    c->d_plans.release(); c->d_plan_off.release(); c->d_ray_i32.release(); c->d_sums.release(); c->d_work.release(); c->d_finf.release();
     c->d_ray_scratch.release(); c->d_obj.release(); c->d_status.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);

@@ -57,7 +57,7 @@ struct sgufp_ctx {
     cudaStream_t st = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
     DevBuf<int32_t> d_plans, d_plan_off, d_ray_i32;
-    DevBuf<unsigned long long> d_sums;
+    DevBuf<unsigned long long> d_sums, d_work;
     DevBuf<long long> d_finf, d_ray_scratch;
     DevBuf<double> d_obj;
     DevBuf<uint8_t> d_status;

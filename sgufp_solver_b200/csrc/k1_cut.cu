@@ -561,7 +561,18 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
     }
     const long long items = (long long)p.K * p.S;
     const long long stride = (long long)gridDim.x * TILES_PER_CTA;
-    for (long long item = (long long)blockIdx.x * TILES_PER_CTA + tile_in_cta; item < items; item += stride) {
+    // Work items come from a queue (one atomic per item, taken by the tile's first lane) when the launch carries one: an item
+    // takes 0.1 - 0.3 ms and varies with the scenario, so with a few items per warp (a rank of an 8-GPU partition of C4 has
+    // 2.1) a fixed assignment leaves most of the GPU waiting for the warps that drew three long ones.  Scenario-minor order
+    // either way: neighbouring tiles stream neighbouring rows.
+    long long item = (long long)blockIdx.x * TILES_PER_CTA + tile_in_cta - stride;
+    for (;;) {
+        if (p.work) {
+            unsigned long long nxt = 0;
+            if (T.tl == 0) nxt = atomicAdd(p.work, 1ull);
+            item = (long long)__shfl_sync(T.mask, nxt, T.base, 32);
+        } else item += stride;
+        if (item >= items) break;
         const int k = (int)(item / p.S), s = (int)(item - (long long)k * p.S);
         if (*reinterpret_cast<volatile long long *>(p.first_inf + k) < 0) continue;   // this candidate was aborted: drain
         int fuel = 1 << 20;   // passes + levels a work item may spend (tile-uniform)

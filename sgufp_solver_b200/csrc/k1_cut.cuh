@@ -14,6 +14,7 @@ struct K1Launch {
     int K, W, L;
     unsigned long long *sums;     // [K][W] exact integer accumulators (two's complement)
     long long *first_inf;         // [K] lowest infeasible global scenario (init LLONG_MAX)
+    unsigned long long *work;     // work-item queue of the warp kernel (one word, zeroed before the launch) or nullptr: fixed assignment
     double *obj;                  // [K][S] or nullptr
     uint8_t *status;              // [K][S] or nullptr
     int max_nch, max_nopen, nc, nav;

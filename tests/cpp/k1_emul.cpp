@@ -85,6 +85,8 @@ extern "C" int emul_paths(int n, int m, int S, const int32_t *tail, const int32_
     p.cap_u = cu.data(); p.cap_l = cl.data(); p.S = S; p.m = m; p.m_pad = m_pad; p.scen_offset = 0;
     p.plans = words.data(); p.plan_off = off.data(); p.K = K; p.W = W; p.L = M.L;
     p.sums = reinterpret_cast<unsigned long long *>(sums); p.first_inf = first_inf; p.obj = obj; p.status = status;
+    unsigned long long work_queue = 0;
+    p.work = (K & 1) ? &work_queue : nullptr;     // both ways of handing out work items are exercised
     g_last_nc = M.nc;
     p.max_nch = max_nch; p.max_nopen = max_nopen; p.nc = M.nc; p.nav = M.nav; p.max_cap = 65535;
     const int wpt = k1_words_per_tile(p);

@@ -128,6 +128,38 @@ def test_fresh_device_tree_gives_the_reference_first_path():
     assert ours.getSolution().tolist() == ref.solution().tolist()
 
 
+def test_sequence_call_first_on_a_host_built_diagram(monkeypatch):
+    """a host-built diagram (SGUFP_DD_BUILD=host, or the fallbacks) whose FIRST apply is a run of cuts
+    (`sgufp_dd_apply_sequence`, what NodeExplorer::process does with the global cuts) must work like the one-by-one calls."""
+    inst = INSTANCES["c2"]()
+    solver = sg.GuroSolver(inst)
+    rng = np.random.default_rng(77)
+    cuts = [random_cut(solver, rng) for _ in range(9)]
+    one = RelaxedDDNew(solver)                             # device-built, cut by cut
+    one.buildTree()
+    want = [one.applyOptimalityCut(c, -1e300, 1e300) for c in cuts]
+    monkeypatch.setenv("SGUFP_DD_BUILD", "host")
+    seq = RelaxedDDNew(solver)
+    seq.buildTree()
+    assert not seq.dump_device()["built_on_device"]
+    bounds, n = seq.applyOptimalityCuts(cuts, -1e300)      # the first apply on this diagram is a sequence call
+    assert n == len(cuts) and bounds.tolist() == want
+    assert seq.getSolution().tolist() == one.getSolution().tolist()
+    feas = RelaxedDDNew(solver)
+    feas.buildTree()
+    fc = [random_cut(solver, rng, cut_type=1) for _ in range(4)]
+    flags, k = feas.applyFeasibilityCuts(fc)
+    monkeypatch.delenv("SGUFP_DD_BUILD")
+    ref = RelaxedDDNew(solver)
+    ref.buildTree()
+    exp = []
+    for c in fc:
+        exp.append(ref.applyFeasibilityCut(c))
+        if not exp[-1]:
+            break
+    assert flags.tolist() == exp and k == len(exp)
+
+
 def test_host_builder_still_reachable(monkeypatch):
     monkeypatch.setenv("SGUFP_DD_BUILD", "host")
     inst = INSTANCES["mid"]()

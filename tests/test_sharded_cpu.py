@@ -85,3 +85,17 @@ def test_shard_bounds_partition():
         for s in (0, S // 2, S - 1):
             lo, hi = cuts[owner_of(s, S, w)]
             assert lo <= s < hi
+
+
+def test_a_shard_keeps_scenario_zero_rewards():
+    """the rows of the dual LP use rewards[0] of the WHOLE instance for every scenario (grb.cpp:53,71,89): a scenario
+    block must hand the library the full instance's column 0, not its own first column; an empty block keeps a reward column."""
+    import dataclasses
+    inst = I.config1(S=12)
+    rew = inst.reward.copy()
+    rew[:, 1:] += (np.arange(1, inst.S)[None, :] % 5) - 2          # rewards that vary with the scenario (the format allows it)
+    inst = dataclasses.replace(inst, reward=rew)
+    for lo, hi in ((0, 5), (5, 12), (7, 7)):
+        part = inst.scenario_slice(lo, hi)
+        assert part.S == hi - lo and (part.reward[:, 0] == inst.reward[:, 0]).all()
+        assert part.upper.shape == (inst.m, hi - lo)
