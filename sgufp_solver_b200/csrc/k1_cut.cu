@@ -259,20 +259,26 @@ __device__ int tight_list(const PlanView &P, int nopen, const Lanes<TILE> &T, TM
 // node's bit is the only one to write its predecessor (tail | (2*chain+dir) << 10), and that tail's bit was set
 // before: the predecessors form a tree rooted at src.  Any tight path will do — the duals do not depend on which
 // optimal flow is found.  If dst is not reached, w.rw holds the complete reached set.
+// Every (sweep, chunk) visit has a number q; a node's predecessor word also carries the visit at which it was reached
+// (7 bits, saturating: tail | (2*chain+dir) << 10 | min(q, 127) << 25).  A node reached at visit q hangs on nodes reached at visits
+// <= q, so after a push the nodes reached BEFORE the first visit that used a now saturated arc keep their place in the set and
+// the next search starts in the middle of a sweep, at that visit's chunk (c0, q), instead of from the root.
 template <int TILE, class TM>
-__device__ bool reach_list(int src, int dst, const PlanView &P, int ntc, int nword, const Lanes<TILE> &T, TM &w, bool keep = false) {
+__device__ bool reach_list(int src, int dst, const PlanView &P, int ntc, int nword, const Lanes<TILE> &T, TM &w, bool keep, int c0, int &q) {
     const int R = w.rw;
-    // keep: the search goes on from the reached set of the last (failed) one — after a dual update its nodes keep their labels
-    // and their predecessors, only more arcs are tight
+    // keep: the search goes on from a reached set that is still valid — after a dual update (the nodes keep their labels and
+    // their predecessors, only more arcs are tight), or after a push (the part of the set reached before the saturated arcs)
     if (!keep) for (int i = T.tl; i < nword; i += TILE) SU(R + (i)) = i == (src >> 5) ? 1u << (src & 31) : 0u;
     T.sync();
+    bool partial = c0 > 0;                                  // the first sweep starts at chunk c0: it can find dst, it cannot prove a fixpoint
     for (;;) {
         bool grew = false;
 #ifdef SGUFP_K1_SKIP_CONFIRM
         bool back = false;          // a backward arc fired, or a usable backward entry is still waiting for its tail
 #endif
-        for (int i0 = 0; i0 < ntc; i0 += TILE) {           // tile-uniform trip count
+        for (int i0 = partial ? c0 * TILE : 0; i0 < ntc; i0 += TILE, q++) {           // tile-uniform trip count
             const int i = i0 + T.tl;
+            const int stamp = min(q, 127) << 25;
             int c = 0, f = 0;
             if (i < ntc) { const int en = SH(2 * w.tc + i); c = en & 0x3fff; f = RGET(c) & (en >> 14); }
             const ChainEnds e(f ? P.ch_st[c] : make_int2(0, 0));
@@ -283,13 +289,13 @@ __device__ bool reach_list(int src, int dst, const PlanView &P, int ntc, int nwo
                 bool g = false;
                 if ((f & 1) && ((SU(R + (e.sv >> 5)) >> (e.sv & 31)) & 1)) {
                     const unsigned bit = 1u << (e.hf & 31);
-                    if (!((SU(R + (e.hf >> 5)) & bit)) && !(atomicOr(&SU(R + (e.hf >> 5)), bit) & bit)) { SI(w.pred + e.hf) = e.sv | ((2 * c) << 10); g = true; }
+                    if (!((SU(R + (e.hf >> 5)) & bit)) && !(atomicOr(&SU(R + (e.hf >> 5)), bit) & bit)) { SI(w.pred + e.hf) = e.sv | ((2 * c) << 10) | stamp; g = true; }
                     f &= ~1;
                 }
                 if ((f & 2) && ((SU(R + (e.ev >> 5)) >> (e.ev & 31)) & 1)) {
                     const unsigned bit = 1u << (e.hb & 31);
                     if (!((SU(R + (e.hb >> 5)) & bit)) && !(atomicOr(&SU(R + (e.hb >> 5)), bit) & bit)) {
-                        SI(w.pred + e.hb) = e.ev | ((2 * c + 1) << 10); g = true;
+                        SI(w.pred + e.hb) = e.ev | ((2 * c + 1) << 10) | stamp; g = true;
 #ifdef SGUFP_K1_SKIP_CONFIRM
                         back = true;
 #endif
@@ -306,7 +312,7 @@ __device__ bool reach_list(int src, int dst, const PlanView &P, int ntc, int nwo
         }
         T.sync();
 #ifdef SGUFP_K1_STATS
-        if (T.tl == 0) { atomicAdd(&g_k1_stats[4], 1ull); atomicAdd(&g_k1_stats[5], (unsigned long long)ntc); }
+        if (T.tl == 0) { atomicAdd(&g_k1_stats[4], 1ull); atomicAdd(&g_k1_stats[5], (unsigned long long)(ntc - (partial ? c0 * TILE : 0))); }
 #endif
         if ((SU(R + (dst >> 5)) >> (dst & 31)) & 1) {
 #ifdef SGUFP_K1_STATS
@@ -314,28 +320,33 @@ __device__ bool reach_list(int src, int dst, const PlanView &P, int ntc, int nwo
 #endif
             return true;
         }
+        if (partial) { partial = false; continue; }          // full sweeps decide
         if (!T.any(grew)) return false;
 #ifdef SGUFP_K1_SKIP_CONFIRM
-        // Experiment (not measured yet, profiles/r01c_summary.md): the list is sorted by the depth of the tails
-        // (model.cpp: build_plan), so a forward entry can only be overtaken by a backward arc that fires after it, and a
-        // waiting backward entry by any later arc: without either, this sweep already reached the fixpoint.
+        // The list is sorted by the depth of the tails (model.cpp: build_plan), so a forward entry can only be overtaken by a
+        // backward arc that fires after it, and a waiting backward entry by any later arc: without either, this sweep already
+        // reached the fixpoint.
         if (!T.any(back)) return false;
 #endif
     }
 }
 
-// list variant of the push: every lane walks the predecessor tree dst -> src, lane 0 writes
+// list variant of the push: every lane walks the predecessor tree dst -> src, then a hop per lane moves the flow.
+// *restart: the visit number from which the reached set has to be searched again (the least visit stamp among the heads of the
+// arcs this push saturates; the nodes reached at or after it are taken out of the set here), or -1: search from the root.
 template <int TILE, class TM>
-__device__ int push_list(int src, int dst, int limit, int nc, const Lanes<TILE> &T, TM &w) {
+__device__ int push_list(int src, int dst, int limit, int nc, const Lanes<TILE> &T, TM &w, int *restart) {
     int v = dst, d = limit, hops = 0;
+    *restart = -1;
 #ifdef SGUFP_K1_PUSH_PAR
-    int mine = -1;                         // the hop this lane will update (hop number == lane number)
+    int mine = 0;                          // the hop this lane will update (hop number == lane number): its predecessor word
+    bool have = false;                     // (a word with a visit stamp of 64 or more is negative: the flag cannot live in its sign)
 #endif
     while (v != src) {
-        const int p = SI(w.pred + v), s = p >> 10, c = s >> 1, xc = SI(w.x + c);
+        const int p = SI(w.pred + v), s = (p >> 10) & 0x7fff, c = s >> 1, xc = SI(w.x + c);
         d = min(d, (s & 1) ? xc - (SI(w.lo + c) >> HB) : (SI(w.up + c) >> HB) - xc);
 #ifdef SGUFP_K1_PUSH_PAR
-        if (hops == T.tl) mine = p;
+        if (hops == T.tl) { mine = p; have = true; }
 #endif
         v = p & 1023;
         if (++hops > nc + 1) { d = 0; break; }
@@ -343,22 +354,32 @@ __device__ int push_list(int src, int dst, int limit, int nc, const Lanes<TILE> 
     T.sync();                              // every lane has its bottleneck before lane 0 moves the flow
     if (d <= 0) return 0;
 #ifdef SGUFP_K1_PUSH_PAR
-    // Experiment (not measured yet, profiles/r01c_summary.md): a path of at most TILE hops is updated in one step, a hop
-    // per lane (the chains of a simple path are distinct), instead of a second walk.
+    // a path of at most TILE hops is updated in one step, a hop per lane (the chains of a simple path are distinct)
     if (hops <= TILE) {
-        if (mine >= 0) {
-            const int s = mine >> 10, c = s >> 1;
+        int sat = 255;                     // visit stamp of this hop's head if the push saturates its arc
+        if (have) {
+            const int s = (mine >> 10) & 0x7fff, c = s >> 1;
             const int xc = SI(w.x + c) + ((s & 1) ? -d : d);
             SI(w.x + c) = xc;
-            RSET(c, (xc < (SI(w.up + c) >> HB) ? 1 : 0) | (xc > (SI(w.lo + c) >> HB) ? 2 : 0));
+            const int fl = (xc < (SI(w.up + c) >> HB) ? 1 : 0) | (xc > (SI(w.lo + c) >> HB) ? 2 : 0);
+            RSET(c, fl);
+            if (!((fl >> (s & 1)) & 1)) sat = (int)((unsigned)mine >> 25);
         }
+#ifndef SGUFP_K1_NO_RESTART
+        const int qs = T.min_i32(sat);     // at least one arc saturates (d is the bottleneck) unless `limit` bound the push
+        if (qs > 0 && qs < 127) {
+            for (int u = T.tl; u <= nc; u += TILE)
+                if (u != src && ((SU(w.rw + (u >> 5)) >> (u & 31)) & 1) && (int)((unsigned)SI(w.pred + u) >> 25) >= qs) atomicAnd(&SU(w.rw + (u >> 5)), ~(1u << (u & 31)));
+            *restart = qs;
+        }
+#endif
         T.sync();
         return d;
     }
 #endif
     v = dst;
     while (v != src) {
-        const int p = SI(w.pred + v), s = p >> 10, c = s >> 1;
+        const int p = SI(w.pred + v), s = (p >> 10) & 0x7fff, c = s >> 1;
         if (T.tl == 0) {
             const int xc = SI(w.x + c) + ((s & 1) ? -d : d);
             SI(w.x + c) = xc;
@@ -377,10 +398,14 @@ struct TightPaths {
     const Lanes<TILE> &T;
     TM &w;
     int nopen, nc, nword, ntc;
+    int rq, q;                            // list search: visit to restart from after a push (-1: from the root), visit counter
     static constexpr bool small = !TM::BIG;
     __device__ TightPaths(const PlanView &P_, const Lanes<TILE> &T_, TM &w_, int nopen_, int nc_)
-        : P(P_), T(T_), w(w_), nopen(nopen_), nc(nc_), nword(reach_words(nc_)), ntc(0) {}
-    __device__ void prepare() { if constexpr (small) tight_small<TILE>(P, nopen, T, w); else ntc = tight_list<TILE>(P, nopen, T, w); }
+        : P(P_), T(T_), w(w_), nopen(nopen_), nc(nc_), nword(reach_words(nc_)), ntc(0), rq(-1), q(0) {}
+    __device__ void prepare() {
+        if constexpr (small) tight_small<TILE>(P, nopen, T, w); else ntc = tight_list<TILE>(P, nopen, T, w);
+        rq = -1;                          // a new list: chunk positions of the old one mean nothing
+    }
     __device__ __forceinline__ bool in_r(int v) const {
         if constexpr (small) return (SU(w.rw) >> v) & 1u; else return (SU(w.rw + (v >> 5)) >> (v & 31)) & 1u;
     }
@@ -419,8 +444,16 @@ struct TightPaths {
         if constexpr (small) {
             const int lev = reach_small<TILE>(src, dst, nc, T, w);
             return lev ? push_small<TILE>(dst, limit, lev, nc, T, w) : 0;
-        } else
-        return reach_list<TILE>(src, dst, P, ntc, nword, T, w, keep) ? push_list<TILE>(src, dst, limit, nc, T, w) : 0;
+        } else {
+            const int nchunk = (ntc + TILE - 1) / TILE;
+            int c0 = 0;
+            if (rq > 0 && nchunk > 0) { c0 = rq % nchunk; q = rq; keep = true; }      // after a push: from the middle of a sweep
+            else if (keep && nchunk > 0) q = (q + nchunk - 1) / nchunk * nchunk;     // after a dual update: a new sweep, visit numbers go on
+            else { q = 0; keep = false; }
+            rq = -1;
+            if (!reach_list<TILE>(src, dst, P, ntc, nword, T, w, keep, c0, q)) return 0;
+            return push_list<TILE>(src, dst, limit, nc, T, w, &rq);
+        }
     }
 };
 
