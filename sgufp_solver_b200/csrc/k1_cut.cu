@@ -368,6 +368,13 @@ __device__ int push_list(int src, int dst, int limit, int nc, const Lanes<TILE> 
 #ifndef SGUFP_K1_NO_RESTART
         const int qs = T.min_i32(sat);     // at least one arc saturates (d is the bottleneck) unless `limit` bound the push
         if (qs > 0 && qs < 127) {
+            if constexpr (TILE == 32) {   // a word of the set per step: the lanes vote on its 32 nodes
+                for (int u = T.tl; u < 32 * reach_words(nc); u += 32) {
+                    const bool in = u <= nc && ((SU(w.rw + (u >> 5)) >> (u & 31)) & 1);
+                    const unsigned word = T.ballot(in && (u == src || (int)((unsigned)SI(w.pred + u) >> 25) < qs));
+                    if (T.tl == 0) SU(w.rw + (u >> 5)) = word;
+                }
+            } else
             for (int u = T.tl; u <= nc; u += TILE)
                 if (u != src && ((SU(w.rw + (u >> 5)) >> (u & 31)) & 1) && (int)((unsigned)SI(w.pred + u) >> 25) >= qs) atomicAnd(&SU(w.rw + (u >> 5)), ~(1u << (u & 31)));
             *restart = qs;
