@@ -35,7 +35,9 @@ static cudaError_t k2_raise_smem_limit(F *kernel) {
 namespace {
 
 constexpr int K2_THREADS = 256;
-constexpr int K2_HYBRID = 2048;        // global-state variant of the batch path: layers up to this width keep their states in shared memory
+constexpr int K2_HYBRID = 0;           // global-state variant of the batch path: layers up to this width would keep their states in shared memory.
+                                       // Measured with 2048: 2.67e11 -> 2.25e11 arcs/s on the relaxed diagrams (32 KB more per CTA: 18 -> 6 CTAs per SM on a
+                                       // latency-bound kernel; the wide last layers hold most of the nodes anyway): off.  SGUFP_K2_HYBRID=<width> turns it on.
 constexpr int K2_TERM_SLICES = 64;     // CTAs per diagram in k2_terminal (scratch: B x 64 partial maxima)
 constexpr int K2_FIN_THREADS = 1024;   // the one-CTA kernels that sweep a (possibly wide) last layer
 
@@ -610,7 +612,9 @@ cudaError_t k2_launch(const K2DD *dds, int B, const double *coef, const double *
         k2_longest_path<true, false><<<grid, threads, tot, st>>>(dds, coef, rhs, C, Tpad, max_width_all, states, last, K2_LI_CACHE);
     } else {
         // global-state variant: layers of at most K2_HYBRID nodes keep their states in two shared buffers all the same
-        const int hyb = (std::min(K2_HYBRID, max_width_all) + 1) & ~1;      // even: the staged layer records behind the buffers are 16-byte aligned
+        int hyb_w = K2_HYBRID;
+        if (const char *e = getenv("SGUFP_K2_HYBRID")) hyb_w = std::max(0, atoi(e));
+        const int hyb = (std::min(hyb_w, max_width_all) + 1) & ~1;      // even: the staged layer records behind the buffers are 16-byte aligned
         const size_t sm2 = ((size_t)Tpad + 2 * (size_t)hyb) * sizeof(double) + (size_t)K2_LI_CACHE * sizeof(int4);
         cudaError_t e = k2_raise_smem_limit(k2_longest_path<false, false>);
         if (e != cudaSuccess) return e;
