@@ -63,15 +63,27 @@ int make_batch(sgufp_ctx *c, const int16_t *paths, int K, int L, Batch &B, bool 
         if (!c->pool || c->pool->size() < nt) { delete c->pool; c->pool = new HostPool(nt - 1); }
         c->pool->run(nt, work);
     } else work(0, 1);
+    for (int k = 0; k < K; k++)
+        if (rc[k]) return fail(c, rc[k], "path " + std::to_string(k) + ": " + errs[k]);   // the lowest failing index, as a serial loop would report
+    // links between consecutive candidates (warm starts inside a work item of the warp kernel, k1_cut.cu)
+    B.links.resize(K); B.link_off.assign(K, -1);
+    if (K > 1) {
+        const std::function<void(int, int)> link = [&](int t, int nt) {
+            for (int k = 1 + t; k < K; k += nt) link_plans(B.plans[k - 1], B.plans[k], B.links[k]);
+        };
+        if (nt > 1) c->pool->run(nt, link); else link(0, 1);
+    }
+    B.links[0].clear();
     size_t total = 0;
     for (int k = 0; k < K; k++) {
-        if (rc[k]) return fail(c, rc[k], "path " + std::to_string(k) + ": " + errs[k]);   // the lowest failing index, as a serial loop would report
         B.off[k] = (int32_t)total;
         total += B.plans[k].words.size();
         B.max_nch = std::max(B.max_nch, B.plans[k].nch);
         B.max_nopen = std::max(B.max_nopen, B.plans[k].nopen);
         B.max_indeg = std::max(B.max_indeg, B.plans[k].max_indeg);
     }
+    for (int k = 1; k < K; k++)
+        if (!B.links[k].empty()) { B.link_off[k] = (int32_t)total; total += B.links[k].size(); }
     B.total_words = total;
     B.key_paths.assign(paths, paths + npath); B.key_K = K; B.key_L = L; B.key_lane = lane_tables;
     return 0;
@@ -80,10 +92,10 @@ int make_batch(sgufp_ctx *c, const int16_t *paths, int K, int L, Batch &B, bool 
 int launch_batch(sgufp_ctx *c, const Batch &B, int K, unsigned long long *d_sums, long long *d_finf, double *d_obj,
                         uint8_t *d_status, cudaStream_t st) {
     CU(c, c->d_plans.reserve(B.total_words));
-    CU(c, c->d_plan_off.reserve(K));
+    CU(c, c->d_plan_off.reserve(2 * (size_t)K));
     // gather the plans (+ offsets + the initial "no infeasible scenario" marks) into pinned memory: the uploads are then
     // true asynchronous copies.  The staging buffer is reused by the next call: an event tells when the copies left it.
-    const size_t o_off = B.total_words, o_inf = (o_off + (size_t)K + 1) & ~(size_t)1, need = o_inf + 2 * (size_t)K;
+    const size_t o_off = B.total_words, o_inf = (o_off + 2 * (size_t)K + 1) & ~(size_t)1, need = o_inf + 2 * (size_t)K;
     if (c->h2d_pending) { CU(c, cudaEventSynchronize(c->ev_h2d)); c->h2d_pending = false; }
     if (c->h_words_cap < need) {
         if (c->h_words) cudaFreeHost(c->h_words);
@@ -92,11 +104,13 @@ int launch_batch(sgufp_ctx *c, const Batch &B, int K, unsigned long long *d_sums
         c->h_words_cap = need * 2;
     }
     for (int k = 0; k < K; k++) std::memcpy(c->h_words + B.off[k], B.plans[k].words.data(), B.plans[k].words.size() * 4);
+    for (int k = 1; k < K; k++) if (B.link_off[k] >= 0) std::memcpy(c->h_words + B.link_off[k], B.links[k].data(), B.links[k].size() * 4);
     std::memcpy(c->h_words + o_off, B.off.data(), (size_t)K * 4);
+    std::memcpy(c->h_words + o_off + K, B.link_off.data(), (size_t)K * 4);
     long long *inf = reinterpret_cast<long long *>(c->h_words + o_inf);
     for (int k = 0; k < K; k++) inf[k] = LLONG_MAX;
     CU(c, cudaMemcpyAsync(c->d_plans.p, c->h_words, B.total_words * 4, cudaMemcpyHostToDevice, st));
-    CU(c, cudaMemcpyAsync(c->d_plan_off.p, c->h_words + o_off, (size_t)K * 4, cudaMemcpyHostToDevice, st));
+    CU(c, cudaMemcpyAsync(c->d_plan_off.p, c->h_words + o_off, 2 * (size_t)K * 4, cudaMemcpyHostToDevice, st));
     CU(c, cudaMemcpyAsync(d_finf, inf, (size_t)K * 8, cudaMemcpyHostToDevice, st));
     CU(c, cudaEventRecord(c->ev_h2d, st));
     c->h2d_pending = true;
@@ -105,7 +119,7 @@ int launch_batch(sgufp_ctx *c, const Batch &B, int K, unsigned long long *d_sums
     CU(c, cudaMemsetAsync(c->d_work.p, 0, 8, st));
     K1Launch p{};
     p.cap_u = c->d_u; p.cap_l = c->d_l; p.S = c->S; p.m = c->M.m; p.m_pad = c->m_pad; p.scen_offset = c->scen_off;
-    p.plans = c->d_plans.p; p.plan_off = c->d_plan_off.p; p.K = K; p.W = c->W(); p.L = c->M.L;
+    p.plans = c->d_plans.p; p.plan_off = c->d_plan_off.p; p.link_off = c->d_plan_off.p + K; p.group = k1_group(K, c->S, c->sm_count); p.K = K; p.W = c->W(); p.L = c->M.L;
     p.sums = d_sums; p.first_inf = d_finf; p.obj = d_obj; p.status = d_status; p.work = c->d_work.p;
     p.max_nch = B.max_nch; p.max_nopen = B.max_nopen; p.nc = c->M.nc; p.nav = c->M.nav; p.max_cap = c->max_cap;
     p.has_lower = c->max_lower > 0; p.lane_tables = B.key_lane; p.sum_abs_r = c->sum_abs_r; p.max_indeg = B.max_indeg;

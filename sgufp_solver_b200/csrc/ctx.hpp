@@ -29,6 +29,8 @@ struct DevBuf {
 struct PlanBatch {
     std::vector<sgufp::Plan> plans;
     std::vector<int32_t> off;
+    std::vector<std::vector<int32_t>> links;   // links[k]: candidate k seen from candidate k-1 (model.hpp: link_plans), empty = none
+    std::vector<int32_t> link_off;   // [K] word offset of links[k] in the pool behind the plans, -1 = none
     size_t total_words = 0;          // the plans are gathered into the handle's pinned staging buffer at launch
     int max_nch = 0, max_nopen = 0, max_indeg = 0;
     std::vector<int16_t> key_paths;  // what the plans were built from (valid when key_K > 0)

@@ -49,10 +49,12 @@ struct TileMemT {
     int tin, tout, hist, path, tab;       // small graphs: bit sets of the tight residual graph, search levels, path, pair table
     int tc;                               // larger graphs: the tight-chain list (same place)
     int rw;                               // reached set of the last search
+    int tg;                               // warm start: the set of nodes a search may end at (deficits; index nc = the root)
     int up, lo, x, res, lab, pred, pot, exc, aq;
 };
 #ifdef SGUFP_K1_EMULATE
 #define k1_smem sgufp_emul_smem           // tests/cpp/k1_emul.cpp: the kernel body compiled for the host
+static long long sgufp_emul_warm[2];
 #else
 extern __shared__ int k1_smem[];
 #endif
@@ -74,7 +76,7 @@ __host__ __device__ inline int k1_search_words(int nc, int max_nopen) {   // bit
     return nc <= SMALL_NC ? 32 + 32 + 34 + 34 + 32 * 32 / 2 : (max_nopen + 1) / 2;   // list entries are 16 bits
 }
 __host__ __device__ inline int k1_words_per_tile(const K1Launch &p) {
-    return 3 * p.max_nopen + (p.nc <= SMALL_NC ? p.max_nopen : (p.max_nopen + 3) / 4) + 3 * (p.nc + 2) + p.nav + 2 + reach_words(p.nc) + k1_search_words(p.nc, p.max_nopen);
+    return 3 * p.max_nopen + (p.nc <= SMALL_NC ? p.max_nopen : (p.max_nopen + 3) / 4) + 3 * (p.nc + 2) + p.nav + 2 + 2 * reach_words(p.nc) + k1_search_words(p.nc, p.max_nopen);
 }
 
 template <int TILE>
@@ -182,8 +184,10 @@ __device__ void tight_small(const PlanView &P, int nopen, const Lanes<TILE> &T, 
 
 // Breadth-first search src -> dst; hist[l] = the nodes first reached at level l.  Returns the level
 // of dst, or 0 if it cannot be reached — then SU(w.rw + 0) holds the complete reached set.
+// dst < 0: the search ends at any node of the target set w.tg and *hit tells which (warm start).
 template <int TILE, class TM>
-__device__ int reach_small(int src, int dst, int nc, const Lanes<TILE> &T, TM &w) {
+__device__ int reach_small(int src, int dst, int nc, const Lanes<TILE> &T, TM &w, int *hit) {
+    const unsigned dm = dst >= 0 ? 1u << dst : SU(w.tg);
     unsigned R = 1u << src, F = R;
     int lev = 0;
     if (T.tl == 0) SU(w.hist + 0) = F;
@@ -195,7 +199,7 @@ __device__ int reach_small(int src, int dst, int nc, const Lanes<TILE> &T, TM &w
         if (!nb) { if (T.tl == 0) SU(w.rw + 0) = R; T.sync(); return 0; }
         R |= nb; F = nb; lev++;
         if (T.tl == 0) SU(w.hist + lev) = F;
-        if ((R >> dst) & 1) { T.sync(); return lev; }
+        if (R & dm) { *hit = __ffs(R & dm) - 1; T.sync(); return lev; }
     }
 }
 
@@ -264,7 +268,7 @@ __device__ int tight_list(const PlanView &P, int nopen, const Lanes<TILE> &T, TM
 // <= q, so after a push the nodes reached BEFORE the first visit that used a now saturated arc keep their place in the set and
 // the next search starts in the middle of a sweep, at that visit's chunk (c0, q), instead of from the root.
 template <int TILE, class TM>
-__device__ bool reach_list(int src, int dst, const PlanView &P, int ntc, int nword, const Lanes<TILE> &T, TM &w, bool keep, int c0, int &q) {
+__device__ bool reach_list(int src, int dst, const PlanView &P, int ntc, int nword, const Lanes<TILE> &T, TM &w, bool keep, int c0, int &q, int *hit) {
     const int R = w.rw;
     // keep: the search goes on from a reached set that is still valid — after a dual update (the nodes keep their labels and
     // their predecessors, only more arcs are tight), or after a push (the part of the set reached before the saturated arcs)
@@ -314,11 +318,19 @@ __device__ bool reach_list(int src, int dst, const PlanView &P, int ntc, int nwo
 #ifdef SGUFP_K1_STATS
         if (T.tl == 0) { atomicAdd(&g_k1_stats[4], 1ull); atomicAdd(&g_k1_stats[5], (unsigned long long)(ntc - (partial ? c0 * TILE : 0))); }
 #endif
-        if ((SU(R + (dst >> 5)) >> (dst & 31)) & 1) {
+        if (dst >= 0) {
+            if ((SU(R + (dst >> 5)) >> (dst & 31)) & 1) {
 #ifdef SGUFP_K1_STATS
-            if (T.tl == 0) atomicAdd(&g_k1_stats[6], 1ull);
+                if (T.tl == 0) atomicAdd(&g_k1_stats[6], 1ull);
 #endif
-            return true;
+                *hit = dst;
+                return true;
+            }
+        } else {                                             // any node of the target set (warm start): the lowest one reached
+            int found = INT_MAX;
+            for (int i = T.tl; i < nword; i += TILE) { const unsigned both = SU(R + i) & SU(w.tg + i); if (both && found == INT_MAX) found = 32 * i + __ffs(both) - 1; }
+            found = T.min_i32(found);
+            if (found != INT_MAX) { *hit = found; return true; }
         }
         if (partial) { partial = false; continue; }          // full sweeps decide
         if (!T.any(grew)) return false;
@@ -406,9 +418,10 @@ struct TightPaths {
     TM &w;
     int nopen, nc, nword, ntc;
     int rq, q;                            // list search: visit to restart from after a push (-1: from the root), visit counter
+    int hit;                              // the node the last successful search ended at
     static constexpr bool small = !TM::BIG;
     __device__ TightPaths(const PlanView &P_, const Lanes<TILE> &T_, TM &w_, int nopen_, int nc_)
-        : P(P_), T(T_), w(w_), nopen(nopen_), nc(nc_), nword(reach_words(nc_)), ntc(0), rq(-1), q(0) {}
+        : P(P_), T(T_), w(w_), nopen(nopen_), nc(nc_), nword(reach_words(nc_)), ntc(0), rq(-1), q(0), hit(0) {}
     __device__ void prepare() {
         if constexpr (small) tight_small<TILE>(P, nopen, T, w); else ntc = tight_list<TILE>(P, nopen, T, w);
         rq = -1;                          // a new list: chunk positions of the old one mean nothing
@@ -421,7 +434,13 @@ struct TightPaths {
     // a non-negative reduced cost), the labels inside R stay exact, at least one more arc becomes tight: ONE pass over the
     // chains instead of a label computation of 3.6 - 3.9 relaxation passes (profiles/r02_summary.md).  Returns false when the
     // flow is optimal: no residual arc leaves R (maximum flow), or the sink's label has reached 0 (no profitable path left).
-    __device__ bool dual_update() {
+    // to_sink = false (repair of a warm start, any source): only "no residual arc leaves R" ends it; root_in: the search
+    // started at the root, whose other face (index nc, the root as a path end) then belongs to R as well.
+    __device__ bool dual_update(bool to_sink = true, bool root_in = false) {
+        if (root_in) {
+            if (T.tl == 0) { if constexpr (small) SU(w.rw) |= 1u << nc; else SU(w.rw + (nc >> 5)) |= 1u << (nc & 31); }
+            T.sync();
+        }
         int best = INT_MAX;
         for (int c = T.tl; c < nopen; c += TILE) {
             const int f = RGET(c) & 3;
@@ -439,18 +458,49 @@ struct TightPaths {
         for (int v = T.tl; v <= nc; v += TILE)
             if (!in_r(v)) { const int l = SI(w.lab + v); if (l != LAB_INF) SI(w.lab + v) = l + delta; }
         T.sync();
-        if (SI(w.lab + nc) >= 0) return false;
+        if (to_sink && SI(w.lab + nc) >= 0) return false;
         prepare();
         return true;
     }
+    // The excess of src to the nodes of the target set w.tg along tight residual paths, with dual updates when a search fails
+    // (warm start: the imbalances left by the chains that changed).  false: stuck (no residual arc leaves the reached set;
+    // cannot happen while total excess equals total deficit) or out of fuel.
+    __device__ bool route(int src, int &fuel) {
+        rq = -1;
+        bool keep = false;
+        int need = SI(w.exc + src);
+        while (need > 0) {
+            if (--fuel <= 0) return false;
+            const int d = augment(src, -1, need, keep);
+            keep = false;
+            if (d > 0) {
+                need -= d;
+                T.sync();
+                if (T.tl == 0) {                       // books: the source, the node it ended at (its target bit goes with its deficit)
+                    const int t = hit == nc ? 0 : hit, left = SI(w.exc + t) + d;
+                    SI(w.exc + src) = need; SI(w.exc + t) = left;
+                    if (!left && hit != nc) SU(w.tg + (hit >> 5)) &= ~(1u << (hit & 31));
+                }
+                T.sync();
+                continue;
+            }
+            if (!dual_update(false, src == 0)) return false;
+            keep = TM::BIG;
+        }
+        return true;
+    }
     // one search and, if dst is reachable, one push of at most `limit`; returns the amount pushed (0: not reachable)
+    // dst < 0 (warm start): to the first node of the target set w.tg the search reaches — at most its deficit; the root (index nc)
+    // takes any amount; hit = that node
     __device__ int augment(int src, int dst, int limit, bool keep = false) {
 #ifdef SGUFP_K1_STATS
         if (T.tl == 0) atomicAdd(&g_k1_stats[2], 1ull);
 #endif
         if constexpr (small) {
-            const int lev = reach_small<TILE>(src, dst, nc, T, w);
-            return lev ? push_small<TILE>(dst, limit, lev, nc, T, w) : 0;
+            const int lev = reach_small<TILE>(src, dst, nc, T, w, &hit);
+            if (!lev) return 0;
+            if (dst < 0 && hit != nc) limit = min(limit, -SI(w.exc + hit));
+            return push_small<TILE>(hit, limit, lev, nc, T, w);
         } else {
             const int nchunk = (ntc + TILE - 1) / TILE;
             int c0 = 0;
@@ -458,8 +508,9 @@ struct TightPaths {
             else if (keep && nchunk > 0) q = (q + nchunk - 1) / nchunk * nchunk;     // after a dual update: a new sweep, visit numbers go on
             else { q = 0; keep = false; }
             rq = -1;
-            if (!reach_list<TILE>(src, dst, P, ntc, nword, T, w, keep, c0, q)) return 0;
-            return push_list<TILE>(src, dst, limit, nc, T, w, &rq);
+            if (!reach_list<TILE>(src, dst, P, ntc, nword, T, w, keep, c0, q, &hit)) return 0;
+            if (dst < 0 && hit != nc) limit = min(limit, -SI(w.exc + hit));
+            return push_list<TILE>(src, hit, limit, nc, T, w, &rq);
         }
     }
 };
@@ -562,6 +613,50 @@ __device__ void canonical_potentials(const PlanView &P, int nopen, int nc, const
     T.sync();
 }
 
+// Warm start (one work item = a run of consecutive candidates on ONE scenario): x holds the previous candidate's optimal
+// flow on the chains this candidate still has (0 on the new ones), lab its potentials (all finite), exc the imbalances the
+// removed chains left behind.  A chain whose reduced cost has the wrong sign for its flow is saturated / emptied (more
+// imbalance); then every excess is routed to the root and every deficit from the root along tight residual paths with dual
+// updates (successive shortest paths for a pseudoflow): the labels stay feasible potentials throughout, so the circulation
+// that is left when the imbalances are gone is optimal.  Consecutive paths of the Benders loop differ in a few layers:
+// ~16 pushes instead of ~100 on the C4 network (profiles/r02_k1_warm.md).  Instances without forced flow only (lo == 0).
+template <int TILE, class TM>
+__device__ bool warm_repair(const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TM &w, TightPaths<TILE, TM> &TP, int &fuel) {
+    for (int c = T.tl; c < nopen; c += TILE) {
+        const ChainEnds e(P.ch_st[c]);
+        const int up = SI(w.up + c) >> HB;
+        int xc = min(SI(w.x + c), up);
+        const int rc = SI(w.lab + e.sv) - e.r - SI(w.lab + e.ev);      // reduced cost of the forward arc (root = index 0 on both sides here)
+        int d = 0;
+        if (rc < 0 && xc < up) { d = up - xc; xc = up; }
+        else if (rc > 0 && xc > 0) { d = -xc; xc = 0; }
+        if (d) { atomicSub(&SI(w.exc + e.sv), d); atomicAdd(&SI(w.exc + e.ev), d); }
+        SI(w.x + c) = xc;
+        RSET(c, (xc < up ? 1 : 0) | (xc > 0 ? 2 : 0));
+    }
+    for (int i = T.tl; i < reach_words(nc); i += TILE) SU(w.tg + i) = 0u;
+    T.sync();
+    // exc[0] is the root's own imbalance (the books above include it: the imbalances sum to zero).  Targets: the nodes with a
+    // deficit, and the root (as a path end: index nc) whatever its own balance — it is ONE node, so what an excess sends there
+    // goes on to the remaining deficits from its other face (index 0) at the end.
+    for (int v = T.tl; v <= nc; v += TILE)
+        if (v == nc || (v > 0 && SI(w.exc + v) < 0)) atomicOr(&SU(w.tg + (v >> 5)), 1u << (v & 31));
+    T.sync();
+    TP.prepare();
+    for (int v0 = 0; v0 < nc; v0 += TILE) {                   // every excess to the nearest deficit; the root's own excess last
+        const int v = v0 + T.tl;
+        unsigned todo = T.ballot(v > 0 && v < nc && SI(w.exc + v) > 0);
+        while (todo) {
+            const int u = v0 + __ffs(todo) - 1;
+            todo &= todo - 1;
+            if (!TP.route(u, fuel)) return false;
+        }
+    }
+    if (T.tl == 0) SU(w.tg + (nc >> 5)) &= ~(1u << (nc & 31));
+    T.sync();
+    return SI(w.exc + 0) <= 0 || TP.route(0, fuel);
+}
+
 // wire potential at the HEAD of arc a (a matched in-arc, or any arc of a chain)
 template <class TM>
 __device__ __forceinline__ int head_potential(int a, const PlanView &P, int nopen, const TM &w) {
@@ -590,6 +685,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         w.tin = base; w.tout = base + 32; w.hist = base + 64; w.path = base + 98; w.tab = base + 132;
         w.tc = base; base += k1_search_words(p.nc, p.max_nopen);
         w.rw = base; base += reach_words(p.nc);
+        w.tg = base; base += reach_words(p.nc);
         w.up = base; base += p.max_nopen;
         w.lo = base; base += p.max_nopen;
         w.x = base; base += p.max_nopen;
@@ -599,7 +695,10 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         w.pot = base; w.exc = base; base += p.nc + 2;   // excesses (lower-bound routing) and potentials are never live together
         w.aq = base;
     }
-    const long long items = (long long)p.K * p.S;
+    // A work item is a RUN of `group` consecutive candidates on one scenario: the first is solved from zero flow, each of the
+    // others from the optimal flow and potentials of the one before it (warm_repair), when the host linked the two plans.
+    const int group = p.group > 1 && p.link_off ? p.group : 1, ngroups = (p.K + group - 1) / group;
+    const long long items = (long long)ngroups * p.S;
     const long long stride = (long long)gridDim.x * TILES_PER_CTA;
     // Work items come from a queue (one atomic per item, taken by the tile's first lane) when the launch carries one: an item
     // takes 0.1 - 0.3 ms and varies with the scenario, so with a few items per warp (a rank of an 8-GPU partition of C4 has
@@ -613,13 +712,40 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
             item = (long long)__shfl_sync(T.mask, nxt, T.base, 32);
         } else item += stride;
         if (item >= items) break;
-        const int k = (int)(item / p.S), s = (int)(item - (long long)k * p.S);
+        const int grp = (int)(item / p.S), s = (int)(item - (long long)grp * p.S);
+        const double *row_u = p.cap_u + (size_t)s * p.m_pad, *row_l = p.cap_l + (size_t)s * p.m_pad;
+        const int32_t *prev_plan = nullptr;     // the candidate whose optimal flow (x) and potentials (pot) this tile still holds
+        for (int k = grp * group, k_end = min(p.K, k + group); k < k_end; k++) {
+        const int32_t *carried = prev_plan;
+        prev_plan = nullptr;
         if (*reinterpret_cast<volatile long long *>(p.first_inf + k) < 0) continue;   // this candidate was aborted: drain
         int fuel = 1 << 20;   // passes + levels a work item may spend (tile-uniform)
         const PlanView P(p.plans + p.plan_off[k]);
         const int nch = P.h->nch, nopen = P.h->nopen, nc = P.h->nc, nav = P.h->nav, m = p.m;
         unsigned long long *sums = p.sums + (size_t)k * p.W;
-        const double *row_u = p.cap_u + (size_t)s * p.m_pad, *row_l = p.cap_l + (size_t)s * p.m_pad;
+        const int32_t *link = nullptr;          // model.hpp: link_plans
+        if (carried) { const int lo = p.link_off[k]; if (lo >= 0) link = p.plans + lo; }
+        if (link) {
+            // labels = the previous candidate's potentials (finite for every node; the root is 0 on both faces), imbalances
+            // of the chains that are gone, and the flow carried over to this candidate's chain numbering (through w.up,
+            // which is rebuilt below)
+            const PlanView Q(carried);
+            for (int v = T.tl; v < nc; v += TILE) SI(w.lab + v) = -SI(w.pot + v);
+            if (T.tl == 0) SI(w.lab + nc) = 0;
+            T.sync();
+            for (int v = T.tl; v <= nc; v += TILE) SI(w.exc + v) = 0;
+            T.sync();
+            const int nrem = link[0];
+            const int32_t *prev_of = link + 2, *removed = prev_of + nopen;
+            for (int i = T.tl; i < nrem; i += TILE) {
+                const int c = removed[i], f = SI(w.x + c);
+                if (f > 0) { const ChainEnds e(Q.ch_st[c]); atomicAdd(&SI(w.exc + e.sv), f); atomicSub(&SI(w.exc + e.ev), f); }
+            }
+            for (int c = T.tl; c < nopen; c += TILE) { const int pc = prev_of[c]; SI(w.up + c) = pc >= 0 ? SI(w.x + pc) : 0; }
+            T.sync();
+            for (int c = T.tl; c < nopen; c += TILE) SI(w.x + c) = SI(w.up + c);
+            T.sync();
+        }
 
         // 1. chain capacities (open chains only: a closed chain carries no flow, it is infeasible iff one of its
         //    arcs has a positive lower bound, and its multipliers are read from the capacity row directly)
@@ -648,14 +774,35 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         T.sync();
         for (int c = T.tl; c < nopen; c += TILE) {
             const int lo = SI(w.lo + c) >> HB, up = SI(w.up + c) >> HB;
-            SI(w.x + c) = lo; bad |= lo > up; forced |= lo > 0;
-            RSET(c, lo < up ? 1 : 0);              // x == lo: forward residual only
+            bad |= lo > up; forced |= lo > 0;
+            if (!link) { SI(w.x + c) = lo; RSET(c, lo < up ? 1 : 0); }   // x == lo: forward residual only
         }
         T.sync();
         bad = T.any(bad);
         forced = T.any(forced);
         // 2. optimal flow
         TightPaths<TILE, TM> TP(P, T, w, nopen, nc);
+        bool solved = false;
+        if (link && !bad && !forced) solved = warm_repair<TILE>(P, nopen, nc, T, w, TP, fuel);
+#ifdef SGUFP_K1_EMULATE
+        if (link && !bad && !forced) sgufp_emul_warm[solved ? 0 : 1]++;   // tests: warm starts taken / given up
+#ifdef SGUFP_K1_WARM_DEBUG
+        if (solved) {
+            for (int v = 0; v < nc; v++) if (SI(w.exc + v) != 0) printf("k=%d s=%d: exc[%d]=%d left\n", k, s, v, SI(w.exc + v));
+            if (SI(w.lab + 0) != SI(w.lab + nc)) printf("k=%d s=%d: lab[0]=%d lab[nc]=%d\n", k, s, SI(w.lab + 0), SI(w.lab + nc));
+            for (int c = 0; c < nopen; c++) {
+                const ChainEnds e(P.ch_st[c]);
+                const int rc = SI(w.lab + e.sv) - e.r - SI(w.lab + e.ev), xc = SI(w.x + c), up = SI(w.up + c) >> HB;
+                if ((rc < 0 && xc < up) || (rc > 0 && xc > 0)) printf("k=%d s=%d: chain %d (%d->%d r=%d) rc=%d x=%d up=%d\n", k, s, c, e.sv, e.ev, e.r, rc, xc, up);
+            }
+        }
+#endif
+#endif
+        if (link && !solved && !bad) {             // forced flow, or the repair got stuck (no valid instance does): from zero flow
+            for (int c = T.tl; c < nopen; c += TILE) { const int lo = SI(w.lo + c) >> HB; SI(w.x + c) = lo; RSET(c, lo < (SI(w.up + c) >> HB) ? 1 : 0); }
+            T.sync();
+            fuel = 1 << 20;
+        }
         if (!bad && forced) bad = !route_lower_bounds<TILE>(P, nopen, nc, T, w, TP, fuel);
         if (bad) {
             if (T.tl == 0) {
@@ -669,6 +816,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
 #ifdef SGUFP_K1_STATS
         if (T.tl == 0) atomicAdd(&g_k1_stats[3], 1ull);
 #endif
+        if (!solved) {
 #ifndef SGUFP_K1_NO_DUAL
         // primal-dual: ONE label computation (shortest distances at the starting flow); then searches over the tight chains push
         // along every shortest path, and when a search fails a dual update — one pass — raises the labels outside its reached
@@ -699,6 +847,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
             while (--fuel > 0 && TP.augment(0, nc, INT_MAX) > 0) {}   // until the search fails: it leaves the reached set for the warm start
         }
 #endif
+        }
         // 3. potentials
         canonical_potentials<TILE>(P, nopen, nc, T, w, fuel);
         if (fuel <= 0) {   // a bound that no valid instance reaches: refuse to answer rather than spin
@@ -785,6 +934,8 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
             if (p.obj) p.obj[(size_t)k * p.S + s] = (double)objv;
         }
         T.sync();
+        if (!forced) prev_plan = p.plans + p.plan_off[k];   // x and pot of this candidate serve the next one of the run
+        }
     }
 }
 
@@ -963,6 +1114,20 @@ static cudaError_t launch_warp(const K1Launch &p, cudaStream_t st, int sm_count)
     if (!best_nw) return cudaErrorInvalidConfiguration;
     cached_words = words; cached_nw = best_nw; cached_dev = dev; cached_big = big;
     return launch_warp_dispatch(best_nw, p, st, sm_count, &rw, false);
+}
+
+// Candidates per work item of the warp kernel (K1Launch::group): as long a run as still leaves every resident warp an item
+// (a warm-started candidate costs about a third of one solved from zero flow), at most 16, in runs of equal length.
+// SGUFP_K1_GROUP=n overrides (1 = every candidate from zero flow).
+int k1_group(int K, int S, int sm_count) {
+    if (const char *e = getenv("SGUFP_K1_GROUP")) { const int g = atoi(e); return g < 1 ? 1 : g > K ? K : g; }
+    const long long slots = (long long)sm_count * 32;
+    long long g = slots > 0 ? (long long)K * S / slots : 1;
+    if (g > 16) g = 16;
+    if (g > K) g = K;
+    if (g < 1) g = 1;
+    const int runs = (int)((K + g - 1) / g);
+    return (K + runs - 1) / runs;
 }
 
 // which kernel: the lane-per-scenario one (k1_lane.cu) for batches it accepts, else the warp-per-scenario one

@@ -11,6 +11,9 @@ struct K1Launch {
     long long scen_offset;        // global index of local scenario 0
     const int32_t *plans;         // device pool of K plans
     const int32_t *plan_off;      // [K] word offset of each plan
+    const int32_t *link_off;      // [K] word offset of the link of candidate k to candidate k-1 (model.hpp: link_plans), -1 = none; or nullptr
+    int group;                    // candidates per work item: a warp takes `group` consecutive candidates on one scenario and warm-starts
+                                  // each from the one before (0 or 1: every candidate from zero flow)
     int K, W, L;
     unsigned long long *sums;     // [K][W] exact integer accumulators (two's complement)
     long long *first_inf;         // [K] lowest infeasible global scenario (init LLONG_MAX)
@@ -31,6 +34,8 @@ struct K1Launch {
 bool k1_lane_tables_wanted();                               // false when the mode rules the lane kernel out
 bool k1_lane_eligible(const K1Launch &p, int sm_count);
 cudaError_t k1_lane_launch(const K1Launch &p, cudaStream_t st, int sm_count);   // cudaErrorInvalidConfiguration: state too large
+
+int k1_group(int K, int S, int sm_count);                   // K1Launch::group for a batch of K candidates on S scenarios
 
 // Returns cudaSuccess or the launch error.  *launches is incremented by the kernels launched.
 cudaError_t k1_launch(const K1Launch &p, cudaStream_t st, int sm_count, int *launches);

@@ -312,6 +312,33 @@ int build_plan(const Model &M, const int16_t *path, int plen, Plan &P, std::stri
     return 0;
 }
 
+void link_plans(const Plan &prev, const Plan &cur, std::vector<int32_t> &out) {
+    out.clear();
+    const int32_t *A = prev.words.data(), *B = cur.words.data();
+    const PlanHeader *ha = reinterpret_cast<const PlanHeader *>(A), *hb = reinterpret_cast<const PlanHeader *>(B);
+    if (ha->m != hb->m || ha->nc != hb->nc) return;
+    const int na = ha->nopen, nb = hb->nopen;
+    const int32_t *cp_a = A + ha->o_arc_cp, *ptr_a = A + ha->o_ch_ptr, *arcs_a = A + ha->o_ch_arcs;
+    const int32_t *ptr_b = B + hb->o_ch_ptr, *arcs_b = B + hb->o_ch_arcs;
+    std::vector<int32_t> prev_of(nb, -1);
+    std::vector<uint8_t> kept(na, 0);
+    int n_new = 0;
+    for (int c = 0; c < nb; c++) {
+        const int b0 = ptr_b[c], len = ptr_b[c + 1] - b0, cpa = cp_a[arcs_b[b0]], ca = cpa >> 10;
+        if ((cpa & 1023) == 0 && ca < na && ptr_a[ca + 1] - ptr_a[ca] == len &&
+            std::memcmp(arcs_a + ptr_a[ca], arcs_b + b0, (size_t)len * sizeof(int32_t)) == 0) { prev_of[c] = ca; kept[ca] = 1; }
+        else n_new++;
+    }
+    std::vector<int32_t> removed;
+    for (int c = 0; c < na; c++) if (!kept[c]) removed.push_back(c);
+    if (4 * (n_new + (int)removed.size()) > std::max(na, nb)) return;
+    out.reserve(2 + nb + removed.size() + 3);
+    out.push_back((int32_t)removed.size()); out.push_back(n_new);
+    out.insert(out.end(), prev_of.begin(), prev_of.end());
+    out.insert(out.end(), removed.begin(), removed.end());
+    while (out.size() & 3) out.push_back(0);
+}
+
 // Split-graph arrays of the feasibility-ray kernel (k1_ray).  A dangling end arc books into its
 // FREE multiplier, every other arc by its endpoints (rule 6).
 void ray_arrays(const Model &M, const Plan &P, std::vector<int32_t> &ts, std::vector<int32_t> &hs, std::vector<int32_t> &info,

@@ -206,6 +206,23 @@ def random_paths(net, K: int, seed: int, unmatched_prob: float = 0.1) -> np.ndar
 
 
 # ---- on-disk formats either side of the path -----------------------------------
+def perturbed_paths(net, K: int, seed: int, changes: int = 3, unmatched_prob: float = 0.1) -> np.ndarray:
+    """K candidates in which each differs from the one before in at most `changes` layers — the shape the Benders loop
+    emits (`NodeExplorer.cpp:949-971`: the argmax path moves a little after every cut) and the one the warm starts of the
+    K1 kernel are made for.  Same encoding and state rule as `random_paths`."""
+    rng = np.random.default_rng(seed)
+    out = np.repeat(random_paths(net, 1, seed, unmatched_prob), K, axis=0)
+    L = out.shape[1]
+    for k in range(1, K):
+        out[k] = out[k - 1]
+        for ell in rng.choice(L, size=min(changes, L), replace=False):
+            q = int(net.head[net.layer_arc[ell]])
+            used = {int(out[k, l2]) for l2 in range(L) if l2 != ell and out[k, l2] >= 0 and int(net.head[net.layer_arc[l2]]) == q}
+            avail = [b for b in net.out_arcs(q) if b not in used]
+            out[k, ell] = -1 if (not avail or rng.random() < unmatched_prob) else int(avail[rng.integers(len(avail))])
+    return out
+
+
 def read_text(path: str, name: str = "file") -> Instance:
     """Parser of the reference's instance format (`Network::Network`, Network.cpp:18-63):
     `n m S`, then per arc `tail head (lb ub reward) x S`, one separator token, then V-bar ids."""

@@ -57,6 +57,9 @@ using namespace sgufp;
 
 // Same contract as sgufp_paths_partial + sgufp_ray_partial, on the host.  sums: [K][W] (W = 1+L+m),
 // first_inf: [K], obj/status: [K][S].  ray_sums[K][W]: filled for candidates with an infeasible scenario.
+static int g_group = 0;
+extern "C" void emul_set_group(int g) { g_group = g; }   // candidates per work item (0: the whole batch, 1: no warm starts)
+extern "C" void emul_warm_counts(long long *out2) { out2[0] = sgufp::sgufp_emul_warm[0]; out2[1] = sgufp::sgufp_emul_warm[1]; sgufp::sgufp_emul_warm[0] = sgufp::sgufp_emul_warm[1] = 0; }
 static int g_last_nc = 0;
 extern "C" int emul_last_nc() { return g_last_nc; }   // contracted nodes of the last instance: which size class ran
 
@@ -79,6 +82,13 @@ extern "C" int emul_paths(int n, int m, int S, const int32_t *tail, const int32_
         words.insert(words.end(), plans[k].words.begin(), plans[k].words.end());
         max_nch = std::max(max_nch, plans[k].nch); max_nopen = std::max(max_nopen, plans[k].nopen);
     }
+    // links of consecutive candidates behind the plans (as capi.cu: make_batch lays them out)
+    std::vector<int32_t> link_off(K, -1);
+    for (int k = 1; k < K; k++) {
+        std::vector<int32_t> lk;
+        link_plans(plans[k - 1], plans[k], lk);
+        if (!lk.empty()) { link_off[k] = (int32_t)words.size(); words.insert(words.end(), lk.begin(), lk.end()); }
+    }
     std::memset(sums, 0, (size_t)K * W * 8);
     for (int k = 0; k < K; k++) first_inf[k] = LLONG_MAX;
     K1Launch p{};
@@ -87,6 +97,7 @@ extern "C" int emul_paths(int n, int m, int S, const int32_t *tail, const int32_
     p.sums = reinterpret_cast<unsigned long long *>(sums); p.first_inf = first_inf; p.obj = obj; p.status = status;
     unsigned long long work_queue = 0;
     p.work = (K & 1) ? &work_queue : nullptr;     // both ways of handing out work items are exercised
+    p.link_off = link_off.data(); p.group = g_group > 0 ? g_group : K;   // runs of warm-started candidates (default: the whole batch is one run)
     g_last_nc = M.nc;
     p.max_nch = max_nch; p.max_nopen = max_nopen; p.nc = M.nc; p.nav = M.nav; p.max_cap = 65535;
     const int wpt = k1_words_per_tile(p);

@@ -244,3 +244,95 @@ def test_experimental_switches_keep_parity(emul_experiments):
         done += 1
         big += emul.emul_last_nc() > 31
     assert done >= 8 and big >= 3, (done, big)
+
+
+# ---- runs of consecutive candidates: warm starts (k1_cut.cu: warm_repair) -----------------------------------------------
+def warm_counts(L):
+    out = (C.c_longlong * 2)()
+    L.emul_warm_counts(out)
+    return int(out[0]), int(out[1])
+
+
+def check_against_oracle(inst, net, paths, out):
+    sums, finf, obj, st, ray = out
+    for k in range(len(paths)):
+        want, first_bad = wlayout_partial(net, inst, paths[k], 0, inst.S)
+        assert (finf[k] if finf[k] != I64_MAX else -1) == (-1 if first_bad is None else first_bad), (inst.name, k)
+        for s in range(inst.S):
+            d = net.scenario_duals(paths[k], s)
+            assert st[k, s] == d["status"], (inst.name, k, s)
+            if d["status"] == 0:
+                assert obj[k, s] == d["obj"], (inst.name, k, s)
+        assert (sums[k] == want).all(), (inst.name, k, np.nonzero(sums[k] != want))
+        if first_bad is not None:
+            assert (ray[k] == ray_wlayout(net, inst, paths[k], first_bad)).all(), (inst.name, k)
+
+
+WARM_CASES = [
+    ("c1", lambda: I.config1(S=30), 8, 1, 1, 0.15),
+    ("c1_lb", lambda: I.config1(S=30, lower_prob=0.3), 8, 2, 1, 0.3),          # forced flow: those scenarios start from zero flow
+    ("c2", lambda: I.config2(S=10), 8, 3, 3, 0.1),
+    ("c2_sparse", lambda: I.config2(S=8), 6, 4, 4, 0.5),
+    ("c2_lb", lambda: I.config2(S=10, lower_prob=0.1), 6, 5, 2, 0.3),
+    ("c4", lambda: I.config4(S=3), 5, 6, 6, 0.15),
+    ("c4_lb", lambda: I.config4(S=3, lower_prob=0.05), 4, 7, 4, 0.3),
+    ("wide", lambda: I.make_layered([70, 70, 70, 70, 60], 1500, 2, 98, 0.3, 0.0, "wide"), 4, 9, 5, 0.2),
+]
+
+
+@pytest.mark.parametrize("group", [0, 2, 3])
+@pytest.mark.parametrize("name,make,K,seed,changes,unm", WARM_CASES, ids=[c[0] for c in WARM_CASES])
+def test_warm_started_runs_match_oracle(emul, name, make, K, seed, changes, unm, group):
+    """Candidates that differ in a few layers, solved in runs of `group` (0: the whole batch): every candidate after the
+    first of a run starts from its predecessor's optimal flow and potentials; sums, objectives, statuses and rays must be
+    what Oracle B gives for each candidate on its own."""
+    inst = make()
+    net = OracleNet(inst)
+    paths = I.perturbed_paths(net, K, seed, changes, unm)
+    emul.emul_set_group(group)
+    warm_counts(emul)
+    try:
+        out = run_emul(emul, inst, net, paths)
+    finally:
+        emul.emul_set_group(0)
+    taken, given_up = warm_counts(emul)
+    check_against_oracle(inst, net, paths, out)
+    assert given_up == 0
+    if inst.lower.max() == 0:
+        runs = -(-K // (group or K))
+        assert taken == (K - runs) * inst.S, (taken, given_up)        # every linked candidate was warm-started on every scenario
+
+
+def test_warm_runs_on_the_bench_candidates(emul):
+    """The DD-emitted paths bench.py uses (consecutive paths of the Benders loop: 2 - 8 layers apart)."""
+    cand = np.load(os.path.join(ROOT, "sgufp_solver_b200", "data", "bench_candidates.npz"))
+    for key, inst, K in (("config2", I.config2(S=6), 12), ("config4", I.config4(S=2), 5)):
+        net = OracleNet(inst)
+        paths = np.ascontiguousarray(cand[key][:K])
+        warm_counts(emul)
+        out = run_emul(emul, inst, net, paths)
+        taken, given_up = warm_counts(emul)
+        check_against_oracle(inst, net, paths, out)
+        assert (taken, given_up) == ((K - 1) * inst.S, 0)
+
+
+@pytest.mark.parametrize("block", range(3))
+def test_warm_runs_fuzz(emul, block):
+    """Random small and larger networks, with and without lower bounds, runs of 1 - 4 changed layers."""
+    rng = np.random.default_rng(7700 + block)
+    done = taken_all = 0
+    for k in range(36):
+        try:
+            inst = _random_larger_instance(rng, 100 * block + k) if k % 3 == 0 else _random_instance(rng, 100 * block + k)
+            net = OracleNet(inst)
+        except Exception:
+            continue
+        paths = I.perturbed_paths(net, 5, k, int(rng.integers(1, 5)), float(rng.choice([0.0, 0.2, 0.6])))
+        warm_counts(emul)
+        out = run_emul(emul, inst, net, paths)
+        taken, given_up = warm_counts(emul)
+        check_against_oracle(inst, net, paths, out)
+        assert given_up == 0, inst.name
+        taken_all += taken
+        done += 1
+    assert done >= 18 and taken_all > 0

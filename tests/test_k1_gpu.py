@@ -360,3 +360,48 @@ def test_fuzz_small_networks(block):
         _compare(inst, gs, net, paths, gs.solve_paths(paths))
         done += 1
     assert done >= 12
+
+
+# ---- runs of consecutive candidates: warm starts inside a work item (k1_cut.cu: warm_repair) --------------------------------
+WARM_CASES = [
+    ("c1", lambda: I.config1(S=50), 8, 1, 1, 0.15),
+    ("c1_lb", lambda: I.config1(S=50, lower_prob=0.3), 8, 2, 1, 0.3),
+    ("c2", lambda: I.config2(S=100), 12, 3, 3, 0.1),
+    ("c2_lb", lambda: I.config2(S=100, lower_prob=0.05), 8, 5, 2, 0.3),
+    ("c4", lambda: I.config4(S=24), 6, 6, 6, 0.15),
+    ("c4_lb", lambda: I.config4(S=24, lower_prob=0.02), 5, 7, 4, 0.3),
+    ("large_m6000", lambda: I.make_layered([100, 100, 100, 100, 100, 90], 6000, 3, 99, 0.7, 0.01, "large"), 4, 8, 5, 0.2),
+]
+
+
+@pytest.mark.parametrize("group", ["2", "16"])
+@pytest.mark.parametrize("name,make,K,seed,changes,unm", WARM_CASES, ids=[c[0] for c in WARM_CASES])
+def test_warm_started_runs_parity_with_oracle(name, make, K, seed, changes, unm, group, monkeypatch):
+    """Candidates a few layers apart (the Benders loop's shape), solved in runs in which every candidate after the first
+    starts from its predecessor's optimal flow and potentials: each cut must be what Oracle B gives for that candidate alone."""
+    monkeypatch.setenv("SGUFP_K1_GROUP", group)
+    inst = make()
+    net = OracleNet(inst)
+    gs = sg.GuroSolver(inst)
+    paths = I.perturbed_paths(net, K, seed, changes, unm)
+    res = gs.solve_paths(paths)
+    _compare(inst, gs, net, paths, res)
+
+
+@pytest.mark.parametrize("wl,S,K", [("c2", 1000, 64), ("c4", 1500, 16)])
+def test_warm_runs_equal_cold_starts_bit_for_bit(wl, S, K, monkeypatch):
+    """The bench's DD-emitted candidates: runs of 1 (every candidate from zero flow), 3, 8 and 16 give identical sums, objectives
+    and cuts — the duals do not depend on which optimal flow the kernel reaches."""
+    import bench
+    inst = I.config2(S=S) if wl == "c2" else I.config4(S=S)
+    gs = sg.GuroSolver(inst)
+    paths, _ = bench.candidate_paths(wl, K, 0)
+    outs = []
+    for group in ("1", "3", "8", "16"):
+        monkeypatch.setenv("SGUFP_K1_GROUP", group)
+        r = gs.solve_paths(paths)
+        outs.append(r)
+        assert (r.cut_type == 0).all() and (r.status == 0).all()
+    for r in outs[1:]:
+        assert (r.rhs == outs[0].rhs).all() and (r.coef_dense == outs[0].coef_dense).all() and (r.obj == outs[0].obj).all()
+        assert (r.nnz == outs[0].nnz).all()
