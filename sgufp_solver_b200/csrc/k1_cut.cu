@@ -35,7 +35,13 @@
 namespace sgufp {
 
 #ifdef SGUFP_K1_STATS
+__device__ unsigned long long g_k1_clk[8];     // SM clocks of the first lane per phase: link, stream, warm repair, flow from zero, potentials, lifting; warm / cold evaluations
+#define K1_CLK(i) do { if (T.tl == 0) { const long long now_ = clock64(); atomicAdd(&g_k1_clk[i], (unsigned long long)(now_ - clk_)); clk_ = now_; } } while (0)
 __device__ unsigned long long g_k1_stats[8];   // relaxation passes, label computations, searches, work items, list sweeps, list entries swept, searches that reached dst, chains per pass
+#endif
+
+#ifndef K1_CLK
+#define K1_CLK(i) do {} while (0)
 #endif
 
 namespace {
@@ -54,7 +60,7 @@ struct TileMemT {
 };
 #ifdef SGUFP_K1_EMULATE
 #define k1_smem sgufp_emul_smem           // tests/cpp/k1_emul.cpp: the kernel body compiled for the host
-static long long sgufp_emul_warm[2];
+static long long sgufp_emul_warm[8];   // warm starts taken / given up / saturated chains / searches / dual updates / sources
 #else
 extern __shared__ int k1_smem[];
 #endif
@@ -118,10 +124,12 @@ struct Lanes {    // the TILE lanes that work on one scenario (32 on the GPU; 1 
 // root end at index nc.
 // WARM: the nodes of the set w.rw (those a failed search could still reach over tight residual
 // arcs) keep their labels — they are still exact, see reach_* — and only the others start over.
+// zero: every node starts at 0 (a source of its own): the labels are then feasible potentials of the residual graph that are
+// finite at EVERY node, which is what routing imbalances needs (forced flow of lower bounds).
 template <int TILE, bool MERGED, bool WARM, class TM>
-__device__ void shortest_paths(int src, const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TM &w, int &fuel) {
+__device__ void shortest_paths(int src, const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TM &w, int &fuel, bool zero = false) {
     for (int v = T.tl; v <= nc; v += TILE)
-        if (!WARM || !((SU(w.rw + (v >> 5)) >> (v & 31)) & 1)) SI(w.lab + v) = LAB_INF;
+        if (!WARM || !((SU(w.rw + (v >> 5)) >> (v & 31)) & 1)) SI(w.lab + v) = zero ? 0 : LAB_INF;
     T.sync();
     if (!WARM && T.tl == 0) SI(w.lab + src) = 0;
     T.sync();
@@ -458,36 +466,71 @@ struct TightPaths {
         for (int v = T.tl; v <= nc; v += TILE)
             if (!in_r(v)) { const int l = SI(w.lab + v); if (l != LAB_INF) SI(w.lab + v) = l + delta; }
         T.sync();
-        if (to_sink && SI(w.lab + nc) >= 0) return false;
+        if (to_sink && SI(w.lab + nc) >= SI(w.lab + 0)) return false;
         prepare();
         return true;
     }
-    // The excess of src to the nodes of the target set w.tg along tight residual paths, with dual updates when a search fails
-    // (warm start: the imbalances left by the chains that changed).  false: stuck (no residual arc leaves the reached set;
-    // cannot happen while total excess equals total deficit) or out of fuel.
-    __device__ bool route(int src, int &fuel) {
-        rq = -1;
+    // The whole flow phase in ONE loop, so that the kernel holds one copy of the search, the push and the dual update (with a
+    // copy per use it is instruction-cache bound: profiles/r02_k1_warm.md).  Stages: (0) imbalances, if the caller booked any
+    // in w.exc with the deficits' bits in w.tg — every excess to the nearest deficit or to the root (index nc), then the
+    // root's own excess (index 0) to the deficits that are left: successive shortest paths for a pseudoflow, the labels stay
+    // feasible potentials throughout; (1) from the root to the sink along tight residual paths until the sink's label reaches
+    // the root's or no residual arc leaves the reached set.  A failed search is followed by a dual update.
+    // Returns 0: optimal flow; 1: an imbalance cannot be routed (forced flow: the scenario is infeasible; warm start: cannot
+    // happen on a valid state, the caller starts over from zero flow); 2: out of fuel.
+    __device__ int solve(bool imbalances, int &fuel) {
+        int stage = imbalances ? 0 : 2;       // 0: nodes with an excess, 1: the root's excess, 2: to the sink (not begun), 3: to the sink
+        int v0 = 0, src = 0, need = 0;
+        unsigned todo = 0;
         bool keep = false;
-        int need = SI(w.exc + src);
-        while (need > 0) {
-            if (--fuel <= 0) return false;
-            const int d = augment(src, -1, need, keep);
+        for (;;) {
+            if (need <= 0) {                  // the next source
+                if (stage == 0) {
+                    while (!todo && v0 < nc) {
+                        const int v = v0 + T.tl;
+                        todo = T.ballot(v > 0 && v < nc && SI(w.exc + v) > 0);
+                        v0 += TILE;
+                    }
+                    if (todo) { src = v0 - TILE + __ffs(todo) - 1; todo &= todo - 1; need = SI(w.exc + src); }
+                    else stage = 1;
+                }
+                if (stage == 1) {             // the root is one node: what reached its end face (nc) leaves from its start face (0)
+                    if (T.tl == 0) SU(w.tg + (nc >> 5)) &= ~(1u << (nc & 31));
+                    T.sync();
+                    stage = 2; src = 0; need = SI(w.exc + 0);
+                }
+                if (stage == 2 && need <= 0) {
+                    const int lt = SI(w.lab + nc);
+                    if (lt == LAB_INF || lt >= SI(w.lab + 0)) return 0;
+                    stage = 3; src = 0; need = INT_MAX;
+                }
+                rq = -1; keep = false;
+#ifdef SGUFP_K1_EMULATE
+                if (stage < 3) sgufp_emul_warm[5]++;
+#endif
+            }
+            if (--fuel <= 0) return 2;
+            const int d = augment(src, stage == 3 ? nc : -1, need, keep);
+#ifdef SGUFP_K1_EMULATE
+            if (stage < 3) { sgufp_emul_warm[3]++; if (d <= 0) sgufp_emul_warm[4]++; }
+#endif
             keep = false;
             if (d > 0) {
-                need -= d;
-                T.sync();
-                if (T.tl == 0) {                       // books: the source, the node it ended at (its target bit goes with its deficit)
-                    const int t = hit == nc ? 0 : hit, left = SI(w.exc + t) + d;
-                    SI(w.exc + src) = need; SI(w.exc + t) = left;
-                    if (!left && hit != nc) SU(w.tg + (hit >> 5)) &= ~(1u << (hit & 31));
+                if (stage < 3) {
+                    need -= d;
+                    T.sync();
+                    if (T.tl == 0) {                   // books: the source, the node it ended at (its target bit goes with its deficit)
+                        const int t = hit == nc ? 0 : hit, left = SI(w.exc + t) + d;
+                        SI(w.exc + src) = need; SI(w.exc + t) = left;
+                        if (!left && hit != nc) SU(w.tg + (hit >> 5)) &= ~(1u << (hit & 31));
+                    }
+                    T.sync();
                 }
-                T.sync();
                 continue;
             }
-            if (!dual_update(false, src == 0)) return false;
+            if (!dual_update(stage == 3, stage < 3 && src == 0)) { if (stage == 3) return 0; return 1; }
             keep = TM::BIG;
         }
-        return true;
     }
     // one search and, if dst is reachable, one push of at most `limit`; returns the amount pushed (0: not reachable)
     // dst < 0 (warm start): to the first node of the target set w.tg the search reaches — at most its deficit; the root (index nc)
@@ -515,54 +558,36 @@ struct TightPaths {
     }
 };
 
-// Forced flow from lower bounds (rare): route every excess / deficit along shortest residual
-// paths.  Returns false if some forced flow cannot be routed (scenario infeasible).
+// Target set of an imbalance routing (TightPaths::solve): the nodes with a deficit, and the root (as a path end: index nc)
+// whatever its own balance — it is ONE node, so what an excess sends there goes on to the remaining deficits from its other
+// face (index 0) at the end.  exc[0] is the root's own imbalance (the books include it: the imbalances sum to zero).
 template <int TILE, class TM>
-__device__ bool route_lower_bounds(const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TM &w, TightPaths<TILE, TM> &TP, int &fuel) {
+__device__ void deficit_targets(int nc, const Lanes<TILE> &T, TM &w) {
+    for (int i = T.tl; i < reach_words(nc); i += TILE) SU(w.tg + i) = 0u;
+    T.sync();
+    for (int v = T.tl; v <= nc; v += TILE)
+        if (v == nc || (v > 0 && SI(w.exc + v) < 0)) atomicOr(&SU(w.tg + (v >> 5)), 1u << (v & 31));
+    T.sync();
+}
+
+// Forced flow from lower bounds (rare): x = lo leaves an excess at the head and a deficit at the tail of every chain with a
+// positive lower bound; the labels are feasible potentials that are finite everywhere.  TightPaths::solve routes the
+// imbalances; one that cannot be routed means the scenario is infeasible.
+template <int TILE, class TM>
+__device__ void forced_flow_init(const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TM &w, int &fuel) {
     for (int v = T.tl; v <= nc; v += TILE) SI(w.exc + v) = 0;
     T.sync();
     for (int c = T.tl; c < nopen; c += TILE) {
         const int lo = SI(w.lo + c) >> HB;
         if (lo > 0) {
-            const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1;
-            if (ev > 0) atomicAdd(&SI(w.exc + ev), lo);
-            if (sv > 0) atomicSub(&SI(w.exc + sv), lo);
+            const ChainEnds e(P.ch_st[c]);
+            atomicAdd(&SI(w.exc + e.ev), lo);
+            atomicSub(&SI(w.exc + e.sv), lo);
         }
     }
     T.sync();
-    for (int v = 1; v < nc; v++) {
-        while (SI(w.exc + v) > 0 && --fuel > 0) {
-            shortest_paths<TILE, false, false>(v, P, nopen, nc, T, w, fuel);
-            unsigned long long best = ~0ull;   // nearest of: the root, a node with a deficit
-            for (int t = T.tl; t <= nc; t += TILE)
-                if ((t == nc || (t > 0 && SI(w.exc + t) < 0)) && SI(w.lab + t) != LAB_INF) {
-                    const unsigned long long key = ((unsigned long long)(unsigned)(SI(w.lab + t) - NEG_INF) << 32) | (unsigned)t;
-                    best = key < best ? key : best;
-                }
-            best = T.min_u64(best);
-            if (best == ~0ull) return false;
-            const int t = (int)(best & 0xffffffffu);
-            int lim = SI(w.exc + v);
-            if (t != nc) lim = min(lim, -SI(w.exc + t));
-            TP.prepare();
-            const int d = TP.augment(v, t, lim);
-            if (d <= 0) return false;
-            if (T.tl == 0) { SI(w.exc + v) -= d; if (t != nc) SI(w.exc + t) += d; }
-            T.sync();
-        }
-    }
-    for (int v = 1; v < nc; v++) {
-        while (SI(w.exc + v) < 0 && --fuel > 0) {
-            shortest_paths<TILE, false, false>(0, P, nopen, nc, T, w, fuel);
-            if (SI(w.lab + v) == LAB_INF) return false;
-            TP.prepare();
-            const int d = TP.augment(0, v, -SI(w.exc + v));
-            if (d <= 0) return false;
-            if (T.tl == 0) SI(w.exc + v) += d;
-            T.sync();
-        }
-    }
-    return true;
+    shortest_paths<TILE, false, false>(0, P, nopen, nc, T, w, fuel, true);
+    deficit_targets<TILE>(nc, T, w);
 }
 
 // SPEC-LP potentials: pot[v] = -(shortest residual distance from the root);
@@ -616,12 +641,12 @@ __device__ void canonical_potentials(const PlanView &P, int nopen, int nc, const
 // Warm start (one work item = a run of consecutive candidates on ONE scenario): x holds the previous candidate's optimal
 // flow on the chains this candidate still has (0 on the new ones), lab its potentials (all finite), exc the imbalances the
 // removed chains left behind.  A chain whose reduced cost has the wrong sign for its flow is saturated / emptied (more
-// imbalance); then every excess is routed to the root and every deficit from the root along tight residual paths with dual
-// updates (successive shortest paths for a pseudoflow): the labels stay feasible potentials throughout, so the circulation
-// that is left when the imbalances are gone is optimal.  Consecutive paths of the Benders loop differ in a few layers:
-// ~16 pushes instead of ~100 on the C4 network (profiles/r02_k1_warm.md).  Instances without forced flow only (lo == 0).
+// imbalance); TightPaths::solve then routes every excess to a deficit or the root and the root's excess to the deficits left,
+// along tight residual paths with dual updates: the labels stay feasible potentials throughout, so the circulation that is
+// left when the imbalances are gone is optimal.  Consecutive paths of the Benders loop differ in a few layers: ~16 pushes
+// instead of ~100 on the C4 network (profiles/r02_k1_warm.md).  Instances without forced flow only (lo == 0).
 template <int TILE, class TM>
-__device__ bool warm_repair(const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TM &w, TightPaths<TILE, TM> &TP, int &fuel) {
+__device__ void warm_init(const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TM &w) {
     for (int c = T.tl; c < nopen; c += TILE) {
         const ChainEnds e(P.ch_st[c]);
         const int up = SI(w.up + c) >> HB;
@@ -631,30 +656,14 @@ __device__ bool warm_repair(const PlanView &P, int nopen, int nc, const Lanes<TI
         if (rc < 0 && xc < up) { d = up - xc; xc = up; }
         else if (rc > 0 && xc > 0) { d = -xc; xc = 0; }
         if (d) { atomicSub(&SI(w.exc + e.sv), d); atomicAdd(&SI(w.exc + e.ev), d); }
+#ifdef SGUFP_K1_EMULATE
+        if (d) sgufp_emul_warm[2]++;
+#endif
         SI(w.x + c) = xc;
         RSET(c, (xc < up ? 1 : 0) | (xc > 0 ? 2 : 0));
     }
-    for (int i = T.tl; i < reach_words(nc); i += TILE) SU(w.tg + i) = 0u;
     T.sync();
-    // exc[0] is the root's own imbalance (the books above include it: the imbalances sum to zero).  Targets: the nodes with a
-    // deficit, and the root (as a path end: index nc) whatever its own balance — it is ONE node, so what an excess sends there
-    // goes on to the remaining deficits from its other face (index 0) at the end.
-    for (int v = T.tl; v <= nc; v += TILE)
-        if (v == nc || (v > 0 && SI(w.exc + v) < 0)) atomicOr(&SU(w.tg + (v >> 5)), 1u << (v & 31));
-    T.sync();
-    TP.prepare();
-    for (int v0 = 0; v0 < nc; v0 += TILE) {                   // every excess to the nearest deficit; the root's own excess last
-        const int v = v0 + T.tl;
-        unsigned todo = T.ballot(v > 0 && v < nc && SI(w.exc + v) > 0);
-        while (todo) {
-            const int u = v0 + __ffs(todo) - 1;
-            todo &= todo - 1;
-            if (!TP.route(u, fuel)) return false;
-        }
-    }
-    if (T.tl == 0) SU(w.tg + (nc >> 5)) &= ~(1u << (nc & 31));
-    T.sync();
-    return SI(w.exc + 0) <= 0 || TP.route(0, fuel);
+    deficit_targets<TILE>(nc, T, w);
 }
 
 // wire potential at the HEAD of arc a (a matched in-arc, or any arc of a chain)
@@ -725,6 +734,9 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         unsigned long long *sums = p.sums + (size_t)k * p.W;
         const int32_t *link = nullptr;          // model.hpp: link_plans
         if (carried) { const int lo = p.link_off[k]; if (lo >= 0) link = p.plans + lo; }
+#ifdef SGUFP_K1_STATS
+        long long clk_ = clock64();
+#endif
         if (link) {
             // labels = the previous candidate's potentials (finite for every node; the root is 0 on both faces), imbalances
             // of the chains that are gone, and the flow carried over to this candidate's chain numbering (through w.up,
@@ -747,6 +759,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
             T.sync();
         }
 
+        K1_CLK(0);
         // 1. chain capacities (open chains only: a closed chain carries no flow, it is infeasible iff one of its
         //    arcs has a positive lower bound, and its multipliers are read from the capacity row directly)
         // lo[c] packs (greatest lower bound << 10 | position of its LAST arc): with no positive lower bound on the chain
@@ -782,28 +795,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         forced = T.any(forced);
         // 2. optimal flow
         TightPaths<TILE, TM> TP(P, T, w, nopen, nc);
-        bool solved = false;
-        if (link && !bad && !forced) solved = warm_repair<TILE>(P, nopen, nc, T, w, TP, fuel);
-#ifdef SGUFP_K1_EMULATE
-        if (link && !bad && !forced) sgufp_emul_warm[solved ? 0 : 1]++;   // tests: warm starts taken / given up
-#ifdef SGUFP_K1_WARM_DEBUG
-        if (solved) {
-            for (int v = 0; v < nc; v++) if (SI(w.exc + v) != 0) printf("k=%d s=%d: exc[%d]=%d left\n", k, s, v, SI(w.exc + v));
-            if (SI(w.lab + 0) != SI(w.lab + nc)) printf("k=%d s=%d: lab[0]=%d lab[nc]=%d\n", k, s, SI(w.lab + 0), SI(w.lab + nc));
-            for (int c = 0; c < nopen; c++) {
-                const ChainEnds e(P.ch_st[c]);
-                const int rc = SI(w.lab + e.sv) - e.r - SI(w.lab + e.ev), xc = SI(w.x + c), up = SI(w.up + c) >> HB;
-                if ((rc < 0 && xc < up) || (rc > 0 && xc > 0)) printf("k=%d s=%d: chain %d (%d->%d r=%d) rc=%d x=%d up=%d\n", k, s, c, e.sv, e.ev, e.r, rc, xc, up);
-            }
-        }
-#endif
-#endif
-        if (link && !solved && !bad) {             // forced flow, or the repair got stuck (no valid instance does): from zero flow
-            for (int c = T.tl; c < nopen; c += TILE) { const int lo = SI(w.lo + c) >> HB; SI(w.x + c) = lo; RSET(c, lo < (SI(w.up + c) >> HB) ? 1 : 0); }
-            T.sync();
-            fuel = 1 << 20;
-        }
-        if (!bad && forced) bad = !route_lower_bounds<TILE>(P, nopen, nc, T, w, TP, fuel);
+        K1_CLK(1);
         if (bad) {
             if (T.tl == 0) {
                 atomicMin(p.first_inf + k, p.scen_offset + s);
@@ -813,43 +805,45 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
             T.sync();
             continue;
         }
-#ifdef SGUFP_K1_STATS
-        if (T.tl == 0) atomicAdd(&g_k1_stats[3], 1ull);
-#endif
-        if (!solved) {
-#ifndef SGUFP_K1_NO_DUAL
-        // primal-dual: ONE label computation (shortest distances at the starting flow); then searches over the tight chains push
-        // along every shortest path, and when a search fails a dual update — one pass — raises the labels outside its reached
-        // set until the next arc becomes tight (labels stay feasible potentials, pushes along tight arcs keep the flow optimal
-        // for its value).  Done when the sink's label reaches 0 or no residual arc leaves the reached set.
-        shortest_paths<TILE, false, false>(0, P, nopen, nc, T, w, fuel);
-        {
-            const int lt = SI(w.lab + nc);
-            if (lt != LAB_INF && lt < 0) {
-                TP.prepare();
-                bool keep = false;
-                while (fuel > 0) {
-                    while (--fuel > 0 && TP.augment(0, nc, INT_MAX, keep) > 0) keep = false;   // until a search fails: w.rw = its reached set
-                    if (!TP.dual_update()) break;
-                    keep = TM::BIG;                     // the list search goes on from that set; the bit-set search starts over (it is cheap)
-                }
-            }
+        if (link && forced) {                        // a run goes on from zero flow where a scenario has forced flow
+            for (int c = T.tl; c < nopen; c += TILE) { const int lo = SI(w.lo + c) >> HB; SI(w.x + c) = lo; RSET(c, lo < (SI(w.up + c) >> HB) ? 1 : 0); }
+            T.sync();
         }
-#else
-        // one label computation per distinct path length; in between, breadth-first searches over the
-        // tight chains find the other shortest paths of that length (labels stay feasible potentials)
-        for (bool warm = false; fuel > 0; warm = true) {
-            if (warm) shortest_paths<TILE, false, true>(0, P, nopen, nc, T, w, fuel);
-            else shortest_paths<TILE, false, false>(0, P, nopen, nc, T, w, fuel);
-            const int lt = SI(w.lab + nc);
-            if (lt == LAB_INF || lt >= 0) break;
+        // ONE call of the flow loop serves the three starts (a second round only when a warm start gets stuck, which no valid
+        // state does): warm (the previous candidate's flow and potentials), forced (x = lo), from zero flow.
+        bool warm = link && !forced;
+        int rc;
+        for (;;) {
+            if (warm) warm_init<TILE>(P, nopen, nc, T, w);
+            else if (forced) forced_flow_init<TILE>(P, nopen, nc, T, w, fuel);
+            else shortest_paths<TILE, false, false>(0, P, nopen, nc, T, w, fuel);   // shortest distances at the starting flow: the ONE label computation
             TP.prepare();
-            while (--fuel > 0 && TP.augment(0, nc, INT_MAX) > 0) {}   // until the search fails: it leaves the reached set for the warm start
-        }
+            rc = TP.solve(warm || forced, fuel);
+#ifdef SGUFP_K1_EMULATE
+            if (warm) sgufp_emul_warm[rc ? 1 : 0]++;   // tests: warm starts taken / given up
 #endif
+#ifdef SGUFP_K1_STATS
+            if (T.tl == 0) atomicAdd(&g_k1_clk[warm && !rc ? 6 : 7], 1ull);
+#endif
+            if (!warm || rc != 1) break;
+            for (int c = T.tl; c < nopen; c += TILE) { SI(w.x + c) = 0; RSET(c, (SI(w.up + c) >> HB) > 0 ? 1 : 0); }   // from zero flow (lo == 0 here)
+            T.sync();
+            warm = false; fuel = 1 << 20;
+        }
+        K1_CLK(2);
+        if (rc == 1) {                               // forced flow that cannot be routed: infeasible
+            if (T.tl == 0) {
+                atomicMin(p.first_inf + k, p.scen_offset + s);
+                if (p.status) p.status[(size_t)k * p.S + s] = 1;
+                if (p.obj) p.obj[(size_t)k * p.S + s] = 0.0;
+            }
+            T.sync();
+            continue;
         }
         // 3. potentials
+        K1_CLK(3);
         canonical_potentials<TILE>(P, nopen, nc, T, w, fuel);
+        K1_CLK(4);
         if (fuel <= 0) {   // a bound that no valid instance reaches: refuse to answer rather than spin
             if (T.tl == 0) atomicMin(p.first_inf + k, -1LL);
             T.sync();
@@ -934,6 +928,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
             if (p.obj) p.obj[(size_t)k * p.S + s] = (double)objv;
         }
         T.sync();
+        K1_CLK(5);
         if (!forced) prev_plan = p.plans + p.plan_off[k];   // x and pot of this candidate serve the next one of the run
         }
     }
@@ -1160,6 +1155,12 @@ cudaError_t relayout_launch(const int32_t *src, double *dst, int na, int S, int 
 
 #if defined(SGUFP_K1_STATS) && !defined(SGUFP_K1_EMULATE)
 // debug build only (-DSGUFP_K1_STATS): relaxation passes / label computations since the last call
+extern "C" int sgufp_debug_k1_clk(unsigned long long *out8) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaError_t e = cudaMemcpyFromSymbol(out8, sgufp::g_k1_clk, sizeof(z));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(sgufp::g_k1_clk, z, sizeof(z));
+    return e == cudaSuccess ? 0 : -6;
+}
 extern "C" int sgufp_debug_k1_stats(unsigned long long *out8) {
     unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaError_t e = cudaMemcpyFromSymbol(out8, sgufp::g_k1_stats, sizeof(z));

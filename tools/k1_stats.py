@@ -37,11 +37,17 @@ def main():
     L.sgufp_debug_k1_lane_stats.restype = C.c_int
     L.sgufp_debug_k1_lane_stats.argtypes = [C.POINTER(C.c_ulonglong)]
     lane = (C.c_ulonglong * 8)()
+    L.sgufp_debug_k1_clk.restype = C.c_int
+    L.sgufp_debug_k1_clk.argtypes = [C.POINTER(C.c_ulonglong)]
+    clk = (C.c_ulonglong * 8)()
+    import bench
     for name in [a for a in sys.argv[1:] if not a.startswith("-")]:
         inst, K = {"c2": (lambda: (I.config2(S=1000), 64)), "c4": (lambda: (I.config4(S=2000), 8))}[name]()
         solver = GuroSolver(inst)
-        paths = I.random_paths(solver, K, 31, 0.1)
+        # the bench's DD-emitted candidates (consecutive paths of the Benders loop) unless random matchings are asked for
+        paths = I.random_paths(solver, K, 31, 0.1) if "--random" in sys.argv else bench.candidate_paths(name, K, 0)[0]
         L.sgufp_debug_k1_stats(out)
+        L.sgufp_debug_k1_clk(clk)
         L.sgufp_debug_k1_lane_stats(lane)
         solver.solve_paths(np.asarray(paths, dtype=np.int16))
         L.sgufp_debug_k1_stats(out)
@@ -50,6 +56,10 @@ def main():
             print(f"{name}: lane kernel, blocks {lane[0]}  sweeps/block {lane[1] / lane[0]:.1f}  steps/block {lane[2] / lane[0]:.0f}  "
                   f"dual updates/scenario {lane[3] / max(1, lane[5]):.1f}  pushes/scenario {lane[4] / max(1, lane[5]):.1f}  ms {solver.last_kernel_ms():.3f}")
             continue
+        L.sgufp_debug_k1_clk(clk)
+        tot = max(1, sum(clk[:6]))
+        print(f"{name}: group {os.environ.get('SGUFP_K1_GROUP', 'auto')}  warm {clk[6]} cold {clk[7]}  clocks per evaluation {tot / max(1, clk[6] + clk[7]):.0f}: "
+              + "  ".join(f"{n} {100.0 * clk[i] / tot:.1f}%" for i, n in enumerate(("link", "stream", "repair", "from zero", "potentials", "lifting"))))
         ev = max(1, out[3])
         print(f"{name}: evals {out[3]}  passes/eval {out[0] / ev:.1f}  label computations/eval {out[1] / ev:.1f}  searches/eval {out[2] / ev:.1f}  ms {solver.last_kernel_ms():.3f}")
         if out[4]:
