@@ -7,7 +7,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsgufp_b200.so")
-SOURCES = ["capi.cu", "capi_shard.cu", "cache.cu", "capi_dd.cu", "k1_cut.cu", "k1_lane.cu", "k2_dd.cu", "k2_build.cu", "dd_host.cpp", "model.cpp"]
+SOURCES = ["capi.cu", "capi_shard.cu", "cache.cu", "capi_dd.cu", "k1_cut.cu", "k1_cut_small.cu", "k1_lane.cu", "k2_dd.cu", "k2_build.cu", "dd_host.cpp", "model.cpp"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-shared",
               # K1 list search / push variants, A/B-timed on a B200 (profiles/r02_summary.md: C4 28.15 -> 27.21 ms, C2 unchanged)

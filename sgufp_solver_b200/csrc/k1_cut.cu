@@ -34,6 +34,9 @@
 
 namespace sgufp {
 
+#if defined(SGUFP_K1_STATS) && defined(SGUFP_K1_SMALL_TU)
+#undef SGUFP_K1_STATS                       // the counters live in the main translation unit (no relocatable device code)
+#endif
 #ifdef SGUFP_K1_STATS
 __device__ unsigned long long g_k1_clk[8];     // SM clocks of the first lane per phase: link, stream, warm repair, flow from zero, potentials, lifting; warm / cold evaluations
 #define K1_CLK(i) do { if (T.tl == 0) { const long long now_ = clock64(); atomicAdd(&g_k1_clk[i], (unsigned long long)(now_ - clk_)); clk_ = now_; } } while (0)
@@ -42,6 +45,14 @@ __device__ unsigned long long g_k1_stats[8];   // relaxation passes, label compu
 
 #ifndef K1_CLK
 #define K1_CLK(i) do {} while (0)
+#endif
+// No loop of the kernel is unrolled: a warp goes through every phase once per evaluation and the warps of an SM are in
+// different phases, so the kernel is bound by its instruction-cache footprint, not by loop overhead (unrolled: 105 KB of SASS
+// and a no_instruction stall of 3.9 warps per issue on C4; profiles/r02_k1_warm.md).  -DSGUFP_K1_UNROLL leaves it to the compiler.
+#if defined(SGUFP_K1_UNROLL) || defined(SGUFP_K1_EMULATE)
+#define K1_LOOP
+#else
+#define K1_LOOP _Pragma("unroll 1")
 #endif
 
 namespace {
@@ -104,6 +115,7 @@ struct Lanes {    // the TILE lanes that work on one scenario (32 on the GPU; 1 
         else { for (int o = TILE / 2; o; o >>= 1) v |= __shfl_xor_sync(mask, v, o, TILE); return v; }
     }
     __device__ __forceinline__ long long sum(long long v) const {
+        K1_LOOP
         for (int o = TILE / 2; o; o >>= 1) v += __shfl_xor_sync(mask, v, o, TILE);
         return v;
     }
@@ -112,6 +124,7 @@ struct Lanes {    // the TILE lanes that work on one scenario (32 on the GPU; 1 
         else { for (int o = TILE / 2; o; o >>= 1) { const int t = __shfl_xor_sync(mask, v, o, TILE); v = t < v ? t : v; } return v; }
     }
     __device__ __forceinline__ unsigned long long min_u64(unsigned long long v) const {
+        K1_LOOP
         for (int o = TILE / 2; o; o >>= 1) { const unsigned long long t = __shfl_xor_sync(mask, v, o, TILE); v = t < v ? t : v; }
         return v;
     }
@@ -128,6 +141,7 @@ struct Lanes {    // the TILE lanes that work on one scenario (32 on the GPU; 1 
 // finite at EVERY node, which is what routing imbalances needs (forced flow of lower bounds).
 template <int TILE, bool MERGED, bool WARM, class TM>
 __device__ void shortest_paths(int src, const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TM &w, int &fuel, bool zero = false) {
+    K1_LOOP
     for (int v = T.tl; v <= nc; v += TILE)
         if (!WARM || !((SU(w.rw + (v >> 5)) >> (v & 31)) & 1)) SI(w.lab + v) = zero ? 0 : LAB_INF;
     T.sync();
@@ -136,6 +150,7 @@ __device__ void shortest_paths(int src, const PlanView &P, int nopen, int nc, co
     bool changed;
     do {
         changed = false;
+        K1_LOOP
         for (int c = T.tl; c < nopen; c += TILE) {
             const int f = RGET(c);                // bit 0 forward residual, bit 1 backward residual
             const ChainEnds e(P.ch_st[c]);
@@ -175,8 +190,10 @@ __device__ void shortest_paths(int src, const PlanView &P, int nopen, int nc, co
 
 template <int TILE, class TM>
 __device__ void tight_small(const PlanView &P, int nopen, const Lanes<TILE> &T, TM &w) {
+    K1_LOOP
     for (int i = T.tl; i < 64; i += TILE) SU(w.tin + i) = 0u;    // tin[32] and tout[32] are adjacent
     T.sync();
+    K1_LOOP
     for (int c = T.tl; c < nopen; c += TILE) {
         const ChainEnds e(P.ch_st[c]);
         const int ls = SI(w.lab + e.sv), le = SI(w.lab + e.ev), f = RGET(c) & 3;
@@ -199,8 +216,10 @@ __device__ int reach_small(int src, int dst, int nc, const Lanes<TILE> &T, TM &w
     unsigned R = 1u << src, F = R;
     int lev = 0;
     if (T.tl == 0) SU(w.hist + 0) = F;
+    K1_LOOP
     for (;;) {
         unsigned nb = 0;
+        K1_LOOP
         for (int u = T.tl; u <= nc; u += TILE)
             if ((F >> u) & 1) nb |= SU(w.tout + u);
         nb = T.reduce_or(nb) & ~R;
@@ -216,6 +235,7 @@ __device__ int reach_small(int src, int dst, int nc, const Lanes<TILE> &T, TM &w
 template <int TILE, class TM>
 __device__ int push_small(int dst, int limit, int lev, int nc, const Lanes<TILE> &T, TM &w) {
     int v = dst, d = limit, h = 0;
+    K1_LOOP
     for (int l = lev; l > 0; l--, h++) {
         const unsigned m = SU(w.tin + v) & SU(w.hist + l - 1);
         if (!m) { d = 0; break; }              // cannot happen: v was reached from level l-1
@@ -226,6 +246,7 @@ __device__ int push_small(int dst, int limit, int lev, int nc, const Lanes<TILE>
     }
     T.sync();
     if (d <= 0) return 0;
+    K1_LOOP
     for (int i = T.tl; i < h; i += TILE) {
         const int rec = SI(w.path + i), s = rec & 0xffff, u = (rec >> 16) & 31, vv = (rec >> 21) & 31, c = s >> 1, dir = s & 1;
         const int xc = SI(w.x + c) + (dir ? -d : d);
@@ -248,6 +269,7 @@ __device__ int push_small(int dst, int limit, int lev, int nc, const Lanes<TILE>
 template <int TILE, class TM>
 __device__ int tight_list(const PlanView &P, int nopen, const Lanes<TILE> &T, TM &w) {
     int n = 0;
+    K1_LOOP
     for (int c0 = 0; c0 < nopen; c0 += TILE) {     // tile-uniform trip count
         const int c = c0 + T.tl;
         int tf = 0;
@@ -283,11 +305,13 @@ __device__ bool reach_list(int src, int dst, const PlanView &P, int ntc, int nwo
     if (!keep) for (int i = T.tl; i < nword; i += TILE) SU(R + (i)) = i == (src >> 5) ? 1u << (src & 31) : 0u;
     T.sync();
     bool partial = c0 > 0;                                  // the first sweep starts at chunk c0: it can find dst, it cannot prove a fixpoint
+    K1_LOOP
     for (;;) {
         bool grew = false;
 #ifdef SGUFP_K1_SKIP_CONFIRM
         bool back = false;          // a backward arc fired, or a usable backward entry is still waiting for its tail
 #endif
+        K1_LOOP
         for (int i0 = partial ? c0 * TILE : 0; i0 < ntc; i0 += TILE, q++) {           // tile-uniform trip count
             const int i = i0 + T.tl;
             const int stamp = min(q, 127) << 25;
@@ -336,6 +360,7 @@ __device__ bool reach_list(int src, int dst, const PlanView &P, int ntc, int nwo
             }
         } else {                                             // any node of the target set (warm start): the lowest one reached
             int found = INT_MAX;
+            K1_LOOP
             for (int i = T.tl; i < nword; i += TILE) { const unsigned both = SU(R + i) & SU(w.tg + i); if (both && found == INT_MAX) found = 32 * i + __ffs(both) - 1; }
             found = T.min_i32(found);
             if (found != INT_MAX) { *hit = found; return true; }
@@ -362,6 +387,7 @@ __device__ int push_list(int src, int dst, int limit, int nc, const Lanes<TILE> 
     int mine = 0;                          // the hop this lane will update (hop number == lane number): its predecessor word
     bool have = false;                     // (a word with a visit stamp of 64 or more is negative: the flag cannot live in its sign)
 #endif
+    K1_LOOP
     while (v != src) {
         const int p = SI(w.pred + v), s = (p >> 10) & 0x7fff, c = s >> 1, xc = SI(w.x + c);
         d = min(d, (s & 1) ? xc - (SI(w.lo + c) >> HB) : (SI(w.up + c) >> HB) - xc);
@@ -389,12 +415,14 @@ __device__ int push_list(int src, int dst, int limit, int nc, const Lanes<TILE> 
         const int qs = T.min_i32(sat);     // at least one arc saturates (d is the bottleneck) unless `limit` bound the push
         if (qs > 0 && qs < 127) {
             if constexpr (TILE == 32) {   // a word of the set per step: the lanes vote on its 32 nodes
+                K1_LOOP
                 for (int u = T.tl; u < 32 * reach_words(nc); u += 32) {
                     const bool in = u <= nc && ((SU(w.rw + (u >> 5)) >> (u & 31)) & 1);
                     const unsigned word = T.ballot(in && (u == src || (int)((unsigned)SI(w.pred + u) >> 25) < qs));
                     if (T.tl == 0) SU(w.rw + (u >> 5)) = word;
                 }
             } else
+            K1_LOOP
             for (int u = T.tl; u <= nc; u += TILE)
                 if (u != src && ((SU(w.rw + (u >> 5)) >> (u & 31)) & 1) && (int)((unsigned)SI(w.pred + u) >> 25) >= qs) atomicAnd(&SU(w.rw + (u >> 5)), ~(1u << (u & 31)));
             *restart = qs;
@@ -405,6 +433,7 @@ __device__ int push_list(int src, int dst, int limit, int nc, const Lanes<TILE> 
     }
 #endif
     v = dst;
+    K1_LOOP
     while (v != src) {
         const int p = SI(w.pred + v), s = (p >> 10) & 0x7fff, c = s >> 1;
         if (T.tl == 0) {
@@ -450,6 +479,7 @@ struct TightPaths {
             T.sync();
         }
         int best = INT_MAX;
+        K1_LOOP
         for (int c = T.tl; c < nopen; c += TILE) {
             const int f = RGET(c) & 3;
             if (!f) continue;
@@ -463,6 +493,7 @@ struct TightPaths {
 #endif
         if (delta == INT_MAX) return false;
         T.sync();
+        K1_LOOP
         for (int v = T.tl; v <= nc; v += TILE)
             if (!in_r(v)) { const int l = SI(w.lab + v); if (l != LAB_INF) SI(w.lab + v) = l + delta; }
         T.sync();
@@ -483,9 +514,11 @@ struct TightPaths {
         int v0 = 0, src = 0, need = 0;
         unsigned todo = 0;
         bool keep = false;
+        K1_LOOP
         for (;;) {
             if (need <= 0) {                  // the next source
                 if (stage == 0) {
+                    K1_LOOP
                     while (!todo && v0 < nc) {
                         const int v = v0 + T.tl;
                         todo = T.ballot(v > 0 && v < nc && SI(w.exc + v) > 0);
@@ -563,8 +596,10 @@ struct TightPaths {
 // face (index 0) at the end.  exc[0] is the root's own imbalance (the books include it: the imbalances sum to zero).
 template <int TILE, class TM>
 __device__ void deficit_targets(int nc, const Lanes<TILE> &T, TM &w) {
+    K1_LOOP
     for (int i = T.tl; i < reach_words(nc); i += TILE) SU(w.tg + i) = 0u;
     T.sync();
+    K1_LOOP
     for (int v = T.tl; v <= nc; v += TILE)
         if (v == nc || (v > 0 && SI(w.exc + v) < 0)) atomicOr(&SU(w.tg + (v >> 5)), 1u << (v & 31));
     T.sync();
@@ -575,8 +610,10 @@ __device__ void deficit_targets(int nc, const Lanes<TILE> &T, TM &w) {
 // imbalances; one that cannot be routed means the scenario is infeasible.
 template <int TILE, class TM>
 __device__ void forced_flow_init(const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TM &w, int &fuel) {
+    K1_LOOP
     for (int v = T.tl; v <= nc; v += TILE) SI(w.exc + v) = 0;
     T.sync();
+    K1_LOOP
     for (int c = T.tl; c < nopen; c += TILE) {
         const int lo = SI(w.lo + c) >> HB;
         if (lo > 0) {
@@ -597,6 +634,7 @@ template <int TILE, class TM>
 __device__ void canonical_potentials(const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TM &w, int &fuel) {
     shortest_paths<TILE, true, false>(0, P, nopen, nc, T, w, fuel);
     bool missing = false;
+    K1_LOOP
     for (int v = T.tl; v < nc; v += TILE) {
         const int l = SI(w.lab + v);
         if (l == LAB_INF) { missing = true; SI(w.pot + v) = NEG_INF; SI(w.pred + v) = 0; } else { SI(w.pot + v) = l; SI(w.pred + v) = 1; }
@@ -607,6 +645,7 @@ __device__ void canonical_potentials(const PlanView &P, int nopen, int nc, const
         bool changed;
         do {
             changed = false;
+            K1_LOOP
             for (int c = T.tl; c < nopen; c += TILE) {
                 const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1, r = P.ch_r[c];
                 const int xc = SI(w.x + c), up = SI(w.up + c) >> HB, lo = SI(w.lo + c) >> HB;
@@ -617,12 +656,14 @@ __device__ void canonical_potentials(const PlanView &P, int nopen, int nc, const
             changed = T.any(changed) && --fuel > 0;
         } while (changed);
         bool iso = false;
+        K1_LOOP
         for (int v = T.tl; v < nc; v += TILE)
             if (SI(w.pot + v) == NEG_INF) { SI(w.pot + v) = 0; SI(w.pred + v) = 2; iso = true; }
         T.sync();
         if (T.any(iso)) {
             do {
                 changed = false;
+                K1_LOOP
                 for (int c = T.tl; c < nopen; c += TILE) {
                     const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1, r = P.ch_r[c];
                     const int xc = SI(w.x + c), up = SI(w.up + c) >> HB, lo = SI(w.lo + c) >> HB;
@@ -634,6 +675,7 @@ __device__ void canonical_potentials(const PlanView &P, int nopen, int nc, const
             } while (changed);
         }
     }
+    K1_LOOP
     for (int v = T.tl; v < nc; v += TILE) SI(w.pot + v) = -SI(w.pot + v);
     T.sync();
 }
@@ -647,6 +689,7 @@ __device__ void canonical_potentials(const PlanView &P, int nopen, int nc, const
 // instead of ~100 on the C4 network (profiles/r02_k1_warm.md).  Instances without forced flow only (lo == 0).
 template <int TILE, class TM>
 __device__ void warm_init(const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TM &w) {
+    K1_LOOP
     for (int c = T.tl; c < nopen; c += TILE) {
         const ChainEnds e(P.ch_st[c]);
         const int up = SI(w.up + c) >> HB;
@@ -714,6 +757,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
     // 2.1) a fixed assignment leaves most of the GPU waiting for the warps that drew three long ones.  Scenario-minor order
     // either way: neighbouring tiles stream neighbouring rows.
     long long item = (long long)blockIdx.x * TILES_PER_CTA + tile_in_cta - stride;
+    K1_LOOP
     for (;;) {
         if (p.work) {
             unsigned long long nxt = 0;
@@ -724,6 +768,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         const int grp = (int)(item / p.S), s = (int)(item - (long long)grp * p.S);
         const double *row_u = p.cap_u + (size_t)s * p.m_pad, *row_l = p.cap_l + (size_t)s * p.m_pad;
         const int32_t *prev_plan = nullptr;     // the candidate whose optimal flow (x) and potentials (pot) this tile still holds
+        K1_LOOP
         for (int k = grp * group, k_end = min(p.K, k + group); k < k_end; k++) {
         const int32_t *carried = prev_plan;
         prev_plan = nullptr;
@@ -742,19 +787,24 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
             // of the chains that are gone, and the flow carried over to this candidate's chain numbering (through w.up,
             // which is rebuilt below)
             const PlanView Q(carried);
+            K1_LOOP
             for (int v = T.tl; v < nc; v += TILE) SI(w.lab + v) = -SI(w.pot + v);
             if (T.tl == 0) SI(w.lab + nc) = 0;
             T.sync();
+            K1_LOOP
             for (int v = T.tl; v <= nc; v += TILE) SI(w.exc + v) = 0;
             T.sync();
             const int nrem = link[0];
             const int32_t *prev_of = link + 2, *removed = prev_of + nopen;
+            K1_LOOP
             for (int i = T.tl; i < nrem; i += TILE) {
                 const int c = removed[i], f = SI(w.x + c);
                 if (f > 0) { const ChainEnds e(Q.ch_st[c]); atomicAdd(&SI(w.exc + e.sv), f); atomicSub(&SI(w.exc + e.ev), f); }
             }
+            K1_LOOP
             for (int c = T.tl; c < nopen; c += TILE) { const int pc = prev_of[c]; SI(w.up + c) = pc >= 0 ? SI(w.x + pc) : 0; }
             T.sync();
+            K1_LOOP
             for (int c = T.tl; c < nopen; c += TILE) SI(w.x + c) = SI(w.up + c);
             T.sync();
         }
@@ -764,11 +814,13 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         //    arcs has a positive lower bound, and its multipliers are read from the capacity row directly)
         // lo[c] packs (greatest lower bound << 10 | position of its LAST arc): with no positive lower bound on the chain
         // that is (0, last position), known up front, so only positive lower bounds (rare) need the atomic
+        K1_LOOP
         for (int c = T.tl; c < nopen; c += TILE) { SI(w.up + c) = INT_MAX; SI(w.lo + c) = P.ch_ptr[c + 1] - P.ch_ptr[c] - 1; }
         T.sync();
         bool bad = false, forced = false;
         {
             const double2 *ru = reinterpret_cast<const double2 *>(row_u), *rl = reinterpret_cast<const double2 *>(row_l);
+            K1_LOOP
             for (int a2 = T.tl; a2 < p.m_pad / 2; a2 += TILE) {
                 const double2 u2 = __ldg(ru + a2), l2 = __ldg(rl + a2);
                 const int a = 2 * a2;
@@ -785,6 +837,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
             }
         }
         T.sync();
+        K1_LOOP
         for (int c = T.tl; c < nopen; c += TILE) {
             const int lo = SI(w.lo + c) >> HB, up = SI(w.up + c) >> HB;
             bad |= lo > up; forced |= lo > 0;
@@ -806,6 +859,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
             continue;
         }
         if (link && forced) {                        // a run goes on from zero flow where a scenario has forced flow
+            K1_LOOP
             for (int c = T.tl; c < nopen; c += TILE) { const int lo = SI(w.lo + c) >> HB; SI(w.x + c) = lo; RSET(c, lo < (SI(w.up + c) >> HB) ? 1 : 0); }
             T.sync();
         }
@@ -813,6 +867,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         // state does): warm (the previous candidate's flow and potentials), forced (x = lo), from zero flow.
         bool warm = link && !forced;
         int rc;
+        K1_LOOP
         for (;;) {
             if (warm) warm_init<TILE>(P, nopen, nc, T, w);
             else if (forced) forced_flow_init<TILE>(P, nopen, nc, T, w, fuel);
@@ -826,6 +881,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
             if (T.tl == 0) atomicAdd(&g_k1_clk[warm && !rc ? 6 : 7], 1ull);
 #endif
             if (!warm || rc != 1) break;
+            K1_LOOP
             for (int c = T.tl; c < nopen; c += TILE) { SI(w.x + c) = 0; RSET(c, (SI(w.up + c) >> HB) > 0 ? 1 : 0); }   // from zero flow (lo == 0 here)
             T.sync();
             warm = false; fuel = 1 << 20;
@@ -851,6 +907,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         }
         // 4. lifting + folding
         long long rhs = 0, objv = 0;
+        K1_LOOP
         for (int c = T.tl; c < nopen; c += TILE) {
             const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1, r = P.ch_r[c];
             const int dp = SI(w.pot + ev) - SI(w.pot + sv);
@@ -863,11 +920,13 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
                 if ((info & 3) == KIND_GAMMA) rhs += v; else atomicAdd(sums + 1 + p.L + a, (unsigned long long)v);
             } else if (g < 0) rhs -= (long long)lo * (-g);
         }
+        K1_LOOP
         for (int i = T.tl; i < nav; i += TILE) {
             const int b0 = P.av_ptr[i], b1 = P.av_ptr[i + 1];
             int alpha = 0;
             if (b1 > b0) {
                 alpha = head_potential(P.av_arcs[b0], P, nopen, w);
+                K1_LOOP
                 for (int t = b0 + 1; t < b1; t++) {
                     const int a = P.av_arcs[t];
                     const int dl = head_potential(a, P, nopen, w) - alpha;
@@ -885,6 +944,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
                 }
             } else {
                 bool found = false;
+                K1_LOOP
                 for (int t = P.fb_ptr[i]; t < P.fb_ptr[i + 1]; t++) {
                     const int c = P.fb_ch[t], ev = (P.ch_ends[c] >> 16) - 1;
                     const int cand = SI(w.pot + ev) - P.ch_r[c];
@@ -894,6 +954,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
             SI(w.aq + i) = alpha;
         }
         T.sync();
+        K1_LOOP
         for (int c = nopen + T.tl; c < nch; c += TILE) {
             const int b0 = P.ch_ptr[c], b1 = P.ch_ptr[c + 1], first = P.ch_arcs[b0], last = P.ch_arcs[b1 - 1];
             const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1;
@@ -934,6 +995,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
     }
 }
 
+#ifndef SGUFP_K1_SMALL_TU
 // ---- feasibility ray of ONE scenario (replaces GRB_DoubleAttr_UnbdRay, grb.cpp:304-344) --------
 // Cold path: runs once per call that meets an infeasible scenario.  One thread, split graph
 // (DESIGN.md §3): minimal min-cut of the lower-bound feasibility network.
@@ -1031,6 +1093,7 @@ __global__ void relayout_caps(const int32_t *__restrict__ src, double *__restric
 }
 
 #endif  // SGUFP_K1_EMULATE
+#endif  // SGUFP_K1_SMALL_TU
 
 }  // namespace
 
@@ -1070,13 +1133,22 @@ static cudaError_t launch_warp_nw(const K1Launch &p, cudaStream_t st, int sm_cou
     return cudaGetLastError();
 }
 
-static cudaError_t launch_warp_dispatch(int nw, const K1Launch &p, cudaStream_t st, int sm_count, int *rw, bool dry) {
-    if (p.nc <= SMALL_NC) switch (nw) {
+// The kernels of the small size class are compiled in their own translation unit (k1_cut_small.cu: this file once more, with the
+// compiler's own loop unrolling — measured faster there, while the larger graphs' kernels are faster without any: K1_LOOP).
+#ifdef SGUFP_K1_SMALL_TU
+cudaError_t k1_launch_small_class(int nw, const K1Launch &p, cudaStream_t st, int sm_count, int *rw, bool dry) {
+    switch (nw) {
         case 8: return launch_warp_nw<8, false>(p, st, sm_count, rw, dry);
         case 4: return launch_warp_nw<4, false>(p, st, sm_count, rw, dry);
         case 2: return launch_warp_nw<2, false>(p, st, sm_count, rw, dry);
         default: return launch_warp_nw<1, false>(p, st, sm_count, rw, dry);
     }
+}
+#else
+cudaError_t k1_launch_small_class(int nw, const K1Launch &p, cudaStream_t st, int sm_count, int *rw, bool dry);
+
+static cudaError_t launch_warp_dispatch(int nw, const K1Launch &p, cudaStream_t st, int sm_count, int *rw, bool dry) {
+    if (p.nc <= SMALL_NC) return k1_launch_small_class(nw, p, st, sm_count, rw, dry);
     switch (nw) {
         case 8: return launch_warp_nw<8, true>(p, st, sm_count, rw, dry);
         case 4: return launch_warp_nw<4, true>(p, st, sm_count, rw, dry);
@@ -1149,11 +1221,12 @@ cudaError_t relayout_launch(const int32_t *src, double *dst, int na, int S, int 
     return cudaGetLastError();
 }
 
+#endif  // SGUFP_K1_SMALL_TU
 #endif  // SGUFP_K1_EMULATE
 
 }  // namespace sgufp
 
-#if defined(SGUFP_K1_STATS) && !defined(SGUFP_K1_EMULATE)
+#if defined(SGUFP_K1_STATS) && !defined(SGUFP_K1_EMULATE) && !defined(SGUFP_K1_SMALL_TU)
 // debug build only (-DSGUFP_K1_STATS): relaxation passes / label computations since the last call
 extern "C" int sgufp_debug_k1_clk(unsigned long long *out8) {
     unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
