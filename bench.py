@@ -383,9 +383,13 @@ def measure(wl, args, rank, world, local, dev, flush, steps, warmup, sample_cloc
         peak, how = load_peaks()
         plan_bytes = int(sum(_plan_words(solver, paths[k]) for k in range(K))) * 4 + K * 4 + K * 8
         traffic = measured_traffic(wl) if world == 1 else None
+        run_len = solver.run_length(K)
         rec = {
             "value": evals_step * steps / (total_ms / 1e3), "unit": "evals/s", "ms_per_step": total_ms / steps, "scaling": w["scaling"],
             "config": config_of(wl, world, inst.n, m, L, T, K, pinfo),
+            "k1": {"candidates_per_run": run_len,
+                   "note": "a warp takes a run of consecutive candidates on one scenario: the first from zero flow, the others warm-started from "
+                           "the optimal flow and potentials of the one before (the cuts do not depend on it: tests/test_k1_gpu.py)"},
             "e2e": {"value": evals_step * steps / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": plan_bytes,
                     "d2h_bytes_per_step": int(K * W * 8 + 2 * K * 8), "ms_per_step": 1e3 * e2e_s / steps,
                     "call": "GuroSolver.solve_paths (sgufp_solve_paths): host int16 paths -> host Inavap::Cut list" +
@@ -394,7 +398,8 @@ def measure(wl, args, rank, world, local, dev, flush, steps, warmup, sample_cloc
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": how, "kernel": "k1_cut_eval", "kernel_ms": k_ms,
                          "bytes_per_eval": bytes_per_eval, "evals_per_launch": K * S,
-                         "note": "K1 is instruction-bound (an exact LP per scenario), not HBM-bound: DESIGN.md §6"},
+                         "note": "K1 is instruction-bound (an exact LP per scenario), not HBM-bound: DESIGN.md §6; a run of candidates reads its capacity row from "
+                                 "HBM once and from L2 afterwards, so the measured DRAM traffic is below the algorithmic bytes"},
             "exchange": None if world == 1 else {"collectives_per_step": info["exchanges_last_call"], "inside_library": True, "nccl": info["nccl"],
                                                  "words": K * W + K},
             "sharded_parity": parity,

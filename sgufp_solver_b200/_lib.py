@@ -43,6 +43,7 @@ SIGNATURES = {
     "sgufp_clone": (C.c_int, [vp, C.POINTER(vp)]),
     "sgufp_cut_hash": (C.c_uint64, [u64p, dp, C.c_int]),
     "sgufp_last_stats": (C.c_int, [vp, cip, C.POINTER(C.c_float)]),
+    "sgufp_run_length": (C.c_int, [vp, C.c_int]),
     "sgufp_last_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
 }
 

@@ -472,6 +472,11 @@ int sgufp_solve_path(sgufp_ctx *c, const int16_t *path, int L, int *cut_type, do
 
 uint64_t sgufp_cut_hash(const uint64_t *keys, const double *vals, int nnz) { return cut_hash(keys, vals, nnz); }
 
+int sgufp_run_length(const sgufp_ctx *c, int K) {
+    if (!c || K < 1) return SGUFP_ERR_ARG;
+    return k1_group(K, c->S, c->sm_count);
+}
+
 int sgufp_last_stats(const sgufp_ctx *c, int *kernel_launches, float *device_ms) {
     if (!c) return SGUFP_ERR_ARG;
     if (kernel_launches) *kernel_launches = c->last_launches;

@@ -49,10 +49,21 @@ __device__ unsigned long long g_k1_stats[8];   // relaxation passes, label compu
 // No loop of the kernel is unrolled: a warp goes through every phase once per evaluation and the warps of an SM are in
 // different phases, so the kernel is bound by its instruction-cache footprint, not by loop overhead (unrolled: 105 KB of SASS
 // and a no_instruction stall of 3.9 warps per issue on C4; profiles/r02_k1_warm.md).  -DSGUFP_K1_UNROLL leaves it to the compiler.
+// K1_LOOP: the loops of the flow phase (label computation, tight chains, search, push, dual update); K1_LOOPB: the others
+// (streaming, potentials, lifting).  -DSGUFP_K1_UNROLL_FLOW / -DSGUFP_K1_UNROLL_BODY leave that group to the compiler.
 #if defined(SGUFP_K1_UNROLL) || defined(SGUFP_K1_EMULATE)
+#define SGUFP_K1_UNROLL_FLOW
+#define SGUFP_K1_UNROLL_BODY
+#endif
+#ifdef SGUFP_K1_UNROLL_FLOW
 #define K1_LOOP
 #else
 #define K1_LOOP _Pragma("unroll 1")
+#endif
+#ifdef SGUFP_K1_UNROLL_BODY
+#define K1_LOOPB
+#else
+#define K1_LOOPB _Pragma("unroll 1")
 #endif
 
 namespace {
@@ -596,10 +607,10 @@ struct TightPaths {
 // face (index 0) at the end.  exc[0] is the root's own imbalance (the books include it: the imbalances sum to zero).
 template <int TILE, class TM>
 __device__ void deficit_targets(int nc, const Lanes<TILE> &T, TM &w) {
-    K1_LOOP
+    K1_LOOPB
     for (int i = T.tl; i < reach_words(nc); i += TILE) SU(w.tg + i) = 0u;
     T.sync();
-    K1_LOOP
+    K1_LOOPB
     for (int v = T.tl; v <= nc; v += TILE)
         if (v == nc || (v > 0 && SI(w.exc + v) < 0)) atomicOr(&SU(w.tg + (v >> 5)), 1u << (v & 31));
     T.sync();
@@ -610,10 +621,10 @@ __device__ void deficit_targets(int nc, const Lanes<TILE> &T, TM &w) {
 // imbalances; one that cannot be routed means the scenario is infeasible.
 template <int TILE, class TM>
 __device__ void forced_flow_init(const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TM &w, int &fuel) {
-    K1_LOOP
+    K1_LOOPB
     for (int v = T.tl; v <= nc; v += TILE) SI(w.exc + v) = 0;
     T.sync();
-    K1_LOOP
+    K1_LOOPB
     for (int c = T.tl; c < nopen; c += TILE) {
         const int lo = SI(w.lo + c) >> HB;
         if (lo > 0) {
@@ -634,7 +645,7 @@ template <int TILE, class TM>
 __device__ void canonical_potentials(const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TM &w, int &fuel) {
     shortest_paths<TILE, true, false>(0, P, nopen, nc, T, w, fuel);
     bool missing = false;
-    K1_LOOP
+    K1_LOOPB
     for (int v = T.tl; v < nc; v += TILE) {
         const int l = SI(w.lab + v);
         if (l == LAB_INF) { missing = true; SI(w.pot + v) = NEG_INF; SI(w.pred + v) = 0; } else { SI(w.pot + v) = l; SI(w.pred + v) = 1; }
@@ -645,7 +656,7 @@ __device__ void canonical_potentials(const PlanView &P, int nopen, int nc, const
         bool changed;
         do {
             changed = false;
-            K1_LOOP
+            K1_LOOPB
             for (int c = T.tl; c < nopen; c += TILE) {
                 const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1, r = P.ch_r[c];
                 const int xc = SI(w.x + c), up = SI(w.up + c) >> HB, lo = SI(w.lo + c) >> HB;
@@ -656,14 +667,14 @@ __device__ void canonical_potentials(const PlanView &P, int nopen, int nc, const
             changed = T.any(changed) && --fuel > 0;
         } while (changed);
         bool iso = false;
-        K1_LOOP
+        K1_LOOPB
         for (int v = T.tl; v < nc; v += TILE)
             if (SI(w.pot + v) == NEG_INF) { SI(w.pot + v) = 0; SI(w.pred + v) = 2; iso = true; }
         T.sync();
         if (T.any(iso)) {
             do {
                 changed = false;
-                K1_LOOP
+                K1_LOOPB
                 for (int c = T.tl; c < nopen; c += TILE) {
                     const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1, r = P.ch_r[c];
                     const int xc = SI(w.x + c), up = SI(w.up + c) >> HB, lo = SI(w.lo + c) >> HB;
@@ -675,7 +686,7 @@ __device__ void canonical_potentials(const PlanView &P, int nopen, int nc, const
             } while (changed);
         }
     }
-    K1_LOOP
+    K1_LOOPB
     for (int v = T.tl; v < nc; v += TILE) SI(w.pot + v) = -SI(w.pot + v);
     T.sync();
 }
@@ -689,7 +700,7 @@ __device__ void canonical_potentials(const PlanView &P, int nopen, int nc, const
 // instead of ~100 on the C4 network (profiles/r02_k1_warm.md).  Instances without forced flow only (lo == 0).
 template <int TILE, class TM>
 __device__ void warm_init(const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TM &w) {
-    K1_LOOP
+    K1_LOOPB
     for (int c = T.tl; c < nopen; c += TILE) {
         const ChainEnds e(P.ch_st[c]);
         const int up = SI(w.up + c) >> HB;
@@ -757,7 +768,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
     // 2.1) a fixed assignment leaves most of the GPU waiting for the warps that drew three long ones.  Scenario-minor order
     // either way: neighbouring tiles stream neighbouring rows.
     long long item = (long long)blockIdx.x * TILES_PER_CTA + tile_in_cta - stride;
-    K1_LOOP
+    K1_LOOPB
     for (;;) {
         if (p.work) {
             unsigned long long nxt = 0;
@@ -768,7 +779,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         const int grp = (int)(item / p.S), s = (int)(item - (long long)grp * p.S);
         const double *row_u = p.cap_u + (size_t)s * p.m_pad, *row_l = p.cap_l + (size_t)s * p.m_pad;
         const int32_t *prev_plan = nullptr;     // the candidate whose optimal flow (x) and potentials (pot) this tile still holds
-        K1_LOOP
+        K1_LOOPB
         for (int k = grp * group, k_end = min(p.K, k + group); k < k_end; k++) {
         const int32_t *carried = prev_plan;
         prev_plan = nullptr;
@@ -787,24 +798,24 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
             // of the chains that are gone, and the flow carried over to this candidate's chain numbering (through w.up,
             // which is rebuilt below)
             const PlanView Q(carried);
-            K1_LOOP
+            K1_LOOPB
             for (int v = T.tl; v < nc; v += TILE) SI(w.lab + v) = -SI(w.pot + v);
             if (T.tl == 0) SI(w.lab + nc) = 0;
             T.sync();
-            K1_LOOP
+            K1_LOOPB
             for (int v = T.tl; v <= nc; v += TILE) SI(w.exc + v) = 0;
             T.sync();
             const int nrem = link[0];
             const int32_t *prev_of = link + 2, *removed = prev_of + nopen;
-            K1_LOOP
+            K1_LOOPB
             for (int i = T.tl; i < nrem; i += TILE) {
                 const int c = removed[i], f = SI(w.x + c);
                 if (f > 0) { const ChainEnds e(Q.ch_st[c]); atomicAdd(&SI(w.exc + e.sv), f); atomicSub(&SI(w.exc + e.ev), f); }
             }
-            K1_LOOP
+            K1_LOOPB
             for (int c = T.tl; c < nopen; c += TILE) { const int pc = prev_of[c]; SI(w.up + c) = pc >= 0 ? SI(w.x + pc) : 0; }
             T.sync();
-            K1_LOOP
+            K1_LOOPB
             for (int c = T.tl; c < nopen; c += TILE) SI(w.x + c) = SI(w.up + c);
             T.sync();
         }
@@ -814,13 +825,13 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         //    arcs has a positive lower bound, and its multipliers are read from the capacity row directly)
         // lo[c] packs (greatest lower bound << 10 | position of its LAST arc): with no positive lower bound on the chain
         // that is (0, last position), known up front, so only positive lower bounds (rare) need the atomic
-        K1_LOOP
+        K1_LOOPB
         for (int c = T.tl; c < nopen; c += TILE) { SI(w.up + c) = INT_MAX; SI(w.lo + c) = P.ch_ptr[c + 1] - P.ch_ptr[c] - 1; }
         T.sync();
         bool bad = false, forced = false;
         {
             const double2 *ru = reinterpret_cast<const double2 *>(row_u), *rl = reinterpret_cast<const double2 *>(row_l);
-            K1_LOOP
+            K1_LOOPB
             for (int a2 = T.tl; a2 < p.m_pad / 2; a2 += TILE) {
                 const double2 u2 = __ldg(ru + a2), l2 = __ldg(rl + a2);
                 const int a = 2 * a2;
@@ -837,7 +848,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
             }
         }
         T.sync();
-        K1_LOOP
+        K1_LOOPB
         for (int c = T.tl; c < nopen; c += TILE) {
             const int lo = SI(w.lo + c) >> HB, up = SI(w.up + c) >> HB;
             bad |= lo > up; forced |= lo > 0;
@@ -859,7 +870,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
             continue;
         }
         if (link && forced) {                        // a run goes on from zero flow where a scenario has forced flow
-            K1_LOOP
+            K1_LOOPB
             for (int c = T.tl; c < nopen; c += TILE) { const int lo = SI(w.lo + c) >> HB; SI(w.x + c) = lo; RSET(c, lo < (SI(w.up + c) >> HB) ? 1 : 0); }
             T.sync();
         }
@@ -867,7 +878,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         // state does): warm (the previous candidate's flow and potentials), forced (x = lo), from zero flow.
         bool warm = link && !forced;
         int rc;
-        K1_LOOP
+        K1_LOOPB
         for (;;) {
             if (warm) warm_init<TILE>(P, nopen, nc, T, w);
             else if (forced) forced_flow_init<TILE>(P, nopen, nc, T, w, fuel);
@@ -881,7 +892,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
             if (T.tl == 0) atomicAdd(&g_k1_clk[warm && !rc ? 6 : 7], 1ull);
 #endif
             if (!warm || rc != 1) break;
-            K1_LOOP
+            K1_LOOPB
             for (int c = T.tl; c < nopen; c += TILE) { SI(w.x + c) = 0; RSET(c, (SI(w.up + c) >> HB) > 0 ? 1 : 0); }   // from zero flow (lo == 0 here)
             T.sync();
             warm = false; fuel = 1 << 20;
@@ -907,7 +918,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         }
         // 4. lifting + folding
         long long rhs = 0, objv = 0;
-        K1_LOOP
+        K1_LOOPB
         for (int c = T.tl; c < nopen; c += TILE) {
             const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1, r = P.ch_r[c];
             const int dp = SI(w.pot + ev) - SI(w.pot + sv);
@@ -920,13 +931,13 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
                 if ((info & 3) == KIND_GAMMA) rhs += v; else atomicAdd(sums + 1 + p.L + a, (unsigned long long)v);
             } else if (g < 0) rhs -= (long long)lo * (-g);
         }
-        K1_LOOP
+        K1_LOOPB
         for (int i = T.tl; i < nav; i += TILE) {
             const int b0 = P.av_ptr[i], b1 = P.av_ptr[i + 1];
             int alpha = 0;
             if (b1 > b0) {
                 alpha = head_potential(P.av_arcs[b0], P, nopen, w);
-                K1_LOOP
+                K1_LOOPB
                 for (int t = b0 + 1; t < b1; t++) {
                     const int a = P.av_arcs[t];
                     const int dl = head_potential(a, P, nopen, w) - alpha;
@@ -944,7 +955,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
                 }
             } else {
                 bool found = false;
-                K1_LOOP
+                K1_LOOPB
                 for (int t = P.fb_ptr[i]; t < P.fb_ptr[i + 1]; t++) {
                     const int c = P.fb_ch[t], ev = (P.ch_ends[c] >> 16) - 1;
                     const int cand = SI(w.pot + ev) - P.ch_r[c];
@@ -954,7 +965,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
             SI(w.aq + i) = alpha;
         }
         T.sync();
-        K1_LOOP
+        K1_LOOPB
         for (int c = nopen + T.tl; c < nch; c += TILE) {
             const int b0 = P.ch_ptr[c], b1 = P.ch_ptr[c + 1], first = P.ch_arcs[b0], last = P.ch_arcs[b1 - 1];
             const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1;
@@ -1183,17 +1194,17 @@ static cudaError_t launch_warp(const K1Launch &p, cudaStream_t st, int sm_count)
     return launch_warp_dispatch(best_nw, p, st, sm_count, &rw, false);
 }
 
-// Candidates per work item of the warp kernel (K1Launch::group): as long a run as still leaves every resident warp an item
-// (a warm-started candidate costs about a third of one solved from zero flow), at most 16, in runs of equal length.
-// SGUFP_K1_GROUP=n overrides (1 = every candidate from zero flow).
+// Candidates per work item of the warp kernel (K1Launch::group).  A warm-started candidate costs about a third of one
+// solved from zero flow, so long runs save work; but a launch ends with its slowest warp, and with A = K * S / (resident
+// warps) evaluations per warp the time follows (A / g + 0.45) * (0.65 + 0.35 g) — the 0.45 is the measured cost of the last,
+// partly filled round of items (C2, C4 on a B200: profiles/r02_k1_warm.md).  Least at g = sqrt(4 A); at most 32, in runs of
+// equal length.  SGUFP_K1_GROUP=n overrides (1 = every candidate from zero flow).
 int k1_group(int K, int S, int sm_count) {
     if (const char *e = getenv("SGUFP_K1_GROUP")) { const int g = atoi(e); return g < 1 ? 1 : g > K ? K : g; }
-    const long long slots = (long long)sm_count * 32;
-    long long g = slots > 0 ? (long long)K * S / slots : 1;
-    if (g > 16) g = 16;
-    if (g > K) g = K;
-    if (g < 1) g = 1;
-    const int runs = (int)((K + g - 1) / g);
+    const double A = (double)K * S / ((double)(sm_count > 0 ? sm_count : 1) * 32.0);
+    int g = 1;
+    while (g < 32 && g < K && (double)(g + 1) * (g + 1) <= 4.0 * A + (double)g + 1.0) g++;      // (g + 1/2)^2 <= 4 A: round to nearest
+    const int runs = (K + g - 1) / g;
     return (K + runs - 1) / runs;
 }
 

@@ -231,6 +231,11 @@ class GuroSolver:
         _lib.lib().sgufp_last_stats(self.h, C.byref(a), C.byref(b))
         return a.value, b.value
 
+    def run_length(self, K: int) -> int:
+        """Candidates per run of a batch of K (sgufp_run_length): every candidate of a run after the first is warm-started
+        from its predecessor on the same scenario."""
+        return int(_lib.lib().sgufp_run_length(self.h, int(K)))
+
     def last_kernel_ms(self) -> float:
         """Device time of the last K1 launch (CUDA events on the launching stream)."""
         t = C.c_float()

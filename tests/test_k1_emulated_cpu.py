@@ -219,13 +219,12 @@ def test_kernel_body_fuzz_larger_graphs(emul, block):
 
 @pytest.fixture(scope="module")
 def emul_experiments(tmp_path_factory):
-    return _build_emul(tmp_path_factory, ["SGUFP_K1_NO_DUAL"])
+    return _build_emul(tmp_path_factory, [])
 
 
 def test_experimental_switches_keep_parity(emul_experiments):
-    """The kernel body WITHOUT the two list-search / push switches the product build turns on (build.py) and with label
-    computations instead of dual updates (-DSGUFP_K1_NO_DUAL, the round-1 flow phase kept for A/B timing) must give Oracle B's
-    sums too: every compiled-out code path stays parity-checked."""
+    """The kernel body WITHOUT the two list-search / push switches the product build turns on (build.py: SGUFP_K1_SKIP_CONFIRM,
+    SGUFP_K1_PUSH_PAR) must give Oracle B's sums too: every compiled-out code path stays parity-checked."""
     emul = emul_experiments
     rng = np.random.default_rng(1234)
     done = big = 0
