@@ -91,11 +91,33 @@ int make_batch(sgufp_ctx *c, const int16_t *paths, int K, int L, Batch &B, bool 
 
 int launch_batch(sgufp_ctx *c, const Batch &B, int K, unsigned long long *d_sums, long long *d_finf, double *d_obj,
                         uint8_t *d_status, cudaStream_t st) {
-    CU(c, c->d_plans.reserve(B.total_words));
+    // State between launches (one-path-at-a-time callers): when the whole batch is one run per scenario, its first candidate is
+    // linked to the last candidate of the previous launch on this handle, whose flow and potentials every scenario's row of
+    // d_state holds, and its last candidate leaves its own there.  SGUFP_K1_STATE=0 turns it off.
+    const int group = k1_group(K, c->S, c->sm_count);
+    const char *state_env = getenv("SGUFP_K1_STATE");
+    const bool state_on = !state_env || atoi(state_env) != 0;
+    int state_io = 0;
+    std::vector<int32_t> link0;
+    if (state_on && group >= K && c->S > 0) {
+        const int stride = 1 + c->M.nc + c->M.m;
+        if (!c->d_state.p) {
+            if (c->d_state.reserve((size_t)c->S * stride) == cudaSuccess) {
+                c->state_stride = stride; c->state_valid = false;
+                CU(c, cudaMemsetAsync(c->d_state.p, 0, (size_t)c->S * stride * 4, st));
+            } else cudaGetLastError();               // no room for it: every launch starts from zero flow
+        }
+        if (c->d_state.p) {
+            state_io = 2;
+            if (c->state_valid) { link_plans(c->state_plan, B.plans[0], link0); if (!link0.empty()) state_io |= 1; }
+        }
+    }
+    const size_t pool_words = B.total_words + link0.size();
+    CU(c, c->d_plans.reserve(pool_words));
     CU(c, c->d_plan_off.reserve(2 * (size_t)K));
     // gather the plans (+ offsets + the initial "no infeasible scenario" marks) into pinned memory: the uploads are then
     // true asynchronous copies.  The staging buffer is reused by the next call: an event tells when the copies left it.
-    const size_t o_off = B.total_words, o_inf = (o_off + 2 * (size_t)K + 1) & ~(size_t)1, need = o_inf + 2 * (size_t)K;
+    const size_t o_off = pool_words, o_inf = (o_off + 2 * (size_t)K + 1) & ~(size_t)1, need = o_inf + 2 * (size_t)K;
     if (c->h2d_pending) { CU(c, cudaEventSynchronize(c->ev_h2d)); c->h2d_pending = false; }
     if (c->h_words_cap < need) {
         if (c->h_words) cudaFreeHost(c->h_words);
@@ -107,9 +129,10 @@ int launch_batch(sgufp_ctx *c, const Batch &B, int K, unsigned long long *d_sums
     for (int k = 1; k < K; k++) if (B.link_off[k] >= 0) std::memcpy(c->h_words + B.link_off[k], B.links[k].data(), B.links[k].size() * 4);
     std::memcpy(c->h_words + o_off, B.off.data(), (size_t)K * 4);
     std::memcpy(c->h_words + o_off + K, B.link_off.data(), (size_t)K * 4);
+    if (state_io & 1) { std::memcpy(c->h_words + B.total_words, link0.data(), link0.size() * 4); c->h_words[o_off + K] = (int32_t)B.total_words; }
     long long *inf = reinterpret_cast<long long *>(c->h_words + o_inf);
     for (int k = 0; k < K; k++) inf[k] = LLONG_MAX;
-    CU(c, cudaMemcpyAsync(c->d_plans.p, c->h_words, B.total_words * 4, cudaMemcpyHostToDevice, st));
+    CU(c, cudaMemcpyAsync(c->d_plans.p, c->h_words, pool_words * 4, cudaMemcpyHostToDevice, st));
     CU(c, cudaMemcpyAsync(c->d_plan_off.p, c->h_words + o_off, 2 * (size_t)K * 4, cudaMemcpyHostToDevice, st));
     CU(c, cudaMemcpyAsync(d_finf, inf, (size_t)K * 8, cudaMemcpyHostToDevice, st));
     CU(c, cudaEventRecord(c->ev_h2d, st));
@@ -119,7 +142,8 @@ int launch_batch(sgufp_ctx *c, const Batch &B, int K, unsigned long long *d_sums
     CU(c, cudaMemsetAsync(c->d_work.p, 0, 8, st));
     K1Launch p{};
     p.cap_u = c->d_u; p.cap_l = c->d_l; p.S = c->S; p.m = c->M.m; p.m_pad = c->m_pad; p.scen_offset = c->scen_off;
-    p.plans = c->d_plans.p; p.plan_off = c->d_plan_off.p; p.link_off = c->d_plan_off.p + K; p.group = k1_group(K, c->S, c->sm_count); p.K = K; p.W = c->W(); p.L = c->M.L;
+    p.plans = c->d_plans.p; p.plan_off = c->d_plan_off.p; p.link_off = c->d_plan_off.p + K; p.group = group; p.K = K;
+    p.state = state_io ? c->d_state.p : nullptr; p.state_stride = c->state_stride; p.state_io = state_io; p.W = c->W(); p.L = c->M.L;
     p.sums = d_sums; p.first_inf = d_finf; p.obj = d_obj; p.status = d_status; p.work = c->d_work.p;
     p.max_nch = B.max_nch; p.max_nopen = B.max_nopen; p.nc = c->M.nc; p.nav = c->M.nav; p.max_cap = c->max_cap;
     p.has_lower = c->max_lower > 0; p.lane_tables = B.key_lane; p.sum_abs_r = c->sum_abs_r; p.max_indeg = B.max_indeg;
@@ -134,6 +158,9 @@ int launch_batch(sgufp_ctx *c, const Batch &B, int K, unsigned long long *d_sums
         CU(c, cudaEventRecord(c->evk1, st));
         c->kernel_timed = true;
     }
+    // what the rows of d_state describe after this launch
+    if (state_io & 2) { c->state_plan = B.plans[K - 1]; c->state_valid = true; }
+    else c->state_valid = false;
     return 0;
 }
 
@@ -315,7 +342,7 @@ void sgufp_destroy(sgufp_ctx *c) {
         c->caps = nullptr; c->d_u = c->d_l = nullptr;
     }
     c->d_plans.release(); c->d_plan_off.release(); c->d_ray_i32.release(); c->d_sums.release(); c->d_work.release(); c->d_finf.release();
-    c->d_ray_scratch.release(); c->d_obj.release(); c->d_status.release();
+    c->d_ray_scratch.release(); c->d_obj.release(); c->d_status.release(); c->d_state.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->evk0) cudaEventDestroy(c->evk0);

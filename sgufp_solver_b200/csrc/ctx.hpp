@@ -65,6 +65,12 @@ struct sgufp_ctx {
     DevBuf<uint8_t> d_status;
     std::string err;
     PlanBatch batch;                            // plans of the last batch (reused when the next call brings the same paths)
+    // K1 state kept between launches (k1_cut.cuh: K1Launch::state): per scenario the optimal flow and potentials of the last
+    // candidate of the previous launch, and that candidate's plan on the host (the next launch links its first plan to it)
+    DevBuf<int32_t> d_state;
+    sgufp::Plan state_plan;
+    bool state_valid = false;
+    int state_stride = 0;
     sgufp::HostPool *pool = nullptr;            // persistent host threads for the plans of a batch (created on first use)
     int32_t *h_words = nullptr;                 // pinned staging of a batch's plans (cudaHostAlloc), h_words_cap int32 words
     size_t h_words_cap = 0;

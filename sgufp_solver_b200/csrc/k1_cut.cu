@@ -778,11 +778,22 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         if (item >= items) break;
         const int grp = (int)(item / p.S), s = (int)(item - (long long)grp * p.S);
         const double *row_u = p.cap_u + (size_t)s * p.m_pad, *row_l = p.cap_l + (size_t)s * p.m_pad;
-        const int32_t *prev_plan = nullptr;     // the candidate whose optimal flow (x) and potentials (pot) this tile still holds
+        bool holds = false;                     // this tile holds the optimal flow (x) and potentials (pot) of the candidate before k
+        int32_t *srow = p.state && ngroups == 1 ? p.state + (size_t)s * p.state_stride : nullptr;   // this scenario's row of the handle's state
+        if (srow && (p.state_io & 1) && srow[0]) {         // left by the last candidate of the previous launch on this handle
+            const int nprev = (p.plans + p.link_off[0])[1];
+            K1_LOOPB
+            for (int v = T.tl; v < p.nc; v += TILE) SI(w.pot + v) = srow[1 + v];
+            K1_LOOPB
+            for (int c = T.tl; c < nprev; c += TILE) SI(w.x + c) = srow[1 + p.nc + c];
+            holds = true;
+        }
+        T.sync();
+        if (srow && (p.state_io & 2) && T.tl == 0) srow[0] = 0;   // until the last candidate of this launch has filled it
         K1_LOOPB
         for (int k = grp * group, k_end = min(p.K, k + group); k < k_end; k++) {
-        const int32_t *carried = prev_plan;
-        prev_plan = nullptr;
+        const bool carried = holds;
+        holds = false;
         if (*reinterpret_cast<volatile long long *>(p.first_inf + k) < 0) continue;   // this candidate was aborted: drain
         int fuel = 1 << 20;   // passes + levels a work item may spend (tile-uniform)
         const PlanView P(p.plans + p.plan_off[k]);
@@ -797,7 +808,6 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
             // labels = the previous candidate's potentials (finite for every node; the root is 0 on both faces), imbalances
             // of the chains that are gone, and the flow carried over to this candidate's chain numbering (through w.up,
             // which is rebuilt below)
-            const PlanView Q(carried);
             K1_LOOPB
             for (int v = T.tl; v < nc; v += TILE) SI(w.lab + v) = -SI(w.pot + v);
             if (T.tl == 0) SI(w.lab + nc) = 0;
@@ -806,11 +816,11 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
             for (int v = T.tl; v <= nc; v += TILE) SI(w.exc + v) = 0;
             T.sync();
             const int nrem = link[0];
-            const int32_t *prev_of = link + 2, *removed = prev_of + nopen;
+            const int32_t *prev_of = link + 2, *removed = prev_of + nopen, *ends = removed + nrem;
             K1_LOOPB
             for (int i = T.tl; i < nrem; i += TILE) {
-                const int c = removed[i], f = SI(w.x + c);
-                if (f > 0) { const ChainEnds e(Q.ch_st[c]); atomicAdd(&SI(w.exc + e.sv), f); atomicSub(&SI(w.exc + e.ev), f); }
+                const int f = SI(w.x + removed[i]);
+                if (f > 0) { const int e = ends[i]; atomicAdd(&SI(w.exc + (e & 1023)), f); atomicSub(&SI(w.exc + (e >> 10)), f); }
             }
             K1_LOOPB
             for (int c = T.tl; c < nopen; c += TILE) { const int pc = prev_of[c]; SI(w.up + c) = pc >= 0 ? SI(w.x + pc) : 0; }
@@ -1001,7 +1011,15 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         }
         T.sync();
         K1_CLK(5);
-        if (!forced) prev_plan = p.plans + p.plan_off[k];   // x and pot of this candidate serve the next one of the run
+        holds = !forced;                                    // x and pot of this candidate serve the next one of the run
+        if (srow && (p.state_io & 2) && k == p.K - 1 && holds) {   // ... and the first one of the next launch on this handle
+            K1_LOOPB
+            for (int v = T.tl; v < nc; v += TILE) srow[1 + v] = SI(w.pot + v);
+            K1_LOOPB
+            for (int c = T.tl; c < nopen; c += TILE) srow[1 + nc + c] = SI(w.x + c);
+            T.sync();
+            if (T.tl == 0) srow[0] = 1;
+        }
         }
     }
 }

@@ -15,6 +15,13 @@ struct K1Launch {
     int group;                    // candidates per work item: a warp takes `group` consecutive candidates on one scenario and warm-starts
                                   // each from the one before (0 or 1: every candidate from zero flow)
     int K, W, L;
+    // State kept between launches on one handle (one-path-at-a-time callers: the reference's Benders loop hands solveSubProblem
+    // one path per iteration, NodeExplorer.cpp:949-971): per scenario { valid, pot[nc], x[open chains] } of the LAST candidate
+    // of the previous launch, so that the first candidate of this one can be warm-started too.  Only when the whole batch
+    // is one run per scenario (group >= K): the warp that reads a scenario's row is the one that rewrites it.
+    int32_t *state;               // [S][state_stride] or nullptr
+    int state_stride;             // >= 1 + nc + max open chains
+    int state_io;                 // bit 0: link_off[0] describes the step from the stored candidate, read the row; bit 1: write it
     unsigned long long *sums;     // [K][W] exact integer accumulators (two's complement)
     long long *first_inf;         // [K] lowest infeasible global scenario (init LLONG_MAX)
     unsigned long long *work;     // work-item queue of the warp kernel (one word, zeroed before the launch) or nullptr: fixed assignment

@@ -332,10 +332,12 @@ void link_plans(const Plan &prev, const Plan &cur, std::vector<int32_t> &out) {
     std::vector<int32_t> removed;
     for (int c = 0; c < na; c++) if (!kept[c]) removed.push_back(c);
     if (4 * (n_new + (int)removed.size()) > std::max(na, nb)) return;
-    out.reserve(2 + nb + removed.size() + 3);
-    out.push_back((int32_t)removed.size()); out.push_back(n_new);
+    out.reserve(2 + nb + 2 * removed.size() + 3);
+    out.push_back((int32_t)removed.size()); out.push_back(na);
     out.insert(out.end(), prev_of.begin(), prev_of.end());
     out.insert(out.end(), removed.begin(), removed.end());
+    const int32_t *st_a = A + ha->o_ch_st;
+    for (int c : removed) out.push_back(st_a[2 * c] & 0xfffff);        // sv | ev << 10 of the removed chain (model.hpp: o_ch_st)
     while (out.size() & 3) out.push_back(0);
 }
 

@@ -86,9 +86,10 @@ int build_plan(const Model &M, const int16_t *path, int plen, Plan &P, std::stri
 
 // Link of two consecutive candidates of a batch (k1_cut.cu: warm start of candidate k from the optimal flow of candidate
 // k-1 on the same scenario; consecutive paths of the Benders loop differ in a few layers, NodeExplorer.cpp:949-971).
-// out = { n_removed, n_new, prev[nopen(cur)], removed[n_removed] }: prev[c] = the open chain of `prev` made of the same
-// arcs as open chain c of `cur` (-1: none), removed = the open chains of `prev` that `cur` does not have.  out stays
-// empty when more than a quarter of the chains differ (a cold start is cheaper then).
+// out = { n_removed, nopen(prev), prev[nopen(cur)], removed[n_removed], ends[n_removed] }: prev[c] = the open chain of `prev`
+// made of the same arcs as open chain c of `cur` (-1: none), removed = the open chains of `prev` that `cur` does not have,
+// ends = their contracted end nodes sv | ev << 10.  out stays empty when more than a quarter of the chains differ (a cold
+// start is cheaper then).
 void link_plans(const Plan &prev, const Plan &cur, std::vector<int32_t> &out);
 
 void ray_arrays(const Model &M, const Plan &P, std::vector<int32_t> &ts, std::vector<int32_t> &hs, std::vector<int32_t> &info,

@@ -57,6 +57,12 @@ using namespace sgufp;
 
 // Same contract as sgufp_paths_partial + sgufp_ray_partial, on the host.  sums: [K][W] (W = 1+L+m),
 // first_inf: [K], obj/status: [K][S].  ray_sums[K][W]: filled for candidates with an infeasible scenario.
+// state between calls (K1Launch::state), as capi.cu: launch_batch keeps it on a handle: rows of the last candidate of the
+// previous call + its plan.  emul_state(1) turns it on (and forgets what was stored), emul_state(0) off.
+static bool g_state_on = false, g_state_valid = false;
+static std::vector<int32_t> g_state;
+static sgufp::Plan g_state_plan;
+extern "C" void emul_state(int on) { g_state_on = on != 0; g_state_valid = false; g_state.clear(); }
 static int g_group = 0;
 extern "C" void emul_set_group(int g) { g_group = g; }   // candidates per work item (0: the whole batch, 1: no warm starts)
 extern "C" void emul_warm_counts(long long *out2) { out2[0] = sgufp::sgufp_emul_warm[0]; out2[1] = sgufp::sgufp_emul_warm[1]; sgufp::sgufp_emul_warm[0] = sgufp::sgufp_emul_warm[1] = 0; }
@@ -90,6 +96,17 @@ extern "C" int emul_paths(int n, int m, int S, const int32_t *tail, const int32_
         link_plans(plans[k - 1], plans[k], lk);
         if (!lk.empty()) { link_off[k] = (int32_t)words.size(); words.insert(words.end(), lk.begin(), lk.end()); }
     }
+    const int group = g_group > 0 ? g_group : K;
+    int state_io = 0, state_stride = 1 + M.nc + m;
+    if (g_state_on && group >= K && !lane_variant) {
+        if (g_state.size() != (size_t)S * state_stride) { g_state.assign((size_t)S * state_stride, 0); g_state_valid = false; }
+        state_io = 2;
+        if (g_state_valid) {
+            std::vector<int32_t> lk;
+            link_plans(g_state_plan, plans[0], lk);
+            if (!lk.empty()) { state_io |= 1; link_off[0] = (int32_t)words.size(); words.insert(words.end(), lk.begin(), lk.end()); }
+        }
+    }
     std::memset(sums, 0, (size_t)K * W * 8);
     for (int k = 0; k < K; k++) first_inf[k] = LLONG_MAX;
     K1Launch p{};
@@ -98,7 +115,9 @@ extern "C" int emul_paths(int n, int m, int S, const int32_t *tail, const int32_
     p.sums = reinterpret_cast<unsigned long long *>(sums); p.first_inf = first_inf; p.obj = obj; p.status = status;
     unsigned long long work_queue = 0;
     p.work = (K & 1) ? &work_queue : nullptr;     // both ways of handing out work items are exercised
-    p.link_off = link_off.data(); p.group = g_group > 0 ? g_group : K;   // runs of warm-started candidates (default: the whole batch is one run)
+    p.link_off = link_off.data(); p.group = group;   // runs of warm-started candidates (default: the whole batch is one run)
+    p.state = state_io ? g_state.data() : nullptr; p.state_stride = state_stride; p.state_io = state_io;
+    if (state_io) { g_state_plan = plans[K - 1]; g_state_valid = true; } else g_state_valid = false;
     g_last_nc = M.nc;
     p.max_nch = max_nch; p.max_nopen = max_nopen; p.nc = M.nc; p.nav = M.nav; p.max_cap = 65535;
     const int wpt = k1_words_per_tile(p);

@@ -335,3 +335,25 @@ def test_warm_runs_fuzz(emul, block):
         taken_all += taken
         done += 1
     assert done >= 18 and taken_all > 0
+
+
+@pytest.mark.parametrize("name,make,K,seed,changes,unm", WARM_CASES, ids=[c[0] for c in WARM_CASES])
+@pytest.mark.parametrize("per_call", [1, 2])
+def test_state_between_calls_matches_oracle(emul, name, make, K, seed, changes, unm, per_call):
+    """One path (or two) per call, as NodeExplorer::process hands them to solveSubProblem: the first candidate of a call starts
+    from the flow and potentials the last candidate of the previous call left in the handle's per-scenario state."""
+    inst = make()
+    net = OracleNet(inst)
+    paths = I.perturbed_paths(net, K, seed, changes, unm)
+    emul.emul_state(1)
+    warm_counts(emul)
+    try:
+        for k0 in range(0, K, per_call):
+            sub = np.ascontiguousarray(paths[k0:k0 + per_call])
+            check_against_oracle(inst, net, sub, run_emul(emul, inst, net, sub))
+    finally:
+        emul.emul_state(0)
+    taken, given_up = warm_counts(emul)
+    assert given_up == 0
+    if inst.lower.max() == 0:
+        assert taken == (K - 1) * inst.S, (taken, K, inst.S)       # every candidate but the very first was warm-started

@@ -405,3 +405,25 @@ def test_warm_runs_equal_cold_starts_bit_for_bit(wl, S, K, monkeypatch):
     for r in outs[1:]:
         assert (r.rhs == outs[0].rhs).all() and (r.coef_dense == outs[0].coef_dense).all() and (r.obj == outs[0].obj).all()
         assert (r.nnz == outs[0].nnz).all()
+
+
+@pytest.mark.parametrize("name,make,K,seed,changes,unm", WARM_CASES[:6], ids=[c[0] for c in WARM_CASES[:6]])
+def test_one_path_per_call_keeps_state_between_calls(name, make, K, seed, changes, unm):
+    """solveSubProblem(path) call after call, as NodeExplorer::process does it (NodeExplorer.cpp:949-971): the handle keeps the
+    optimal flow and potentials of the last candidate per scenario and warm-starts the next call from them; every cut must be
+    what a fresh handle (which starts from zero flow) and Oracle B give for that path alone."""
+    inst = make()
+    net = OracleNet(inst)
+    gs = sg.GuroSolver(inst)
+    paths = I.perturbed_paths(net, K, seed, changes, unm)
+    seq = [gs.solve_paths(paths[k:k + 1]) for k in range(K)]
+    fresh = sg.GuroSolver(inst)
+    for k in range(K):
+        _compare(inst, gs, net, paths[k:k + 1], seq[k])
+        one = sg.GuroSolver(inst).solve_paths(paths[k:k + 1]) if k % 3 == 0 else None
+        if one is not None:
+            assert (one.rhs == seq[k].rhs).all() and (one.coef_dense == seq[k].coef_dense).all() and (one.obj == seq[k].obj).all()
+    # batches after single paths and the other way round share the same state
+    both = gs.solve_paths(paths)
+    alone = fresh.solve_paths(paths)
+    assert (both.rhs == alone.rhs).all() and (both.coef_dense == alone.coef_dense).all() and (both.obj == alone.obj).all()
