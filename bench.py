@@ -360,6 +360,20 @@ def measure(wl, args, rank, world, local, dev, flush, steps, warmup, sample_cloc
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_t.item())
     clocks = sampler.stop() if sampler else None
+
+    # ---- the same step with every candidate solved from zero flow (no runs, no state between steps): what the warm starts buy ----
+    cold_ms = None
+    if world == 1:
+        os.environ["SGUFP_K1_GROUP"], os.environ["SGUFP_K1_STATE"] = "1", "0"
+        try:
+            device_step(); barrier()
+            cev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
+            for a, b in cev:
+                flush.zero_(); a.record(stream); device_step(); b.record(stream)
+            barrier()
+            cold_ms = sum(a.elapsed_time(b) for a, b in cev) / len(cev)
+        finally:
+            os.environ.pop("SGUFP_K1_GROUP", None); os.environ.pop("SGUFP_K1_STATE", None)
     assert (res.cut_type == 0).all() and np.isfinite(res.rhs).all(), "the throughput workload has no lower bounds: every cut is an optimality cut"
     info = solver.comm_info()
 
@@ -387,9 +401,14 @@ def measure(wl, args, rank, world, local, dev, flush, steps, warmup, sample_cloc
         rec = {
             "value": evals_step * steps / (total_ms / 1e3), "unit": "evals/s", "ms_per_step": total_ms / steps, "scaling": w["scaling"],
             "config": config_of(wl, world, inst.n, m, L, T, K, pinfo),
-            "k1": {"candidates_per_run": run_len,
-                   "note": "a warp takes a run of consecutive candidates on one scenario: the first from zero flow, the others warm-started from "
-                           "the optimal flow and potentials of the one before (the cuts do not depend on it: tests/test_k1_gpu.py)"},
+            "k1": {"candidates_per_run": run_len, "state_between_steps": bool(run_len >= K),
+                   "from_zero_flow": None if cold_ms is None else {"value": evals_step / (cold_ms / 1e3), "unit": "evals/s", "ms_per_step": cold_ms,
+                                                                    "how": "SGUFP_K1_GROUP=1 SGUFP_K1_STATE=0, 3 steps"},
+                   "note": "a warp takes a run of consecutive candidates on one scenario and warm-starts each from the optimal flow and potentials "
+                           "of the one before; when the whole batch is one run the handle keeps the last candidate's state per scenario, so the "
+                           "first candidate of a step starts from the last one of the step before (consecutive paths of the Benders loop are a "
+                           "few layers apart).  Every (candidate, scenario) LP is solved to optimality in every step; the cuts are bit-identical "
+                           "to the ones from zero flow (tests/test_k1_gpu.py)"},
             "e2e": {"value": evals_step * steps / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": plan_bytes,
                     "d2h_bytes_per_step": int(K * W * 8 + 2 * K * 8), "ms_per_step": 1e3 * e2e_s / steps,
                     "call": "GuroSolver.solve_paths (sgufp_solve_paths): host int16 paths -> host Inavap::Cut list" +
@@ -452,7 +471,7 @@ def main():
         line = {"metric": METRIC, "value": head["value"], "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": head["scaling"], "vs_baseline": None,
                 "dtype": DTYPE, "data": "synthetic", "config": head["config"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
-                "roofline": head["roofline"], "exchange": head["exchange"], "sharded_parity": head["sharded_parity"], "clocks": head["clocks"],
+                "roofline": head["roofline"], "k1": head["k1"], "exchange": head["exchange"], "sharded_parity": head["sharded_parity"], "clocks": head["clocks"],
                 "sub": {k: ({kk: vv for kk, vv in v.items() if kk != "clocks"} if isinstance(v, dict) else v) for k, v in subs.items()},
                 "dd": None}
         if not args.no_cpu_baseline and world == 1:

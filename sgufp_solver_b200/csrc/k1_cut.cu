@@ -65,6 +65,18 @@ __device__ unsigned long long g_k1_stats[8];   // relaxation passes, label compu
 #else
 #define K1_LOOPB _Pragma("unroll 1")
 #endif
+// K1_LOOP1: loops that run once per evaluation over a handful of words (state rows, the link of a warm start, targets):
+// never unrolled, in either size class
+#ifdef SGUFP_K1_EMULATE
+#define K1_LOOP1
+#else
+#define K1_LOOP1 _Pragma("unroll 1")
+#endif
+#if defined(SGUFP_K1_EMULATE) || defined(SGUFP_K1_UNROLL2)
+#define K1_LOOP2
+#else
+#define K1_LOOP2 _Pragma("unroll 1")
+#endif
 
 namespace {
 
@@ -607,10 +619,10 @@ struct TightPaths {
 // face (index 0) at the end.  exc[0] is the root's own imbalance (the books include it: the imbalances sum to zero).
 template <int TILE, class TM>
 __device__ void deficit_targets(int nc, const Lanes<TILE> &T, TM &w) {
-    K1_LOOPB
+    K1_LOOP1
     for (int i = T.tl; i < reach_words(nc); i += TILE) SU(w.tg + i) = 0u;
     T.sync();
-    K1_LOOPB
+    K1_LOOP1
     for (int v = T.tl; v <= nc; v += TILE)
         if (v == nc || (v > 0 && SI(w.exc + v) < 0)) atomicOr(&SU(w.tg + (v >> 5)), 1u << (v & 31));
     T.sync();
@@ -621,10 +633,10 @@ __device__ void deficit_targets(int nc, const Lanes<TILE> &T, TM &w) {
 // imbalances; one that cannot be routed means the scenario is infeasible.
 template <int TILE, class TM>
 __device__ void forced_flow_init(const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TM &w, int &fuel) {
-    K1_LOOPB
+    K1_LOOP1
     for (int v = T.tl; v <= nc; v += TILE) SI(w.exc + v) = 0;
     T.sync();
-    K1_LOOPB
+    K1_LOOP1
     for (int c = T.tl; c < nopen; c += TILE) {
         const int lo = SI(w.lo + c) >> HB;
         if (lo > 0) {
@@ -645,7 +657,7 @@ template <int TILE, class TM>
 __device__ void canonical_potentials(const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TM &w, int &fuel) {
     shortest_paths<TILE, true, false>(0, P, nopen, nc, T, w, fuel);
     bool missing = false;
-    K1_LOOPB
+    K1_LOOP2
     for (int v = T.tl; v < nc; v += TILE) {
         const int l = SI(w.lab + v);
         if (l == LAB_INF) { missing = true; SI(w.pot + v) = NEG_INF; SI(w.pred + v) = 0; } else { SI(w.pot + v) = l; SI(w.pred + v) = 1; }
@@ -656,7 +668,7 @@ __device__ void canonical_potentials(const PlanView &P, int nopen, int nc, const
         bool changed;
         do {
             changed = false;
-            K1_LOOPB
+            K1_LOOP2
             for (int c = T.tl; c < nopen; c += TILE) {
                 const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1, r = P.ch_r[c];
                 const int xc = SI(w.x + c), up = SI(w.up + c) >> HB, lo = SI(w.lo + c) >> HB;
@@ -667,14 +679,14 @@ __device__ void canonical_potentials(const PlanView &P, int nopen, int nc, const
             changed = T.any(changed) && --fuel > 0;
         } while (changed);
         bool iso = false;
-        K1_LOOPB
+        K1_LOOP2
         for (int v = T.tl; v < nc; v += TILE)
             if (SI(w.pot + v) == NEG_INF) { SI(w.pot + v) = 0; SI(w.pred + v) = 2; iso = true; }
         T.sync();
         if (T.any(iso)) {
             do {
                 changed = false;
-                K1_LOOPB
+                K1_LOOP2
                 for (int c = T.tl; c < nopen; c += TILE) {
                     const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1, r = P.ch_r[c];
                     const int xc = SI(w.x + c), up = SI(w.up + c) >> HB, lo = SI(w.lo + c) >> HB;
@@ -686,7 +698,7 @@ __device__ void canonical_potentials(const PlanView &P, int nopen, int nc, const
             } while (changed);
         }
     }
-    K1_LOOPB
+    K1_LOOP2
     for (int v = T.tl; v < nc; v += TILE) SI(w.pot + v) = -SI(w.pot + v);
     T.sync();
 }
@@ -700,7 +712,7 @@ __device__ void canonical_potentials(const PlanView &P, int nopen, int nc, const
 // instead of ~100 on the C4 network (profiles/r02_k1_warm.md).  Instances without forced flow only (lo == 0).
 template <int TILE, class TM>
 __device__ void warm_init(const PlanView &P, int nopen, int nc, const Lanes<TILE> &T, TM &w) {
-    K1_LOOPB
+    K1_LOOP2
     for (int c = T.tl; c < nopen; c += TILE) {
         const ChainEnds e(P.ch_st[c]);
         const int up = SI(w.up + c) >> HB;
@@ -782,9 +794,9 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         int32_t *srow = p.state && ngroups == 1 ? p.state + (size_t)s * p.state_stride : nullptr;   // this scenario's row of the handle's state
         if (srow && (p.state_io & 1) && srow[0]) {         // left by the last candidate of the previous launch on this handle
             const int nprev = (p.plans + p.link_off[0])[1];
-            K1_LOOPB
+            K1_LOOP1
             for (int v = T.tl; v < p.nc; v += TILE) SI(w.pot + v) = srow[1 + v];
-            K1_LOOPB
+            K1_LOOP1
             for (int c = T.tl; c < nprev; c += TILE) SI(w.x + c) = srow[1 + p.nc + c];
             holds = true;
         }
@@ -808,24 +820,24 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
             // labels = the previous candidate's potentials (finite for every node; the root is 0 on both faces), imbalances
             // of the chains that are gone, and the flow carried over to this candidate's chain numbering (through w.up,
             // which is rebuilt below)
-            K1_LOOPB
+            K1_LOOP1
             for (int v = T.tl; v < nc; v += TILE) SI(w.lab + v) = -SI(w.pot + v);
             if (T.tl == 0) SI(w.lab + nc) = 0;
             T.sync();
-            K1_LOOPB
+            K1_LOOP1
             for (int v = T.tl; v <= nc; v += TILE) SI(w.exc + v) = 0;
             T.sync();
             const int nrem = link[0];
             const int32_t *prev_of = link + 2, *removed = prev_of + nopen, *ends = removed + nrem;
-            K1_LOOPB
+            K1_LOOP1
             for (int i = T.tl; i < nrem; i += TILE) {
                 const int f = SI(w.x + removed[i]);
                 if (f > 0) { const int e = ends[i]; atomicAdd(&SI(w.exc + (e & 1023)), f); atomicSub(&SI(w.exc + (e >> 10)), f); }
             }
-            K1_LOOPB
+            K1_LOOP1
             for (int c = T.tl; c < nopen; c += TILE) { const int pc = prev_of[c]; SI(w.up + c) = pc >= 0 ? SI(w.x + pc) : 0; }
             T.sync();
-            K1_LOOPB
+            K1_LOOP1
             for (int c = T.tl; c < nopen; c += TILE) SI(w.x + c) = SI(w.up + c);
             T.sync();
         }
@@ -835,7 +847,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         //    arcs has a positive lower bound, and its multipliers are read from the capacity row directly)
         // lo[c] packs (greatest lower bound << 10 | position of its LAST arc): with no positive lower bound on the chain
         // that is (0, last position), known up front, so only positive lower bounds (rare) need the atomic
-        K1_LOOPB
+        K1_LOOP2
         for (int c = T.tl; c < nopen; c += TILE) { SI(w.up + c) = INT_MAX; SI(w.lo + c) = P.ch_ptr[c + 1] - P.ch_ptr[c] - 1; }
         T.sync();
         bool bad = false, forced = false;
@@ -858,7 +870,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
             }
         }
         T.sync();
-        K1_LOOPB
+        K1_LOOP2
         for (int c = T.tl; c < nopen; c += TILE) {
             const int lo = SI(w.lo + c) >> HB, up = SI(w.up + c) >> HB;
             bad |= lo > up; forced |= lo > 0;
@@ -1013,9 +1025,9 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         K1_CLK(5);
         holds = !forced;                                    // x and pot of this candidate serve the next one of the run
         if (srow && (p.state_io & 2) && k == p.K - 1 && holds) {   // ... and the first one of the next launch on this handle
-            K1_LOOPB
+            K1_LOOP1
             for (int v = T.tl; v < nc; v += TILE) srow[1 + v] = SI(w.pot + v);
-            K1_LOOPB
+            K1_LOOP1
             for (int c = T.tl; c < nopen; c += TILE) srow[1 + nc + c] = SI(w.x + c);
             T.sync();
             if (T.tl == 0) srow[0] = 1;
