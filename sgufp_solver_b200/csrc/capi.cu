@@ -100,7 +100,7 @@ int launch_batch(sgufp_ctx *c, const Batch &B, int K, unsigned long long *d_sums
     int state_io = 0;
     std::vector<int32_t> link0;
     if (state_on && group >= K && c->S > 0) {
-        const int stride = 1 + c->M.nc + c->M.m;
+        const int stride = 2 + c->M.nc + c->M.m;
         if (!c->d_state.p) {
             if (c->d_state.reserve((size_t)c->S * stride) == cudaSuccess) {
                 c->state_stride = stride; c->state_valid = false;
@@ -143,7 +143,10 @@ int launch_batch(sgufp_ctx *c, const Batch &B, int K, unsigned long long *d_sums
     K1Launch p{};
     p.cap_u = c->d_u; p.cap_l = c->d_l; p.S = c->S; p.m = c->M.m; p.m_pad = c->m_pad; p.scen_offset = c->scen_off;
     p.plans = c->d_plans.p; p.plan_off = c->d_plan_off.p; p.link_off = c->d_plan_off.p + K; p.group = group; p.K = K;
-    p.state = state_io ? c->d_state.p : nullptr; p.state_stride = c->state_stride; p.state_io = state_io; p.W = c->W(); p.L = c->M.L;
+    p.state = state_io ? c->d_state.p : nullptr; p.state_stride = c->state_stride; p.state_io = state_io;
+    p.xstride = std::max(1, B.max_nopen);
+    CU(c, c->d_xout.reserve((size_t)K * std::max(1, c->S) * p.xstride));
+    p.xout = c->d_xout.p; p.W = c->W(); p.L = c->M.L;
     p.sums = d_sums; p.first_inf = d_finf; p.obj = d_obj; p.status = d_status; p.work = c->d_work.p;
     p.max_nch = B.max_nch; p.max_nopen = B.max_nopen; p.nc = c->M.nc; p.nav = c->M.nav; p.max_cap = c->max_cap;
     p.has_lower = c->max_lower > 0; p.lane_tables = B.key_lane; p.sum_abs_r = c->sum_abs_r; p.max_indeg = B.max_indeg;
@@ -342,7 +345,7 @@ void sgufp_destroy(sgufp_ctx *c) {
         c->caps = nullptr; c->d_u = c->d_l = nullptr;
     }
     c->d_plans.release(); c->d_plan_off.release(); c->d_ray_i32.release(); c->d_sums.release(); c->d_work.release(); c->d_finf.release();
-    c->d_ray_scratch.release(); c->d_obj.release(); c->d_status.release(); c->d_state.release();
+    c->d_ray_scratch.release(); c->d_obj.release(); c->d_status.release(); c->d_state.release(); c->d_xout.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->evk0) cudaEventDestroy(c->evk0);

@@ -68,6 +68,7 @@ struct sgufp_ctx {
     // K1 state kept between launches (k1_cut.cuh: K1Launch::state): per scenario the optimal flow and potentials of the last
     // candidate of the previous launch, and that candidate's plan on the host (the next launch links its first plan to it)
     DevBuf<int32_t> d_state;
+    DevBuf<int32_t> d_xout;                     // [K][S][max open chains]: optimal flows, flow kernel -> cut kernel
     sgufp::Plan state_plan;
     bool state_valid = false;
     int state_stride = 0;

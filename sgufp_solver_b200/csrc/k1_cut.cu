@@ -510,10 +510,14 @@ struct TightPaths {
             if ((f & 1) && in_r(e.sv) && !in_r(e.hf)) { const int lh = SI(w.lab + e.hf); if (lh != LAB_INF) best = min(best, SI(w.lab + e.sv) - e.r - lh); }
             if ((f & 2) && in_r(e.ev) && !in_r(e.hb)) { const int lh = SI(w.lab + e.hb); if (lh != LAB_INF) best = min(best, SI(w.lab + e.ev) + e.r - lh); }
         }
-        const int delta = T.min_i32(best);
+        int delta = T.min_i32(best);
 #ifdef SGUFP_K1_STATS
         if (T.tl == 0) atomicAdd(&g_k1_stats[1], 1ull);
 #endif
+        // to the sink: never past the root's label (a smaller step keeps the potentials feasible too), and when no residual arc
+        // leaves R — any step does — exactly up to it: a finished flow leaves lab[nc] == lab[0], the root's ONE potential,
+        // which is what the next candidate of the run starts from
+        if (to_sink) delta = min(delta, SI(w.lab + 0) - SI(w.lab + nc));
         if (delta == INT_MAX) return false;
         T.sync();
         K1_LOOP
@@ -646,7 +650,6 @@ __device__ void forced_flow_init(const PlanView &P, int nopen, int nc, const Lan
         }
     }
     T.sync();
-    shortest_paths<TILE, false, false>(0, P, nopen, nc, T, w, fuel, true);
     deficit_targets<TILE>(nc, T, w);
 }
 
@@ -747,6 +750,61 @@ __device__ __forceinline__ int head_potential(int a, const PlanView &P, int nope
     return pre;
 }
 
+// this tile's slice of the CTA's shared memory (both kernels lay it out alike; k1_words_per_tile sizes it)
+template <class TM>
+__device__ __forceinline__ void tile_mem(TM &w, int tile_in_cta, int words_per_tile, const K1Launch &p) {
+    int base = tile_in_cta * words_per_tile;   // the fixed-size arrays first: constant offsets from the tile base
+    w.tin = base; w.tout = base + 32; w.hist = base + 64; w.path = base + 98; w.tab = base + 132;
+    w.tc = base; base += k1_search_words(p.nc, p.max_nopen);
+    w.rw = base; base += reach_words(p.nc);
+    w.tg = base; base += reach_words(p.nc);
+    w.up = base; base += p.max_nopen;
+    w.lo = base; base += p.max_nopen;
+    w.x = base; base += p.max_nopen;
+    w.res = base; base += TM::BIG ? (p.max_nopen + 3) / 4 : p.max_nopen;
+    w.lab = base; base += p.nc + 2;
+    w.pred = base; base += p.nc + 2;
+    w.pot = base; w.exc = base; base += p.nc + 2;   // imbalances (flow kernel) and potentials (cut kernel) share a place
+    w.aq = base;
+}
+
+// 1. chain capacities of one scenario (open chains only: a closed chain carries no flow, it is infeasible iff one of its arcs
+//    has a positive lower bound, and its multipliers are read from the capacity row directly): the row is streamed with 128-bit
+//    loads, segmented min / max into up[c] = (least capacity << 10 | position of its FIRST arc) and lo[c] = (greatest lower bound
+//    << 10 | position of its LAST arc) — with no positive lower bound on the chain that is (0, last position), known up front, so
+//    only positive lower bounds (rare) need the atomic.  Returns this lane's share of "a closed chain has a positive lower bound".
+template <int TILE, class TM>
+__device__ __forceinline__ bool stream_row(const PlanView &P, int nopen, int m, int m_pad, const double *row_u, const double *row_l, const Lanes<TILE> &T, TM &w) {
+    K1_LOOP2
+    for (int c = T.tl; c < nopen; c += TILE) { SI(w.up + c) = INT_MAX; SI(w.lo + c) = P.ch_ptr[c + 1] - P.ch_ptr[c] - 1; }
+    T.sync();
+    bool bad = false;
+    const double2 *ru = reinterpret_cast<const double2 *>(row_u), *rl = reinterpret_cast<const double2 *>(row_l);
+    K1_LOOPB
+    for (int a2 = T.tl; a2 < m_pad / 2; a2 += TILE) {
+        const double2 u2 = __ldg(ru + a2), l2 = __ldg(rl + a2);
+        const int a = 2 * a2;
+        {
+            const int cp = P.arc_cp[a], c = cp >> 10, pos = cp & 1023;
+            if (c < nopen) { atomicMin(&SI(w.up + c), ((int)u2.x << HB) | pos); if ((int)l2.x > 0) atomicMax(&SI(w.lo + c), ((int)l2.x << HB) | pos); }
+            else bad |= (int)l2.x > 0;
+        }
+        if (a + 1 < m) {
+            const int cp = P.arc_cp[a + 1], c = cp >> 10, pos = cp & 1023;
+            if (c < nopen) { atomicMin(&SI(w.up + c), ((int)u2.y << HB) | pos); if ((int)l2.y > 0) atomicMax(&SI(w.lo + c), ((int)l2.y << HB) | pos); }
+            else bad |= (int)l2.y > 0;
+        }
+    }
+    T.sync();
+    return bad;
+}
+
+// K1 is two kernels per launch (profiles/r02_k1_warm.md):
+//   k1_cut_eval (the FLOW kernel): a warp takes a run of consecutive candidates on one scenario, finds an optimal flow of each
+//     (the first from zero flow, the others from the one before) and writes it to xout[k][s][chain];
+//   k1_cut_fold (the CUT kernel): a warp per (candidate, scenario), candidate-major, so that the warps of an SM read ONE plan and
+//     run the same few hundred instructions: SPEC-LP potentials of the flow's residual graph, lifting, and the fold into the
+//     candidate's accumulators.
 // BIG: the contracted graph has more than SMALL_NC nodes (list searches, flag bytes); the launcher picks the instantiation.
 template <int TILE, int NW, bool BIG>
 __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 4 ? 2 * SGUFP_K1_MINBLOCKS : 1) k1_cut_eval(K1Launch p, int words_per_tile) {
@@ -755,21 +813,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
     const int tile_in_cta = threadIdx.x / TILE;
     using TM = TileMemT<BIG>;
     TM w;
-    {
-        int base = tile_in_cta * words_per_tile;   // the fixed-size arrays first: constant offsets from the tile base
-        w.tin = base; w.tout = base + 32; w.hist = base + 64; w.path = base + 98; w.tab = base + 132;
-        w.tc = base; base += k1_search_words(p.nc, p.max_nopen);
-        w.rw = base; base += reach_words(p.nc);
-        w.tg = base; base += reach_words(p.nc);
-        w.up = base; base += p.max_nopen;
-        w.lo = base; base += p.max_nopen;
-        w.x = base; base += p.max_nopen;
-        w.res = base; base += BIG ? (p.max_nopen + 3) / 4 : p.max_nopen;
-        w.lab = base; base += p.nc + 2;
-        w.pred = base; base += p.nc + 2;
-        w.pot = base; w.exc = base; base += p.nc + 2;   // excesses (lower-bound routing) and potentials are never live together
-        w.aq = base;
-    }
+    tile_mem(w, tile_in_cta, words_per_tile, p);
     // A work item is a RUN of `group` consecutive candidates on one scenario: the first is solved from zero flow, each of the
     // others from the optimal flow and potentials of the one before it (warm_repair), when the host linked the two plans.
     const int group = p.group > 1 && p.link_off ? p.group : 1, ngroups = (p.K + group - 1) / group;
@@ -790,14 +834,14 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         if (item >= items) break;
         const int grp = (int)(item / p.S), s = (int)(item - (long long)grp * p.S);
         const double *row_u = p.cap_u + (size_t)s * p.m_pad, *row_l = p.cap_l + (size_t)s * p.m_pad;
-        bool holds = false;                     // this tile holds the optimal flow (x) and potentials (pot) of the candidate before k
+        bool holds = false;                     // this tile holds the optimal flow (x) and the labels (lab: feasible potentials, finite everywhere) of the candidate before k
         int32_t *srow = p.state && ngroups == 1 ? p.state + (size_t)s * p.state_stride : nullptr;   // this scenario's row of the handle's state
         if (srow && (p.state_io & 1) && srow[0]) {         // left by the last candidate of the previous launch on this handle
             const int nprev = (p.plans + p.link_off[0])[1];
             K1_LOOP1
-            for (int v = T.tl; v < p.nc; v += TILE) SI(w.pot + v) = srow[1 + v];
+            for (int v = T.tl; v <= p.nc; v += TILE) SI(w.lab + v) = srow[1 + v];
             K1_LOOP1
-            for (int c = T.tl; c < nprev; c += TILE) SI(w.x + c) = srow[1 + p.nc + c];
+            for (int c = T.tl; c < nprev; c += TILE) SI(w.x + c) = srow[2 + p.nc + c];
             holds = true;
         }
         T.sync();
@@ -817,13 +861,9 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         long long clk_ = clock64();
 #endif
         if (link) {
-            // labels = the previous candidate's potentials (finite for every node; the root is 0 on both faces), imbalances
-            // of the chains that are gone, and the flow carried over to this candidate's chain numbering (through w.up,
-            // which is rebuilt below)
-            K1_LOOP1
-            for (int v = T.tl; v < nc; v += TILE) SI(w.lab + v) = -SI(w.pot + v);
-            if (T.tl == 0) SI(w.lab + nc) = 0;
-            T.sync();
+            // the labels stay (the previous candidate's final potentials: finite at every node, the root's two faces equal);
+            // imbalances of the chains that are gone, and the flow carried over to this candidate's chain numbering (through
+            // w.up, which is rebuilt below)
             K1_LOOP1
             for (int v = T.tl; v <= nc; v += TILE) SI(w.exc + v) = 0;
             T.sync();
@@ -843,33 +883,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         }
 
         K1_CLK(0);
-        // 1. chain capacities (open chains only: a closed chain carries no flow, it is infeasible iff one of its
-        //    arcs has a positive lower bound, and its multipliers are read from the capacity row directly)
-        // lo[c] packs (greatest lower bound << 10 | position of its LAST arc): with no positive lower bound on the chain
-        // that is (0, last position), known up front, so only positive lower bounds (rare) need the atomic
-        K1_LOOP2
-        for (int c = T.tl; c < nopen; c += TILE) { SI(w.up + c) = INT_MAX; SI(w.lo + c) = P.ch_ptr[c + 1] - P.ch_ptr[c] - 1; }
-        T.sync();
-        bool bad = false, forced = false;
-        {
-            const double2 *ru = reinterpret_cast<const double2 *>(row_u), *rl = reinterpret_cast<const double2 *>(row_l);
-            K1_LOOPB
-            for (int a2 = T.tl; a2 < p.m_pad / 2; a2 += TILE) {
-                const double2 u2 = __ldg(ru + a2), l2 = __ldg(rl + a2);
-                const int a = 2 * a2;
-                {
-                    const int cp = P.arc_cp[a], c = cp >> 10, pos = cp & 1023;
-                    if (c < nopen) { atomicMin(&SI(w.up + c), ((int)u2.x << HB) | pos); if ((int)l2.x > 0) atomicMax(&SI(w.lo + c), ((int)l2.x << HB) | pos); }
-                    else bad |= (int)l2.x > 0;
-                }
-                if (a + 1 < m) {
-                    const int cp = P.arc_cp[a + 1], c = cp >> 10, pos = cp & 1023;
-                    if (c < nopen) { atomicMin(&SI(w.up + c), ((int)u2.y << HB) | pos); if ((int)l2.y > 0) atomicMax(&SI(w.lo + c), ((int)l2.y << HB) | pos); }
-                    else bad |= (int)l2.y > 0;
-                }
-            }
-        }
-        T.sync();
+        bool bad = stream_row<TILE>(P, nopen, m, p.m_pad, row_u, row_l, T, w), forced = false;
         K1_LOOP2
         for (int c = T.tl; c < nopen; c += TILE) {
             const int lo = SI(w.lo + c) >> HB, up = SI(w.up + c) >> HB;
@@ -882,11 +896,13 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         // 2. optimal flow
         TightPaths<TILE, TM> TP(P, T, w, nopen, nc);
         K1_CLK(1);
+        int *xrow = p.xout + ((size_t)k * p.S + s) * p.xstride;
         if (bad) {
             if (T.tl == 0) {
                 atomicMin(p.first_inf + k, p.scen_offset + s);
                 if (p.status) p.status[(size_t)k * p.S + s] = 1;
                 if (p.obj) p.obj[(size_t)k * p.S + s] = 0.0;
+                xrow[0] = INT_MIN;
             }
             T.sync();
             continue;
@@ -903,8 +919,8 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         K1_LOOPB
         for (;;) {
             if (warm) warm_init<TILE>(P, nopen, nc, T, w);
-            else if (forced) forced_flow_init<TILE>(P, nopen, nc, T, w, fuel);
-            else shortest_paths<TILE, false, false>(0, P, nopen, nc, T, w, fuel);   // shortest distances at the starting flow: the ONE label computation
+            else { if (forced) forced_flow_init<TILE>(P, nopen, nc, T, w, fuel); shortest_paths<TILE, false, false>(0, P, nopen, nc, T, w, fuel, true);   // the ONE label computation: feasible potentials at the starting flow, finite at every node
+            }
             TP.prepare();
             rc = TP.solve(warm || forced, fuel);
 #ifdef SGUFP_K1_EMULATE
@@ -925,14 +941,67 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
                 atomicMin(p.first_inf + k, p.scen_offset + s);
                 if (p.status) p.status[(size_t)k * p.S + s] = 1;
                 if (p.obj) p.obj[(size_t)k * p.S + s] = 0.0;
+                xrow[0] = INT_MIN;
             }
             T.sync();
             continue;
         }
-        // 3. potentials
+        if (rc == 2 || fuel <= 0) {   // a bound that no valid instance reaches: refuse to answer rather than spin
+            if (T.tl == 0) atomicMin(p.first_inf + k, -1LL);
+            T.sync();
+            continue;
+        }
+        // the optimal flow goes to the cut kernel
+        if (nopen == 0 && T.tl == 0) xrow[0] = 0;
+        K1_LOOP1
+        for (int c = T.tl; c < nopen; c += TILE) xrow[c] = SI(w.x + c);
         K1_CLK(3);
+        holds = !forced;                                    // x and lab of this candidate serve the next one of the run
+        if (srow && (p.state_io & 2) && k == p.K - 1 && holds) {   // ... and the first one of the next launch on this handle
+            K1_LOOP1
+            for (int v = T.tl; v <= nc; v += TILE) srow[1 + v] = SI(w.lab + v);
+            K1_LOOP1
+            for (int c = T.tl; c < nopen; c += TILE) srow[2 + nc + c] = SI(w.x + c);
+            T.sync();
+            if (T.tl == 0) srow[0] = 1;
+        }
+        }
+    }
+}
+
+// The CUT kernel: SPEC-LP potentials, lifting, fold — of the optimal flow the flow kernel left in xout.  A warp per (candidate,
+// scenario), candidate-major and scenario-minor: neighbouring warps stream neighbouring rows and read the same plan.
+template <int TILE, int NW, bool BIG>
+__global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 4 ? 2 * SGUFP_K1_MINBLOCKS : 1) k1_cut_fold(K1Launch p, int words_per_tile) {
+    const Lanes<TILE> T;
+    constexpr int TILES_PER_CTA = NW * 32 / TILE;
+    const int tile_in_cta = threadIdx.x / TILE;
+    using TM = TileMemT<BIG>;
+    TM w;
+    tile_mem(w, tile_in_cta, words_per_tile, p);
+    const long long items = (long long)p.K * p.S;
+    const long long stride = (long long)gridDim.x * TILES_PER_CTA;
+    K1_LOOPB
+    for (long long item = (long long)blockIdx.x * TILES_PER_CTA + tile_in_cta; item < items; item += stride) {
+        const int k = (int)(item / p.S), s = (int)(item - (long long)k * p.S);
+        if (*reinterpret_cast<volatile long long *>(p.first_inf + k) < 0) continue;   // this candidate was aborted
+        const int *xrow = p.xout + ((size_t)k * p.S + s) * p.xstride;
+        if (xrow[0] == INT_MIN) continue;                                             // infeasible scenario: no flow, no cut term
+        int fuel = 1 << 20;
+        const PlanView P(p.plans + p.plan_off[k]);
+        const int nch = P.h->nch, nopen = P.h->nopen, nc = P.h->nc, nav = P.h->nav, m = p.m;
+        unsigned long long *sums = p.sums + (size_t)k * p.W;
+        const double *row_u = p.cap_u + (size_t)s * p.m_pad, *row_l = p.cap_l + (size_t)s * p.m_pad;
+        stream_row<TILE>(P, nopen, m, p.m_pad, row_u, row_l, T, w);
+        K1_LOOP2
+        for (int c = T.tl; c < nopen; c += TILE) {
+            const int xc = xrow[c];
+            SI(w.x + c) = xc;
+            RSET(c, (xc < (SI(w.up + c) >> HB) ? 1 : 0) | (xc > (SI(w.lo + c) >> HB) ? 2 : 0));
+        }
+        T.sync();
+        // 3. potentials
         canonical_potentials<TILE>(P, nopen, nc, T, w, fuel);
-        K1_CLK(4);
         if (fuel <= 0) {   // a bound that no valid instance reaches: refuse to answer rather than spin
             if (T.tl == 0) atomicMin(p.first_inf + k, -1LL);
             T.sync();
@@ -1022,17 +1091,6 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
             if (p.obj) p.obj[(size_t)k * p.S + s] = (double)objv;
         }
         T.sync();
-        K1_CLK(5);
-        holds = !forced;                                    // x and pot of this candidate serve the next one of the run
-        if (srow && (p.state_io & 2) && k == p.K - 1 && holds) {   // ... and the first one of the next launch on this handle
-            K1_LOOP1
-            for (int v = T.tl; v < nc; v += TILE) srow[1 + v] = SI(w.pot + v);
-            K1_LOOP1
-            for (int c = T.tl; c < nopen; c += TILE) srow[1 + nc + c] = SI(w.x + c);
-            T.sync();
-            if (T.tl == 0) srow[0] = 1;
-        }
-        }
     }
 }
 
@@ -1152,7 +1210,8 @@ static cudaError_t launch_warp_nw(const K1Launch &p, cudaStream_t st, int sm_cou
     int per_sm = 1, dev = 0;
     cudaGetDevice(&dev);
     if (!((limit_raised.load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) {
-        const cudaError_t e = cudaFuncSetAttribute(k1_cut_eval<32, NW, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k1_cut_eval<32, NW, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_cut_fold<32, NW, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         limit_raised.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
@@ -1171,6 +1230,8 @@ static cudaError_t launch_warp_nw(const K1Launch &p, cudaStream_t st, int sm_cou
     if (want < grid) grid = want;
     if (grid < 1) grid = 1;
     k1_cut_eval<32, NW, BIG><<<(unsigned)grid, NW * 32, smem, st>>>(p, words);
+    if (const cudaError_t e = cudaGetLastError()) return e;
+    k1_cut_fold<32, NW, BIG><<<(unsigned)grid, NW * 32, smem, st>>>(p, words);
     return cudaGetLastError();
 }
 

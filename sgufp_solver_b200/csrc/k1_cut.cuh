@@ -19,8 +19,10 @@ struct K1Launch {
     // one path per iteration, NodeExplorer.cpp:949-971): per scenario { valid, pot[nc], x[open chains] } of the LAST candidate
     // of the previous launch, so that the first candidate of this one can be warm-started too.  Only when the whole batch
     // is one run per scenario (group >= K): the warp that reads a scenario's row is the one that rewrites it.
-    int32_t *state;               // [S][state_stride] or nullptr
-    int state_stride;             // >= 1 + nc + max open chains
+    int32_t *state;               // [S][state_stride] or nullptr: { valid, lab[nc + 1], x[open chains] }
+    int state_stride;             // >= 2 + nc + max open chains
+    int32_t *xout;                // [K][S][xstride]: the optimal flow per open chain, flow kernel -> cut kernel (x[0] = INT_MIN: infeasible scenario)
+    int xstride;                  // >= max(1, max open chains)
     int state_io;                 // bit 0: link_off[0] describes the step from the stored candidate, read the row; bit 1: write it
     unsigned long long *sums;     // [K][W] exact integer accumulators (two's complement)
     long long *first_inf;         // [K] lowest infeasible global scenario (init LLONG_MAX)

@@ -97,7 +97,7 @@ extern "C" int emul_paths(int n, int m, int S, const int32_t *tail, const int32_
         if (!lk.empty()) { link_off[k] = (int32_t)words.size(); words.insert(words.end(), lk.begin(), lk.end()); }
     }
     const int group = g_group > 0 ? g_group : K;
-    int state_io = 0, state_stride = 1 + M.nc + m;
+    int state_io = 0, state_stride = 2 + M.nc + m;
     if (g_state_on && group >= K && !lane_variant) {
         if (g_state.size() != (size_t)S * state_stride) { g_state.assign((size_t)S * state_stride, 0); g_state_valid = false; }
         state_io = 2;
@@ -120,6 +120,9 @@ extern "C" int emul_paths(int n, int m, int S, const int32_t *tail, const int32_
     if (state_io) { g_state_plan = plans[K - 1]; g_state_valid = true; } else g_state_valid = false;
     g_last_nc = M.nc;
     p.max_nch = max_nch; p.max_nopen = max_nopen; p.nc = M.nc; p.nav = M.nav; p.max_cap = 65535;
+    p.xstride = std::max(1, max_nopen);
+    std::vector<int32_t> xout((size_t)K * std::max(1, S) * p.xstride, 0);
+    p.xout = xout.data();
     const int wpt = k1_words_per_tile(p);
     std::vector<int> smem((size_t)WARPS * 32 * wpt, 0);
     sgufp_emul_smem = smem.data();
@@ -145,7 +148,10 @@ extern "C" int emul_paths(int n, int m, int S, const int32_t *tail, const int32_
         const int rc = lane_variant == 1 ? run(CfgSmall{}) : lane_variant == 2 ? run(CfgMid{}) : run(CfgWide{});
         if (rc) return rc;
     } else
-    for (int t = 0; t < WARPS * 32; t++) { threadIdx.x = t; if (p.nc <= SMALL_NC) k1_cut_eval<1, WARPS, false>(p, wpt); else k1_cut_eval<1, WARPS, true>(p, wpt); }
+    {
+        for (int t = 0; t < WARPS * 32; t++) { threadIdx.x = t; if (p.nc <= SMALL_NC) k1_cut_eval<1, WARPS, false>(p, wpt); else k1_cut_eval<1, WARPS, true>(p, wpt); }
+        for (int t = 0; t < WARPS * 32; t++) { threadIdx.x = t; if (p.nc <= SMALL_NC) k1_cut_fold<1, WARPS, false>(p, wpt); else k1_cut_fold<1, WARPS, true>(p, wpt); }
+    }
     for (int k = 0; k < K; k++) {
         if (first_inf[k] == LLONG_MAX || first_inf[k] < 0) continue;
         std::vector<int32_t> ts, hs, info, pl, nx, aq, fw;
