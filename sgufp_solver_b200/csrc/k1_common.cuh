@@ -20,13 +20,14 @@ constexpr int WARPS = 8;               // warps per CTA (warp kernel)
 
 struct PlanView {
     const PlanHeader *h;
+    const int2 *arc_av;            // per arc: the V-bar node it enters as a matched in-arc (-1: none), its matched out-arc
     const int32_t *arc_cp, *arc_info, *arc_pre, *ch_ends, *ch_r, *ch_ptr, *ch_arcs, *ch_q, *av_ptr, *av_arcs, *fb_ptr, *fb_ch;
     const int2 *ch_st;             // static half of an open chain (model.hpp)
     const int2 *slots;             // lane kernel: in-slots sorted by head
     const int32_t *in_pd;          // lane kernel: first slot | in-degree << 16 per head index
     __device__ explicit PlanView(const int32_t *base) {
         h = reinterpret_cast<const PlanHeader *>(base);
-        arc_cp = base + h->o_arc_cp; arc_info = base + h->o_arc_info; arc_pre = base + h->o_arc_pre;
+        arc_av = reinterpret_cast<const int2 *>(base + h->o_arc_av); arc_cp = base + h->o_arc_cp; arc_info = base + h->o_arc_info; arc_pre = base + h->o_arc_pre;
         ch_ends = base + h->o_ch_ends; ch_r = base + h->o_ch_r; ch_ptr = base + h->o_ch_ptr; ch_arcs = base + h->o_ch_arcs;
         ch_q = base + h->o_ch_q; av_ptr = base + h->o_av_ptr; av_arcs = base + h->o_av_arcs; fb_ptr = base + h->o_fb_ptr; fb_ch = base + h->o_fb_ch;
         ch_st = reinterpret_cast<const int2 *>(base + h->o_ch_st);

@@ -853,8 +853,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         if (*reinterpret_cast<volatile long long *>(p.first_inf + k) < 0) continue;   // this candidate was aborted: drain
         int fuel = 1 << 20;   // passes + levels a work item may spend (tile-uniform)
         const PlanView P(p.plans + p.plan_off[k]);
-        const int nch = P.h->nch, nopen = P.h->nopen, nc = P.h->nc, nav = P.h->nav, m = p.m;
-        unsigned long long *sums = p.sums + (size_t)k * p.W;
+        const int nopen = P.h->nopen, nc = P.h->nc, m = p.m;
         const int32_t *link = nullptr;          // model.hpp: link_plans
         if (carried) { const int lo = p.link_off[k]; if (lo >= 0) link = p.plans + lo; }
 #ifdef SGUFP_K1_STATS
@@ -1009,42 +1008,24 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         }
         // 4. lifting + folding
         long long rhs = 0, objv = 0;
+        // (a) per open chain: objective, the lower-bound multiplier's term, and r - dp kept in place of the flow (which is done):
+        //     its positive part is the capacity multiplier of the chain, booked below by the arc that carries it
         K1_LOOPB
         for (int c = T.tl; c < nopen; c += TILE) {
             const int e = P.ch_ends[c], sv = (e & 0xffff) - 1, ev = (e >> 16) - 1, r = P.ch_r[c];
-            const int dp = SI(w.pot + ev) - SI(w.pot + sv);
-            const int g = r - dp, up = SI(w.up + c) >> HB, lo = SI(w.lo + c) >> HB;
+            const int g = r - (SI(w.pot + ev) - SI(w.pot + sv));
             objv += (long long)r * SI(w.x + c);
-            if (g > 0) {
-                const int a = P.ch_arcs[P.ch_ptr[c] + (SI(w.up + c) & 1023)];
-                const int info = P.arc_info[a];
-                const long long v = (long long)up * g;
-                if ((info & 3) == KIND_GAMMA) rhs += v; else atomicAdd(sums + 1 + p.L + a, (unsigned long long)v);
-            } else if (g < 0) rhs -= (long long)lo * (-g);
+            if (g < 0) rhs -= (long long)(SI(w.lo + c) >> HB) * (-g);
+            SI(w.x + c) = g;
         }
+        // (b) alpha of every active V-bar node: the wire potential of its first matched pair, else the least start potential of
+        //     the end-anchored chains leaving it, else 0 (rule 5)
         K1_LOOPB
         for (int i = T.tl; i < nav; i += TILE) {
             const int b0 = P.av_ptr[i], b1 = P.av_ptr[i + 1];
             int alpha = 0;
-            if (b1 > b0) {
-                alpha = head_potential(P.av_arcs[b0], P, nopen, w);
-                K1_LOOPB
-                for (int t = b0 + 1; t < b1; t++) {
-                    const int a = P.av_arcs[t];
-                    const int dl = head_potential(a, P, nopen, w) - alpha;
-                    if (dl != 0) {
-                        long long v;
-                        if (dl > 0) v = (long long)(int)row_u[a] * dl;
-                        else {
-                            const int cp = P.arc_cp[a];
-                            const int bnext = P.ch_arcs[P.ch_ptr[cp >> 10] + (cp & 1023) + 1];
-                            v = (long long)(int)row_u[bnext] * (-dl);
-                        }
-                        rhs += v;
-                        atomicAdd(sums + 1 + (P.arc_info[a] >> 2) - 1, (unsigned long long)v);
-                    }
-                }
-            } else {
+            if (b1 > b0) alpha = head_potential(P.av_arcs[b0], P, nopen, w);
+            else {
                 bool found = false;
                 K1_LOOPB
                 for (int t = P.fb_ptr[i]; t < P.fb_ptr[i + 1]; t++) {
@@ -1056,6 +1037,32 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
             SI(w.aq + i) = alpha;
         }
         T.sync();
+        // (c) per ARC, a lane each (coalesced plan reads, every lane busy; the per-node loop over matched pairs this replaces ran
+        //     with 9 - 14 of 32 lanes behind chains of dependent loads): the capacity multiplier of an open chain sits on its first
+        //     arc of least capacity; lambda - mu of a matched pair is its wire potential minus the node's alpha
+        K1_LOOPB
+        for (int a = T.tl; a < m; a += TILE) {
+            const int cp = P.arc_cp[a], c = cp >> 10, pos = cp & 1023;
+            const int2 av = P.arc_av[a];
+            const int q = av.x;
+            if (c < nopen) {
+                const int g = SI(w.x + c), upw = SI(w.up + c);
+                if (g > 0 && pos == (upw & 1023)) {
+                    const long long v = (long long)(upw >> HB) * g;
+                    if ((P.arc_info[a] & 3) == KIND_GAMMA) rhs += v; else atomicAdd(sums + 1 + p.L + a, (unsigned long long)v);
+                }
+            }
+            if (q >= 0) {
+                const int dl = head_potential(a, P, nopen, w) - SI(w.aq + q);
+                if (dl != 0) {
+                    long long v;
+                    if (dl > 0) v = (long long)(int)row_u[a] * dl;
+                    else v = (long long)(int)row_u[av.y] * (-dl);      // the matched out-arc
+                    rhs += v;
+                    atomicAdd(sums + 1 + (P.arc_info[a] >> 2) - 1, (unsigned long long)v);
+                }
+            }
+        }
         K1_LOOPB
         for (int c = nopen + T.tl; c < nch; c += TILE) {
             const int b0 = P.ch_ptr[c], b1 = P.ch_ptr[c + 1], first = P.ch_arcs[b0], last = P.ch_arcs[b1 - 1];

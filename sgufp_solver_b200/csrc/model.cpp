@@ -277,6 +277,11 @@ int build_plan(const Model &M, const int16_t *path, int plen, Plan &P, std::stri
     W.assign(sizeof(PlanHeader) / 4, 0);
     auto put = [&](const std::vector<int32_t> &v) { int32_t off = (int32_t)W.size(); W.insert(W.end(), v.begin(), v.end()); if (W.size() & 1) W.push_back(0); return off; };
     H.o_arc_cp = put(arc_cp); H.o_arc_info = put(arc_info); H.o_arc_pre = put(arc_pre);
+    {
+        std::vector<int32_t> arc_av(2 * (size_t)m, -1);
+        for (int a = 0; a < m; a++) if (M.active[M.head[a]] && P.match_out[a] >= 0) { arc_av[2 * a] = M.av_index[M.head[a]]; arc_av[2 * a + 1] = P.match_out[a]; }
+        H.o_arc_av = put(arc_av);   // W.size() is even before every put: 8-byte aligned
+    }
     H.o_ch_ends = put(ch_ends); H.o_ch_r = put(ch_r); H.o_ch_ptr = put(ch_ptr); H.o_ch_arcs = put(ch_arcs); H.o_ch_q = put(ch_q);
     H.o_av_ptr = put(av_ptr); H.o_av_arcs = put(av_arcs); H.o_fb_ptr = put(fb_ptr); H.o_fb_ch = put(fb_ch);
     {

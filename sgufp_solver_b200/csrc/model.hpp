@@ -68,7 +68,8 @@ struct PlanHeader {
                            //   (dir 0: the chain's forward arc sv->ev at cost -r; dir 1: its backward arc ev->sv at cost +r)
     int32_t o_in_pd;       // [nc+2]     first slot | in-degree << 16 of every head index (index 0, the root as a source, has none)
     int32_t max_indeg;     // largest in-degree (decides the cursor width of the lane kernel)
-    int32_t pad_;
+    int32_t o_arc_av;      // [2m]     int2 per arc: x = compact index of the active V-bar node the arc enters as a MATCHED in-arc (-1 otherwise),
+                           //          y = its matched out-arc (cut kernel: lambda / mu per arc)
     int32_t total;         // int32 words used by this plan, header included (the header is an even number of words)
 };
 

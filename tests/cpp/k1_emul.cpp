@@ -48,6 +48,7 @@ static inline int __any_sync(unsigned, int p) { return p; }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int, int = 32) { return v; }
 template <class T> static inline T __shfl_sync(unsigned, T v, int, int = 32) { return v; }
 static inline double2 __ldg(const double2 *p) { return *p; }
+static inline double2 __ldcs(const double2 *p) { return *p; }
 
 #include "../../sgufp_solver_b200/csrc/k1_cut.cu"
 #include "../../sgufp_solver_b200/csrc/k1_lane.cu"
