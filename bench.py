@@ -415,7 +415,8 @@ def measure(wl, args, rank, world, local, dev, flush, steps, warmup, sample_cloc
                             ("" if world == 1 else "; collective call on the partition: K1 -> one ncclAllReduce inside the library -> cuts on every rank")},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": how, "kernel": "k1_cut_eval", "kernel_ms": k_ms,
+                         "traffic": traffic, "peak_source": how, "kernel": "k1_cut_eval + k1_cut_fold (the two kernels of one K1 launch)", "kernel_ms": k_ms,
+                         "kernels_under_ncu": _traffic_file().get("kernels", {}).get(wl) if world == 1 else None,
                          "bytes_per_eval": bytes_per_eval, "evals_per_launch": K * S,
                          "note": "K1 is instruction-bound (an exact LP per scenario), not HBM-bound: DESIGN.md §6; a run of candidates reads its capacity row from "
                                  "HBM once and from L2 afterwards, so the measured DRAM traffic is below the algorithmic bytes"},

@@ -1314,6 +1314,7 @@ cudaError_t k1_launch(const K1Launch &p, cudaStream_t st, int sm_count, int *lau
         if (e != cudaErrorInvalidConfiguration) return e;
         cudaGetLastError();          // the state of this batch does not fit one SM's shared memory: the warp kernel takes it
     }
+    if (launches) (*launches)++;     // the warp path is two kernels: flow, cut
     return launch_warp(p, st, sm_count);
 }
 
