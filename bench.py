@@ -176,8 +176,18 @@ def config_of(workload, world, inst_n, inst_m, L, T, K, paths_info):
 CANDIDATES_FILE = os.path.join(ROOT, "sgufp_solver_b200", "data", "bench_candidates.npz")
 
 
-def candidate_paths(workload, K, device):
-    """K candidate paths as the DD master emits them (sgufp_solver_b200/candidates.py).  The committed file holds the
+def step_batches(paths, K):
+    """The batches the timed steps go through in turn: consecutive windows of K paths of the DD master's emission (two for
+    C4 / C5: the committed emission holds 16 paths; one for C2).  Step i evaluates batch i % len(batches), so no step sees the
+    paths of the step before it: what a step takes over from its predecessor is a STARTING flow for a different path, as
+    consecutive calls of the Benders loop do (NodeExplorer.cpp:949-971), never a result."""
+    nb = max(1, paths.shape[0] // K)
+    return [np.ascontiguousarray(paths[b * K:(b + 1) * K]) for b in range(min(nb, 2))]
+
+
+def candidate_paths(workload, K, device, want=None):
+    """K candidate paths (`want` of them when the committed emission holds that many) as the DD master emits them
+    (sgufp_solver_b200/candidates.py).  The committed file holds the
     emission of tools/make_bench_candidates.py (tests/test_e2e_gpu.py re-emits and compares), so both arms and every rank
     read the same list; without the file the master runs here (GPU), and random matchings fill in only if it cannot
     produce K distinct paths within its budget."""
@@ -187,9 +197,11 @@ def candidate_paths(workload, K, device):
     if os.path.exists(CANDIDATES_FILE):
         z = np.load(CANDIDATES_FILE)
         if net in z.files and z[net].shape[0] >= K:
-            p = np.ascontiguousarray(z[net][:K], dtype=np.int16)
+            n = K * max(1, min(want or K, z[net].shape[0]) // K)
+            p = np.ascontiguousarray(z[net][:n], dtype=np.int16)
+            how = "" if n == K else f"; the steps go through {n // K} batches of {K} consecutive emitted paths in turn"
             return p, ("DD-emitted: the paths RelaxedDDNew::getSolution hands to solveSubProblem in the Benders loop on a 32-scenario copy "
-                       f"of the network (sgufp_solver_b200/data/bench_candidates.npz); matched fraction {float((p >= 0).mean()):.2f}")
+                       f"of the network (sgufp_solver_b200/data/bench_candidates.npz); matched fraction {float((p >= 0).mean()):.2f}{how}")
     fn = getattr(I, net)
     small = fn(S=32)
     paths, info = dd_emitted_paths(small, K, device=device, budget_s=45.0)
@@ -251,14 +263,16 @@ def run_reference(args, rank, world):
     inst = scenario_range(wl, 0, min(S_total, CPU_SAMPLE_SCENARIOS))
     model = GuroSolver(inst, device=-1)
     if os.path.exists(CANDIDATES_FILE):
-        paths, pinfo = candidate_paths(wl, K, int(os.environ.get("LOCAL_RANK", "0")))     # the committed DD emission: no GPU work in this arm
+        paths, pinfo = candidate_paths(wl, K, int(os.environ.get("LOCAL_RANK", "0")), want=2 * K)     # the committed DD emission: no GPU work in this arm
+        batches = step_batches(paths, K)
     else:
         paths, pinfo = np.asarray(I.random_paths(model, K, 31, 0.1), np.int16), "random matchings (no committed DD emission)"
+        batches = [paths]
     threads = os.cpu_count() or 1
     per_step_s = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
     vals, samples = [], ""
     for it in range(args.warmup + args.steps):
-        v, evals, dt, samples = cpu_port_throughput(inst, paths, per_step_s, threads)
+        v, evals, dt, samples = cpu_port_throughput(inst, batches[it % len(batches)], per_step_s, threads)   # the batches in turn, like the GPU arm
         if it >= args.warmup:
             vals.append((evals, dt))
     evals = sum(e for e, _ in vals); dt = sum(d for _, d in vals)
@@ -297,7 +311,15 @@ def measure(wl, args, rank, world, local, dev, flush, steps, warmup, sample_cloc
         dist.broadcast(idt, src=0)
         solver.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
     m, L, T, W = inst.m, solver.L, solver.T, solver.W
-    paths, pinfo = candidate_paths(wl, K, local)
+    all_paths, pinfo = candidate_paths(wl, K, local, want=2 * K)
+    batches = step_batches(all_paths, K)
+    paths = batches[0]
+    turn = [0]                       # the batch the next step evaluates
+
+    def next_batch():
+        b = batches[turn[0] % len(batches)]
+        turn[0] += 1
+        return b
     lib = _lib.lib()
     stream = torch.cuda.ExternalStream(solver.stream_ptr(), device=dev)     # the handle's own stream: events are recorded where the kernel runs
     torch.cuda.set_stream(stream)
@@ -305,10 +327,11 @@ def measure(wl, args, rank, world, local, dev, flush, steps, warmup, sample_cloc
     finf = torch.empty((K,), dtype=torch.int64, device=dev)
 
     def device_step():
+        p = next_batch()
         if world > 1:
-            solver.paths_reduced(paths)             # K1 on this block + pack flags + the ONE ncclAllReduce, asynchronous
+            solver.paths_reduced(p)                 # K1 on this block + pack flags + the ONE ncclAllReduce, asynchronous
         else:
-            solver._check(lib.sgufp_paths_partial(solver.h, paths.ctypes.data_as(_lib.i16p), K, paths.shape[1], C.c_void_p(sums.data_ptr()),
+            solver._check(lib.sgufp_paths_partial(solver.h, p.ctypes.data_as(_lib.i16p), K, p.shape[1], C.c_void_p(sums.data_ptr()),
                                                   C.c_void_p(finf.data_ptr()), None, None, None))
 
     def barrier():
@@ -317,8 +340,11 @@ def measure(wl, args, rank, world, local, dev, flush, steps, warmup, sample_cloc
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    last = [paths]                   # the batch of the last api_call (the sharded-parity check recomputes that one)
+
     def api_call():
-        return solver.solve_paths(paths, want_obj=False, want_status=False, want_dense=True)
+        last[0] = next_batch()
+        return solver.solve_paths(last[0], want_obj=False, want_status=False, want_dense=True)
 
     # ---- device-timed value ----
     for _ in range(warmup):
@@ -382,7 +408,7 @@ def measure(wl, args, rank, world, local, dev, flush, steps, warmup, sample_cloc
     if world > 1:
         if rank == 0:
             full = GuroSolver(scenario_range(wl, 0, S_total), device=local)
-            ref = full.solve_paths(paths, want_obj=False, want_status=False, want_dense=True)
+            ref = full.solve_paths(last[0], want_obj=False, want_status=False, want_dense=True)
             same = bool((ref.rhs == res.rhs).all() and (ref.coef_dense == res.coef_dense).all() and (ref.nnz == res.nnz).all())
             parity = "bit-identical" if same else "MISMATCH"
             full.close()
@@ -404,11 +430,13 @@ def measure(wl, args, rank, world, local, dev, flush, steps, warmup, sample_cloc
             "k1": {"candidates_per_run": run_len, "state_between_steps": bool(run_len >= K),
                    "from_zero_flow": None if cold_ms is None else {"value": evals_step / (cold_ms / 1e3), "unit": "evals/s", "ms_per_step": cold_ms,
                                                                     "how": "SGUFP_K1_GROUP=1 SGUFP_K1_STATE=0, 3 steps"},
+                   "batches_in_turn": len(batches),
                    "note": "a warp takes a run of consecutive candidates on one scenario and warm-starts each from the optimal flow and potentials "
                            "of the one before; when the whole batch is one run the handle keeps the last candidate's state per scenario, so the "
                            "first candidate of a step starts from the last one of the step before (consecutive paths of the Benders loop are a "
-                           "few layers apart).  Every (candidate, scenario) LP is solved to optimality in every step; the cuts are bit-identical "
-                           "to the ones from zero flow (tests/test_k1_gpu.py)"},
+                           "few layers apart: 4 - 8 of 538 on C4 / C5, also across the batches the steps alternate between).  Every (candidate, "
+                           "scenario) LP is solved to optimality in every step and no step repeats the paths of the one before it (C4 / C5); the "
+                           "cuts are bit-identical to the ones from zero flow (tests/test_k1_gpu.py)"},
             "e2e": {"value": evals_step * steps / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": plan_bytes,
                     "d2h_bytes_per_step": int(K * W * 8 + 2 * K * 8), "ms_per_step": 1e3 * e2e_s / steps,
                     "call": "GuroSolver.solve_paths (sgufp_solve_paths): host int16 paths -> host Inavap::Cut list" +
@@ -418,8 +446,9 @@ def measure(wl, args, rank, world, local, dev, flush, steps, warmup, sample_cloc
                          "traffic": traffic, "peak_source": how, "kernel": "k1_cut_eval + k1_cut_fold (the two kernels of one K1 launch)", "kernel_ms": k_ms,
                          "kernels_under_ncu": _traffic_file().get("kernels", {}).get(wl) if world == 1 else None,
                          "bytes_per_eval": bytes_per_eval, "evals_per_launch": K * S,
-                         "note": "K1 is instruction-bound (an exact LP per scenario), not HBM-bound: DESIGN.md §6; a run of candidates reads its capacity row from "
-                                 "HBM once and from L2 afterwards, so the measured DRAM traffic is below the algorithmic bytes"},
+                         "note": "K1 is bound by instruction issue (flow kernel) and memory latency (cut kernel), not by HBM bandwidth: DESIGN.md §6.  The flow "
+                                 "kernel reads a capacity row once per run of candidates, the cut kernel once per evaluation, and the optimal flows travel "
+                                 "between the two through HBM: the measured DRAM traffic (traffic) is ~1.5 x the scope table's bytes on C4 / C5"},
             "exchange": None if world == 1 else {"collectives_per_step": info["exchanges_last_call"], "inside_library": True, "nccl": info["nccl"],
                                                  "words": K * W + K},
             "sharded_parity": parity,

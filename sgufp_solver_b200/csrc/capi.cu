@@ -151,10 +151,11 @@ int launch_batch(sgufp_ctx *c, const Batch &B, int K, unsigned long long *d_sums
     p.max_nch = B.max_nch; p.max_nopen = B.max_nopen; p.nc = c->M.nc; p.nav = c->M.nav; p.max_cap = c->max_cap;
     p.has_lower = c->max_lower > 0; p.lane_tables = B.key_lane; p.sum_abs_r = c->sum_abs_r; p.max_indeg = B.max_indeg;
     c->kernel_timed = false;
+    bool state_kept = false;
     if (c->S > 0) {
         CU(c, cudaEventRecord(c->evk0, st));
         {
-            const cudaError_t ek = k1_launch(p, st, c->sm_count, &c->last_launches);
+            const cudaError_t ek = k1_launch(p, st, c->sm_count, &c->last_launches, &state_kept);
             if (ek == cudaErrorInvalidConfiguration) { cudaGetLastError(); return fail(c, SGUFP_ERR_LIMITS, "the per-scenario state of this network does not fit one SM's shared memory (227 KB) even with one warp per CTA"); }
             CU(c, ek);
         }
@@ -162,7 +163,8 @@ int launch_batch(sgufp_ctx *c, const Batch &B, int K, unsigned long long *d_sums
         c->kernel_timed = true;
     }
     // what the rows of d_state describe after this launch
-    if (state_io & 2) { c->state_plan = B.plans[K - 1]; c->state_valid = true; }
+    // (the lane kernel, SGUFP_K1_MODE=lane, does not touch them: a launch through it leaves no state to go on from)
+    if ((state_io & 2) && state_kept) { c->state_plan = B.plans[K - 1]; c->state_valid = true; }
     else c->state_valid = false;
     return 0;
 }

@@ -46,6 +46,9 @@ __device__ unsigned long long g_k1_stats[8];   // relaxation passes, label compu
 #ifndef K1_CLK
 #define K1_CLK(i) do {} while (0)
 #endif
+#ifndef SGUFP_K1_EMULATE
+#define K1_CNT(i, n) do {} while (0)
+#endif
 // No loop of the kernel is unrolled: a warp goes through every phase once per evaluation and the warps of an SM are in
 // different phases, so the kernel is bound by its instruction-cache footprint, not by loop overhead (unrolled: 105 KB of SASS
 // and a no_instruction stall of 3.9 warps per issue on C4; profiles/r02_k1_warm.md).  -DSGUFP_K1_UNROLL leaves it to the compiler.
@@ -95,6 +98,8 @@ struct TileMemT {
 #ifdef SGUFP_K1_EMULATE
 #define k1_smem sgufp_emul_smem           // tests/cpp/k1_emul.cpp: the kernel body compiled for the host
 static long long sgufp_emul_warm[8];   // warm starts taken / given up / saturated chains / searches / dual updates / sources
+static long long sgufp_emul_cnt[16];   // tools/proto/flow_census.py: searches (repair ok / failed, to the sink ok / failed), chunk visits, ... (K1_CNT below)
+#define K1_CNT(i, n) (sgufp_emul_cnt[i] += (n))
 #else
 extern __shared__ int k1_smem[];
 #endif
@@ -337,6 +342,14 @@ __device__ bool reach_list(int src, int dst, const PlanView &P, int ntc, int nwo
         K1_LOOP
         for (int i0 = partial ? c0 * TILE : 0; i0 < ntc; i0 += TILE, q++) {           // tile-uniform trip count
             const int i = i0 + T.tl;
+#ifdef SGUFP_K1_EMULATE
+            {   // census: chunk visits, and those made after the target was already in the set
+                bool there = false;
+                if (dst >= 0) there = (SU(R + (dst >> 5)) >> (dst & 31)) & 1;
+                else for (int j = 0; j < nword; j++) there |= (SU(R + j) & SU(w.tg + j)) != 0;
+                K1_CNT(4, 1); if (there) K1_CNT(6, 1);
+            }
+#endif
             const int stamp = min(q, 127) << 25;
             int c = 0, f = 0;
             if (i < ntc) { const int en = SH(2 * w.tc + i); c = en & 0x3fff; f = RGET(c) & (en >> 14); }
@@ -364,6 +377,7 @@ __device__ bool reach_list(int src, int dst, const PlanView &P, int ntc, int nwo
                 T.sync();
                 again = T.any(g);
                 grew |= again;
+                K1_CNT(5, 1);
             } while (again);
 #ifdef SGUFP_K1_SKIP_CONFIRM
             back |= (f & 2) != 0;
@@ -373,6 +387,7 @@ __device__ bool reach_list(int src, int dst, const PlanView &P, int ntc, int nwo
 #ifdef SGUFP_K1_STATS
         if (T.tl == 0) { atomicAdd(&g_k1_stats[4], 1ull); atomicAdd(&g_k1_stats[5], (unsigned long long)(ntc - (partial ? c0 * TILE : 0))); }
 #endif
+        K1_CNT(7, 1);
         if (dst >= 0) {
             if ((SU(R + (dst >> 5)) >> (dst & 31)) & 1) {
 #ifdef SGUFP_K1_STATS
@@ -420,6 +435,7 @@ __device__ int push_list(int src, int dst, int limit, int nc, const Lanes<TILE> 
         v = p & 1023;
         if (++hops > nc + 1) { d = 0; break; }
     }
+    K1_CNT(8, hops); K1_CNT(9, 1);
     T.sync();                              // every lane has its bottleneck before lane 0 moves the flow
     if (d <= 0) return 0;
 #ifdef SGUFP_K1_PUSH_PAR
@@ -484,6 +500,7 @@ struct TightPaths {
         : P(P_), T(T_), w(w_), nopen(nopen_), nc(nc_), nword(reach_words(nc_)), ntc(0), rq(-1), q(0), hit(0) {}
     __device__ void prepare() {
         if constexpr (small) tight_small<TILE>(P, nopen, T, w); else ntc = tight_list<TILE>(P, nopen, T, w);
+        K1_CNT(11, 1); K1_CNT(12, ntc);
         rq = -1;                          // a new list: chunk positions of the old one mean nothing
     }
     __device__ __forceinline__ bool in_r(int v) const {
@@ -502,6 +519,7 @@ struct TightPaths {
             T.sync();
         }
         int best = INT_MAX;
+        K1_CNT(10, 1);
         K1_LOOP
         for (int c = T.tl; c < nopen; c += TILE) {
             const int f = RGET(c) & 3;
@@ -575,6 +593,7 @@ struct TightPaths {
             if (stage < 3) { sgufp_emul_warm[3]++; if (d <= 0) sgufp_emul_warm[4]++; }
 #endif
             keep = false;
+            K1_CNT((stage < 3 ? 0 : 2) + (d > 0 ? 0 : 1), 1);
             if (d > 0) {
                 if (stage < 3) {
                     need -= d;
@@ -921,6 +940,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
             else { if (forced) forced_flow_init<TILE>(P, nopen, nc, T, w, fuel); shortest_paths<TILE, false, false>(0, P, nopen, nc, T, w, fuel, true);   // the ONE label computation: feasible potentials at the starting flow, finite at every node
             }
             TP.prepare();
+            K1_CNT(13, nopen); K1_CNT(14, 1); K1_CNT(15, nc);
             rc = TP.solve(warm || forced, fuel);
 #ifdef SGUFP_K1_EMULATE
             if (warm) sgufp_emul_warm[rc ? 1 : 0]++;   // tests: warm starts taken / given up
@@ -1307,14 +1327,16 @@ int k1_group(int K, int S, int sm_count) {
 }
 
 // which kernel: the lane-per-scenario one (k1_lane.cu) for batches it accepts, else the warp-per-scenario one
-cudaError_t k1_launch(const K1Launch &p, cudaStream_t st, int sm_count, int *launches) {
+cudaError_t k1_launch(const K1Launch &p, cudaStream_t st, int sm_count, int *launches, bool *state_kept) {
     if (launches) (*launches)++;
+    if (state_kept) *state_kept = false;     // only the warp kernels read and write K1Launch::state
     if (k1_lane_eligible(p, sm_count)) {
         const cudaError_t e = k1_lane_launch(p, st, sm_count);
         if (e != cudaErrorInvalidConfiguration) return e;
         cudaGetLastError();          // the state of this batch does not fit one SM's shared memory: the warp kernel takes it
     }
     if (launches) (*launches)++;     // the warp path is two kernels: flow, cut
+    if (state_kept) *state_kept = p.state != nullptr && (p.state_io & 2);
     return launch_warp(p, st, sm_count);
 }
 

@@ -47,7 +47,8 @@ cudaError_t k1_lane_launch(const K1Launch &p, cudaStream_t st, int sm_count);   
 int k1_group(int K, int S, int sm_count);                   // K1Launch::group for a batch of K candidates on S scenarios
 
 // Returns cudaSuccess or the launch error.  *launches is incremented by the kernels launched.
-cudaError_t k1_launch(const K1Launch &p, cudaStream_t st, int sm_count, int *launches);
+// state_kept: the launch left K1Launch::state describing the last candidate (false for the lane kernel, which ignores it)
+cudaError_t k1_launch(const K1Launch &p, cudaStream_t st, int sm_count, int *launches, bool *state_kept = nullptr);
 
 struct RayLaunch {
     const double *cap_u, *cap_l;

@@ -68,6 +68,7 @@ static int g_group = 0;
 extern "C" void emul_set_group(int g) { g_group = g; }   // candidates per work item (0: the whole batch, 1: no warm starts)
 extern "C" void emul_warm_counts(long long *out2) { out2[0] = sgufp::sgufp_emul_warm[0]; out2[1] = sgufp::sgufp_emul_warm[1]; sgufp::sgufp_emul_warm[0] = sgufp::sgufp_emul_warm[1] = 0; }
 extern "C" void emul_warm_counts8(long long *out8) { for (int i = 0; i < 8; i++) { out8[i] = sgufp::sgufp_emul_warm[i]; sgufp::sgufp_emul_warm[i] = 0; } }
+extern "C" void emul_counts16(long long *out16) { for (int i = 0; i < 16; i++) { out16[i] = sgufp::sgufp_emul_cnt[i]; sgufp::sgufp_emul_cnt[i] = 0; } }   // tools/proto/flow_census.py
 static int g_last_nc = 0;
 extern "C" int emul_last_nc() { return g_last_nc; }   // contracted nodes of the last instance: which size class ran
 
