@@ -38,7 +38,11 @@ namespace sgufp {
 #undef SGUFP_K1_STATS                       // the counters live in the main translation unit (no relocatable device code)
 #endif
 #ifdef SGUFP_K1_STATS
-__device__ unsigned long long g_k1_clk[8];     // SM clocks of the first lane per phase: link, stream, warm repair, flow from zero, potentials, lifting; warm / cold evaluations
+// SM clocks of the first lane per phase.  Flow kernel: 0 link (flow carried over), 1 row + start, 2 warm_init / the one label
+// computation + the first tight list, 3 searches, 4 pushes, 5 dual updates (+ tight lists), 6 flow and state written, 7 evaluations;
+// cut kernel: 8 row + flow read, 9 SPEC-LP potentials, 10 chains + alphas, 11 per-arc lifting, 12 closed chains + sums, 13 evaluations;
+// 14 / 15: warm / cold evaluations of the flow kernel
+__device__ unsigned long long g_k1_clk[16];
 #define K1_CLK(i) do { if (T.tl == 0) { const long long now_ = clock64(); atomicAdd(&g_k1_clk[i], (unsigned long long)(now_ - clk_)); clk_ = now_; } } while (0)
 __device__ unsigned long long g_k1_stats[8];   // relaxation passes, label computations, searches, work items, list sweeps, list entries swept, searches that reached dst, chains per pass
 #endif
@@ -495,6 +499,9 @@ struct TightPaths {
     int nopen, nc, nword, ntc;
     int rq, q;                            // list search: visit to restart from after a push (-1: from the root), visit counter
     int hit;                              // the node the last successful search ended at
+#ifdef SGUFP_K1_STATS
+    long long clk_ = 0;                   // K1_CLK inside the flow loop (handed over by the kernel around solve)
+#endif
     static constexpr bool small = !TM::BIG;
     __device__ TightPaths(const PlanView &P_, const Lanes<TILE> &T_, TM &w_, int nopen_, int nc_)
         : P(P_), T(T_), w(w_), nopen(nopen_), nc(nc_), nword(reach_words(nc_)), ntc(0), rq(-1), q(0), hit(0) {}
@@ -607,7 +614,9 @@ struct TightPaths {
                 }
                 continue;
             }
-            if (!dual_update(stage == 3, stage < 3 && src == 0)) { if (stage == 3) return 0; return 1; }
+            const bool more = dual_update(stage == 3, stage < 3 && src == 0);
+            K1_CLK(5);
+            if (!more) { if (stage == 3) return 0; return 1; }
             keep = TM::BIG;
         }
     }
@@ -620,9 +629,12 @@ struct TightPaths {
 #endif
         if constexpr (small) {
             const int lev = reach_small<TILE>(src, dst, nc, T, w, &hit);
+            K1_CLK(3);
             if (!lev) return 0;
             if (dst < 0 && hit != nc) limit = min(limit, -SI(w.exc + hit));
-            return push_small<TILE>(hit, limit, lev, nc, T, w);
+            const int d = push_small<TILE>(hit, limit, lev, nc, T, w);
+            K1_CLK(4);
+            return d;
         } else {
             const int nchunk = (ntc + TILE - 1) / TILE;
             int c0 = 0;
@@ -630,9 +642,13 @@ struct TightPaths {
             else if (keep && nchunk > 0) q = (q + nchunk - 1) / nchunk * nchunk;     // after a dual update: a new sweep, visit numbers go on
             else { q = 0; keep = false; }
             rq = -1;
-            if (!reach_list<TILE>(src, dst, P, ntc, nword, T, w, keep, c0, q, &hit)) return 0;
+            const bool found = reach_list<TILE>(src, dst, P, ntc, nword, T, w, keep, c0, q, &hit);
+            K1_CLK(3);
+            if (!found) return 0;
             if (dst < 0 && hit != nc) limit = min(limit, -SI(w.exc + hit));
-            return push_list<TILE>(src, hit, limit, nc, T, w, &rq);
+            const int d = push_list<TILE>(src, hit, limit, nc, T, w, &rq);
+            K1_CLK(4);
+            return d;
         }
     }
 };
@@ -940,13 +956,20 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
             else { if (forced) forced_flow_init<TILE>(P, nopen, nc, T, w, fuel); shortest_paths<TILE, false, false>(0, P, nopen, nc, T, w, fuel, true);   // the ONE label computation: feasible potentials at the starting flow, finite at every node
             }
             TP.prepare();
+            K1_CLK(2);
+#ifdef SGUFP_K1_STATS
+            TP.clk_ = clk_;
+#endif
             K1_CNT(13, nopen); K1_CNT(14, 1); K1_CNT(15, nc);
             rc = TP.solve(warm || forced, fuel);
+#ifdef SGUFP_K1_STATS
+            clk_ = TP.clk_;
+#endif
 #ifdef SGUFP_K1_EMULATE
             if (warm) sgufp_emul_warm[rc ? 1 : 0]++;   // tests: warm starts taken / given up
 #endif
 #ifdef SGUFP_K1_STATS
-            if (T.tl == 0) atomicAdd(&g_k1_clk[warm && !rc ? 6 : 7], 1ull);
+            if (T.tl == 0) { atomicAdd(&g_k1_clk[warm && !rc ? 14 : 15], 1ull); atomicAdd(&g_k1_clk[7], 1ull); }
 #endif
             if (!warm || rc != 1) break;
             K1_LOOPB
@@ -954,7 +977,6 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
             T.sync();
             warm = false; fuel = 1 << 20;
         }
-        K1_CLK(2);
         if (rc == 1) {                               // forced flow that cannot be routed: infeasible
             if (T.tl == 0) {
                 atomicMin(p.first_inf + k, p.scen_offset + s);
@@ -974,7 +996,6 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         if (nopen == 0 && T.tl == 0) xrow[0] = 0;
         K1_LOOP1
         for (int c = T.tl; c < nopen; c += TILE) xrow[c] = SI(w.x + c);
-        K1_CLK(3);
         holds = !forced;                                    // x and lab of this candidate serve the next one of the run
         if (srow && (p.state_io & 2) && k == p.K - 1 && holds) {   // ... and the first one of the next launch on this handle
             K1_LOOP1
@@ -984,6 +1005,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
             T.sync();
             if (T.tl == 0) srow[0] = 1;
         }
+        K1_CLK(6);
         }
     }
 }
@@ -1011,6 +1033,9 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         const int nch = P.h->nch, nopen = P.h->nopen, nc = P.h->nc, nav = P.h->nav, m = p.m;
         unsigned long long *sums = p.sums + (size_t)k * p.W;
         const double *row_u = p.cap_u + (size_t)s * p.m_pad, *row_l = p.cap_l + (size_t)s * p.m_pad;
+#ifdef SGUFP_K1_STATS
+        long long clk_ = clock64();
+#endif
         stream_row<TILE>(P, nopen, m, p.m_pad, row_u, row_l, T, w);
         K1_LOOP2
         for (int c = T.tl; c < nopen; c += TILE) {
@@ -1019,8 +1044,10 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
             RSET(c, (xc < (SI(w.up + c) >> HB) ? 1 : 0) | (xc > (SI(w.lo + c) >> HB) ? 2 : 0));
         }
         T.sync();
+        K1_CLK(8);
         // 3. potentials
         canonical_potentials<TILE>(P, nopen, nc, T, w, fuel);
+        K1_CLK(9);
         if (fuel <= 0) {   // a bound that no valid instance reaches: refuse to answer rather than spin
             if (T.tl == 0) atomicMin(p.first_inf + k, -1LL);
             T.sync();
@@ -1057,6 +1084,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
             SI(w.aq + i) = alpha;
         }
         T.sync();
+        K1_CLK(10);
         // (c) per ARC, a lane each (coalesced plan reads, every lane busy; the per-node loop over matched pairs this replaces ran
         //     with 9 - 14 of 32 lanes behind chains of dependent loads): the capacity multiplier of an open chain sits on its first
         //     arc of least capacity; lambda - mu of a matched pair is its wire potential minus the node's alpha
@@ -1083,6 +1111,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
                 }
             }
         }
+        K1_CLK(11);
         K1_LOOPB
         for (int c = nopen + T.tl; c < nch; c += TILE) {
             const int b0 = P.ch_ptr[c], b1 = P.ch_ptr[c + 1], first = P.ch_arcs[b0], last = P.ch_arcs[b1 - 1];
@@ -1118,6 +1147,10 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
             if (p.obj) p.obj[(size_t)k * p.S + s] = (double)objv;
         }
         T.sync();
+        K1_CLK(12);
+#ifdef SGUFP_K1_STATS
+        if (T.tl == 0) atomicAdd(&g_k1_clk[13], 1ull);
+#endif
     }
 }
 
@@ -1360,9 +1393,9 @@ cudaError_t relayout_launch(const int32_t *src, double *dst, int na, int S, int 
 
 #if defined(SGUFP_K1_STATS) && !defined(SGUFP_K1_EMULATE) && !defined(SGUFP_K1_SMALL_TU)
 // debug build only (-DSGUFP_K1_STATS): relaxation passes / label computations since the last call
-extern "C" int sgufp_debug_k1_clk(unsigned long long *out8) {
-    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    cudaError_t e = cudaMemcpyFromSymbol(out8, sgufp::g_k1_clk, sizeof(z));
+extern "C" int sgufp_debug_k1_clk(unsigned long long *out16) {
+    unsigned long long z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    cudaError_t e = cudaMemcpyFromSymbol(out16, sgufp::g_k1_clk, sizeof(z));
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(sgufp::g_k1_clk, z, sizeof(z));
     return e == cudaSuccess ? 0 : -6;
 }

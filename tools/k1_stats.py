@@ -39,17 +39,26 @@ def main():
     lane = (C.c_ulonglong * 8)()
     L.sgufp_debug_k1_clk.restype = C.c_int
     L.sgufp_debug_k1_clk.argtypes = [C.POINTER(C.c_ulonglong)]
-    clk = (C.c_ulonglong * 8)()
+    clk = (C.c_ulonglong * 16)()
     import bench
+    FLOW = ("link", "row + start", "warm_init / labels + tight list", "searches", "pushes", "dual updates + tight lists", "flow + state out")
+    CUT = ("row + flow in", "SPEC-LP potentials", "chains + alphas", "per-arc lifting", "closed chains + sums")
     for name in [a for a in sys.argv[1:] if not a.startswith("-")]:
-        inst, K = {"c2": (lambda: (I.config2(S=1000), 64)), "c4": (lambda: (I.config4(S=2000), 8))}[name]()
+        K = bench.WORKLOADS[name]["K"]
+        inst = bench.scenario_range(name, 0, 10000 if name != "c2" else 1000)
         solver = GuroSolver(inst)
-        # the bench's DD-emitted candidates (consecutive paths of the Benders loop) unless random matchings are asked for
-        paths = I.random_paths(solver, K, 31, 0.1) if "--random" in sys.argv else bench.candidate_paths(name, K, 0)[0]
-        L.sgufp_debug_k1_stats(out)
-        L.sgufp_debug_k1_clk(clk)
-        L.sgufp_debug_k1_lane_stats(lane)
-        solver.solve_paths(np.asarray(paths, dtype=np.int16))
+        # the bench's DD-emitted candidates (consecutive paths of the Benders loop) unless random matchings are asked for; the
+        # counters are those of the LAST of three calls that alternate between the batches (the bench's steady state)
+        if "--random" in sys.argv:
+            batches = [np.asarray(I.random_paths(solver, K, 31, 0.1), dtype=np.int16)]
+        else:
+            batches = bench.step_batches(bench.candidate_paths(name, K, 0, want=2 * K)[0], K)
+        calls = 1 if "--first" in sys.argv else 3
+        for it in range(calls):
+            L.sgufp_debug_k1_stats(out)
+            L.sgufp_debug_k1_clk(clk)
+            L.sgufp_debug_k1_lane_stats(lane)
+            solver.solve_paths(batches[it % len(batches)])
         L.sgufp_debug_k1_stats(out)
         L.sgufp_debug_k1_lane_stats(lane)
         if lane[0]:      # the lane-per-scenario kernel ran: counters per block of 32 scenarios (warp level) and per scenario (lane level)
@@ -57,13 +66,15 @@ def main():
                   f"dual updates/scenario {lane[3] / max(1, lane[5]):.1f}  pushes/scenario {lane[4] / max(1, lane[5]):.1f}  ms {solver.last_kernel_ms():.3f}")
             continue
         L.sgufp_debug_k1_clk(clk)
-        tot = max(1, sum(clk[:6]))
-        print(f"{name}: group {os.environ.get('SGUFP_K1_GROUP', 'auto')}  warm {clk[6]} cold {clk[7]}  clocks per evaluation {tot / max(1, clk[6] + clk[7]):.0f}: "
-              + "  ".join(f"{n} {100.0 * clk[i] / tot:.1f}%" for i, n in enumerate(("link", "stream", "repair", "from zero", "potentials", "lifting"))))
+        ft, ct = max(1, sum(clk[:7])), max(1, sum(clk[8:13]))
+        print(f"{name}: group {os.environ.get('SGUFP_K1_GROUP', 'auto')}  warm {clk[14]} cold {clk[15]}  kernel {solver.last_kernel_ms():.3f} ms (stats build)")
+        print(f"    flow kernel: {ft / max(1, clk[7]):.0f} clocks per evaluation: " + "  ".join(f"{n} {100.0 * clk[i] / ft:.1f}%" for i, n in enumerate(FLOW)))
+        print(f"    cut kernel:  {ct / max(1, clk[13]):.0f} clocks per evaluation: " + "  ".join(f"{n} {100.0 * clk[8 + i] / ct:.1f}%" for i, n in enumerate(CUT)))
         ev = max(1, out[3])
-        print(f"{name}: evals {out[3]}  passes/eval {out[0] / ev:.1f}  label computations/eval {out[1] / ev:.1f}  searches/eval {out[2] / ev:.1f}  ms {solver.last_kernel_ms():.3f}")
+        print(f"    evals {out[3]}  passes/eval {out[0] / ev:.1f}  label computations + dual updates/eval {out[1] / ev:.1f}  searches/eval {out[2] / ev:.1f}")
         if out[4]:
             print(f"    list searches: sweeps/search {out[4] / max(1, out[2]):.2f}  entries/sweep {out[5] / out[4]:.0f}  reached dst {100.0 * out[6] / max(1, out[2]):.0f} %  open chains/pass {out[7] / max(1, out[0]):.0f}")
+        solver.close()
 
 
 if __name__ == "__main__":
