@@ -136,6 +136,19 @@ int sgufp_create_from_cache(sgufp_ctx **out, const char *path, int device, int64
     };
     if (std::memcmp(H.magic, "SGUFPC01", 8) != 0 || H.version != 1 || (size_t)H.file_bytes > bytes || H.m_pad != ((H.m + 1) & ~1))
         return bail(SGUFP_ERR_ARG, "not an SGUFPC01 cache file (or truncated)");
+    {   // the offsets are the writer's layout, nothing else: a damaged header must not send the reads outside the mapping
+        if (H.n < 2 || H.m < 1 || H.S < 0 || H.nvbar < 0) return bail(SGUFP_ERR_ARG, "cache file header: bad sizes");
+        size_t off = HEADER_BYTES;
+        const size_t o_tail = off; off += (size_t)H.m * 4;
+        const size_t o_head = off; off += (size_t)H.m * 4;
+        const size_t o_rew = off; off += (size_t)H.m * 4;
+        const size_t o_vbar = off; off += (size_t)H.nvbar * 4;
+        off = up4k(off);
+        const size_t rows = (size_t)H.S * H.m_pad * 8, o_u = off, o_l = off + rows, total = off + 2 * rows;
+        if ((size_t)H.off_tail != o_tail || (size_t)H.off_head != o_head || (size_t)H.off_rew != o_rew || (size_t)H.off_vbar != o_vbar ||
+            (size_t)H.off_u != o_u || (size_t)H.off_l != o_l || (size_t)H.file_bytes != total)
+            return bail(SGUFP_ERR_ARG, "cache file header: offsets do not match the layout of its sizes");
+    }
     if (S_local < 0) S_local = H.S - scenario_offset;
     if (scenario_offset < 0 || S_local < 0 || scenario_offset + S_local > H.S) return bail(SGUFP_ERR_ARG, "scenario block must lie inside [0, S) of the file");
     c = new sgufp_ctx();

@@ -49,17 +49,15 @@ struct NcclApi {
     bool ok() const { return lib != nullptr; }
 };
 
-NcclApi &nccl() {
-    static NcclApi api;
-    static bool tried = false;
-    if (tried) return api;
-    tried = true;
+// loaded once per process, by whichever thread asks first (a function-local static: its initialisation is thread-safe)
+NcclApi load_nccl() {
+    NcclApi api;
     void *h = nullptr;
     for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
         h = dlopen(name, RTLD_NOW | RTLD_LOCAL);
         if (h) break;
     }
-    if (!h) { api.err = std::string("NCCL not found (dlopen libnccl.so.2): ") + (dlerror() ? dlerror() : ""); return api; }
+    if (!h) { const char *de = dlerror(); api.err = std::string("NCCL not found (dlopen libnccl.so.2): ") + (de ? de : ""); return api; }
     bool all = true;
     auto sym = [&](const char *n) { void *p = dlsym(h, n); if (!p) { all = false; api.err = std::string("NCCL symbol missing: ") + n; } return p; };
     api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
@@ -71,6 +69,11 @@ NcclApi &nccl() {
     api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
     api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
     if (all) api.lib = h;
+    return api;
+}
+
+NcclApi &nccl() {
+    static NcclApi api = load_nccl();
     return api;
 }
 

@@ -70,3 +70,15 @@ def test_cache_file_holds_the_device_layout(tmp_path, built_lib):
         sg.GuroSolver.from_cache(str(tmp_path / "missing.sgufpc"), device=-1)
     c = a.clone()                                   # a model-only handle clones too (nothing to share)
     assert c.L == a.L
+    # a damaged header (an offset that points outside the layout of its own sizes, a size that no longer fits the file) is refused,
+    # not followed
+    for where, value in ((40, 1 << 40), (40 + 4 * 8, 8), (16, inst.m + 2), (20, inst.S * 1000)):      # off_tail, off_u, m, S
+        bad = bytearray(raw)
+        struct.pack_into("<q" if where >= 40 else "<i", bad, where, value)
+        pbad = str(tmp_path / f"bad{where}.sgufpc")
+        open(pbad, "wb").write(bytes(bad))
+        with pytest.raises(sg.solver.SgufpError):
+            sg.GuroSolver.from_cache(pbad, device=-1)
+    open(str(tmp_path / "short.sgufpc"), "wb").write(raw[: len(raw) // 2])
+    with pytest.raises(sg.solver.SgufpError):
+        sg.GuroSolver.from_cache(str(tmp_path / "short.sgufpc"), device=-1)
