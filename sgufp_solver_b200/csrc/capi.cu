@@ -65,15 +65,19 @@ int make_batch(sgufp_ctx *c, const int16_t *paths, int K, int L, Batch &B, bool 
     } else work(0, 1);
     for (int k = 0; k < K; k++)
         if (rc[k]) return fail(c, rc[k], "path " + std::to_string(k) + ": " + errs[k]);   // the lowest failing index, as a serial loop would report
-    // links between consecutive candidates (warm starts inside a work item of the warp kernel, k1_cut.cu)
+    // the order in which a run takes the candidates, and the links between neighbours in that order (warm starts inside a work
+    // item of the warp kernel, k1_cut.cu): the chain starts at the path whose state the handle holds, if it holds one
+    const char *order_env = getenv("SGUFP_K1_ORDER");
+    if (order_env && atoi(order_env) == 0) { B.order.resize(K); for (int k = 0; k < K; k++) B.order[k] = k; }
+    else order_batch(paths, K, L, c->state_valid && (int)c->state_path.size() == L ? c->state_path.data() : nullptr, B.order);
     B.links.resize(K); B.link_off.assign(K, -1);
+    for (int k = 0; k < K; k++) B.links[k].clear();
     if (K > 1) {
         const std::function<void(int, int)> link = [&](int t, int nt) {
-            for (int k = 1 + t; k < K; k += nt) link_plans(B.plans[k - 1], B.plans[k], B.links[k]);
+            for (int j = 1 + t; j < K; j += nt) link_plans(B.plans[B.order[j - 1]], B.plans[B.order[j]], B.links[B.order[j]]);
         };
         if (nt > 1) c->pool->run(nt, link); else link(0, 1);
     }
-    B.links[0].clear();
     size_t total = 0;
     for (int k = 0; k < K; k++) {
         B.off[k] = (int32_t)total;
@@ -82,7 +86,7 @@ int make_batch(sgufp_ctx *c, const int16_t *paths, int K, int L, Batch &B, bool 
         B.max_nopen = std::max(B.max_nopen, B.plans[k].nopen);
         B.max_indeg = std::max(B.max_indeg, B.plans[k].max_indeg);
     }
-    for (int k = 1; k < K; k++)
+    for (int k = 0; k < K; k++)
         if (!B.links[k].empty()) { B.link_off[k] = (int32_t)total; total += B.links[k].size(); }
     B.total_words = total;
     B.key_paths.assign(paths, paths + npath); B.key_K = K; B.key_L = L; B.key_lane = lane_tables;
@@ -109,15 +113,15 @@ int launch_batch(sgufp_ctx *c, const Batch &B, int K, unsigned long long *d_sums
         }
         if (c->d_state.p) {
             state_io = 2;
-            if (c->state_valid) { link_plans(c->state_plan, B.plans[0], link0); if (!link0.empty()) state_io |= 1; }
+            if (c->state_valid) { link_plans(c->state_plan, B.plans[B.order[0]], link0); if (!link0.empty()) state_io |= 1; }
         }
     }
     const size_t pool_words = B.total_words + link0.size();
     CU(c, c->d_plans.reserve(pool_words));
-    CU(c, c->d_plan_off.reserve(2 * (size_t)K));
+    CU(c, c->d_plan_off.reserve(3 * (size_t)K));
     // gather the plans (+ offsets + the initial "no infeasible scenario" marks) into pinned memory: the uploads are then
     // true asynchronous copies.  The staging buffer is reused by the next call: an event tells when the copies left it.
-    const size_t o_off = pool_words, o_inf = (o_off + 2 * (size_t)K + 1) & ~(size_t)1, need = o_inf + 2 * (size_t)K;
+    const size_t o_off = pool_words, o_inf = (o_off + 3 * (size_t)K + 1) & ~(size_t)1, need = o_inf + 2 * (size_t)K;
     if (c->h2d_pending) { CU(c, cudaEventSynchronize(c->ev_h2d)); c->h2d_pending = false; }
     if (c->h_words_cap < need) {
         if (c->h_words) cudaFreeHost(c->h_words);
@@ -126,14 +130,15 @@ int launch_batch(sgufp_ctx *c, const Batch &B, int K, unsigned long long *d_sums
         c->h_words_cap = need * 2;
     }
     for (int k = 0; k < K; k++) std::memcpy(c->h_words + B.off[k], B.plans[k].words.data(), B.plans[k].words.size() * 4);
-    for (int k = 1; k < K; k++) if (B.link_off[k] >= 0) std::memcpy(c->h_words + B.link_off[k], B.links[k].data(), B.links[k].size() * 4);
+    for (int k = 0; k < K; k++) if (B.link_off[k] >= 0) std::memcpy(c->h_words + B.link_off[k], B.links[k].data(), B.links[k].size() * 4);
     std::memcpy(c->h_words + o_off, B.off.data(), (size_t)K * 4);
     std::memcpy(c->h_words + o_off + K, B.link_off.data(), (size_t)K * 4);
-    if (state_io & 1) { std::memcpy(c->h_words + B.total_words, link0.data(), link0.size() * 4); c->h_words[o_off + K] = (int32_t)B.total_words; }
+    std::memcpy(c->h_words + o_off + 2 * (size_t)K, B.order.data(), (size_t)K * 4);
+    if (state_io & 1) { std::memcpy(c->h_words + B.total_words, link0.data(), link0.size() * 4); c->h_words[o_off + K + B.order[0]] = (int32_t)B.total_words; }
     long long *inf = reinterpret_cast<long long *>(c->h_words + o_inf);
     for (int k = 0; k < K; k++) inf[k] = LLONG_MAX;
     CU(c, cudaMemcpyAsync(c->d_plans.p, c->h_words, pool_words * 4, cudaMemcpyHostToDevice, st));
-    CU(c, cudaMemcpyAsync(c->d_plan_off.p, c->h_words + o_off, 2 * (size_t)K * 4, cudaMemcpyHostToDevice, st));
+    CU(c, cudaMemcpyAsync(c->d_plan_off.p, c->h_words + o_off, 3 * (size_t)K * 4, cudaMemcpyHostToDevice, st));
     CU(c, cudaMemcpyAsync(d_finf, inf, (size_t)K * 8, cudaMemcpyHostToDevice, st));
     CU(c, cudaEventRecord(c->ev_h2d, st));
     c->h2d_pending = true;
@@ -142,7 +147,7 @@ int launch_batch(sgufp_ctx *c, const Batch &B, int K, unsigned long long *d_sums
     CU(c, cudaMemsetAsync(c->d_work.p, 0, 8, st));
     K1Launch p{};
     p.cap_u = c->d_u; p.cap_l = c->d_l; p.S = c->S; p.m = c->M.m; p.m_pad = c->m_pad; p.scen_offset = c->scen_off;
-    p.plans = c->d_plans.p; p.plan_off = c->d_plan_off.p; p.link_off = c->d_plan_off.p + K; p.group = group; p.K = K;
+    p.plans = c->d_plans.p; p.plan_off = c->d_plan_off.p; p.link_off = c->d_plan_off.p + K; p.order = c->d_plan_off.p + 2 * (size_t)K; p.group = group; p.K = K;
     p.state = state_io ? c->d_state.p : nullptr; p.state_stride = c->state_stride; p.state_io = state_io;
     p.xstride = std::max(1, B.max_nopen);
     CU(c, c->d_xout.reserve((size_t)K * std::max(1, c->S) * p.xstride));
@@ -164,7 +169,11 @@ int launch_batch(sgufp_ctx *c, const Batch &B, int K, unsigned long long *d_sums
     }
     // what the rows of d_state describe after this launch
     // (the lane kernel, SGUFP_K1_MODE=lane, does not touch them: a launch through it leaves no state to go on from)
-    if ((state_io & 2) && state_kept) { c->state_plan = B.plans[K - 1]; c->state_valid = true; }
+    if ((state_io & 2) && state_kept) {
+        const int last = B.order[K - 1];
+        c->state_plan = B.plans[last]; c->state_valid = true;
+        c->state_path.assign(B.key_paths.begin() + (size_t)last * B.key_L, B.key_paths.begin() + (size_t)(last + 1) * B.key_L);
+    }
     else c->state_valid = false;
     return 0;
 }

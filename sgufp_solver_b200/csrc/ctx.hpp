@@ -31,6 +31,7 @@ struct PlanBatch {
     std::vector<int32_t> off;
     std::vector<std::vector<int32_t>> links;   // links[k]: candidate k seen from candidate k-1 (model.hpp: link_plans), empty = none
     std::vector<int32_t> link_off;   // [K] word offset of links[k] in the pool behind the plans, -1 = none
+    std::vector<int32_t> order;      // [K] the order in which a run takes the candidates (model.hpp: order_batch); links[order[j]] is seen from order[j-1]
     size_t total_words = 0;          // the plans are gathered into the handle's pinned staging buffer at launch
     int max_nch = 0, max_nopen = 0, max_indeg = 0;
     std::vector<int16_t> key_paths;  // what the plans were built from (valid when key_K > 0)
@@ -70,6 +71,7 @@ struct sgufp_ctx {
     DevBuf<int32_t> d_state;
     DevBuf<int32_t> d_xout;                     // [K][S][max open chains]: optimal flows, flow kernel -> cut kernel
     sgufp::Plan state_plan;
+    std::vector<int16_t> state_path;            // the path state_plan was built from (where the next batch's order starts)
     bool state_valid = false;
     int state_stride = 0;
     sgufp::HostPool *pool = nullptr;            // persistent host threads for the plans of a batch (created on first use)

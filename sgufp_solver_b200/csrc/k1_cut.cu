@@ -872,7 +872,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         bool holds = false;                     // this tile holds the optimal flow (x) and the labels (lab: feasible potentials, finite everywhere) of the candidate before k
         int32_t *srow = p.state && ngroups == 1 ? p.state + (size_t)s * p.state_stride : nullptr;   // this scenario's row of the handle's state
         if (srow && (p.state_io & 1) && srow[0]) {         // left by the last candidate of the previous launch on this handle
-            const int nprev = (p.plans + p.link_off[0])[1];
+            const int nprev = (p.plans + p.link_off[p.order ? p.order[0] : 0])[1];
             K1_LOOP1
             for (int v = T.tl; v <= p.nc; v += TILE) SI(w.lab + v) = srow[1 + v];
             K1_LOOP1
@@ -882,7 +882,8 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         T.sync();
         if (srow && (p.state_io & 2) && T.tl == 0) srow[0] = 0;   // until the last candidate of this launch has filled it
         K1_LOOPB
-        for (int k = grp * group, k_end = min(p.K, k + group); k < k_end; k++) {
+        for (int j = grp * group, j_end = min(p.K, j + group); j < j_end; j++) {
+        const int k = p.order ? p.order[j] : j;            // the run takes the candidates in the host's order (model.hpp: order_batch)
         const bool carried = holds;
         holds = false;
         if (*reinterpret_cast<volatile long long *>(p.first_inf + k) < 0) continue;   // this candidate was aborted: drain
@@ -997,7 +998,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? SGUFP_K1_MINBLOCKS : NW == 
         K1_LOOP1
         for (int c = T.tl; c < nopen; c += TILE) xrow[c] = SI(w.x + c);
         holds = !forced;                                    // x and lab of this candidate serve the next one of the run
-        if (srow && (p.state_io & 2) && k == p.K - 1 && holds) {   // ... and the first one of the next launch on this handle
+        if (srow && (p.state_io & 2) && j == p.K - 1 && holds) {   // ... and the first one of the next launch on this handle
             K1_LOOP1
             for (int v = T.tl; v <= nc; v += TILE) srow[1 + v] = SI(w.lab + v);
             K1_LOOP1

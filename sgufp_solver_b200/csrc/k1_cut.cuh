@@ -12,6 +12,7 @@ struct K1Launch {
     const int32_t *plans;         // device pool of K plans
     const int32_t *plan_off;      // [K] word offset of each plan
     const int32_t *link_off;      // [K] word offset of the link of candidate k to candidate k-1 (model.hpp: link_plans), -1 = none; or nullptr
+    const int32_t *order;         // [K] the order in which a run takes the candidates (link_off[order[j]] is the step from order[j-1]); or nullptr: as given
     int group;                    // candidates per work item: a warp takes `group` consecutive candidates on one scenario and warm-starts
                                   // each from the one before (0 or 1: every candidate from zero flow)
     int K, W, L;
@@ -23,7 +24,7 @@ struct K1Launch {
     int state_stride;             // >= 2 + nc + max open chains
     int32_t *xout;                // [K][S][xstride]: the optimal flow per open chain, flow kernel -> cut kernel (x[0] = INT_MIN: infeasible scenario)
     int xstride;                  // >= max(1, max open chains)
-    int state_io;                 // bit 0: link_off[0] describes the step from the stored candidate, read the row; bit 1: write it
+    int state_io;                 // bit 0: the link of the FIRST candidate taken (order[0]) is the step from the stored candidate, read the row; bit 1: write it
     unsigned long long *sums;     // [K][W] exact integer accumulators (two's complement)
     long long *first_inf;         // [K] lowest infeasible global scenario (init LLONG_MAX)
     unsigned long long *work;     // work-item queue of the warp kernel (one word, zeroed before the launch) or nullptr: fixed assignment

@@ -2,6 +2,7 @@
 #include "model.hpp"
 
 #include <algorithm>
+#include <climits>
 #include <cstring>
 #include <functional>
 #include <numeric>
@@ -344,6 +345,27 @@ void link_plans(const Plan &prev, const Plan &cur, std::vector<int32_t> &out) {
     const int32_t *st_a = A + ha->o_ch_st;
     for (int c : removed) out.push_back(st_a[2 * c] & 0xfffff);        // sv | ev << 10 of the removed chain (model.hpp: o_ch_st)
     while (out.size() & 3) out.push_back(0);
+}
+
+void order_batch(const int16_t *paths, int K, int L, const int16_t *start, std::vector<int32_t> &order) {
+    order.resize(K);
+    for (int k = 0; k < K; k++) order[k] = k;
+    if (K > 128 || L <= 0 || K < 2 || (K == 2 && !start)) return;
+    std::vector<char> used(K, 0);
+    const int16_t *cur = start;
+    int j = 0;
+    if (!cur) { used[0] = 1; cur = paths; j = 1; }
+    for (; j < K; j++) {
+        int best = -1, bd = INT_MAX;
+        for (int i = 0; i < K; i++) {
+            if (used[i]) continue;
+            const int16_t *p = paths + (size_t)i * L;
+            int d = 0;
+            for (int t = 0; t < L; t++) d += p[t] != cur[t];
+            if (d < bd) { bd = d; best = i; }          // ties: the order given
+        }
+        order[j] = best; used[best] = 1; cur = paths + (size_t)best * L;
+    }
 }
 
 // Split-graph arrays of the feasibility-ray kernel (k1_ray).  A dangling end arc books into its

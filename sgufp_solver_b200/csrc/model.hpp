@@ -93,6 +93,13 @@ int build_plan(const Model &M, const int16_t *path, int plen, Plan &P, std::stri
 // start is cheaper then).
 void link_plans(const Plan &prev, const Plan &cur, std::vector<int32_t> &out);
 
+// The order in which the flow kernel takes the candidates of a batch: a nearest-neighbour chain by the number of layers in which
+// two paths differ, from `start` (the path whose state the handle holds; nullptr: from candidate 0).  The cuts do not depend on
+// it; a warm start costs what the step changes, and the paths a Benders loop emits at one node stay within a few layers of EACH
+// OTHER, not only of their predecessor (the 16 committed C4 emissions: 2 - 8 layers between any two), so the chain's steps are
+// shorter than the emission's (profiles/r02_k1_flow_census.md).  Batches of more than 128 candidates keep the order given.
+void order_batch(const int16_t *paths, int K, int L, const int16_t *start, std::vector<int32_t> &order);
+
 void ray_arrays(const Model &M, const Plan &P, std::vector<int32_t> &ts, std::vector<int32_t> &hs, std::vector<int32_t> &info,
                 std::vector<int32_t> &pair_layer, std::vector<int32_t> &next, std::vector<int32_t> &aq, std::vector<int32_t> &first_wire, int &nn);
 

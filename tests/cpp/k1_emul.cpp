@@ -63,7 +63,10 @@ using namespace sgufp;
 static bool g_state_on = false, g_state_valid = false;
 static std::vector<int32_t> g_state;
 static sgufp::Plan g_state_plan;
-extern "C" void emul_state(int on) { g_state_on = on != 0; g_state_valid = false; g_state.clear(); }
+static std::vector<int16_t> g_state_path;
+extern "C" void emul_state(int on) { g_state_on = on != 0; g_state_valid = false; g_state.clear(); g_state_path.clear(); }
+static int g_order = 1;
+extern "C" void emul_set_order(int on) { g_order = on; }   // 1 (as capi.cu: make_batch): runs take the candidates along a nearest-neighbour chain; 0: as given
 static int g_group = 0;
 extern "C" void emul_set_group(int g) { g_group = g; }   // candidates per work item (0: the whole batch, 1: no warm starts)
 extern "C" void emul_warm_counts(long long *out2) { out2[0] = sgufp::sgufp_emul_warm[0]; out2[1] = sgufp::sgufp_emul_warm[1]; sgufp::sgufp_emul_warm[0] = sgufp::sgufp_emul_warm[1] = 0; }
@@ -91,12 +94,15 @@ extern "C" int emul_paths(int n, int m, int S, const int32_t *tail, const int32_
         words.insert(words.end(), plans[k].words.begin(), plans[k].words.end());
         max_nch = std::max(max_nch, plans[k].nch); max_nopen = std::max(max_nopen, plans[k].nopen);
     }
-    // links of consecutive candidates behind the plans (as capi.cu: make_batch lays them out)
+    // the order of the candidates in a run and the links of neighbours in that order, behind the plans (as capi.cu: make_batch lays them out)
+    std::vector<int32_t> order(K);
+    for (int k = 0; k < K; k++) order[k] = k;
+    if (g_order) order_batch(paths, K, L, g_state_on && g_state_valid && (int)g_state_path.size() == L ? g_state_path.data() : nullptr, order);
     std::vector<int32_t> link_off(K, -1);
-    for (int k = 1; k < K; k++) {
+    for (int j = 1; j < K; j++) {
         std::vector<int32_t> lk;
-        link_plans(plans[k - 1], plans[k], lk);
-        if (!lk.empty()) { link_off[k] = (int32_t)words.size(); words.insert(words.end(), lk.begin(), lk.end()); }
+        link_plans(plans[order[j - 1]], plans[order[j]], lk);
+        if (!lk.empty()) { link_off[order[j]] = (int32_t)words.size(); words.insert(words.end(), lk.begin(), lk.end()); }
     }
     const int group = g_group > 0 ? g_group : K;
     int state_io = 0, state_stride = 2 + M.nc + m;
@@ -105,8 +111,8 @@ extern "C" int emul_paths(int n, int m, int S, const int32_t *tail, const int32_
         state_io = 2;
         if (g_state_valid) {
             std::vector<int32_t> lk;
-            link_plans(g_state_plan, plans[0], lk);
-            if (!lk.empty()) { state_io |= 1; link_off[0] = (int32_t)words.size(); words.insert(words.end(), lk.begin(), lk.end()); }
+            link_plans(g_state_plan, plans[order[0]], lk);
+            if (!lk.empty()) { state_io |= 1; link_off[order[0]] = (int32_t)words.size(); words.insert(words.end(), lk.begin(), lk.end()); }
         }
     }
     std::memset(sums, 0, (size_t)K * W * 8);
@@ -117,9 +123,9 @@ extern "C" int emul_paths(int n, int m, int S, const int32_t *tail, const int32_
     p.sums = reinterpret_cast<unsigned long long *>(sums); p.first_inf = first_inf; p.obj = obj; p.status = status;
     unsigned long long work_queue = 0;
     p.work = (K & 1) ? &work_queue : nullptr;     // both ways of handing out work items are exercised
-    p.link_off = link_off.data(); p.group = group;   // runs of warm-started candidates (default: the whole batch is one run)
+    p.link_off = link_off.data(); p.order = order.data(); p.group = group;   // runs of warm-started candidates (default: the whole batch is one run)
     p.state = state_io ? g_state.data() : nullptr; p.state_stride = state_stride; p.state_io = state_io;
-    if (state_io) { g_state_plan = plans[K - 1]; g_state_valid = true; } else g_state_valid = false;
+    if (state_io) { g_state_plan = plans[order[K - 1]]; g_state_valid = true; g_state_path.assign(paths + (size_t)order[K - 1] * L, paths + (size_t)(order[K - 1] + 1) * L); } else g_state_valid = false;
     g_last_nc = M.nc;
     p.max_nch = max_nch; p.max_nopen = max_nopen; p.nc = M.nc; p.nav = M.nav; p.max_cap = 65535;
     p.xstride = std::max(1, max_nopen);

@@ -315,6 +315,31 @@ def test_warm_runs_on_the_bench_candidates(emul):
         assert (taken, given_up) == ((K - 1) * inst.S, 0)
 
 
+def test_the_order_of_a_run_does_not_change_the_cuts(emul):
+    """Runs take the candidates along a nearest-neighbour chain (model.hpp: order_batch, from the path whose state is kept) or as
+    given: the same sums either way, and Oracle B's; the chain's steps are no longer than the emission's."""
+    cand = np.load(os.path.join(ROOT, "sgufp_solver_b200", "data", "bench_candidates.npz"))
+    for key, inst, K in (("config2", I.config2(S=5), 16), ("config4", I.config4(S=2), 8)):
+        net = OracleNet(inst)
+        outs = []
+        for order in (1, 0):
+            emul.emul_set_order(order)
+            emul.emul_state(1)
+            try:
+                got = []
+                for b in range(2):
+                    paths = np.ascontiguousarray(cand[key][b * K:(b + 1) * K]) if len(cand[key]) >= 2 * K else np.ascontiguousarray(cand[key][:K][::(1 if b == 0 else -1)])
+                    out = run_emul(emul, inst, net, paths)
+                    check_against_oracle(inst, net, paths, out)
+                    got.append(out[0].copy())
+                outs.append(got)
+            finally:
+                emul.emul_state(0)
+                emul.emul_set_order(1)
+        for a, b in zip(*outs):
+            assert (a == b).all()
+
+
 @pytest.mark.parametrize("block", range(3))
 def test_warm_runs_fuzz(emul, block):
     """Random small and larger networks, with and without lower bounds, runs of 1 - 4 changed layers."""

@@ -402,6 +402,9 @@ def test_warm_runs_equal_cold_starts_bit_for_bit(wl, S, K, monkeypatch):
         r = gs.solve_paths(paths)
         outs.append(r)
         assert (r.cut_type == 0).all() and (r.status == 0).all()
+    monkeypatch.setenv("SGUFP_K1_GROUP", "8")
+    monkeypatch.setenv("SGUFP_K1_ORDER", "0")          # the runs take the candidates as given instead of along the nearest-neighbour chain
+    outs.append(gs.solve_paths(paths))
     for r in outs[1:]:
         assert (r.rhs == outs[0].rhs).all() and (r.coef_dense == outs[0].coef_dense).all() and (r.obj == outs[0].obj).all()
         assert (r.nnz == outs[0].nnz).all()

@@ -3,7 +3,7 @@ for the host (tests/cpp/k1_emul.cpp, one lane per scenario; the counters live un
 Per evaluation: searches of the repair (successful / failed), searches to the sink, chunk visits of the list search and
 how many of them were made after the target was already in the reached set, push hops, dual updates, list lengths.
 
-    python tools/proto/flow_census.py [config4|config2] [S] [group]
+    python tools/proto/flow_census.py [config4|config2] [S] [group] [order: 1 = nearest-neighbour chain (as built), 0 = as emitted]
 """
 import ctypes as C
 import os
@@ -42,6 +42,7 @@ def main():
     from oracle.oracle import OracleNet
     net = OracleNet(inst)
     L.emul_set_group(group)
+    L.emul_set_order(int(sys.argv[4]) if len(sys.argv) > 4 else 1)
     L.emul_state(1)
     out = (C.c_longlong * 16)()
     batches = [paths[b * K:(b + 1) * K] for b in range(max(1, len(paths) // K))]
