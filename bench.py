@@ -99,7 +99,8 @@ def issue_roofline(workload, kernel_ms, sm_mhz, sms):
     achieved = n / (kernel_ms * 1e-3) / 1e9
     peak = sms * 4 * sm_mhz * 1e6 / 1e9
     return {"bound": "issue", "achieved": achieved, "peak": peak, "unit": "G warp-inst/s", "frac": achieved / peak,
-            "warp_instructions_per_launch": n, "peak_source": "%d SMs x 4 schedulers x %.0f MHz (sampled under load)" % (sms, sm_mhz)}
+            "warp_instructions_per_launch": n, "peak_source": "%d SMs x 4 schedulers x %.0f MHz (sampled under load)" % (sms, sm_mhz),
+            "note": _traffic_file().get("_note_order")}
 
 
 class ClockSampler:
