@@ -165,8 +165,9 @@ int sgufp_last_stats(const sgufp_ctx *ctx, int *kernel_launches, float *device_m
 /* Device time of the last K1 launch alone (CUDA events recorded on the launching stream right
  * around the kernel); blocks until that launch has finished. */
 int sgufp_last_kernel_ms(sgufp_ctx *ctx, float *kernel_ms);
-/* How sgufp_solve_paths takes a batch of K candidates on this handle's scenarios: in runs of this many consecutive
- * candidates per scenario.  The first candidate of a run is solved from zero flow, each of the others from the optimal flow
+/* How sgufp_solve_paths takes a batch of K candidates on this handle's scenarios: in runs of this many
+ * candidates per scenario, neighbours in a nearest-neighbour chain the library lays through the batch's paths (K <= 128;
+ * SGUFP_K1_ORDER=0: neighbours in the order given).  Results always come back in the order given.  The first candidate of a run is solved from zero flow, each of the others from the optimal flow
  * and potentials of the one before it (the paths NodeExplorer::process emits one after the other, NodeExplorer.cpp:949-971,
  * differ in a few layers).  The cuts do not depend on it.  1 = no warm starts; SGUFP_K1_GROUP=n overrides the choice. */
 int sgufp_run_length(const sgufp_ctx *ctx, int K);
