@@ -72,6 +72,11 @@ extern "C" void emul_set_group(int g) { g_group = g; }   // candidates per work 
 extern "C" void emul_warm_counts(long long *out2) { out2[0] = sgufp::sgufp_emul_warm[0]; out2[1] = sgufp::sgufp_emul_warm[1]; sgufp::sgufp_emul_warm[0] = sgufp::sgufp_emul_warm[1] = 0; }
 extern "C" void emul_warm_counts8(long long *out8) { for (int i = 0; i < 8; i++) { out8[i] = sgufp::sgufp_emul_warm[i]; sgufp::sgufp_emul_warm[i] = 0; } }
 extern "C" void emul_counts16(long long *out16) { for (int i = 0; i < 16; i++) { out16[i] = sgufp::sgufp_emul_cnt[i]; sgufp::sgufp_emul_cnt[i] = 0; } }   // tools/proto/flow_census.py
+extern "C" void emul_order(const int16_t *paths, int K, int L, const int16_t *start, int32_t *order) {   // model.hpp: order_batch, as the product calls it
+    std::vector<int32_t> o;
+    sgufp::order_batch(paths, K, L, start, o);
+    std::memcpy(order, o.data(), (size_t)K * 4);
+}
 static int g_last_nc = 0;
 extern "C" int emul_last_nc() { return g_last_nc; }   // contracted nodes of the last instance: which size class ran
 

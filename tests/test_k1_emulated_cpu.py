@@ -340,6 +340,46 @@ def test_the_order_of_a_run_does_not_change_the_cuts(emul):
             assert (a == b).all()
 
 
+def test_order_batch_is_a_nearest_neighbour_chain(emul):
+    """model.hpp: order_batch — a permutation; every step goes to the closest path not yet taken (ties: the order given); the chain
+    starts at candidate 0, or at the path closest to `start`; batches of more than 128 candidates, and of one, keep the order given."""
+    i16p, ip = C.POINTER(C.c_int16), C.POINTER(C.c_int32)
+    rng = np.random.default_rng(5)
+
+    def order(paths, start=None):
+        K, L = paths.shape
+        out = np.zeros(K, np.int32)
+        emul.emul_order(np.ascontiguousarray(paths).ctypes.data_as(i16p), K, L,
+                        None if start is None else np.ascontiguousarray(start).ctypes.data_as(i16p), out.ctypes.data_as(ip))
+        return out.tolist()
+
+    for K, L, with_start in ((1, 9, False), (1, 9, True), (2, 9, False), (2, 9, True), (7, 30, False), (16, 83, True), (64, 83, True), (128, 20, False)):
+        base = rng.integers(-1, 6, size=L).astype(np.int16)
+        paths = np.repeat(base[None, :], K, axis=0)
+        for k in range(K):                                  # a few layers away from a common path, some rows identical
+            idx = rng.integers(0, L, size=int(rng.integers(0, 5)))
+            paths[k, idx] = rng.integers(-1, 6, size=len(idx))
+        start = None
+        if with_start:
+            start = base.copy(); start[rng.integers(0, L, size=2)] = 7
+        o = order(paths, start)
+        assert sorted(o) == list(range(K))
+        cur, left = start, set(range(K))
+        if start is None and K > 2:
+            assert o[0] == 0
+        if K == 2 and start is None:
+            assert o == [0, 1]
+        if K >= 2 and not (K == 2 and start is None):
+            for j, k in enumerate(o):
+                if cur is not None:
+                    d = {i: int((paths[i] != cur).sum()) for i in left}
+                    best = min(d.values())
+                    assert d[k] == best and k == min(i for i in left if d[i] == best), (K, j)
+                left.discard(k); cur = paths[k]
+    big = rng.integers(-1, 6, size=(129, 12)).astype(np.int16)
+    assert order(big, big[5]) == list(range(129))
+
+
 @pytest.mark.parametrize("block", range(3))
 def test_warm_runs_fuzz(emul, block):
     """Random small and larger networks, with and without lower bounds, runs of 1 - 4 changed layers."""
