@@ -166,8 +166,8 @@ int sgufp_last_stats(const sgufp_ctx *ctx, int *kernel_launches, float *device_m
  * around the kernel); blocks until that launch has finished. */
 int sgufp_last_kernel_ms(sgufp_ctx *ctx, float *kernel_ms);
 /* How sgufp_solve_paths takes a batch of K candidates on this handle's scenarios: in runs of this many
- * candidates per scenario, neighbours in a nearest-neighbour chain the library lays through the batch's paths (K <= 128;
- * SGUFP_K1_ORDER=0: neighbours in the order given).  Results always come back in the order given.  The first candidate of a run is solved from zero flow, each of the others from the optimal flow
+ * candidates per scenario, neighbours in a nearest-neighbour chain the library lays through the batch's paths when that is
+ * cheap against the batch (K <= 128 and K * L <= 4 * S; SGUFP_K1_ORDER=0 / 1: never / whenever K <= 128), else in the order given.  Results always come back in the order given.  The first candidate of a run is solved from zero flow, each of the others from the optimal flow
  * and potentials of the one before it (the paths NodeExplorer::process emits one after the other, NodeExplorer.cpp:949-971,
  * differ in a few layers).  The cuts do not depend on it.  1 = no warm starts; SGUFP_K1_GROUP=n overrides the choice. */
 int sgufp_run_length(const sgufp_ctx *ctx, int K);

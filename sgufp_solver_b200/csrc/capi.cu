@@ -67,8 +67,12 @@ int make_batch(sgufp_ctx *c, const int16_t *paths, int K, int L, Batch &B, bool 
         if (rc[k]) return fail(c, rc[k], "path " + std::to_string(k) + ": " + errs[k]);   // the lowest failing index, as a serial loop would report
     // the order in which a run takes the candidates, and the links between neighbours in that order (warm starts inside a work
     // item of the warp kernel, k1_cut.cu): the chain starts at the path whose state the handle holds, if it holds one
+    // Laying the chain costs ~0.2 ns x K^2 L on one host thread (64 candidates of C2: ~60 us), the shorter steps save ~6 % of
+    // K x S evaluations of 16 - 70 ns each: it pays when K L is small against S (C4, C5: 4 304 against 10 000 - 100 000 scenarios),
+    // not for 64 candidates on 1000 scenarios of C2 — those batches keep the order given.  SGUFP_K1_ORDER=0 / 1 decides for all.
     const char *order_env = getenv("SGUFP_K1_ORDER");
-    if (order_env && atoi(order_env) == 0) { B.order.resize(K); for (int k = 0; k < K; k++) B.order[k] = k; }
+    const bool order_on = order_env ? atoi(order_env) != 0 : (long long)K * L <= 4LL * std::max(1, c->S);
+    if (!order_on) { B.order.resize(K); for (int k = 0; k < K; k++) B.order[k] = k; }
     else order_batch(paths, K, L, c->state_valid && (int)c->state_path.size() == L ? c->state_path.data() : nullptr, B.order);
     B.links.resize(K); B.link_off.assign(K, -1);
     for (int k = 0; k < K; k++) B.links[k].clear();

@@ -397,6 +397,7 @@ def test_warm_runs_equal_cold_starts_bit_for_bit(wl, S, K, monkeypatch):
     gs = sg.GuroSolver(inst)
     paths, _ = bench.candidate_paths(wl, K, 0)
     outs = []
+    monkeypatch.setenv("SGUFP_K1_ORDER", "1")          # the runs follow the nearest-neighbour chain whatever the batch's size
     for group in ("1", "3", "8", "16"):
         monkeypatch.setenv("SGUFP_K1_GROUP", group)
         r = gs.solve_paths(paths)
